@@ -1,0 +1,511 @@
+// ff_conv_gemm: implicit-GEMM convolution / linear layer for sm_100a.
+//   TMA (4-D shifted boxes, hardware zero fill)  ->  128B-swizzled smem ring
+//   -> tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32 in TMEM, double-buffered accumulators)
+//   -> tcgen05.ld epilogue (bias / activation / gates / residual / PixelShuffle store).
+// Persistent CTAs (one per SM), warp-specialised: warp0 = TMA producer, warp1 = TMEM alloc + MMA
+// issuer, warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+#include "ff_common.cuh"
+#include "../../include/ffb200.h"
+
+namespace {
+
+constexpr int TILE_M = 128;   // output pixels per tile (8 rows x 16 cols)
+constexpr int TILE_W = 16;
+constexpr int TILE_H = 8;
+constexpr int BLOCK_K = 64;   // bf16 elements per k-block = 128 B = one swizzle row
+constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 2;
+constexpr int NUM_THREADS = 192;
+
+struct Args {
+  FFConvGemm p;
+  int Ho, Wo;
+  int tiles_x, tiles_per_img, m_tiles, n_tiles;
+  int ntaps, cchunks;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case FF_ACT_GELU: return gelu_erf(v);
+    case FF_ACT_RELU: return fmaxf(v, 0.f);
+    case FF_ACT_LRELU: return v > 0.f ? v : 0.01f * v;
+    case FF_ACT_SIGMOID: return sigmoidf_(v);
+    case FF_ACT_CLAMP01: return fminf(fmaxf(v, 0.f), 1.f);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ void load_bf16x16(const bf16* ptr, float (&o)[16]) {
+  const uint4* q = reinterpret_cast<const uint4*>(ptr);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[2 * i] = __uint_as_float(w[i] << 16);
+    o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// Fused epilogue for 16 consecutive output channels [n0, n0+16) of one output pixel.
+__device__ __forceinline__ void epilogue16(const Args& a, float (&v)[16], int b, int oy, int ox, int n0) {
+  const FFConvGemm& p = a.p;
+  if (n0 >= p.n_store) return;
+  if (p.bias) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n0 + i);
+  }
+  if (p.gate_pairs) {
+    const long long gpix = ((long long)(b * a.Ho + oy)) * a.Wo + ox;
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i] * v[2 * i + 8], v[2 * i + 1] * v[2 * i + 9]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_bf16) + gpix * p.out_ld + (n0 >> 1)) = make_uint4(w[0], w[1], w[2], w[3]);
+    return;
+  }
+  if (p.act) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act);
+  }
+  if (p.alpha != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
+  }
+  if (p.col_scale) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= __ldg(p.col_scale + n0 + i);
+  }
+  // output location (optionally PixelShuffle(2): packed column n = (i*2+j)*Cq + c)
+  long long opix;
+  int oc;
+  if (p.pixel_shuffle == 2) {
+    const int cq = p.n_store >> 2;
+    const int sub = n0 / cq;
+    oc = n0 - sub * cq;
+    opix = ((long long)(b * 2 * a.Ho + 2 * oy + (sub >> 1))) * (2 * a.Wo) + 2 * ox + (sub & 1);
+  } else {
+    oc = n0;
+    opix = ((long long)(b * a.Ho + oy)) * a.Wo + ox;
+  }
+  const bool full = (oc + 16 <= ((p.pixel_shuffle == 2) ? (p.n_store >> 2) : p.n_store));
+  const int nvalid = full ? 16 : (((p.pixel_shuffle == 2) ? (p.n_store >> 2) : p.n_store) - oc);
+  if (p.mul) {
+    const bf16* q = reinterpret_cast<const bf16*>(p.mul) + opix * p.mul_ld + oc;
+    if (full) {
+      float m[16];
+      load_bf16x16(q, m);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] *= m[i];
+    } else {
+      for (int i = 0; i < nvalid; ++i) v[i] *= __bfloat162float(q[i]);
+    }
+  }
+  if (p.aux) {
+    const bf16* q = reinterpret_cast<const bf16*>(p.aux) + opix * p.aux_ld + oc;
+    float m[16];
+    if (full) {
+      load_bf16x16(q, m);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) m[i] = (i < nvalid) ? __bfloat162float(q[i]) : 0.f;
+    }
+    if (p.aux_chan) {
+      const float* ch = p.aux_chan + (long long)b * p.aux_chan_ld + oc;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += p.aux_alpha * m[i] * ((i < nvalid) ? __ldg(ch + i) : 0.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += p.aux_alpha * m[i];
+    }
+  }
+  if (p.res) {
+    if (p.res_is_f32) {
+      const float* q = reinterpret_cast<const float*>(p.res) + opix * p.res_ld + oc;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 r = __ldg(reinterpret_cast<const float4*>(q) + i);
+          v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+        }
+      } else {
+        for (int i = 0; i < nvalid; ++i) v[i] += q[i];
+      }
+    } else {
+      const bf16* q = reinterpret_cast<const bf16*>(p.res) + opix * p.res_ld + oc;
+      if (full) {
+        float m[16];
+        load_bf16x16(q, m);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += m[i];
+      } else {
+        for (int i = 0; i < nvalid; ++i) v[i] += __bfloat162float(q[i]);
+      }
+    }
+  }
+  if (p.post_act) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.post_act);
+  }
+  if (p.out_f32) {
+    float* q = p.out_f32 + opix * p.out_f32_ld + oc;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<float4*>(q)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+      for (int i = 0; i < nvalid; ++i) q[i] = v[i];
+    }
+  }
+  if (p.out_bf16) {
+    bf16* q = reinterpret_cast<bf16*>(p.out_bf16) + opix * p.out_ld + oc;
+    if (full) {
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      reinterpret_cast<uint4*>(q)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      reinterpret_cast<uint4*>(q)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+      for (int i = 0; i < nvalid; ++i) q[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ----------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ Args a) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t tmem_full[2];
+  __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = a.m_tiles * a.n_tiles;
+  const int kblocks = a.ntaps * a.cchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+        const int b = m_tile / a.tiles_per_img;
+        const int t = m_tile - b * a.tiles_per_img;
+        const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        const int y0 = ty * TILE_H, x0 = tx * TILE_W;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int tap = kb / a.cchunks, cc = kb - tap * a.cchunks;
+          int cx, cy;
+          if (a.p.kind == FF_CONV_3X3) {
+            cx = x0 + (tap % 3) - 1;
+            cy = y0 + (tap / 3) - 1;
+          } else if (a.p.kind == FF_CONV_2X2S2) {
+            cx = 2 * x0 + (tap & 1);
+            cy = 2 * y0 + (tap >> 1);
+          } else {
+            cx = x0;
+            cy = y0;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_4d(sa, &tmA, &full_bar[stage], cc * BLOCK_K, cx, cy, b);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, b * a.p.w_batch_rows + n_tile * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            tc_mma_bf16(d_tmem, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // accumulator row == TMEM lane
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+      const int b = m_tile / a.tiles_per_img;
+      const int t = m_tile - b * a.tiles_per_img;
+      const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+      const int oy = ty * TILE_H + (r >> 4), ox = tx * TILE_W + (r & 15);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int j = 0; j < BN / 16; ++j) {
+        uint32_t raw[16];
+        tmem_ld16(taddr + j * 16, raw);
+        tc_wait_ld();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+        epilogue16(a, v, b, oy, ox, n_tile * BN + j * 16);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// SIMT reference main loop (testing only; same epilogue).  One thread per output pixel.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) conv_gemm_simt_kernel(const __grid_constant__ Args a) {
+  const FFConvGemm& p = a.p;
+  const int m_tile = blockIdx.x;
+  const int r = threadIdx.x;
+  const int b = m_tile / a.tiles_per_img;
+  const int t = m_tile - b * a.tiles_per_img;
+  const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+  const int oy = ty * TILE_H + (r >> 4), ox = tx * TILE_W + (r & 15);
+  const bf16* x = reinterpret_cast<const bf16*>(p.x);
+  const bf16* w = reinterpret_cast<const bf16*>(p.w);
+  const int K = a.ntaps * p.cin;
+  for (int n0 = blockIdx.y * 16; n0 < p.n_pad; n0 += gridDim.y * 16) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    for (int tap = 0; tap < a.ntaps; ++tap) {
+      int iy, ix;
+      if (p.kind == FF_CONV_3X3) { iy = oy + tap / 3 - 1; ix = ox + tap % 3 - 1; }
+      else if (p.kind == FF_CONV_2X2S2) { iy = 2 * oy + (tap >> 1); ix = 2 * ox + (tap & 1); }
+      else { iy = oy; ix = ox; }
+      if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;
+      const bf16* xr = x + ((long long)(b * p.H + iy) * p.W + ix) * p.x_ld;
+      for (int c = 0; c < p.cin; ++c) {
+        const float xv = __bfloat162float(xr[c]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += xv * __bfloat162float(w[(long long)(b * p.w_batch_rows + n0 + i) * K + tap * p.cin + c]);
+      }
+    }
+    epilogue16(a, v, b, oy, ox, n0);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      ff_set_error("ff_conv_gemm: cudaFuncSetAttribute(%d) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return FF_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int tiles = a.m_tiles * a.n_tiles;
+  const int grid = tiles < ff_num_sms() ? tiles : ff_num_sms();
+  conv_gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, a);
+  FF_CHECK_LAUNCH("ff_conv_gemm");
+  return FF_OK;
+}
+
+}  // namespace
+
+extern long long g_ff_launches;
+
+extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
+  FF_CHECK_ARG(pp != nullptr, "ff_conv_gemm: null params");
+  Args a;
+  a.p = *pp;
+  const FFConvGemm& p = a.p;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FF_CHECK_ARG(p.x && p.w, "ff_conv_gemm: null x/w");
+  FF_CHECK_ARG(p.kind >= 0 && p.kind <= 2, "ff_conv_gemm: bad kind %d", p.kind);
+  FF_CHECK_ARG(p.cin > 0 && p.cin % BLOCK_K == 0 && p.cin <= p.x_ld, "ff_conv_gemm: cin=%d must be a multiple of 64 and <= x_ld=%d", p.cin, p.x_ld);
+  FF_CHECK_ARG(p.x_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0, "ff_conv_gemm: x must be 16B aligned with x_ld%%8==0");
+  FF_CHECK_ARG(p.n_pad > 0 && p.n_pad % 16 == 0 && p.n_store > 0 && p.n_store <= p.n_pad, "ff_conv_gemm: bad n_pad=%d n_store=%d", p.n_pad, p.n_store);
+  FF_CHECK_ARG(p.out_bf16 || p.out_f32, "ff_conv_gemm: no output buffer");
+  a.Ho = (p.kind == FF_CONV_2X2S2) ? p.H / 2 : p.H;
+  a.Wo = (p.kind == FF_CONV_2X2S2) ? p.W / 2 : p.W;
+  FF_CHECK_ARG(a.Ho % TILE_H == 0 && a.Wo % TILE_W == 0 && a.Ho > 0, "ff_conv_gemm: output %dx%d must be a multiple of %dx%d", a.Ho, a.Wo, TILE_H, TILE_W);
+  if (p.gate_pairs) {
+    FF_CHECK_ARG(p.out_bf16 && !p.out_f32 && !p.act && !p.mul && !p.aux && !p.res && !p.pixel_shuffle && !p.col_scale && p.n_store % 16 == 0,
+                 "ff_conv_gemm: gate_pairs supports bias + bf16 store only");
+    FF_CHECK_ARG(p.out_ld >= p.n_store / 2 && p.out_ld % 8 == 0, "ff_conv_gemm: gate_pairs out_ld too small");
+  }
+  if (p.w_batch_rows) FF_CHECK_ARG(p.w_batch_rows >= p.n_pad, "ff_conv_gemm: w_batch_rows < n_pad");
+  if (p.pixel_shuffle) {
+    FF_CHECK_ARG(p.pixel_shuffle == 2 && p.n_store % 64 == 0, "ff_conv_gemm: pixel_shuffle needs r=2 and n_store%%64==0");
+    FF_CHECK_ARG(!p.mul && !p.aux, "ff_conv_gemm: pixel_shuffle supports bias/act/res only");
+  }
+  const int width_ok = p.pixel_shuffle ? (p.n_store >> 2) : p.gate_pairs ? (p.n_store >> 1) : p.n_store;
+  const bool vec = width_ok >= 16;  // narrower outputs take the scalar store path: no alignment requirement
+  if (p.out_bf16) FF_CHECK_ARG(p.out_ld >= width_ok && (!vec || (p.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0)), "ff_conv_gemm: bad out_ld=%d", p.out_ld);
+  if (p.out_f32) FF_CHECK_ARG(p.out_f32_ld >= width_ok && (!vec || (p.out_f32_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0)), "ff_conv_gemm: bad out_f32_ld=%d", p.out_f32_ld);
+  if (p.mul) FF_CHECK_ARG(p.mul_ld >= width_ok && (!vec || (p.mul_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.mul) & 15) == 0)), "ff_conv_gemm: bad mul_ld");
+  if (p.aux) FF_CHECK_ARG(p.aux_ld >= width_ok && (!vec || (p.aux_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)), "ff_conv_gemm: bad aux_ld");
+  if (p.res) FF_CHECK_ARG(p.res_ld >= width_ok && (!vec || (p.res_ld % (p.res_is_f32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0)), "ff_conv_gemm: bad res_ld");
+
+  a.tiles_x = a.Wo / TILE_W;
+  a.tiles_per_img = a.tiles_x * (a.Ho / TILE_H);
+  a.m_tiles = a.tiles_per_img * p.B;
+  a.ntaps = (p.kind == FF_CONV_3X3) ? 9 : (p.kind == FF_CONV_2X2S2) ? 4 : 1;
+  a.cchunks = p.cin / BLOCK_K;
+
+  if (p.debug_simt) {
+    a.n_tiles = 1;
+    dim3 grid(a.m_tiles, p.n_pad / 16 < 8 ? p.n_pad / 16 : 8);
+    conv_gemm_simt_kernel<<<grid, 128, 0, st>>>(a);
+    ++g_ff_launches;
+    FF_CHECK_LAUNCH("ff_conv_gemm(simt)");
+    return FF_OK;
+  }
+
+  int BN;
+  if (p.n_pad % 256 == 0) BN = 256;
+  else if (p.n_pad % 192 == 0) BN = 192;
+  else if (p.n_pad % 128 == 0) BN = 128;
+  else if (p.n_pad % 64 == 0) BN = 64;
+  else if (p.n_pad % 32 == 0) BN = 32;
+  else BN = 16;
+  a.n_tiles = p.n_pad / BN;
+
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    ff_set_error("ff_conv_gemm: cuTensorMapEncodeTiled entry point unavailable");
+    return FF_ERR_DRIVER;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    const int es = (p.kind == FF_CONV_2X2S2) ? 2 : 1;
+    cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    cuuint64_t strides[3] = {(cuuint64_t)p.x_ld * 2, (cuuint64_t)p.x_ld * 2 * p.W, (cuuint64_t)p.x_ld * 2 * p.W * p.H};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(TILE_W * es), (cuuint32_t)(TILE_H * es), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ff_set_error("ff_conv_gemm: cuTensorMapEncodeTiled(A) failed with %d (B=%d H=%d W=%d ld=%d cin=%d)", (int)r, p.B, p.H, p.W, p.x_ld, p.cin);
+      return FF_ERR_DRIVER;
+    }
+  }
+  {
+    const cuuint64_t K = (cuuint64_t)a.ntaps * p.cin;
+    cuuint64_t dims[2] = {K, (cuuint64_t)(p.w_batch_rows ? (long long)p.w_batch_rows * p.B : p.n_pad)};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ff_set_error("ff_conv_gemm: cuTensorMapEncodeTiled(B) failed with %d (K=%llu n_pad=%d)", (int)r, (unsigned long long)K, p.n_pad);
+      return FF_ERR_DRIVER;
+    }
+  }
+  ++g_ff_launches;
+  switch (BN) {
+    case 256: return launch_tc<256>(tmA, tmB, a, st);
+    case 192: return launch_tc<192>(tmA, tmB, a, st);
+    case 128: return launch_tc<128>(tmA, tmB, a, st);
+    case 64: return launch_tc<64>(tmA, tmB, a, st);
+    case 32: return launch_tc<32>(tmA, tmB, a, st);
+    default: return launch_tc<16>(tmA, tmB, a, st);
+  }
+}

@@ -1,0 +1,28 @@
+// Library-wide state of the C ABI: error text, ABI version, launch counter, device properties.
+#include "ff_common.cuh"
+#include "../../include/ffb200.h"
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+long long g_ff_launches = 0;
+
+void ff_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int ff_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+extern "C" int ff_abi_version(void) { return FFB200_ABI_VERSION; }
+extern "C" const char* ff_last_error(void) { return g_err; }
+extern "C" long long ff_launch_count(void) { return g_ff_launches; }

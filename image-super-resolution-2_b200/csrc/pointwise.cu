@@ -1,0 +1,444 @@
+// Memory-bound building blocks shared by the three experts and the fusion head (NHWC layouts):
+// layer norm, global average pool, tiny per-sample linear layers (SE / SCA / AIM heads), depthwise
+// convolutions with fused gates, direct small-channel convolutions (fp32), layout conversion.
+#include "ff_common.cuh"
+#include "../../include/ffb200.h"
+
+extern long long g_ff_launches;
+
+namespace {
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case FF_ACT_GELU: return gelu_erf(v);
+    case FF_ACT_RELU: return fmaxf(v, 0.f);
+    case FF_ACT_LRELU: return v > 0.f ? v : 0.01f * v;
+    case FF_ACT_SIGMOID: return sigmoidf_(v);
+    case FF_ACT_CLAMP01: return fminf(fmaxf(v, 0.f), 1.f);
+    default: return v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the channel axis of [rows][ld]; one warp per row, values kept in registers.
+// ------------------------------------------------------------------------------------------
+template <typename TIn, int MAXV>  // MAXV = ceil(C/32) upper bound
+__global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ x, int in_ld, long long rows, int C,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, bf16* __restrict__ out_bf16, int out_ld, int out_cols,
+                                                       float* __restrict__ out_f32, int out_f32_ld) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const TIn* xr = x + row * in_ld;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (c < C) ? (float)xr[c] : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    const float d = (c < C) ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < out_cols) {
+      float y = 0.f;
+      if (c < C) y = (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      if (out_bf16) out_bf16[row * out_ld + c] = __float2bfloat16_rn(y);
+      if (out_f32) out_f32[row * out_f32_ld + c] = y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Global average pool over pixels: x [B][P][ld] -> partial sums [B][nsplit][C] -> mean [B][out_ld]
+// (two phases, fixed summation order => deterministic).
+// ------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256) gap_partial_kernel(const TIn* __restrict__ x, int ld, int P, int C, int nsplit,
+                                                         float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  const int b = blockIdx.z, split = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  const int per = (P + nsplit - 1) / nsplit;
+  const int p0 = split * per, p1 = min(P, p0 + per);
+  float s = 0.f;
+  if (c < C) {
+    const TIn* xb = x + ((long long)b * P) * ld + c;
+    for (int p = p0 + w; p < p1; p += 8) s += (float)xb[(long long)p * ld];
+  }
+  red[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    if (c < C) partial[((long long)b * nsplit + split) * C + c] = t;
+  }
+}
+__global__ void gap_final_kernel(const float* __restrict__ partial, int C, int nsplit, float inv, float* __restrict__ out,
+                                 int out_ld) {
+  const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= out_ld) return;
+  float t = 0.f;
+  if (c < C)
+    for (int s = 0; s < nsplit; ++s) t += partial[((long long)b * nsplit + s) * C + c];
+  out[(long long)b * out_ld + c] = t * inv;
+}
+
+// ------------------------------------------------------------------------------------------
+// y[r][n] = act(sum_k x[r][k] * W[n][k] + bias[n])  for a handful of rows (per-sample vectors).
+// One warp per output element.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vec_linear_kernel(const float* __restrict__ x, int x_ld, int R, int K,
+                                                        const float* __restrict__ W, const float* __restrict__ bias, int N,
+                                                        int act, float* __restrict__ y, int y_ld, int y_cols) {
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= R * y_cols) return;
+  const int r = gw / y_cols, n = gw - r * y_cols;
+  float s = 0.f;
+  if (n < N) {
+    const float* xr = x + (long long)r * x_ld;
+    const float* wr = W + (long long)n * K;
+    for (int k = lane; k < K; k += 32) s += xr[k] * __ldg(wr + k);
+    s = warp_sum(s);
+    if (bias) s += __ldg(bias + n);
+    s = act_apply(s, act);
+  }
+  if (lane == 0) y[(long long)r * y_ld + n] = (n < N) ? s : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// Depthwise convolution, NHWC, 8 channels per thread (16-byte bf16 vectors).
+//   mode 0: out[c] = act(dw(x)[c] + bias[c]) (* mul[c])
+//   mode 1 (SimpleGate): out[c] = (dw(x)[c]+bias[c]) * (dw(x)[c+Cout]+bias[c+Cout]),  c < Cout = C/2
+// Weights are fp32 [kh*kw][C] (tap-major) so channel vectors are contiguous.
+// ------------------------------------------------------------------------------------------
+struct DwArgs {
+  const bf16* x; int x_ld;
+  int B, H, W, C;
+  int kh, kw;
+  const float* w; const float* bias;
+  int act; int mode;
+  const bf16* mul; int mul_ld;
+  bf16* out; int out_ld;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ void dw_accum(const DwArgs& a, int b, int y, int x, int c0, float (&acc)[8]) {
+  const int ph = a.kh >> 1, pw = a.kw >> 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = a.bias ? __ldg(a.bias + c0 + i) : 0.f;
+  for (int dy = 0; dy < a.kh; ++dy) {
+    const int yy = y + dy - ph;
+    if (yy < 0 || yy >= a.H) continue;
+    for (int dx = 0; dx < a.kw; ++dx) {
+      const int xx = x + dx - pw;
+      if (xx < 0 || xx >= a.W) continue;
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.x + ((long long)(b * a.H + yy) * a.W + xx) * a.x_ld + c0));
+      float f[8];
+      unpack8(q, f);
+      const float* wp = a.w + (long long)(dy * a.kw + dx) * a.C + c0;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp) + 1);
+      acc[0] += f[0] * w0.x; acc[1] += f[1] * w0.y; acc[2] += f[2] * w0.z; acc[3] += f[3] * w0.w;
+      acc[4] += f[4] * w1.x; acc[5] += f[5] * w1.y; acc[6] += f[6] * w1.z; acc[7] += f[7] * w1.w;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dwconv_kernel(const __grid_constant__ DwArgs a) {
+  const int cout = a.mode == 1 ? a.C / 2 : a.C;
+  const int groups = cout >> 3;
+  const long long total = (long long)a.B * a.H * a.W * groups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const long long pix = idx / groups;
+  const int x = (int)(pix % a.W);
+  const int y = (int)((pix / a.W) % a.H);
+  const int b = (int)(pix / ((long long)a.W * a.H));
+  const int c0 = g * 8;
+  float acc[8];
+  dw_accum(a, b, y, x, c0, acc);
+  if (a.mode == 1) {
+    float acc2[8];
+    dw_accum(a, b, y, x, c0 + cout, acc2);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= acc2[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = act_apply(acc[i], a.act);
+    if (a.mul) {
+      float m[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a.mul + pix * a.mul_ld + c0)), m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= m[i];
+    }
+  }
+  *reinterpret_cast<uint4*>(a.out + pix * a.out_ld + c0) = pack8(acc);
+}
+
+// x[p][c] *= s[b][c]  (bf16 in place), 8 channels per thread
+__global__ void __launch_bounds__(256) scale_channels_kernel(bf16* __restrict__ x, int ld, long long P_per_b, int B, int C,
+                                                            const float* __restrict__ s, int s_ld) {
+  const int groups = C >> 3;
+  const long long total = (long long)B * P_per_b * groups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const long long pix = idx / groups;
+  const int b = (int)(pix / P_per_b);
+  uint4* ptr = reinterpret_cast<uint4*>(x + pix * ld + g * 8);
+  float f[8];
+  unpack8(*ptr, f);
+  const float* sp = s + (long long)b * s_ld + g * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] *= __ldg(sp + i);
+  *ptr = pack8(f);
+}
+
+// ------------------------------------------------------------------------------------------
+// Direct convolution (1x1 or 3x3, zero pad) in fp32 for small channel counts.
+// Block = 16x8 output pixels, each thread computes 8 output channels of one pixel; grid.y walks
+// groups of 8 output channels.  Input patch and the weight slice are staged in shared memory.
+// ------------------------------------------------------------------------------------------
+struct DirectArgs {
+  const void* x; int x_is_bf16; int x_ld;
+  int B, H, W, Cin, k;
+  const float* w;     // [Cout_pad][k*k*Cin], Cout_pad multiple of 8 (zero rows as padding)
+  const float* bias;  // [Cout_pad] or null
+  int Cout_pad, n_store;
+  int act;
+  const float* mul_f32; int mul_ld;   // optional multiply by an fp32 NHWC tensor (same pixel, channel n) after act
+  bf16* out_bf16; int out_ld;
+  float* out_f32; int out_f32_ld;
+};
+
+__global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant__ DirectArgs a) {
+  extern __shared__ float sm[];
+  const int pad = a.k >> 1;
+  const int PW = 16 + 2 * pad, PH = 8 + 2 * pad;
+  const int cs = a.Cin | 1;  // odd pitch -> conflict-free
+  float* sIn = sm;                       // [PH*PW][cs]
+  float* sW = sm + PH * PW * cs;         // [k*k*Cin][8]
+  const int tiles_x = a.W / 16, tiles_y = a.H / 8;
+  int t = blockIdx.x;
+  const int b = t / (tiles_x * tiles_y);
+  t -= b * tiles_x * tiles_y;
+  const int ty = t / tiles_x, tx = t - ty * tiles_x;
+  const int y0 = ty * 8 - pad, x0 = tx * 16 - pad;
+  for (int i = threadIdx.x; i < PH * PW * a.Cin; i += 128) {
+    const int c = i % a.Cin, pp = i / a.Cin;
+    const int py = pp / PW, px = pp - py * PW;
+    const int y = y0 + py, x = x0 + px;
+    float v = 0.f;
+    if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+      const long long off = ((long long)(b * a.H + y) * a.W + x) * a.x_ld + c;
+      v = a.x_is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(a.x)[off]) : reinterpret_cast<const float*>(a.x)[off];
+    }
+    sIn[pp * cs + c] = v;
+  }
+  const int KK = a.k * a.k * a.Cin;
+  const int n0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < KK * 8; i += 128) {
+    const int o = i & 7, kk = i >> 3;
+    sW[kk * 8 + o] = __ldg(a.w + (long long)(n0 + o) * KK + kk);
+  }
+  __syncthreads();
+  const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = a.bias ? __ldg(a.bias + n0 + o) : 0.f;
+  for (int dy = 0; dy < a.k; ++dy)
+    for (int dx = 0; dx < a.k; ++dx) {
+      const float* ip = sIn + ((py + dy) * PW + px + dx) * cs;
+      const float* wp = sW + (dy * a.k + dx) * a.Cin * 8;
+      for (int c = 0; c < a.Cin; ++c) {
+        const float xv = ip[c];
+        const float4 w0 = *reinterpret_cast<const float4*>(wp + c * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + c * 8 + 4);
+        acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
+        acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+      }
+    }
+  const long long opix = (long long)(b * a.H + ty * 8 + py) * a.W + tx * 16 + px;
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const int n = n0 + o;
+    if (n < a.n_store) {
+      float v = act_apply(acc[o], a.act);
+      if (a.mul_f32) v *= a.mul_f32[opix * a.mul_ld + n];
+      if (a.out_f32) a.out_f32[opix * a.out_f32_ld + n] = v;
+      if (a.out_bf16) a.out_bf16[opix * a.out_ld + n] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// NCHW fp32 image -> NHWC fp32 [pixels][ld] with per-channel offset subtraction (x - mean)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int C, int H, int W, const float* __restrict__ sub,
+                                    float* __restrict__ out, int ld) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * W;
+  if (idx >= total) return;
+  const long long hw = (long long)H * W;
+  const int b = (int)(idx / hw);
+  const long long p = idx - b * hw;
+  for (int c = 0; c < ld; ++c) {
+    float v = 0.f;
+    if (c < C) v = x[((long long)b * C + c) * hw + p] - (sub ? sub[c] : 0.f);
+    out[idx * ld + c] = v;
+  }
+}
+// NHWC fp32 [pixels][ld] (first C channels) -> NCHW fp32
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int ld, int coff, int B, int C, int H, int W,
+                                    float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * W;
+  if (idx >= total) return;
+  const long long hw = (long long)H * W;
+  const int b = (int)(idx / hw);
+  const long long p = idx - b * hw;
+  for (int c = 0; c < C; ++c) out[((long long)b * C + c) * hw + p] = x[idx * ld + coff + c];
+}
+
+}  // namespace
+
+extern "C" int ff_layernorm(const void* x, int x_is_bf16, int in_ld, long long rows, int C, const float* gamma,
+                            const float* beta, float eps, void* out_bf16, int out_ld, int out_cols, float* out_f32,
+                            int out_f32_ld, void* stream) {
+  FF_CHECK_ARG(x && gamma && beta && (out_bf16 || out_f32), "ff_layernorm: null buffer");
+  FF_CHECK_ARG(C > 0 && C <= 1024 && out_cols >= C && out_cols <= 1024, "ff_layernorm: C=%d out_cols=%d unsupported", C, out_cols);
+  if (rows <= 0) return FF_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ff_cdiv(rows, 8);
+  const int maxv = ff_cdiv(out_cols, 32);
+#define LN_LAUNCH(T, MV) layernorm_kernel<T, MV><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(x), in_ld, rows, C, gamma, beta, eps, reinterpret_cast<bf16*>(out_bf16), out_ld, out_cols, out_f32, out_f32_ld)
+  if (x_is_bf16) {
+    if (maxv <= 2) LN_LAUNCH(bf16, 2); else if (maxv <= 4) LN_LAUNCH(bf16, 4); else if (maxv <= 8) LN_LAUNCH(bf16, 8); else if (maxv <= 16) LN_LAUNCH(bf16, 16); else LN_LAUNCH(bf16, 32);
+  } else {
+    if (maxv <= 2) LN_LAUNCH(float, 2); else if (maxv <= 4) LN_LAUNCH(float, 4); else if (maxv <= 8) LN_LAUNCH(float, 8); else if (maxv <= 16) LN_LAUNCH(float, 16); else LN_LAUNCH(float, 32);
+  }
+#undef LN_LAUNCH
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_layernorm");
+  return FF_OK;
+}
+
+extern "C" int ff_gap(const void* x, int x_is_bf16, int ld, int B, int P, int C, float* out, int out_ld, float* scratch,
+                      size_t scratch_bytes, void* stream) {
+  FF_CHECK_ARG(x && out && scratch, "ff_gap: null buffer");
+  FF_CHECK_ARG(out_ld >= C, "ff_gap: out_ld < C");
+  int nsplit = P / 512;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > 64) nsplit = 64;
+  FF_CHECK_ARG(scratch_bytes >= (size_t)B * nsplit * C * sizeof(float), "ff_gap: scratch too small (%zu)", scratch_bytes);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(ff_cdiv(C, 32), nsplit, B);
+  if (x_is_bf16) gap_partial_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ld, P, C, nsplit, scratch);
+  else gap_partial_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), ld, P, C, nsplit, scratch);
+  gap_final_kernel<<<dim3(ff_cdiv(out_ld, 128), B), 128, 0, st>>>(scratch, C, nsplit, 1.0f / P, out, out_ld);
+  g_ff_launches += 2;
+  FF_CHECK_LAUNCH("ff_gap");
+  return FF_OK;
+}
+
+extern "C" int ff_vec_linear(const float* x, int x_ld, int R, int K, const float* W, const float* bias, int N, int act,
+                             float* y, int y_ld, int y_cols, void* stream) {
+  FF_CHECK_ARG(x && W && y, "ff_vec_linear: null buffer");
+  FF_CHECK_ARG(y_cols >= N && y_ld >= y_cols, "ff_vec_linear: bad y_cols/y_ld");
+  vec_linear_kernel<<<ff_cdiv((long long)R * y_cols, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_ld, R, K, W, bias, N, act, y, y_ld, y_cols);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_vec_linear");
+  return FF_OK;
+}
+
+extern "C" int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, int kh, int kw, const float* w,
+                         const float* bias, int act, int mode, const void* mul, int mul_ld, void* out, int out_ld,
+                         void* stream) {
+  FF_CHECK_ARG(x && w && out, "ff_dwconv: null buffer");
+  FF_CHECK_ARG(C % 8 == 0 && x_ld % 8 == 0 && out_ld % 8 == 0 && (mode != 1 || C % 16 == 0), "ff_dwconv: channels/pitches must be multiples of 8");
+  FF_CHECK_ARG((kh & 1) && (kw & 1), "ff_dwconv: odd kernel sizes only");
+  DwArgs a{reinterpret_cast<const bf16*>(x), x_ld, B, H, W, C, kh, kw, w, bias, act, mode, reinterpret_cast<const bf16*>(mul), mul_ld, reinterpret_cast<bf16*>(out), out_ld};
+  const long long total = (long long)B * H * W * ((mode == 1 ? C / 2 : C) / 8);
+  dwconv_kernel<<<ff_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_dwconv");
+  return FF_OK;
+}
+
+extern "C" int ff_scale_channels(void* x, int ld, int B, long long pixels_per_sample, int C, const float* s, int s_ld,
+                                 void* stream) {
+  FF_CHECK_ARG(x && s && C % 8 == 0 && ld % 8 == 0, "ff_scale_channels: bad args");
+  const long long total = (long long)B * pixels_per_sample * (C / 8);
+  scale_channels_kernel<<<ff_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<bf16*>(x), ld, pixels_per_sample, B, C, s, s_ld);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_scale_channels");
+  return FF_OK;
+}
+
+extern "C" int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int H, int W, int Cin, int k, const float* w,
+                              const float* bias, int Cout_pad, int n_store, int act, const float* mul_f32, int mul_ld,
+                              void* out_bf16, int out_ld, float* out_f32, int out_f32_ld, void* stream) {
+  FF_CHECK_ARG(x && w && (out_bf16 || out_f32), "ff_conv_direct: null buffer");
+  FF_CHECK_ARG((k == 1 || k == 3) && Cin > 0 && Cin <= 192, "ff_conv_direct: k=%d Cin=%d unsupported", k, Cin);
+  FF_CHECK_ARG(H % 8 == 0 && W % 16 == 0, "ff_conv_direct: %dx%d must be a multiple of 8x16", H, W);
+  FF_CHECK_ARG(Cout_pad % 8 == 0 && n_store <= Cout_pad, "ff_conv_direct: Cout_pad must be a multiple of 8");
+  DirectArgs a{x, x_is_bf16, x_ld, B, H, W, Cin, k, w, bias, Cout_pad, n_store, act, mul_f32, mul_ld, reinterpret_cast<bf16*>(out_bf16), out_ld, out_f32, out_f32_ld};
+  const int pad = k / 2;
+  const size_t smem = ((size_t)(16 + 2 * pad) * (8 + 2 * pad) * (Cin | 1) + (size_t)k * k * Cin * 8) * sizeof(float);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ff_set_error("ff_conv_direct: smem %zu: %s", smem, cudaGetErrorString(e)); return FF_ERR_CUDA; }
+    configured = smem;
+  }
+  dim3 grid(B * (H / 8) * (W / 16), Cout_pad / 8);
+  conv_direct_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_conv_direct");
+  return FF_OK;
+}
+
+extern "C" int ff_nchw_to_nhwc(const float* x, int B, int C, int H, int W, const float* sub, float* out, int ld, void* stream) {
+  FF_CHECK_ARG(x && out && ld >= C, "ff_nchw_to_nhwc: bad args");
+  nchw_to_nhwc_kernel<<<ff_cdiv((long long)B * H * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, B, C, H, W, sub, out, ld);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_nchw_to_nhwc");
+  return FF_OK;
+}
+extern "C" int ff_nhwc_to_nchw(const float* x, int ld, int coff, int B, int C, int H, int W, float* out, void* stream) {
+  FF_CHECK_ARG(x && out && ld >= coff + C, "ff_nhwc_to_nchw: bad args");
+  nhwc_to_nchw_kernel<<<ff_cdiv((long long)B * H * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ld, coff, B, C, H, W, out);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_nhwc_to_nchw");
+  return FF_OK;
+}

@@ -1,0 +1,265 @@
+// ff_window_attention: fused (shifted-)window multi-head attention for HAT W-MSA/SW-MSA, HAT OCAB and
+// DAT rectangular-window spatial attention.  One CTA = one (window, head):
+//   gather Q/K/V rows (cyclic shift and OCAB zero padding resolved by index arithmetic, no roll/unfold copies)
+//   -> S = Q K^T on tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate)
+//   -> + relative-position bias (table in smem, index computed arithmetically) + {0,-100} shift mask
+//   -> online softmax (fp32) -> O = P V -> normalise -> store at the un-shifted token position.
+// The logits never leave registers (the reference materialises [nW*B, heads, 256, 256|576] fp32 in HBM).
+// q is pre-scaled by head_dim^-0.5 through the packed qkv weights.
+#include "ff_common.cuh"
+#include "../../include/ffb200.h"
+
+namespace {
+
+constexpr int HD = 32;       // padded head dim
+constexpr int ROWP = 40;     // smem row pitch (bf16) -> conflict-free ldmatrix
+constexpr int NQ = 256;
+constexpr int KCHUNK = 64;
+constexpr int NTHREADS = 512;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ int region3(int p, int size, int win, int shift) {
+  return p < size - win ? 0 : (p < size - shift ? 1 : 2);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) window_attention_kernel(const __grid_constant__ FFWinAttn p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int NK = p.kh * p.kw;
+  bf16* sQ = reinterpret_cast<bf16*>(smem);
+  bf16* sK = sQ + NQ * ROWP;
+  bf16* sV = sK + NK * ROWP;
+  float* sT = reinterpret_cast<float*>(sV + NK * ROWP);       // bias column of this head, [T]
+  uint16_t* sQc = reinterpret_cast<uint16_t*>(sT + p.T);      // per query: (i<<8 | j)
+  uint16_t* sKc = sQc + NQ;                                    // per key:   (i<<8 | j)
+  uint8_t* sQr = reinterpret_cast<uint8_t*>(sKc + NK);         // per query region id
+  uint8_t* sKr = sQr + NQ;                                     // per key region id (255 = padded key)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int head = p.head_off + blockIdx.y;
+  const int nwx = p.W / p.ww, nwy = p.H / p.wh;
+  int win = blockIdx.x;
+  const int b = win / (nwx * nwy);
+  win -= b * nwx * nwy;
+  const int wy = win / nwx, wx = win - wy * nwx;
+  const bf16* base = reinterpret_cast<const bf16*>(p.qkv);
+  const long long img0 = (long long)b * p.H * p.W;
+  const bool shifted = (p.shift_y | p.shift_x) != 0;
+
+  // ---- gather Q (4 x 16B per row) ----
+  for (int idx = tid; idx < NQ * 4; idx += NTHREADS) {
+    const int t = idx >> 2, part = idx & 3;
+    const int i = t / p.ww, j = t - i * p.ww;
+    const int ys = wy * p.wh + i, xs = wx * p.ww + j;  // shifted-frame coordinates
+    int y = ys + p.shift_y; if (y >= p.H) y -= p.H;
+    int x = xs + p.shift_x; if (x >= p.W) x -= p.W;
+    const bf16* src = base + (img0 + (long long)y * p.W + x) * p.ld + p.q_off + head * HD + part * 8;
+    *reinterpret_cast<uint4*>(sQ + t * ROWP + part * 8) = __ldg(reinterpret_cast<const uint4*>(src));
+    if (part == 0) {
+      sQc[t] = (uint16_t)((i << 8) | j);
+      sQr[t] = shifted ? (uint8_t)(region3(ys, p.H, p.wh, p.shift_y) * 3 + region3(xs, p.W, p.ww, p.shift_x)) : 0;
+    }
+  }
+  // ---- gather K, V ----
+  for (int idx = tid; idx < NK * 4; idx += NTHREADS) {
+    const int t = idx >> 2, part = idx & 3;
+    const int i = t / p.kw, j = t - i * p.kw;
+    const int ys = wy * p.wh - p.kpad_y + i, xs = wx * p.ww - p.kpad_x + j;
+    const bool inside = ys >= 0 && ys < p.H && xs >= 0 && xs < p.W;
+    uint4 kq = make_uint4(0, 0, 0, 0), vq = kq;
+    if (inside) {
+      int y = ys + p.shift_y; if (y >= p.H) y -= p.H;
+      int x = xs + p.shift_x; if (x >= p.W) x -= p.W;
+      const bf16* src = base + (img0 + (long long)y * p.W + x) * p.ld + head * HD + part * 8;
+      kq = __ldg(reinterpret_cast<const uint4*>(src + p.k_off));
+      vq = __ldg(reinterpret_cast<const uint4*>(src + p.v_off));
+    }
+    *reinterpret_cast<uint4*>(sK + t * ROWP + part * 8) = kq;
+    *reinterpret_cast<uint4*>(sV + t * ROWP + part * 8) = vq;
+    if (part == 0) {
+      sKc[t] = (uint16_t)((i << 8) | j);
+      sKr[t] = (shifted && inside) ? (uint8_t)(region3(ys, p.H, p.wh, p.shift_y) * 3 + region3(xs, p.W, p.ww, p.shift_x)) : 0;
+    }
+  }
+  for (int i = tid; i < p.T; i += NTHREADS) sT[i] = __ldg(p.bias_table + (long long)i * p.bias_heads + p.bias_head_off + blockIdx.y);
+  __syncthreads();
+
+  // ---- per-warp: 16 query rows ----
+  const int q0 = warp * 16;
+  uint32_t qa[2][4];
+  {
+    // A fragment (16x16) via ldmatrix.x4: matrices (rows 0-7,k 0-7), (rows 8-15,k 0-7), (rows 0-7,k 8-15), (rows 8-15,k 8-15)
+    const int row = q0 + (lane & 15);
+    const int kofs = (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[ks], smem_u32(sQ + row * ROWP + ks * 16 + kofs));
+  }
+  const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
+  const int qc0 = sQc[r0], qc1 = sQc[r1];
+  const int qi0 = qc0 >> 8, qj0 = qc0 & 255, qi1 = qc1 >> 8, qj1 = qc1 & 255;
+  const int qr0 = sQr[r0], qr1 = sQr[r1];
+
+  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
+  float o[4][4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
+
+  for (int kc = 0; kc < NK; kc += KCHUNK) {
+    float s[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[n][i] = 0.f;
+    // S = Q K^T : B fragments (k16 x n8) come from K rows [key][dim] (non-transposed ldmatrix)
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {  // pairs of n8 tiles (16 keys)
+      // x4: (keys 0-7, dims 0-7), (keys 0-7, dims 8-15), (keys 8-15, dims 0-7), (keys 8-15, dims 8-15) for k-step ks
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t kb[4];
+        const int key = kc + np * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int dofs = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(kb, smem_u32(sK + key * ROWP + dofs));
+        mma16816(s[2 * np], qa[ks], kb[0], kb[1]);
+        mma16816(s[2 * np + 1], qa[ks], kb[2], kb[3]);
+      }
+    }
+    // bias + mask, running max
+    float cm0 = -1e30f, cm1 = -1e30f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = kc + n * 8 + 2 * (lane & 3) + e;
+        const int kcd = sKc[key];
+        const int ki = kcd >> 8, kj = kcd & 255;
+        const int kr = sKr[key];
+        int i0 = (p.rel_sign * (qi0 - ki) + p.rel_off_y) * p.rel_stride + p.rel_sign * (qj0 - kj) + p.rel_off_x;
+        int i1 = (p.rel_sign * (qi1 - ki) + p.rel_off_y) * p.rel_stride + p.rel_sign * (qj1 - kj) + p.rel_off_x;
+        if (i0 < 0) i0 += p.T;
+        if (i1 < 0) i1 += p.T;
+        float v0 = s[n][e] + sT[i0];
+        float v1 = s[n][2 + e] + sT[i1];
+        if (shifted) {
+          if (kr != qr0) v0 -= 100.f;
+          if (kr != qr1) v1 -= 100.f;
+        }
+        s[n][e] = v0;
+        s[n][2 + e] = v1;
+        cm0 = fmaxf(cm0, v0);
+        cm1 = fmaxf(cm1, v1);
+      }
+    }
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+    const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);
+    const float sc0 = __expf(m0 - nm0), sc1 = __expf(m1 - nm1);
+    m0 = nm0; m1 = nm1;
+    l0 *= sc0; l1 *= sc1;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { o[n][0] *= sc0; o[n][1] *= sc0; o[n][2] *= sc1; o[n][3] *= sc1; }
+    // P = exp(S - m), accumulate row sums, O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {  // k16 steps over the 64 keys of the chunk
+      uint32_t pa[4];
+      float e00 = __expf(s[2 * kk][0] - m0), e01 = __expf(s[2 * kk][1] - m0);
+      float e02 = __expf(s[2 * kk][2] - m1), e03 = __expf(s[2 * kk][3] - m1);
+      float e10 = __expf(s[2 * kk + 1][0] - m0), e11 = __expf(s[2 * kk + 1][1] - m0);
+      float e12 = __expf(s[2 * kk + 1][2] - m1), e13 = __expf(s[2 * kk + 1][3] - m1);
+      l0 += e00 + e01 + e10 + e11;
+      l1 += e02 + e03 + e12 + e13;
+      pa[0] = pack_bf16(e00, e01);
+      pa[1] = pack_bf16(e02, e03);
+      pa[2] = pack_bf16(e10, e11);
+      pa[3] = pack_bf16(e12, e13);
+      // B fragments of V (k16 keys x n8 dims) via transposed ldmatrix on V rows [key][dim]
+#pragma unroll
+      for (int dp = 0; dp < 2; ++dp) {  // pairs of n8 tiles (16 dims)
+        uint32_t vb[4];
+        const int key = kc + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int dofs = dp * 16 + (lane >> 4) * 8;
+        ldsm_x4_t(vb, smem_u32(sV + key * ROWP + dofs));
+        mma16816(o[2 * dp], pa, vb[0], vb[1]);
+        mma16816(o[2 * dp + 1], pa, vb[2], vb[3]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+
+  // ---- store at the un-shifted token position ----
+  bf16* outp = reinterpret_cast<bf16*>(p.out);
+  {
+    const int ys0 = wy * p.wh + qi0, xs0 = wx * p.ww + qj0;
+    int y = ys0 + p.shift_y; if (y >= p.H) y -= p.H;
+    int x = xs0 + p.shift_x; if (x >= p.W) x -= p.W;
+    bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + head * HD + 2 * (lane & 3);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) *reinterpret_cast<uint32_t*>(dst + n * 8) = pack_bf16(o[n][0] * inv0, o[n][1] * inv0);
+  }
+  {
+    const int ys1 = wy * p.wh + qi1, xs1 = wx * p.ww + qj1;
+    int y = ys1 + p.shift_y; if (y >= p.H) y -= p.H;
+    int x = xs1 + p.shift_x; if (x >= p.W) x -= p.W;
+    bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + head * HD + 2 * (lane & 3);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) *reinterpret_cast<uint32_t*>(dst + n * 8) = pack_bf16(o[n][2] * inv1, o[n][3] * inv1);
+  }
+}
+
+}  // namespace
+
+extern long long g_ff_launches;
+
+extern "C" int ff_window_attention(const FFWinAttn* pp, void* stream) {
+  FF_CHECK_ARG(pp != nullptr, "ff_window_attention: null params");
+  const FFWinAttn& p = *pp;
+  FF_CHECK_ARG(p.qkv && p.out && p.bias_table, "ff_window_attention: null buffer");
+  FF_CHECK_ARG(p.wh * p.ww == NQ, "ff_window_attention: query window must hold 256 tokens (got %dx%d)", p.wh, p.ww);
+  FF_CHECK_ARG(p.wh < 256 && p.ww < 256 && p.kh < 256 && p.kw < 256, "ff_window_attention: window too large");
+  const int NK = p.kh * p.kw;
+  FF_CHECK_ARG(NK % KCHUNK == 0 && NK >= KCHUNK, "ff_window_attention: key window %dx%d not a multiple of 64 tokens", p.kh, p.kw);
+  FF_CHECK_ARG(p.H % p.wh == 0 && p.W % p.ww == 0, "ff_window_attention: image %dx%d not divisible by window %dx%d", p.H, p.W, p.wh, p.ww);
+  FF_CHECK_ARG(p.ld % 8 == 0 && p.out_ld % 8 == 0 && p.q_off % 8 == 0 && p.k_off % 8 == 0 && p.v_off % 8 == 0 && p.out_off % 8 == 0, "ff_window_attention: offsets/pitches must be multiples of 8");
+  FF_CHECK_ARG(p.heads > 0 && p.T > 0 && p.rel_stride > 0, "ff_window_attention: bad heads/T");
+  FF_CHECK_ARG(p.shift_y >= 0 && p.shift_y < p.wh && p.shift_x >= 0 && p.shift_x < p.ww, "ff_window_attention: bad shift");
+  size_t smem = (size_t)(NQ + 2 * NK) * ROWP * 2 + (size_t)p.T * 4 + (size_t)(NQ + NK) * 2 + (size_t)(NQ + NK) + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      ff_set_error("ff_window_attention: smem %zu: %s", smem, cudaGetErrorString(e));
+      return FF_ERR_CUDA;
+    }
+    configured = smem;
+  }
+  dim3 grid(p.B * (p.H / p.wh) * (p.W / p.ww), p.heads);
+  window_attention_kernel<<<grid, NTHREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_window_attention");
+  return FF_OK;
+}

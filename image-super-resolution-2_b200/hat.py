@@ -1,0 +1,200 @@
+"""HAT-L x4 expert on the ffb200 kernels.
+
+Host-side mirror of `HAT.forward` (reference src/models/hat/hat_arch.py:971-984) for the HAT-L
+configuration built by `create_hat_model` (hat/__init__.py:63-118): embed 180, 12 RHAG x (6 HAB + OCAB),
+6 heads, window 16, shift 8, mlp_ratio 2, compress 3, squeeze 30, conv_scale 0.01, overlap 0.5.
+Consumes the reference state_dict unchanged (keys of Appendix A of SURVEY.md).
+
+Data layout: tokens are NHWC rows [B*H*W][192]; the fp32 residual stream stays fp32, every GEMM
+operand is bf16.  q/k/v and the attention output use the head-padded channel layout (30 -> 32).
+"""
+import torch
+
+from . import ops
+from .ops import ACT_CLAMP01, ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, CONV_1X1, CONV_3X3
+from .packing import (BF16, F32, head_pad_index, pack_conv, pack_conv_direct, pack_matrix, pack_vector,
+                      pixel_shuffle_rows)
+
+C = 180
+CP = 192
+HEADS = 6
+WS = 16
+RGB_MEAN = (0.4488, 0.4371, 0.4040)   # hat_arch.py:775 (plain attribute, not in the state dict)
+
+
+class Workspace:
+    """Named device buffers cached per shape (keeps addresses stable for CUDA-graph capture)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, rows, cols, dtype, zero=False):
+        key = (name, rows, cols, dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.zeros(rows, cols, dtype=dtype, device=self.device)
+            self.bufs[key] = t
+        elif zero:
+            t.zero_()
+        return t
+
+
+def _qkv_rows():
+    o = torch.arange(3 * C)
+    return (o // C) * CP + head_pad_index(o % C)
+
+
+class HATRunner:
+    def __init__(self, sd, device="cuda", depths=12, blocks=6):
+        self.device = device
+        self.depths, self.blocks = depths, blocks
+        self.ws = Workspace(device)
+        g = lambda k: sd[k].detach().to("cpu", F32)
+        dev = device
+        hp = head_pad_index(torch.arange(C))
+        scale = (C // HEADS) ** -0.5
+        self.mean = torch.tensor(RGB_MEAN, dtype=F32, device=dev)
+        self.conv_first_w = pack_conv_direct(g("conv_first.weight"), CP, dev)
+        self.conv_first_b = pack_vector(g("conv_first.bias"), CP, device=dev)
+        self.pe_norm = (g("patch_embed.norm.weight").to(dev), g("patch_embed.norm.bias").to(dev))
+
+        def attn_pack(prefix):
+            wq = g(prefix + "qkv.weight").clone()
+            bq = g(prefix + "qkv.bias").clone()
+            wq[:C] *= scale   # q = q * scale (hat_arch.py:175) folded into the projection
+            bq[:C] *= scale
+            return dict(
+                qkv_w=pack_matrix(wq, 3 * CP, CP, row_index=_qkv_rows(), device=dev),
+                qkv_b=pack_vector(bq, 3 * CP, index=_qkv_rows(), device=dev),
+                proj_w=pack_matrix(g(prefix + "proj.weight"), CP, CP, col_index=hp, device=dev),
+                proj_b=pack_vector(g(prefix + "proj.bias"), CP, device=dev),
+                table=g(prefix + "relative_position_bias_table").to(dev).contiguous(),
+            )
+
+        def mlp_pack(prefix):
+            return dict(
+                fc1_w=pack_matrix(g(prefix + "fc1.weight"), 2 * CP, CP, device=dev),
+                fc1_b=pack_vector(g(prefix + "fc1.bias"), 2 * CP, device=dev),
+                fc2_w=pack_matrix(g(prefix + "fc2.weight"), CP, 2 * CP, device=dev),
+                fc2_b=pack_vector(g(prefix + "fc2.bias"), CP, device=dev),
+            )
+
+        def ln(prefix):
+            return (g(prefix + "weight").to(dev), g(prefix + "bias").to(dev))
+
+        self.layers = []
+        for i in range(depths):
+            pre = f"layers.{i}.residual_group."
+            habs = []
+            for j in range(blocks):
+                bp = pre + f"blocks.{j}."
+                d = dict(norm1=ln(bp + "norm1."), norm2=ln(bp + "norm2."))
+                d.update(attn_pack(bp + "attn."))
+                d.update(mlp_pack(bp + "mlp."))
+                d["cab1_w"] = pack_conv(g(bp + "conv_block.cab.0.weight"), 64, CP, device=dev)
+                d["cab1_b"] = pack_vector(g(bp + "conv_block.cab.0.bias"), 64, device=dev)
+                d["cab2_w"] = pack_conv(g(bp + "conv_block.cab.2.weight"), CP, 64, device=dev)
+                d["cab2_b"] = pack_vector(g(bp + "conv_block.cab.2.bias"), CP, device=dev)
+                d["se1_w"] = g(bp + "conv_block.cab.3.attention.1.weight").reshape(6, C).to(dev).contiguous()
+                d["se1_b"] = g(bp + "conv_block.cab.3.attention.1.bias").to(dev)
+                d["se2_w"] = g(bp + "conv_block.cab.3.attention.3.weight").reshape(C, 6).to(dev).contiguous()
+                d["se2_b"] = g(bp + "conv_block.cab.3.attention.3.bias").to(dev)
+                habs.append(d)
+            op = pre + "overlap_attn."
+            oc = dict(norm1=ln(op + "norm1."), norm2=ln(op + "norm2."))
+            oc.update(attn_pack(op))
+            oc.update(mlp_pack(op + "mlp."))
+            conv_w = pack_conv(g(f"layers.{i}.conv.weight"), CP, CP, device=dev)
+            conv_b = pack_vector(g(f"layers.{i}.conv.bias"), CP, device=dev)
+            self.layers.append(dict(habs=habs, ocab=oc, conv_w=conv_w, conv_b=conv_b))
+        self.norm = ln("norm.")
+        self.cab_w = pack_conv(g("conv_after_body.weight"), CP, CP, device=dev)
+        self.cab_b = pack_vector(g("conv_after_body.bias"), CP, device=dev)
+        self.cbu_w = pack_conv(g("conv_before_upsample.0.weight"), 64, CP, device=dev)
+        self.cbu_b = pack_vector(g("conv_before_upsample.0.bias"), 64, device=dev)
+        ps = pixel_shuffle_rows(256)
+        self.up0_w = pack_conv(g("upsample.0.weight"), 256, 64, row_index=ps, device=dev)
+        self.up0_b = pack_vector(g("upsample.0.bias"), 256, index=ps, device=dev)
+        self.up2_w = pack_conv(g("upsample.2.weight"), 256, 64, row_index=ps, device=dev)
+        self.up2_b = pack_vector(g("upsample.2.bias"), 256, index=ps, device=dev)
+        self.last_w = pack_conv(g("conv_last.weight"), 16, 64, device=dev)
+        # x / img_range + mean (hat_arch.py:982) folded into the bias (img_range == 1)
+        self.last_b = pack_vector(g("conv_last.bias") + torch.tensor(RGB_MEAN), 16, device=dev)
+
+    # ------------------------------------------------------------------------------------------
+    def _mlp(self, d, X, t, h, B, H, W, M, extra_bf16=None):
+        ops.layernorm(X, M, C, d["norm2"][0], d["norm2"][1], 1e-5, out_bf16=t, out_cols=CP)
+        ops.conv_gemm(t, B, H, W, CP, d["fc1_w"], n_store=2 * CP, bias=d["fc1_b"], act=ACT_GELU, out_bf16=h)
+        ops.conv_gemm(h, B, H, W, 2 * CP, d["fc2_w"], n_store=CP, bias=d["fc2_b"], res=X, out_f32=X, out_bf16=extra_bf16)
+
+    def forward(self, x, out, out_off=0):
+        """x: fp32 NCHW [B,3,H,W] (H, W multiples of 16) on the GPU.
+        out: fp32 [B*4H*4W][ld] expert stack; channels out_off..out_off+2 receive clamp(SR, 0, 1)
+        (= ExpertEnsemble.forward_hat, expert_loader.py:592-621, for window-aligned inputs)."""
+        B, _, H, W = x.shape
+        if H % WS or W % WS:
+            raise ValueError("HATRunner needs H, W multiples of 16 (pad in the caller)")
+        M = B * H * W
+        ws = self.ws
+        img = ws.get("img", M, 4, F32)
+        x0 = ws.get("x0", M, CP, F32)
+        G = ws.get("G", M, CP, F32)
+        X = ws.get("X", M, CP, F32)
+        t = ws.get("t", M, CP, BF16)
+        qkv = ws.get("qkv", M, 3 * CP, BF16)
+        att = ws.get("att", M, CP, BF16)
+        cab1 = ws.get("cab1", M, 64, BF16)
+        cab2 = ws.get("cab2", M, CP, BF16)
+        h = ws.get("h", M, 2 * CP, BF16)
+        Xb = ws.get("Xb", M, CP, BF16)
+        gapv = ws.get("gap", B, CP, F32)
+        se_h = ws.get("se_h", B, 8, F32)
+        se = ws.get("se", B, CP, F32)
+        scratch = ws.get("gap_scratch", 1, B * 64 * CP, F32)
+
+        ops.nchw_to_nhwc(x, img, sub=self.mean)
+        ops.conv_direct(img, B, H, W, 3, 3, self.conv_first_w, self.conv_first_b, n_store=CP, out_f32=x0)
+        ops.layernorm(x0, M, C, self.pe_norm[0], self.pe_norm[1], 1e-5, out_f32=G, out_cols=CP)
+
+        for layer in self.layers:
+            src = G
+            for j, d in enumerate(layer["habs"]):
+                shift = WS // 2 if (j % 2 == 1) else 0
+                ops.layernorm(src, M, C, d["norm1"][0], d["norm1"][1], 1e-5, out_bf16=t, out_cols=CP)
+                # CAB on the LN1 output (hat_arch.py:272-277)
+                ops.conv_gemm(t, B, H, W, CP, d["cab1_w"], kind=CONV_3X3, n_store=64, bias=d["cab1_b"], act=ACT_GELU, out_bf16=cab1)
+                ops.conv_gemm(cab1, B, H, W, 64, d["cab2_w"], kind=CONV_3X3, n_store=CP, bias=d["cab2_b"], out_bf16=cab2)
+                ops.gap(cab2, B, H * W, C, gapv, scratch)
+                ops.vec_linear(gapv, B, C, d["se1_w"], d["se1_b"], 6, ACT_RELU, se_h, y_cols=8)
+                ops.vec_linear(se_h, B, 6, d["se2_w"], d["se2_b"], C, ACT_SIGMOID, se, y_cols=CP)
+                # (S)W-MSA
+                ops.conv_gemm(t, B, H, W, CP, d["qkv_w"], n_store=3 * CP, bias=d["qkv_b"], out_bf16=qkv)
+                ops.window_attention(qkv, B, H, W, att, bias_table=d["table"], wh=WS, ww=WS, shift=(shift, shift))
+                # x = shortcut + attn + 0.01 * cab   (hat_arch.py:306)
+                ops.conv_gemm(att, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], aux=cab2, aux_chan=se,
+                              aux_alpha=0.01, res=src, out_f32=X)
+                self._mlp(d, X, t, h, B, H, W, M)
+                src = X
+            d = layer["ocab"]
+            ops.layernorm(X, M, C, d["norm1"][0], d["norm1"][1], 1e-5, out_bf16=t, out_cols=CP)
+            ops.conv_gemm(t, B, H, W, CP, d["qkv_w"], n_store=3 * CP, bias=d["qkv_b"], out_bf16=qkv)
+            ops.window_attention(qkv, B, H, W, att, bias_table=d["table"], wh=WS, ww=WS, kh=24, kw=24, kpad=(4, 4),
+                                 rel_sign=-1, rel_off=(-7, -7), rel_stride=39)
+            ops.conv_gemm(att, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], res=X, out_f32=X)
+            self._mlp(d, X, t, h, B, H, W, M, extra_bf16=Xb)
+            # RHAG tail: conv3x3 + group residual (hat_arch.py:618-619)
+            ops.conv_gemm(Xb, B, H, W, CP, layer["conv_w"], kind=CONV_3X3, n_store=CP, bias=layer["conv_b"], res=G, out_f32=G)
+
+        ops.layernorm(G, M, C, self.norm[0], self.norm[1], 1e-5, out_bf16=t, out_cols=CP)
+        y = Xb
+        ops.conv_gemm(t, B, H, W, CP, self.cab_w, kind=CONV_3X3, n_store=CP, bias=self.cab_b, res=x0, out_bf16=y)
+        f64 = ws.get("f64", M, 64, BF16)
+        ops.conv_gemm(y, B, H, W, CP, self.cbu_w, kind=CONV_3X3, n_store=64, bias=self.cbu_b, act=ACT_LRELU, out_bf16=f64)
+        u1 = ws.get("u1", M * 4, 64, BF16)
+        ops.conv_gemm(f64, B, H, W, 64, self.up0_w, kind=CONV_3X3, n_store=256, bias=self.up0_b, pixel_shuffle=2, out_bf16=u1)
+        u2 = ws.get("u2", M * 16, 64, BF16)
+        ops.conv_gemm(u1, B, 2 * H, 2 * W, 64, self.up2_w, kind=CONV_3X3, n_store=256, bias=self.up2_b, pixel_shuffle=2, out_bf16=u2)
+        ops.conv_gemm(u2, B, 4 * H, 4 * W, 64, self.last_w, kind=CONV_3X3, n_store=3, bias=self.last_b, post_act=ACT_CLAMP01,
+                      out_f32=out[:, out_off:])
+        return out

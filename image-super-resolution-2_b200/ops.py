@@ -1,0 +1,152 @@
+"""Thin tensor-level wrappers over the C ABI (include/ffb200.h).
+
+torch is used for device memory and streams only; every arithmetic op on the hot path is one of
+the hand-written kernels in csrc/.  All activations are NHWC; `ld` is the channel pitch.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from .lib import (ACT_CLAMP01, ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, CONV_1X1, CONV_2X2S2, CONV_3X3)
+
+_BF16 = torch.bfloat16
+_F32 = torch.float32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.FFError("ffb200 kernels need CUDA tensors: there is no CPU fallback")
+
+
+def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_NONE, alpha=1.0, col_scale=None,
+              mul=None, aux=None, aux_chan=None, aux_alpha=1.0, res=None, post_act=ACT_NONE, out_bf16=None,
+              out_f32=None, pixel_shuffle=0, gate_pairs=0, w_batch_rows=0, x_ld=None, debug_simt=0):
+    """Implicit-GEMM conv / linear on tcgen05 (see ff_conv_gemm in include/ffb200.h).
+
+    x: bf16 tensor whose last dim is the channel pitch (or pass x_ld); w: packed bf16 [n_pad, taps*cin].
+    Operand tensors (mul/aux/res/out_*) are 2-D-viewable [pixels, ld]; their ld is the last-dim stride owner.
+    """
+    _req_cuda(x, w, bias, col_scale, mul, aux, aux_chan, res, out_bf16, out_f32)
+    p = L.FFConvGemm()
+    p.x = x.data_ptr(); p.B, p.H, p.W = B, H, W
+    p.x_ld = x_ld if x_ld is not None else x.stride(-2)
+    p.cin = cin; p.kind = kind
+    p.w = w.data_ptr(); p.n_pad = w.shape[0] if not w_batch_rows else w_batch_rows; p.n_store = n_store
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.act = act; p.alpha = alpha
+    p.col_scale = col_scale.data_ptr() if col_scale is not None else None
+    if mul is not None:
+        p.mul = mul.data_ptr(); p.mul_ld = mul.stride(-2)
+    if aux is not None:
+        p.aux = aux.data_ptr(); p.aux_ld = aux.stride(-2)
+    if aux_chan is not None:
+        p.aux_chan = aux_chan.data_ptr(); p.aux_chan_ld = aux_chan.stride(0)
+    p.aux_alpha = aux_alpha
+    if res is not None:
+        p.res = res.data_ptr(); p.res_ld = res.stride(-2); p.res_is_f32 = 1 if res.dtype == _F32 else 0
+    p.post_act = post_act
+    if out_bf16 is not None:
+        p.out_bf16 = out_bf16.data_ptr(); p.out_ld = out_bf16.stride(-2)
+    if out_f32 is not None:
+        p.out_f32 = out_f32.data_ptr(); p.out_f32_ld = out_f32.stride(-2)
+    p.pixel_shuffle = pixel_shuffle; p.gate_pairs = gate_pairs; p.w_batch_rows = w_batch_rows
+    p.debug_simt = debug_simt
+    L.check(L.load().ff_conv_gemm(C.byref(p), _stream()), "ff_conv_gemm")
+
+
+def window_attention(qkv, B, H, W, out, *, bias_table, wh, ww, kh=None, kw=None, kpad=(0, 0), shift=(0, 0), heads=6,
+                     head_off=0, bias_head_off=0, rel_sign=1, rel_off=None, rel_stride=None, q_off=0, k_off=192,
+                     v_off=384, out_off=0):
+    _req_cuda(qkv, out, bias_table)
+    kh = wh if kh is None else kh
+    kw = ww if kw is None else kw
+    p = L.FFWinAttn()
+    p.qkv = qkv.data_ptr(); p.ld = qkv.stride(-2)
+    p.q_off, p.k_off, p.v_off = q_off, k_off, v_off
+    p.B, p.H, p.W = B, H, W
+    p.wh, p.ww, p.kh, p.kw = wh, ww, kh, kw
+    p.kpad_y, p.kpad_x = kpad
+    p.shift_y, p.shift_x = shift
+    p.heads, p.head_off = heads, head_off
+    p.bias_table = bias_table.data_ptr(); p.T = bias_table.shape[0]; p.bias_heads = bias_table.shape[1]
+    p.bias_head_off = bias_head_off
+    p.rel_sign = rel_sign
+    p.rel_off_y, p.rel_off_x = rel_off if rel_off is not None else (wh - 1, ww - 1)
+    p.rel_stride = rel_stride if rel_stride is not None else (2 * ww - 1)
+    p.out = out.data_ptr(); p.out_ld = out.stride(-2); p.out_off = out_off
+    L.check(L.load().ff_window_attention(C.byref(p), _stream()), "ff_window_attention")
+
+
+def layernorm(x, rows, C_, gamma, beta, eps, *, out_bf16=None, out_cols=None, out_f32=None, x_ld=None, x_off=0):
+    _req_cuda(x, gamma, beta, out_bf16, out_f32)
+    is_bf16 = 1 if x.dtype == _BF16 else 0
+    esz = 2 if is_bf16 else 4
+    out_cols = out_cols if out_cols is not None else (out_bf16.stride(-2) if out_bf16 is not None else C_)
+    L.check(L.load().ff_layernorm(C.c_void_p(x.data_ptr() + x_off * esz), is_bf16, x_ld if x_ld is not None else x.stride(-2),
+                                  C.c_longlong(rows), C_, _ptr(gamma), _ptr(beta), C.c_float(eps), _ptr(out_bf16),
+                                  out_bf16.stride(-2) if out_bf16 is not None else 0, out_cols, _ptr(out_f32),
+                                  out_f32.stride(-2) if out_f32 is not None else 0, _stream()), "ff_layernorm")
+
+
+def gap(x, B, P, C_, out, scratch, *, x_off=0):
+    _req_cuda(x, out, scratch)
+    is_bf16 = 1 if x.dtype == _BF16 else 0
+    esz = 2 if is_bf16 else 4
+    L.check(L.load().ff_gap(C.c_void_p(x.data_ptr() + x_off * esz), is_bf16, x.stride(-2), B, P, C_, _ptr(out), out.stride(0), _ptr(scratch),
+                            C.c_size_t(scratch.numel() * 4), _stream()), "ff_gap")
+
+
+def vec_linear(x, R, K, W, bias, N, act, y, y_cols=None):
+    _req_cuda(x, W, bias, y)
+    L.check(L.load().ff_vec_linear(_ptr(x), x.stride(0), R, K, _ptr(W), _ptr(bias), N, act, _ptr(y), y.stride(0),
+                                   y_cols if y_cols is not None else N, _stream()), "ff_vec_linear")
+
+
+def dwconv(x, B, H, W, C_, kh, kw, w, bias, out, *, act=ACT_NONE, mode=0, mul=None, x_off=0, mul_off=0, x_ld=None):
+    _req_cuda(x, w, bias, out, mul)
+    L.check(L.load().ff_dwconv(C.c_void_p(x.data_ptr() + 2 * x_off), x_ld if x_ld is not None else x.stride(-2), B, H, W, C_, kh, kw,
+                               _ptr(w), _ptr(bias), act, mode,
+                               C.c_void_p(mul.data_ptr() + 2 * mul_off) if mul is not None else None,
+                               mul.stride(-2) if mul is not None else 0, _ptr(out), out.stride(-2), _stream()), "ff_dwconv")
+
+
+def scale_channels(x, B, pixels_per_sample, C_, s):
+    _req_cuda(x, s)
+    L.check(L.load().ff_scale_channels(_ptr(x), x.stride(-2), B, C.c_longlong(pixels_per_sample), C_, _ptr(s), s.stride(0), _stream()),
+            "ff_scale_channels")
+
+
+def conv_direct(x, B, H, W, Cin, k, w, bias, *, n_store, act=ACT_NONE, mul_f32=None, out_bf16=None, out_f32=None,
+                x_ld=None, x_off=0, out_f32_off=0, out_bf16_off=0):
+    _req_cuda(x, w, bias, mul_f32, out_bf16, out_f32)
+    is_bf16 = 1 if x.dtype == _BF16 else 0
+    esz = 2 if is_bf16 else 4
+    L.check(L.load().ff_conv_direct(C.c_void_p(x.data_ptr() + x_off * esz), is_bf16, x_ld if x_ld is not None else x.stride(-2), B, H, W, Cin, k,
+                                    _ptr(w), _ptr(bias), w.shape[0], n_store, act, _ptr(mul_f32),
+                                    mul_f32.stride(-2) if mul_f32 is not None else 0,
+                                    C.c_void_p(out_bf16.data_ptr() + 2 * out_bf16_off) if out_bf16 is not None else None,
+                                    out_bf16.stride(-2) if out_bf16 is not None else 0,
+                                    C.c_void_p(out_f32.data_ptr() + 4 * out_f32_off) if out_f32 is not None else None,
+                                    out_f32.stride(-2) if out_f32 is not None else 0, _stream()), "ff_conv_direct")
+
+
+def nchw_to_nhwc(x, out, sub=None):
+    _req_cuda(x, out, sub)
+    B, C_, H, W = x.shape
+    L.check(L.load().ff_nchw_to_nhwc(_ptr(x), B, C_, H, W, _ptr(sub), _ptr(out), out.stride(-2), _stream()), "ff_nchw_to_nhwc")
+
+
+def nhwc_to_nchw(x, coff, C_, out):
+    _req_cuda(x, out)
+    B, _, H, W = out.shape
+    L.check(L.load().ff_nhwc_to_nchw(_ptr(x), x.stride(-2), coff, B, C_, H, W, _ptr(out), _stream()), "ff_nhwc_to_nchw")

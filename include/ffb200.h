@@ -1,0 +1,118 @@
+/*
+ * ffb200 -- C ABI of the B200-native FreqFusion x4 inference kernels (sm_100a).
+ *
+ * The reference (Nikhil-AI-Labs/image-super-resolution-2) is 100% PyTorch: there is no FFI in it.
+ * Every entry point below replaces a group of torch operator calls on the hot path named in
+ * BASELINE.json (`models/team29_FreqFusion/io.py:188 main` -> `CompleteEnhancedFusionSR.forward`);
+ * the reference lines each one replaces are cited per function.  INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions:
+ *   - plain pointers + explicit dims; the CALLER owns every buffer (device memory unless stated);
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return 0 on success, negative on error (never throws/aborts); text via ff_last_error();
+ *   - activations are NHWC ("pixel-major"): element (b,y,x,c) at ((b*H+y)*W+x)*ld + c;
+ *   - bf16 buffers are `uint16_t`-sized; channel pitches (`*_ld`) are in ELEMENTS.
+ */
+#ifndef FFB200_H
+#define FFB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFB200_ABI_VERSION 1
+
+int ff_abi_version(void);
+const char* ff_last_error(void);
+/* Number of kernels launched by this library since load (bench.py reports it as gpu_launches). */
+long long ff_launch_count(void);
+
+/* activation codes used by the fused epilogues */
+enum { FF_ACT_NONE = 0, FF_ACT_GELU = 1, FF_ACT_RELU = 2, FF_ACT_LRELU = 3, FF_ACT_SIGMOID = 4, FF_ACT_CLAMP01 = 5 };
+/* convolution kinds of ff_conv_gemm */
+enum { FF_CONV_1X1 = 0, FF_CONV_3X3 = 1, FF_CONV_2X2S2 = 2 };
+
+/*
+ * ff_conv_gemm -- implicit-GEMM convolution / linear layer on tcgen05 tensor cores.
+ *   out[p, n] = epilogue( sum_{tap, c} x[pixel(p)+tap, c] * w[n, tap*cin + c] )
+ * A tiles (128 output pixels = 8 rows x 16 cols) are fetched by 4-D TMA boxes shifted per tap with
+ * hardware zero fill at the image border (= Conv2d zero padding); B tiles by 2-D TMA; fp32
+ * accumulators live in TMEM (double-buffered so the epilogue of tile i overlaps the MMAs of i+1).
+ * Replaces: nn.Linear / nn.Conv2d call sites of hat_arch.py:156-158,83-85,65-69,596,874-893;
+ * dat_arch.py:149-152,379-381,589-591,782; nafnet_arch.py:70-86,163-185; hierarchical_fusion.py:86-120;
+ * enhanced_fusion.py:266-286; edge_enhancement.py:100-106,168-180 (incl. nn.PixelShuffle(2) folded
+ * into the store, hat_arch.py:703, nafnet_arch.py:178-182).
+ * Epilogue order:  v = acc + bias[n];  v = act(v);  v *= alpha;  v *= col_scale[n];  v *= mul[p,n];
+ *                  v += aux_alpha * aux[p,n] * (aux_chan ? aux_chan[b,n] : 1);  v += res[p,n];
+ *                  v = post_act(v);  store bf16 and/or fp32.
+ */
+typedef struct FFConvGemm {
+  const void* x;       /* bf16 NHWC input */
+  int B, H, W;         /* input batch / height / width */
+  int x_ld;            /* channel pitch of x (multiple of 8) */
+  int cin;             /* channels consumed per tap (multiple of 64, <= x_ld) */
+  int kind;            /* FF_CONV_* */
+  const void* w;       /* bf16 packed weights [n_pad][ntaps*cin] */
+  int n_pad;           /* rows of w; multiple of 16 */
+  int n_store;         /* columns written / read from the epilogue operands (<= n_pad) */
+  const float* bias;   /* [n_pad] or NULL */
+  int act;             /* FF_ACT_* applied right after bias */
+  float alpha;         /* scalar scale after act */
+  const float* col_scale; /* [n_pad] or NULL */
+  const void* mul;     /* bf16 [pixels][mul_ld] or NULL */
+  int mul_ld;
+  const void* aux;     /* bf16 [pixels][aux_ld] or NULL */
+  int aux_ld;
+  const float* aux_chan; /* fp32 [B][aux_chan_ld] or NULL */
+  int aux_chan_ld;
+  float aux_alpha;
+  const void* res;     /* residual [pixels][res_ld], fp32 if res_is_f32 else bf16, or NULL */
+  int res_ld;
+  int res_is_f32;
+  int post_act;        /* FF_ACT_* applied after the residual add */
+  void* out_bf16;      /* bf16 [pixels][out_ld] or NULL */
+  int out_ld;
+  float* out_f32;      /* fp32 [pixels][out_f32_ld] or NULL */
+  int out_f32_ld;
+  int pixel_shuffle;   /* 0, or 2: output is [B,2Ho,2Wo,n/4]; w rows must be packed as (i*2+j)*(n/4)+c */
+  int gate_pairs;      /* 1: SimpleGate folded into the store: every 16-column chunk holds 8 x1 then 8 x2 channels,
+                          out[p, n0/2 + i] = (acc+bias)[n0+i] * (acc+bias)[n0+8+i]; only bias + bf16 store apply */
+  int w_batch_rows;    /* 0, or rows of w per sample: sample b uses weight rows [b*w_batch_rows, +n_pad) */
+  int debug_simt;      /* 1: run the slow SIMT reference main loop (same epilogue) -- testing only */
+} FFConvGemm;
+int ff_conv_gemm(const FFConvGemm* p, void* stream);
+
+/*
+ * ff_window_attention -- fused window attention (QK^T + relative-position bias + shift mask + softmax + PV).
+ * Replaces hat_arch.py:165-196 (WindowAttention.forward) with the roll / window_partition / window_reverse
+ * copies of HAB.forward (hat_arch.py:279-303), OCAB's unfold + attention (hat_arch.py:398-435), and DAT's
+ * SpatialAttention.forward (dat_arch.py:290-342) with the rolls of dat_arch.py:514-540.
+ * Layout: qkv is bf16 [B*H*W][ld]; head h of q/k/v sits at channel {q,k,v}_off + (head_off+h)*32 (head dim 30
+ * zero-padded to 32, q pre-scaled).  Query window wh x ww must hold 256 tokens.  Key window kh x kw starts
+ * kpad_{y,x} before the query window; keys outside the image are all-zero rows that still take softmax mass
+ * (nn.Unfold zero padding, hat_arch.py:377).  Bias index for (query (qi,qj), key (ki,kj)) window coordinates:
+ *   idx = (rel_sign*(qi-ki)+rel_off_y)*rel_stride + rel_sign*(qj-kj)+rel_off_x;  idx<0 -> idx+T  (HAT's OCA table
+ *   relies on negative-index wrap-around, hat_arch.py:896-919);  bias = bias_table[idx*bias_heads + bias_head_off + h].
+ * shift_{y,x} != 0 selects the cyclic shift and the {0,-100} region mask of hat_arch.py:921-940 / dat_arch.py:431-489.
+ * Output token (un-shifted position) gets channels out_off + (head_off+h)*32 .. +32 of out (bf16 [B*H*W][out_ld]).
+ */
+typedef struct FFWinAttn {
+  const void* qkv; int ld;
+  int q_off, k_off, v_off;
+  int B, H, W;
+  int wh, ww, kh, kw, kpad_y, kpad_x;
+  int shift_y, shift_x;
+  int heads, head_off;
+  const float* bias_table; int T, bias_heads, bias_head_off;
+  int rel_sign, rel_off_y, rel_off_x, rel_stride;
+  void* out; int out_ld, out_off;
+} FFWinAttn;
+int ff_window_attention(const FFWinAttn* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,293 @@
+"""GPU parity tests of the individual ffb200 kernels against plain fp32 PyTorch on the same
+(bf16-rounded) operands.  Tolerances are stated per test: operands are bf16, accumulation fp32."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _nhwc(x):  # NCHW -> [pixels, C]
+    b, c, h, w = x.shape
+    return x.permute(0, 2, 3, 1).reshape(b * h * w, c).contiguous()
+
+
+def _nchw(x2d, b, h, w):
+    return x2d.reshape(b, h, w, -1).permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("kind,cin,cout,H,W,B", [
+    ("1x1", 192, 576, 16, 16, 1), ("1x1", 384, 192, 32, 48, 2), ("3x3", 192, 64, 32, 32, 2), ("3x3", 64, 192, 16, 32, 1),
+    ("3x3", 64, 256, 32, 32, 1), ("3x3", 64, 16, 32, 32, 1), ("1x1", 1024, 2048, 16, 16, 1), ("2x2s2", 64, 128, 32, 64, 2),
+    ("3x3", 128, 32, 64, 64, 1), ("1x1", 64, 128, 8, 16, 3),
+])
+@pytest.mark.parametrize("simt", [0, 1])
+def test_conv_gemm_plain(kind, cin, cout, H, W, B, simt):
+    from isr2_b200 import ops, packing
+    if simt and cin * cout > 192 * 600:
+        pytest.skip("SIMT debug loop only checked on the small shapes")
+    g = torch.Generator().manual_seed(1)
+    k = {"1x1": 1, "3x3": 3, "2x2s2": 2}[kind]
+    x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
+    w = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(BF16).float()
+    bias = torch.randn(cout, generator=g)
+    if kind == "2x2s2":
+        ref = F.conv2d(x, w, bias, stride=2)
+    else:
+        ref = F.conv2d(x, w, bias, padding=k // 2)
+    xd = _nhwc(x).to(_dev(), BF16)
+    wd = packing.pack_conv(w, cout, cin, device=_dev())
+    bd = bias.to(_dev())
+    Ho, Wo = ref.shape[-2:]
+    out = torch.zeros(B * Ho * Wo, cout, dtype=F32, device=_dev())
+    ops.conv_gemm(xd, B, H, W, cin, wd, kind={"1x1": 0, "3x3": 1, "2x2s2": 2}[kind], n_store=cout, bias=bd, out_f32=out, debug_simt=simt)
+    torch.cuda.synchronize()
+    got = _nchw(out.cpu(), B, Ho, Wo)
+    err = (got - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+def test_conv_gemm_epilogue_chain():
+    """bias -> GELU -> alpha -> col_scale -> mul -> aux*chan -> residual -> clamp, bf16 and fp32 stores."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(2)
+    B, H, W, cin, cout = 2, 16, 32, 192, 192
+    P = B * H * W
+    x = torch.randn(P, cin, generator=g).to(BF16)
+    w = (torch.randn(cout, cin, generator=g) / math.sqrt(cin)).to(BF16)
+    bias, cs = torch.randn(cout, generator=g), torch.rand(cout, generator=g) + 0.5
+    mul = torch.randn(P, cout, generator=g).to(BF16)
+    aux = torch.randn(P, cout, generator=g).to(BF16)
+    chan = torch.rand(B, cout, generator=g)
+    res = torch.randn(P, cout, generator=g)
+    v = F.gelu(x.float() @ w.float().t() + bias) * 0.7 * cs * mul.float()
+    v = v + 0.3 * aux.float() * chan.repeat_interleave(H * W, 0) + res
+    ref = v.clamp(0, 1)
+    d = _dev()
+    o32 = torch.zeros(P, cout, device=d)
+    o16 = torch.zeros(P, cout, device=d, dtype=BF16)
+    ops.conv_gemm(x.to(d), B, H, W, cin, w.to(d), n_store=cout, bias=bias.to(d), act=ops.ACT_GELU, alpha=0.7, col_scale=cs.to(d),
+                  mul=mul.to(d), aux=aux.to(d), aux_chan=chan.to(d), aux_alpha=0.3, res=res.to(d), post_act=ops.ACT_CLAMP01,
+                  out_f32=o32, out_bf16=o16)
+    torch.cuda.synchronize()
+    assert (o32.cpu() - ref).abs().max().item() < 3e-3
+    assert (o16.cpu().float() - ref).abs().max().item() < 1e-2
+
+
+def test_conv_gemm_pixel_shuffle_and_narrow_store():
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(3)
+    B, H, W, cin = 1, 16, 16, 64
+    x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
+    w = (torch.randn(256, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(BF16).float()
+    bias = torch.randn(256, generator=g)
+    ref = F.pixel_shuffle(F.conv2d(x, w, bias, padding=1), 2)
+    d = _dev()
+    rows = packing.pixel_shuffle_rows(256)
+    out = torch.zeros(B * 4 * H * W, 64, dtype=BF16, device=d)
+    ops.conv_gemm(_nhwc(x).to(d, BF16), B, H, W, cin, packing.pack_conv(w, 256, cin, row_index=rows, device=d), kind=1, n_store=256,
+                  bias=packing.pack_vector(bias, 256, index=rows, device=d), pixel_shuffle=2, out_bf16=out)
+    torch.cuda.synchronize()
+    assert (_nchw(out.cpu().float(), B, 2 * H, 2 * W) - ref).abs().max().item() < 3e-2
+    # narrow (3-channel) store into a 12-wide fp32 stack at channel offset 3
+    w3 = (torch.randn(3, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(BF16).float()
+    b3 = torch.randn(3, generator=g)
+    ref3 = F.conv2d(x, w3, b3, padding=1)
+    stack = torch.full((B * H * W, 12), 7.0, device=d)
+    ops.conv_gemm(_nhwc(x).to(d, BF16), B, H, W, cin, packing.pack_conv(w3, 16, cin, device=d), kind=1, n_store=3,
+                  bias=packing.pack_vector(b3, 16, device=d), out_f32=stack[:, 3:])
+    torch.cuda.synchronize()
+    s = stack.cpu()
+    assert (_nchw(s[:, 3:6], B, H, W) - ref3).abs().max().item() < 3e-3
+    assert torch.all(s[:, :3] == 7.0) and torch.all(s[:, 6:] == 7.0)
+
+
+def test_conv_gemm_gate_pairs_and_batch_weights():
+    from isr2_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    B, H, W, cin, c = 2, 16, 16, 64, 64
+    P = B * H * W
+    x = torch.randn(P, cin, generator=g).to(BF16)
+    w = (torch.randn(2 * c, cin, generator=g) / math.sqrt(cin)).to(BF16)     # rows: x1 (c) then x2 (c)
+    bias = torch.randn(2 * c, generator=g)
+    y = x.float() @ w.float().t() + bias
+    ref = y[:, :c] * y[:, c:]
+    # interleave rows: chunk g holds x1[8g:8g+8] then x2[8g:8g+8]
+    perm = torch.cat([torch.cat([torch.arange(8 * i, 8 * i + 8), c + torch.arange(8 * i, 8 * i + 8)]) for i in range(c // 8)])
+    d = _dev()
+    out = torch.zeros(P, c, dtype=BF16, device=d)
+    ops.conv_gemm(x.to(d), B, H, W, cin, w[perm].contiguous().to(d), n_store=2 * c, bias=bias[perm].contiguous().to(d), gate_pairs=1, out_bf16=out)
+    torch.cuda.synchronize()
+    assert (out.cpu().float() - ref).abs().max().item() < 5e-2 * max(1.0, ref.abs().max().item() / 4)
+    # per-sample weights
+    wb = (torch.randn(B, 192, 64, generator=g) / 8).to(BF16)
+    refb = torch.cat([x[b * H * W:(b + 1) * H * W].float() @ wb[b].float().t() for b in range(B)])
+    o2 = torch.zeros(P, 192, device=d)
+    ops.conv_gemm(x.to(d), B, H, W, cin, wb.reshape(B * 192, 64).to(d), n_store=192, w_batch_rows=192, out_f32=o2)
+    torch.cuda.synchronize()
+    assert (o2.cpu() - refb).abs().max().item() < 3e-3
+
+
+@pytest.mark.parametrize("mode", ["sa", "sa_shift", "oca", "dat0_shift", "dat1"])
+def test_window_attention(mode):
+    from isr2_b200 import ops
+    from oracle import hat as ohat
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 2, 32, 64
+    heads, hd = 6, 30
+    q, k, v = [torch.randn(B, H, W, heads, hd, generator=g).to(BF16).float() for _ in range(3)]
+    qkv = torch.zeros(B * H * W, 576, dtype=BF16)
+    for i, t in enumerate((q, k, v)):
+        pad = torch.zeros(B, H, W, heads, 32)
+        pad[..., :hd] = t * (1.0 if i else 1.0)
+        qkv[:, i * 192:(i + 1) * 192] = pad.reshape(B * H * W, 192).to(BF16)
+    d = _dev()
+    out = torch.zeros(B * H * W, 192, dtype=BF16, device=d)
+
+    def attend(qw, kw_, vw, bias, mask):   # [nW*B, heads, n, d]
+        a = qw @ kw_.transpose(-2, -1) + bias.unsqueeze(0)
+        if mask is not None:
+            nw = mask.shape[0]
+            a = (a.view(-1, nw, a.shape[1], a.shape[2], a.shape[3]) + mask.unsqueeze(1).unsqueeze(0)).view(a.shape)
+        return a.softmax(-1) @ vw
+
+    def part(t, wh, ww):   # [B,H,W,heads,d] -> [B*nW, heads, wh*ww, d]
+        x = t.view(B, H // wh, wh, W // ww, ww, t.shape[3], t.shape[4]).permute(0, 1, 3, 5, 2, 4, 6)
+        return x.reshape(-1, t.shape[3], wh * ww, t.shape[4])
+
+    def unpart(o, wh, ww):  # inverse -> [B,H,W,heads,d]
+        nh = o.shape[1]
+        x = o.view(B, H // wh, W // ww, nh, wh, ww, o.shape[-1]).permute(0, 1, 4, 2, 5, 3, 6)
+        return x.reshape(B, H, W, nh, o.shape[-1])
+
+    if mode in ("sa", "sa_shift"):
+        table = torch.randn(961, heads, generator=g)
+        sh = 8 if mode == "sa_shift" else 0
+        roll = (lambda t: torch.roll(t, (-sh, -sh), (1, 2))) if sh else (lambda t: t)
+        bias = table[ohat.rpi_sa().reshape(-1)].view(256, 256, heads).permute(2, 0, 1)
+        mask = ohat.shift_mask(H, W) if sh else None
+        o = unpart(attend(part(roll(q), 16, 16), part(roll(k), 16, 16), part(roll(v), 16, 16), bias, mask), 16, 16)
+        ref = torch.roll(o, (sh, sh), (1, 2)) if sh else o
+        ops.window_attention(qkv.to(d), B, H, W, out, bias_table=table.to(d), wh=16, ww=16, shift=(sh, sh))
+    elif mode == "oca":
+        table = torch.randn(1521, heads, generator=g)
+        bias = table[ohat.rpi_oca().reshape(-1)].view(256, 576, heads).permute(2, 0, 1)
+
+        def ext(t):
+            x = F.pad(t.permute(0, 3, 4, 1, 2).reshape(B, heads * hd, H, W), (4, 4, 4, 4))
+            x = x.unfold(2, 24, 16).unfold(3, 24, 16)  # B C nh nw 24 24
+            x = x.permute(0, 2, 3, 4, 5, 1).reshape(-1, 576, heads, hd).permute(0, 2, 1, 3)
+            return x
+        ref = unpart(attend(part(q, 16, 16), ext(k), ext(v), bias, None), 16, 16)
+        ops.window_attention(qkv.to(d), B, H, W, out, bias_table=table.to(d), wh=16, ww=16, kh=24, kw=24, kpad=(4, 4), rel_sign=-1,
+                             rel_off=(-7, -7), rel_stride=39)
+    else:
+        from oracle import dat as odat
+        br = 0 if mode.startswith("dat0") else 1
+        wh, ww = (8, 32) if br == 0 else (32, 8)
+        sh = (wh // 2, ww // 2) if mode.endswith("shift") else (0, 0)
+        table = torch.randn((2 * wh - 1) * (2 * ww - 1), 3, generator=g)
+        bias = table[odat.rel_index(wh, ww).reshape(-1)].view(256, 256, 3).permute(2, 0, 1)
+        sl = slice(0, 3) if br == 0 else slice(3, 6)
+        roll = (lambda t: torch.roll(t, (-sh[0], -sh[1]), (1, 2))) if sh[0] else (lambda t: t)
+        mask = odat.shift_mask(H, W, wh, ww, sh[0], sh[1]) if sh[0] else None
+        o = unpart(attend(part(roll(q[:, :, :, sl]), wh, ww), part(roll(k[:, :, :, sl]), wh, ww), part(roll(v[:, :, :, sl]), wh, ww), bias, mask), wh, ww)
+        o = torch.roll(o, sh, (1, 2)) if sh[0] else o
+        ref = torch.zeros(B, H, W, heads, hd)
+        ref[:, :, :, sl] = o
+        ops.window_attention(qkv.to(d), B, H, W, out, bias_table=table.to(d), wh=wh, ww=ww, shift=sh, heads=3, head_off=3 * br)
+    torch.cuda.synchronize()
+    got = out.cpu().float().view(B, H, W, heads, 32)
+    assert torch.all(got[..., 30:] == 0)
+    err = (got[..., :hd] - ref).abs().max().item()
+    assert err < 3e-2, f"max abs err {err}"
+
+
+def test_layernorm_gap_vec_linear():
+    from isr2_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    d = _dev()
+    rows, C_ = 1000, 180
+    x = torch.randn(rows, 192, generator=g) * 3 + 1
+    gam, bet = torch.randn(C_, generator=g), torch.randn(C_, generator=g)
+    ref = F.layer_norm(x[:, :C_], (C_,), gam, bet, 1e-5)
+    o16 = torch.full((rows, 192), 5.0, dtype=BF16, device=d)
+    o32 = torch.full((rows, 192), 5.0, device=d)
+    ops.layernorm(x.to(d), rows, C_, gam.to(d), bet.to(d), 1e-5, out_bf16=o16, out_cols=192, out_f32=o32)
+    torch.cuda.synchronize()
+    assert (o32.cpu()[:, :C_] - ref).abs().max().item() < 1e-4
+    assert torch.all(o32.cpu()[:, C_:] == 0) and torch.all(o16.cpu()[:, C_:] == 0)
+    assert (o16.cpu().float()[:, :C_] - ref).abs().max().item() < 3e-2
+    # bf16 input with channel offset (DAT SpatialGate norm) and wide rows (NAFNet 1024)
+    xb = torch.randn(64, 2048, generator=g).to(BF16)
+    g2, b2 = torch.randn(1024, generator=g), torch.randn(1024, generator=g)
+    ref2 = F.layer_norm(xb.float()[:, 1024:], (1024,), g2, b2, 1e-6)
+    o2 = torch.zeros(64, 1024, device=d)
+    ops.layernorm(xb.to(d), 64, 1024, g2.to(d), b2.to(d), 1e-6, out_f32=o2, out_cols=1024, x_off=1024)
+    torch.cuda.synchronize()
+    assert (o2.cpu() - ref2).abs().max().item() < 1e-4
+    # gap + vec_linear
+    B, P = 3, 4096
+    t = torch.randn(B * P, 192, generator=g).to(BF16)
+    outg = torch.zeros(B, 192, device=d)
+    scratch = torch.zeros(1, B * 64 * 192, device=d)
+    ops.gap(t.to(d), B, P, 180, outg, scratch)
+    torch.cuda.synchronize()
+    refg = t.float().view(B, P, 192).mean(1)
+    assert (outg.cpu()[:, :180] - refg[:, :180]).abs().max().item() < 1e-5
+    Wm, bm = torch.randn(6, 180, generator=g), torch.randn(6, generator=g)
+    y = torch.zeros(B, 8, device=d)
+    ops.vec_linear(outg, B, 180, Wm.to(d), bm.to(d), 6, ops.ACT_RELU, y, y_cols=8)
+    torch.cuda.synchronize()
+    refy = F.relu(outg.cpu()[:, :180] @ Wm.t() + bm)
+    assert (y.cpu()[:, :6] - refy).abs().max().item() < 1e-4 and torch.all(y.cpu()[:, 6:] == 0)
+
+
+def test_dwconv_and_conv_direct():
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(7)
+    d = _dev()
+    B, H, W, C_ = 2, 16, 32, 64
+    x = torch.randn(B, C_, H, W, generator=g).to(BF16).float()
+    for kh, kw in ((3, 3), (5, 5), (1, 21), (21, 1)):
+        w = torch.randn(C_, 1, kh, kw, generator=g) / math.sqrt(kh * kw)
+        b = torch.randn(C_, generator=g)
+        ref = F.gelu(F.conv2d(x, w, b, padding=(kh // 2, kw // 2), groups=C_))
+        out = torch.zeros(B * H * W, C_, dtype=BF16, device=d)
+        ops.dwconv(_nhwc(x).to(d, BF16), B, H, W, C_, kh, kw, packing.pack_dw(w, C_, device=d), b.to(d), out, act=ops.ACT_GELU)
+        torch.cuda.synchronize()
+        assert (_nchw(out.cpu().float(), B, H, W) - ref).abs().max().item() < 3e-2
+    # SimpleGate mode
+    w = torch.randn(C_, 1, 3, 3, generator=g) / 3
+    b = torch.randn(C_, generator=g)
+    y = F.conv2d(x, w, b, padding=1, groups=C_)
+    ref = y[:, :C_ // 2] * y[:, C_ // 2:]
+    out = torch.zeros(B * H * W, C_ // 2, dtype=BF16, device=d)
+    ops.dwconv(_nhwc(x).to(d, BF16), B, H, W, C_, 3, 3, packing.pack_dw(w, C_, device=d), b.to(d), out, mode=1)
+    torch.cuda.synchronize()
+    assert (_nchw(out.cpu().float(), B, H, W) - ref).abs().max().item() < 5e-2
+    # direct conv, fp32, 3 -> 20 channels, 3x3 and 1x1, from an NCHW image through nchw_to_nhwc
+    img = torch.rand(B, 3, H, W, generator=g)
+    mean = torch.tensor([0.4, 0.5, 0.6])
+    nh = torch.zeros(B * H * W, 4, device=d)
+    ops.nchw_to_nhwc(img.to(d), nh, sub=mean.to(d))
+    for k in (1, 3):
+        w = torch.randn(20, 3, k, k, generator=g)
+        b = torch.randn(20, generator=g)
+        ref = F.relu(F.conv2d(img - mean.view(1, 3, 1, 1), w, b, padding=k // 2))
+        out = torch.zeros(B * H * W, 24, device=d)
+        ops.conv_direct(nh, B, H, W, 3, k, packing.pack_conv_direct(w, 24, d), packing.pack_vector(b, 24, device=d), n_store=24, act=ops.ACT_RELU, out_f32=out)
+        torch.cuda.synchronize()
+        assert (_nchw(out.cpu()[:, :20], B, H, W) - ref).abs().max().item() < 1e-4
+    back = torch.zeros(B, 3, H, W, device=d)
+    ops.nhwc_to_nchw(nh, 0, 3, back)
+    torch.cuda.synchronize()
+    assert (back.cpu() - (img - mean.view(1, 3, 1, 1))).abs().max().item() < 1e-6
