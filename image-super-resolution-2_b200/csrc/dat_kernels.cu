@@ -1,0 +1,187 @@
+// DAT-specific kernels:
+//  * ff_dat_aim         -- Adaptive Interaction Module tail (dat_arch.py:544-560 / :650-664): per-pixel
+//                          spatial-interaction MLP (C -> C/16 -> 1, BN folded, GELU) + both sigmoid gates + sum.
+//  * ff_dat_chan_gram   -- channel attention statistics (dat_arch.py:636-646): per (sample, head) Gram matrix
+//                          q^T k over all tokens plus the squared L2 norms of the q / k channels, split over
+//                          token chunks (deterministic two-phase reduction).
+//  * ff_dat_chan_softmax -- finalise: cosine-normalise, * temperature, softmax over 30 keys; emits a per-sample
+//                          block-diagonal bf16 [192 x 192] matrix so `attn @ v` runs as a tcgen05 GEMM with
+//                          per-sample weights (ff_conv_gemm, w_batch_rows = 192).
+#include "ff_common.cuh"
+#include "../../include/ffb200.h"
+
+extern long long g_ff_launches;
+
+namespace {
+
+constexpr int CP = 192;
+constexpr int HID_MAX = 16;
+
+struct AimArgs {
+  const bf16* att; int att_ld;
+  const bf16* conv; int conv_ld;
+  const float* cmap; int cmap_ld;   // [B][192] pre-sigmoid channel map
+  const float* w1; const float* b1; // [hid][192], [hid]
+  const float* w2; float b2;        // [hid]
+  int hid;
+  int mode;                         // 0: spatial block, 1: channel block
+  long long M; int pixels_per_sample;
+  bf16* out; int out_ld;
+};
+
+__global__ void __launch_bounds__(256) dat_aim_kernel(const __grid_constant__ AimArgs a) {
+  __shared__ float sW1[HID_MAX * CP];
+  __shared__ float sB1[HID_MAX], sW2[HID_MAX];
+  for (int i = threadIdx.x; i < a.hid * CP; i += 256) sW1[i] = a.w1[i];
+  if (threadIdx.x < a.hid) { sB1[threadIdx.x] = a.b1[threadIdx.x]; sW2[threadIdx.x] = a.w2[threadIdx.x]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * 8;
+  for (long long p = warp0; p < a.M; p += nwarps) {
+    float av[6], cv[6];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int c = i * 64 + lane * 2;
+      const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(a.att + p * a.att_ld + c);
+      const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(a.conv + p * a.conv_ld + c);
+      av[2 * i] = __low2float(x); av[2 * i + 1] = __high2float(x);
+      cv[2 * i] = __low2float(y); cv[2 * i + 1] = __high2float(y);
+    }
+    const float* src = a.mode == 0 ? av : cv;
+    float s = a.b2;
+    for (int h = 0; h < a.hid; ++h) {
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int c = i * 64 + lane * 2;
+        d += src[2 * i] * sW1[h * CP + c] + src[2 * i + 1] * sW1[h * CP + c + 1];
+      }
+      d = warp_sum(d) + sB1[h];
+      s += gelu_erf(d) * sW2[h];
+    }
+    const float sg = sigmoidf_(s);
+    const int b = (int)(p / a.pixels_per_sample);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int c = i * 64 + lane * 2;
+      const float c0 = sigmoidf_(a.cmap[(long long)b * a.cmap_ld + c]), c1 = sigmoidf_(a.cmap[(long long)b * a.cmap_ld + c + 1]);
+      float o0, o1;
+      if (a.mode == 0) { o0 = av[2 * i] * c0 + sg * cv[2 * i]; o1 = av[2 * i + 1] * c1 + sg * cv[2 * i + 1]; }
+      else { o0 = av[2 * i] * sg + cv[2 * i] * c0; o1 = av[2 * i + 1] * sg + cv[2 * i + 1] * c1; }
+      *reinterpret_cast<__nv_bfloat162*>(a.out + p * a.out_ld + c) = __floats2bfloat162_rn(o0, o1);
+    }
+  }
+}
+
+// partial[b*heads+h][chunk][0..1023] = G (i*32+j), [1024..1055] = |q_i|^2, [1056..1087] = |k_j|^2
+constexpr int GRAM_STRIDE = 1088;
+constexpr int GRAM_TOK = 64;
+
+__global__ void __launch_bounds__(256) dat_chan_gram_kernel(const bf16* __restrict__ qkv, int ld, int q_off, int k_off, int N,
+                                                           int heads, int chunk_tokens, float* __restrict__ partial, int nchunks) {
+  __shared__ float sq[GRAM_TOK][33], sk[GRAM_TOK][33];
+  const int bh = blockIdx.x, chunk = blockIdx.y;
+  const int b = bh / heads, h = bh - b * heads;
+  const int t0 = chunk * chunk_tokens, t1 = min(N, t0 + chunk_tokens);
+  const int tid = threadIdx.x;
+  const int i0 = (tid >> 4) * 2, j0 = (tid & 15) * 2;   // 2x2 sub-block of the 32x32 Gram matrix
+  float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f, nq = 0.f, nk = 0.f;
+  const bf16* base = qkv + ((long long)b * N) * ld + h * 32;
+  for (int t = t0; t < t1; t += GRAM_TOK) {
+    // load 64 tokens x 32 dims of q and k (each thread: 8 q + 8 k values)
+    {
+      const int tok = tid >> 2, part = (tid & 3) * 8;
+      float fq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (t + tok < t1) {
+        const bf16* row = base + (long long)(t + tok) * ld + part;
+        const uint4 uq = *reinterpret_cast<const uint4*>(row + q_off);
+        const uint4 uk = *reinterpret_cast<const uint4*>(row + k_off);
+        const uint32_t wq[4] = {uq.x, uq.y, uq.z, uq.w}, wk[4] = {uk.x, uk.y, uk.z, uk.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          fq[2 * e] = __uint_as_float(wq[e] << 16); fq[2 * e + 1] = __uint_as_float(wq[e] & 0xffff0000u);
+          fk[2 * e] = __uint_as_float(wk[e] << 16); fk[2 * e + 1] = __uint_as_float(wk[e] & 0xffff0000u);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sq[tok][part + e] = fq[e]; sk[tok][part + e] = fk[e]; }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int n = 0; n < GRAM_TOK; ++n) {
+      const float a0 = sq[n][i0], a1 = sq[n][i0 + 1], b0 = sk[n][j0], b1 = sk[n][j0 + 1];
+      g00 += a0 * b0; g01 += a0 * b1; g10 += a1 * b0; g11 += a1 * b1;
+    }
+    if (tid < 32) {
+      for (int n = 0; n < GRAM_TOK; ++n) nq += sq[n][tid] * sq[n][tid];
+    } else if (tid < 64) {
+      for (int n = 0; n < GRAM_TOK; ++n) nk += sk[n][tid - 32] * sk[n][tid - 32];
+    }
+    __syncthreads();
+  }
+  float* out = partial + ((long long)bh * nchunks + chunk) * GRAM_STRIDE;
+  out[i0 * 32 + j0] = g00; out[i0 * 32 + j0 + 1] = g01; out[(i0 + 1) * 32 + j0] = g10; out[(i0 + 1) * 32 + j0 + 1] = g11;
+  if (tid < 32) out[1024 + tid] = nq;
+  else if (tid < 64) out[1056 + tid - 32] = nk;
+}
+
+__global__ void __launch_bounds__(1024) dat_chan_softmax_kernel(const float* __restrict__ partial, int nchunks, int heads, int hd,
+                                                               const float* __restrict__ temperature, bf16* __restrict__ wout) {
+  __shared__ float G[32][33], nq[32], nk[32];
+  const int bh = blockIdx.x;
+  const int b = bh / heads, h = bh - b * heads;
+  const int tid = threadIdx.x, i = tid >> 5, j = tid & 31;
+  const float* p = partial + (long long)bh * nchunks * GRAM_STRIDE;
+  float g = 0.f;
+  for (int c = 0; c < nchunks; ++c) g += p[(long long)c * GRAM_STRIDE + tid];
+  G[i][j] = g;
+  if (tid < 64) {
+    float s = 0.f;
+    for (int c = 0; c < nchunks; ++c) s += p[(long long)c * GRAM_STRIDE + 1024 + tid];
+    if (tid < 32) nq[tid] = fmaxf(sqrtf(s), 1e-12f); else nk[tid - 32] = fmaxf(sqrtf(s), 1e-12f);
+  }
+  __syncthreads();
+  // row i: softmax over j < hd of G/(|q_i||k_j|) * temperature[h]
+  float v = -1e30f;
+  if (i < hd && j < hd) v = G[i][j] / (nq[i] * nk[j]) * temperature[h];
+  const float m = warp_max(v);
+  const float e = (i < hd && j < hd) ? __expf(v - m) : 0.f;
+  const float s = warp_sum(e);
+  const float a = (i < hd && j < hd) ? e / s : 0.f;
+  // block-diagonal weight row (out channel h*32+i), column (h*32+j)
+  wout[((long long)b * CP + h * 32 + i) * CP + h * 32 + j] = __float2bfloat16_rn(a);
+}
+
+}  // namespace
+
+extern "C" int ff_dat_aim(const void* att, int att_ld, const void* conv, int conv_ld, const float* cmap, int cmap_ld,
+                          const float* w1, const float* b1, const float* w2, float b2, int hid, int mode, long long M,
+                          int pixels_per_sample, void* out, int out_ld, void* stream) {
+  FF_CHECK_ARG(att && conv && cmap && w1 && b1 && w2 && out, "ff_dat_aim: null buffer");
+  FF_CHECK_ARG(hid > 0 && hid <= HID_MAX, "ff_dat_aim: hid=%d > %d", hid, HID_MAX);
+  AimArgs a{reinterpret_cast<const bf16*>(att), att_ld, reinterpret_cast<const bf16*>(conv), conv_ld, cmap, cmap_ld, w1, b1, w2, b2, hid, mode, M, pixels_per_sample, reinterpret_cast<bf16*>(out), out_ld};
+  int grid = ff_cdiv(M, 8);
+  const int cap = ff_num_sms() * 16;
+  if (grid > cap) grid = cap;
+  dat_aim_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_dat_aim");
+  return FF_OK;
+}
+
+extern "C" int ff_dat_channel_attention_weights(const void* qkv, int ld, int q_off, int k_off, int B, int N, int heads, int hd,
+                                                const float* temperature, void* wout, float* scratch, size_t scratch_bytes,
+                                                void* stream) {
+  FF_CHECK_ARG(qkv && temperature && wout && scratch, "ff_dat_channel_attention_weights: null buffer");
+  FF_CHECK_ARG(heads * 32 == CP && hd <= 32, "ff_dat_channel_attention_weights: expects 6 heads padded to 32 dims");
+  int chunk = 2048;
+  int nchunks = ff_cdiv(N, chunk);
+  FF_CHECK_ARG(scratch_bytes >= (size_t)B * heads * nchunks * GRAM_STRIDE * sizeof(float), "ff_dat_channel_attention_weights: scratch too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dat_chan_gram_kernel<<<dim3(B * heads, nchunks), 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv), ld, q_off, k_off, N, heads, chunk, scratch, nchunks);
+  dat_chan_softmax_kernel<<<B * heads, 1024, 0, st>>>(scratch, nchunks, heads, hd, temperature, reinterpret_cast<bf16*>(wout));
+  g_ff_launches += 2;
+  FF_CHECK_LAUNCH("ff_dat_channel_attention_weights");
+  return FF_OK;
+}

@@ -1,0 +1,131 @@
+"""NAFNet-SIDD-width64 wrapped for x4 SR on the ffb200 kernels.
+
+Host-side mirror of `NAFNetSR.forward` (reference src/models/nafnet/__init__.py:117-139: bicubic x4 -> NAFNet ->
+clamp) and `NAFNet.forward` / `NAFBlock.forward` (src/models/nafnet/nafnet_arch.py:195-225, :110-131) with
+enc [2,2,4,8], middle 12, dec [2,2,2,2], width 64 (expert_loader.py:481-487).  State-dict keys are those of
+the inner `nafnet.` module (the format `load_nafnet_weights` ingests).
+
+NHWC throughout, so LayerNorm2d is a plain per-pixel layer norm; SimpleGate is folded into the depthwise
+kernel (first gate) and into the conv4 epilogue (second gate); both PixelShuffle(2) are folded into stores.
+"""
+import ctypes as C_
+
+import torch
+
+from . import lib as L
+from . import ops
+from .hat import Workspace
+from .ops import ACT_CLAMP01, ACT_NONE, CONV_1X1, CONV_2X2S2, CONV_3X3
+from .packing import BF16, F32, pack_conv, pack_conv_direct, pack_dw, pack_matrix, pack_vector, pixel_shuffle_rows
+
+WIDTH = 64
+ENC = (2, 2, 4, 8)
+DEC = (2, 2, 2, 2)
+MID = 12
+
+
+def _gate_perm(c):
+    """Row order for conv4 so each 16-row chunk holds 8 x1 channels followed by their 8 x2 partners."""
+    return torch.cat([torch.cat([torch.arange(8 * i, 8 * i + 8), c + torch.arange(8 * i, 8 * i + 8)]) for i in range(c // 8)])
+
+
+class NAFNetRunner:
+    def __init__(self, sd, device="cuda", enc=ENC, dec=DEC, mid=MID):
+        self.device = device
+        self.enc, self.dec, self.mid = enc, dec, mid
+        self.ws = Workspace(device)
+        dev = device
+        g = lambda k: sd[k].detach().to("cpu", F32)
+
+        def block(p, c):
+            perm = _gate_perm(c)
+            return dict(
+                c=c,
+                n1=(g(p + "norm1.weight").to(dev), g(p + "norm1.bias").to(dev)),
+                n2=(g(p + "norm2.weight").to(dev), g(p + "norm2.bias").to(dev)),
+                w1=pack_matrix(g(p + "conv1.weight").reshape(2 * c, c), 2 * c, c, device=dev), b1=g(p + "conv1.bias").to(dev),
+                dw=pack_dw(g(p + "conv2.weight"), 2 * c, device=dev), dwb=g(p + "conv2.bias").to(dev),
+                w3=pack_matrix(g(p + "conv3.weight").reshape(c, c), c, c, device=dev), b3=g(p + "conv3.bias").to(dev),
+                sca_w=g(p + "sca.1.weight").reshape(c, c).to(dev).contiguous(), sca_b=g(p + "sca.1.bias").to(dev),
+                w4=pack_matrix(g(p + "conv4.weight").reshape(2 * c, c)[perm], 2 * c, c, device=dev), b4=g(p + "conv4.bias")[perm].contiguous().to(dev),
+                w5=pack_matrix(g(p + "conv5.weight").reshape(c, c), c, c, device=dev), b5=g(p + "conv5.bias").to(dev),
+                beta=g(p + "beta").reshape(-1).to(dev).contiguous(), gamma=g(p + "gamma").reshape(-1).to(dev).contiguous(),
+            )
+
+        self.intro_w = pack_conv_direct(g("intro.weight"), WIDTH, dev)
+        self.intro_b = g("intro.bias").to(dev)
+        self.end_w = pack_conv(g("ending.weight"), 16, WIDTH, device=dev)
+        self.end_b = pack_vector(g("ending.bias"), 16, device=dev)
+        c = WIDTH
+        self.encoders, self.downs = [], []
+        for s, n in enumerate(enc):
+            self.encoders.append([block(f"encoders.{s}.{k}.", c) for k in range(n)])
+            self.downs.append((pack_conv(g(f"downs.{s}.weight"), 2 * c, c, device=dev), g(f"downs.{s}.bias").to(dev)))
+            c *= 2
+        self.middle = [block(f"middle_blks.{k}.", c) for k in range(mid)]
+        self.ups, self.decoders = [], []
+        for s, n in enumerate(dec):
+            rows = pixel_shuffle_rows(2 * c)
+            self.ups.append(pack_matrix(g(f"ups.{s}.0.weight").reshape(2 * c, c), 2 * c, c, row_index=rows, device=dev))
+            c //= 2
+            self.decoders.append([block(f"decoders.{s}.{k}.", c) for k in range(n)])
+
+    def _block(self, d, S, Sb, B, H, W, bufs, want_bf16):
+        """One NAFBlock in place on the fp32 stream S [P, c]; Sb receives a bf16 copy when want_bf16."""
+        c = d["c"]
+        P = B * H * W
+        t, a, gt, gapv, sca, scratch = bufs
+        ops.layernorm(S, P, c, d["n1"][0], d["n1"][1], 1e-6, out_bf16=t, out_cols=c)
+        ops.conv_gemm(t, B, H, W, c, d["w1"], n_store=2 * c, bias=d["b1"], out_bf16=a)
+        ops.dwconv(a, B, H, W, 2 * c, 3, 3, d["dw"], d["dwb"], gt, mode=1)
+        ops.gap(gt, B, H * W, c, gapv, scratch)
+        ops.vec_linear(gapv, B, c, d["sca_w"], d["sca_b"], c, ACT_NONE, sca)
+        ops.scale_channels(gt, B, H * W, c, sca)
+        ops.conv_gemm(gt, B, H, W, c, d["w3"], n_store=c, bias=d["b3"], col_scale=d["beta"], res=S, out_f32=S)
+        ops.layernorm(S, P, c, d["n2"][0], d["n2"][1], 1e-6, out_bf16=t, out_cols=c)
+        ops.conv_gemm(t, B, H, W, c, d["w4"], n_store=2 * c, bias=d["b4"], gate_pairs=1, out_bf16=gt)
+        ops.conv_gemm(gt, B, H, W, c, d["w5"], n_store=c, bias=d["b5"], col_scale=d["gamma"], res=S, out_f32=S,
+                      out_bf16=Sb if want_bf16 else None)
+
+    def forward(self, x, out, out_off=6):
+        """x: fp32 NCHW [B,3,h,w] with 4h, 4w multiples of 256 / 16-aligned at every UNet level (h, w multiples of 64).
+        Writes clamp(NAFNetSR(x), 0, 1) into channels out_off..out_off+2 of the fp32 expert stack."""
+        B, _, h, w = x.shape
+        H, W = 4 * h, 4 * w
+        nlev = len(self.enc)
+        if (H >> nlev) % 8 or (W >> nlev) % 16:
+            raise ValueError("NAFNetRunner: tile too small / unaligned for the 4-level UNet (need h, w multiples of 32/64)")
+        ws = self.ws
+        up = ws.get("up", B * H * W, 4, F32)
+        L.check(L.load().ff_bicubic_up(C_.c_void_p(x.data_ptr()), B, 3, h, w, 4, C_.c_void_p(up.data_ptr()), 4, ops._stream()), "ff_bicubic_up")
+        # per-level buffers
+        lv = []
+        c, Hc, Wc = WIDTH, H, W
+        for _ in range(nlev + 1):
+            P = B * Hc * Wc
+            lv.append(dict(c=c, H=Hc, W=Wc, S=ws.get(f"S{c}", P, c, F32), Sb=ws.get(f"Sb{c}", P, c, BF16),
+                           bufs=(ws.get(f"t{c}", P, c, BF16), ws.get(f"a{c}", P, 2 * c, BF16), ws.get(f"g{c}", P, c, BF16),
+                                 ws.get(f"gap{c}", B, c, F32), ws.get(f"sca{c}", B, c, F32), ws.get("gscratch", 1, B * 64 * 1024, F32))))
+            c, Hc, Wc = 2 * c, Hc // 2, Wc // 2
+        l0 = lv[0]
+        ops.conv_direct(up, B, H, W, 3, 3, self.intro_w, self.intro_b, n_store=WIDTH, out_f32=l0["S"])
+        for s in range(nlev):
+            l = lv[s]
+            blks = self.encoders[s]
+            for k, d in enumerate(blks):
+                self._block(d, l["S"], l["Sb"], B, l["H"], l["W"], l["bufs"], want_bf16=(k == len(blks) - 1))
+            dw_, db_ = self.downs[s]
+            ops.conv_gemm(l["Sb"], B, l["H"], l["W"], l["c"], dw_, kind=CONV_2X2S2, n_store=2 * l["c"], bias=db_, out_f32=lv[s + 1]["S"])
+        l = lv[nlev]
+        for k, d in enumerate(self.middle):
+            self._block(d, l["S"], l["Sb"], B, l["H"], l["W"], l["bufs"], want_bf16=(k == len(self.middle) - 1))
+        for s in range(len(self.dec)):
+            src, dst = lv[nlev - s], lv[nlev - s - 1]
+            # 1x1 conv c -> 2c (no bias) + PixelShuffle(2) + encoder skip, written in place over the skip buffer
+            ops.conv_gemm(src["Sb"], B, src["H"], src["W"], src["c"], self.ups[s], n_store=2 * src["c"], pixel_shuffle=2, res=dst["S"], out_f32=dst["S"])
+            blks = self.decoders[s]
+            for k, d in enumerate(blks):
+                self._block(d, dst["S"], dst["Sb"], B, dst["H"], dst["W"], dst["bufs"], want_bf16=(k == len(blks) - 1))
+        ops.conv_gemm(l0["Sb"], B, H, W, WIDTH, self.end_w, kind=CONV_3X3, n_store=3, bias=self.end_b, res=up, post_act=ACT_CLAMP01,
+                      out_f32=out[:, out_off:])
+        return out

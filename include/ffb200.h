@@ -112,6 +112,72 @@ typedef struct FFWinAttn {
 } FFWinAttn;
 int ff_window_attention(const FFWinAttn* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Memory-bound building blocks (csrc/pointwise.cu).  All NHWC.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* LayerNorm over the channel axis of rows [rows][in_ld] (first C channels), one warp per row, fp32 math.
+ * Writes bf16 and/or fp32; columns C..out_cols-1 are written as zero (channel padding of the GEMM operands).
+ * Replaces nn.LayerNorm (hat_arch.py:232,256,378,391; dat_arch.py:109,686,711) and LayerNorm2d
+ * (nafnet_arch.py:26-41, eps 1e-6, biased variance) -- identical in NHWC. */
+int ff_layernorm(const void* x, int x_is_bf16, int in_ld, long long rows, int C, const float* gamma, const float* beta,
+                 float eps, void* out_bf16, int out_ld, int out_cols, float* out_f32, int out_f32_ld, void* stream);
+
+/* Global average pool over the P pixels of each sample: x [B][P][ld] -> out [B][out_ld] (fp32), two-phase
+ * deterministic reduction through `scratch` (>= B*64*C floats).  nn.AdaptiveAvgPool2d(1) of hat_arch.py:50,
+ * dat_arch.py:411,603, nafnet_arch.py:86. */
+int ff_gap(const void* x, int x_is_bf16, int ld, int B, int P, int C, float* out, int out_ld, float* scratch,
+           size_t scratch_bytes, void* stream);
+
+/* y[r][n] = act(x[r][:K] . W[n][:K] + bias[n]) for per-sample vectors (SE / SCA / channel-interaction heads);
+ * columns N..y_cols-1 are written as zero. */
+int ff_vec_linear(const float* x, int x_ld, int R, int K, const float* W, const float* bias, int N, int act, float* y,
+                  int y_ld, int y_cols, void* stream);
+
+/* Depthwise kh x kw convolution (zero padding), bf16 NHWC in/out, fp32 weights [kh*kw][C] and accumulate.
+ * mode 0: out = act(dw(x)+bias) * (mul ? mul : 1);  mode 1 (SimpleGate, nafnet_arch.py:47-52,112-114):
+ * out[c] = (dw(x)+bias)[c] * (dw(x)+bias)[c + C/2].  Also dat_arch.py:115,403-407 and the LKA chain
+ * (large_kernel_attention.py:59-78). */
+int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, int kh, int kw, const float* w, const float* bias,
+              int act, int mode, const void* mul, int mul_ld, void* out, int out_ld, void* stream);
+
+/* x[p][c] *= s[b][c] in place (bf16): NAFNet simplified channel attention, nafnet_arch.py:118. */
+int ff_scale_channels(void* x, int ld, int B, long long pixels_per_sample, int C, const float* s, int s_ld, void* stream);
+
+/* Direct fp32 convolution (k = 1 or 3, zero pad) for small channel counts: image-space first/last layers and
+ * the fp32 routing path of the fusion head (fusion_network.py:167-236,543-607).  w is fp32 [Cout_pad][k*k*Cin]. */
+int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int H, int W, int Cin, int k, const float* w,
+                   const float* bias, int Cout_pad, int n_store, int act, const float* mul_f32, int mul_ld,
+                   void* out_bf16, int out_ld, float* out_f32, int out_f32_ld, void* stream);
+
+/* Layout conversion at the boundary: NCHW fp32 image <-> NHWC fp32 rows (optional per-channel subtraction,
+ * hat_arch.py:972-973 `(x - mean) * img_range`). */
+int ff_nchw_to_nhwc(const float* x, int B, int C, int H, int W, const float* sub, float* out, int ld, void* stream);
+int ff_nhwc_to_nchw(const float* x, int ld, int coff, int B, int C, int H, int W, float* out, void* stream);
+
+/* Bicubic up-sampling (a = -0.75, align_corners=False, border-clamped taps), NCHW fp32 -> NHWC fp32:
+ * F.interpolate(mode='bicubic') of nafnet/__init__.py:128-133. */
+int ff_bicubic_up(const float* x, int B, int C, int h, int w, int scale, float* out, int ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DAT-specific (csrc/dat_kernels.cu)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Adaptive Interaction Module tail, dat_arch.py:544-560 (mode 0, spatial block) / :650-664 (mode 1, channel block):
+ *   s = w2 . gelu(W1 . (mode ? conv : att)[p] + b1) + b2     (spatial_interaction, BN folded into W1/b1)
+ *   mode 0: out = att * sigmoid(cmap[b]) + sigmoid(s) * conv;   mode 1: out = att * sigmoid(s) + conv * sigmoid(cmap[b])
+ * att / conv / out are bf16 [M][192]; cmap is the pre-sigmoid channel_interaction output [B][192]. */
+int ff_dat_aim(const void* att, int att_ld, const void* conv, int conv_ld, const float* cmap, int cmap_ld, const float* w1,
+               const float* b1, const float* w2, float b2, int hid, int mode, long long M, int pixels_per_sample, void* out,
+               int out_ld, void* stream);
+
+/* Channel attention weights of AdaptiveChannelAttention (dat_arch.py:632-646): per (sample, head)
+ * softmax_j( <q_i,k_j> / (max(|q_i|,1e-12) max(|k_j|,1e-12)) * temperature[h] ) with the contraction over all N tokens,
+ * emitted as a block-diagonal bf16 [B*192][192] matrix so `attn @ v` runs through ff_conv_gemm (w_batch_rows=192).
+ * scratch >= B*heads*ceil(N/2048)*1088 floats. */
+int ff_dat_channel_attention_weights(const void* qkv, int ld, int q_off, int k_off, int B, int N, int heads, int hd,
+                                     const float* temperature, void* wout, float* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
