@@ -178,6 +178,55 @@ int ff_dat_aim(const void* att, int att_ld, const void* conv, int conv_ld, const
 int ff_dat_channel_attention_weights(const void* qkv, int ld, int q_off, int k_off, int B, int N, int heads, int hd,
                                      const float* temperature, void* wout, float* scratch, size_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fusion head (csrc/freq.cu, csrc/head_kernels.cu)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* 9-band frequency decomposition of the LR tile: lr fp32 NCHW [B,3,H,W] -> bands fp32 [B*H*W][27], channel = band*3 + c,
+ * bands = [DCT low/mid/high, DWT LL/LH/HL/HH, FFT low/high].  Replaces MultiDomainFrequencyDecomposition.decompose
+ * (multi_domain_frequency.py:578-591; DCT :146-196, DWT :251-299, FFT :352-385; torch.fft -> four DFT passes).
+ * dct_mat: [64] DCT-II matrix D[k][n]; dct_band_of: [64] band id (0/1/2) of each coefficient; dwt_lo/hi: db4 taps [8];
+ * fft_mask: [H][W/2+1] = sigmoid(bilinear(freq_mask_logits) * clamp(temperature, 1)).  scratch >= B*3*(4*H*(W/2+1) + 4*(H/2+4)*(W/2+4)) floats. */
+int ff_freq_decompose(const float* lr, int B, int H, int W, const float* dct_mat, const int* dct_band_of, const float* dct_scale,
+                      const float* dwt_lo, const float* dwt_hi, const float* dwt_scale, const float* fft_mask, const float* fft_scale,
+                      float* bands, float* scratch, size_t scratch_bytes, void* stream);
+
+/* Cross-band attention front end (large_kernel_attention.py:218-226): per (pixel, band) token, band_proj (1x1, 3->64) then
+ * LayerNorm(64); writes the un-normalised projection (bf16, residual) and the normalised tokens (bf16, MHA input). */
+int ff_cb_embed_ln(const float* bands, long long tokens, const float* proj_w, const float* proj_b, const float* ln_w, const float* ln_b,
+                   void* stacked, void* normed, void* stream);
+/* Core of nn.MultiheadAttention over the num_bands tokens of each pixel (4 heads x 16, :228): qkv bf16 [tokens][192] -> bf16 [tokens][64]. */
+int ff_cb_attention(const void* qkv, long long tokens, int num_bands, void* out, void* stream);
+/* y = x * a[c] + b[c] on bf16 rows (eval-mode BatchNorm that cannot be folded through a zero-padded depthwise conv, :145). */
+int ff_affine_rows(const void* x, long long rows, int C, const float* a, const float* b, void* y, void* stream);
+/* AdaptiveBandFusionModule 9->3 (multi_domain_frequency.py:478-526) fused with the frequency guidance of
+ * enhanced_fusion.py:533-542.  blob layout: see csrc/head_kernels.cu (band_fuse_kernel). */
+int ff_band_fuse(const float* bands, const float* att, int att_ld, long long P, const float* blob, int blob_len, float* feats,
+                 float* guidance, void* stream);
+/* fp32 NHWC bilinear resize, align_corners=False (F.interpolate call sites of fusion_network.py:594-603); accumulate!=0 adds into out. */
+int ff_bilinear_f32(const float* in, int B, int Hi, int Wi, int ld_in, int C, float* out, int Ho, int Wo, int ld_out, int accumulate,
+                    const float* bias, void* stream);
+/* bf16 NHWC bilinear x2 (hierarchical_fusion.py:155-158,177-180) written into channels [0,C) of a wider row. */
+int ff_bilinear_up2_bf16(const void* in, int B, int Hi, int Wi, int ld_in, int C, void* out, int ld_out, void* stream);
+/* DynamicExpertSelector tail (fusion_network.py:221-234), in place on [P][4] = (gate0, gate1, gate2, difficulty). */
+int ff_selector_tail(float* gates_difficulty, long long P, void* stream);
+/* Bilinear resize (factor 1, 2 or 4 down) of the 9 stacked expert channels into a bf16 conv-input buffer (hierarchical_fusion.py:140-171). */
+int ff_experts_resize(const float* stack, int ld, int B, int H, int W, int factor, void* out, int out_ld, int out_off, void* stream);
+/* SpatialGate (hierarchical_fusion.py:25-43), in place: x *= sigmoid(w2 . gelu(W1 x + b1) + b2); C in {32, 64}. */
+int ff_pixel_gate(void* x, int ld, long long P, int C, const float* w1, const float* b1, const float* w2, float b2, void* stream);
+/* HR blend: 0.7*hier + 0.3*freq-weighted experts, dynamic selection (enhanced_fusion.py:550-556, 593-647); also emits
+ * base = fused + residual_scale * bilinear_up4(lr) (:677-681) for the refine-net epilogue. */
+int ff_blend(const float* stack, int ld_s, const float* hier, const float* guidance, const float* gates, const float* lr, int B, int h, int w,
+             float residual_scale, float* fused, float* base, void* stream);
+/* Laplacian pyramid (edge_enhancement.py:182-220): down = avg_pool2(gaussian5x5(cur)); lap = cur - bilinear_up2(down). */
+int ff_gauss_down(const float* cur, int ld, int B, int H, int W, const float* k1d, float* down, int ld_o, void* stream);
+int ff_lap_sub(const float* cur, int ld, const float* down, int ld_d, int B, int H, int W, float* lap, int ld_l, void* stream);
+/* out[:, off:off+C] = weight * bilinear_up(feat * att) for one pyramid level (edge_enhancement.py:240-250). */
+int ff_edge_merge(const void* feat, int ld_f, const float* att, int B, int Hl, int Wl, int C, float weight, void* out, int H, int W, int ld_o,
+                  int off, void* stream);
+/* out_nchw = clamp(sr + gate * strength * edge, 0, 1)  (edge_enhancement.py:256-260); se = [P][8] (sr 0..2, edge 3..5). */
+int ff_edge_final(const float* se, const float* gate, int gate_ld, int B, int H, int W, float strength, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
