@@ -1,0 +1,94 @@
+"""Drop-in replacement of the reference plugin entry point `models/team29_FreqFusion/io.py`.
+
+    main(model_dir, input_path, output_path, device=None)        # reference io.py:188-234, called from test.py:50
+
+Same arguments, side effects and checkpoint handling; the forward runs on the ffb200 sm_100a kernels.
+Differences, both deliberate:
+  * overlapped tiling (tile 128 / overlap 32, the reference's OOM fallback, io.py:226) is the main path and the
+    tiles of an image run batched;
+  * `device` must be a CUDA device -- there is no CPU fallback.
+"""
+import glob
+import os
+
+import numpy as np
+import torch
+from PIL import Image
+
+from . import lib as L
+from . import tiling
+from .model import EXPERT_FILES, FreqFusionB200
+
+# reference io.py:40-58 -- fixed inference configuration (kept for callers that introspect it)
+MODEL_CONFIG = {
+    "scale": 4, "num_experts": 3, "fusion_dim": 64, "num_heads": 4, "refine_depth": 4, "refine_channels": 64,
+    "num_bands": 3, "block_size": 8, "enable_hierarchical": True, "enable_multi_domain_freq": True, "enable_lka": True,
+    "enable_edge_enhance": True, "enable_dynamic_selection": True, "enable_cross_band_attn": True,
+    "enable_adaptive_bands": True, "enable_multi_resolution": True, "enable_collaborative": True,
+}
+
+_PROJECT_ROOT = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+MAX_TILES_PER_BATCH = int(os.environ.get("FFB200_TILE_BATCH", "20"))
+
+
+def _load_image(path):
+    """PNG -> [1,3,H,W] float32 in [0,1]  (reference io.py:64-68)."""
+    arr = np.array(Image.open(path).convert("RGB"), dtype=np.float32) / 255.0
+    return torch.from_numpy(arr).permute(2, 0, 1).unsqueeze(0)
+
+
+def _build_and_load(model_dir, device, pretrained_root=None, verbose=True):
+    model = FreqFusionB200(device=device, verbose=verbose)
+    root = pretrained_root or os.environ.get("FFB200_PRETRAINED_ROOT", _PROJECT_ROOT)
+    for name, rel in EXPERT_FILES.items():
+        model.load_expert_checkpoint(name, os.path.join(root, rel))
+    model.load_fusion_checkpoint(model_dir)
+    return model
+
+
+@torch.no_grad()
+def tiled_forward(model, lr_img, tile_size=128, overlap=32, scale=4, return_u8=False, max_batch=None):
+    """`_tiled_forward` of the reference (io.py:82-121) with batched tiles.  lr_img: [1,3,h,w] on the device.
+    Returns fp32 [1,3,4h,4w] (or uint8 [4h,4w,3] when return_u8)."""
+    dev = lr_img.device
+    _, _, h, w = lr_img.shape
+    pl = tiling.plan(h, w, tile_size, overlap, scale)
+    tiles = tiling.extract_tiles(lr_img, pl)
+    T = tiles.shape[0]
+    mb = max_batch or MAX_TILES_PER_BATCH
+    ts = tile_size * scale
+    sr = torch.empty(T, 3, ts, ts, dtype=torch.float32, device=dev)
+    for i in range(0, T, mb):
+        model.forward(tiles[i:i + mb], out=sr[i:i + mb])
+    st = tiling.Stitcher(pl, dev)
+    if return_u8:
+        u8 = torch.empty(h * scale, w * scale, 3, dtype=torch.uint8, device=dev)
+        st(sr, out_u8=u8)
+        return u8
+    out = torch.empty(3, h * scale, w * scale, dtype=torch.float32, device=dev)
+    st(sr, out=out)
+    return out.unsqueeze(0)
+
+
+@torch.no_grad()
+def main(model_dir, input_path, output_path, device=None):
+    """NTIRE2026 plugin interface (same contract as the reference's main)."""
+    if device is None:
+        device = torch.device("cuda")
+    device = torch.device(device)
+    if device.type != "cuda" or not torch.cuda.is_available():
+        raise L.FFError("team29_FreqFusion (b200 build) needs a CUDA device: there is no CPU fallback")
+    print(f"[team29_FreqFusion/b200] Device: {device}")
+    model = _build_and_load(model_dir, device)
+    input_imgs = sorted(glob.glob(os.path.join(input_path, "*.[pP][nN][gG]")))
+    if not input_imgs:
+        input_imgs = sorted(glob.glob(os.path.join(input_path, "*.[jJ][pP]*[gG]")))
+    print(f"[team29_FreqFusion/b200] Found {len(input_imgs)} images in {input_path}")
+    os.makedirs(output_path, exist_ok=True)
+    for img_path in input_imgs:
+        lr_img = _load_image(img_path).to(device)
+        _, _, h, w = lr_img.shape
+        tile, ov = tiling.choose_tile(h, w)
+        u8 = tiled_forward(model, lr_img, tile_size=tile, overlap=ov, scale=4, return_u8=True)
+        Image.fromarray(u8.cpu().numpy()).save(os.path.join(output_path, os.path.basename(img_path)), format="PNG")
+    print(f"[team29_FreqFusion/b200] Done. {len(input_imgs)} images saved to {output_path}")

@@ -1,0 +1,153 @@
+"""FreqFusion x4 (3 frozen experts + fusion head) on the ffb200 kernels, with the reference's checkpoint contract.
+
+Mirrors `CompleteEnhancedFusionSR.forward` in eval mode (reference src/models/enhanced_fusion.py:694-754) with
+`ExpertEnsemble.forward_all` (src/models/expert_loader.py:768-777, experts in the order hat, dat, nafnet).
+Checkpoint ingestion follows io._build_and_load (models/team29_FreqFusion/io.py:127-182), load_checkpoint_flexible
+(expert_loader.py:99-169) and NAFNetSR.load_nafnet_weights (nafnet/__init__.py:84-115): same accepted container keys,
+`module.` / `model.` prefix stripping, name+shape filter, missing files tolerated with a warning.
+"""
+import os
+from collections import OrderedDict
+
+import torch
+
+from . import lib as L
+from . import ops, weights
+from .dat import DATRunner
+from .hat import HATRunner
+from .head import HeadRunner
+from .nafnet import NAFNetRunner
+
+EXPERT_FILES = {
+    "hat": os.path.join("pretrained", "hat", "HAT-L_SRx4_ImageNet-pretrain.pth"),
+    "dat": os.path.join("pretrained", "dat", "DAT_x4.pth"),
+    "nafnet": os.path.join("pretrained", "nafnet", "NAFNet-SIDD-width64.pth"),
+}
+
+
+def _extract_state(ckpt, keys):
+    for k in keys:
+        if isinstance(ckpt, dict) and k in ckpt:
+            return ckpt[k]
+    return ckpt
+
+
+def _filtered_update(base, incoming, prefixes=("module.",), replace_anywhere=False):
+    """name + shape filter of the reference loaders; returns the number of tensors taken."""
+    n = 0
+    for key, val in incoming.items():
+        ck = key
+        if replace_anywhere:
+            ck = ck.replace("module.", "")
+        else:
+            for p in prefixes:
+                if ck.startswith(p):
+                    ck = ck[len(p):]
+        if ck in base and torch.is_tensor(val) and tuple(val.shape) == tuple(base[ck].shape):
+            base[ck] = val.detach().to("cpu", torch.float32)
+            n += 1
+    return n
+
+
+class FreqFusionB200:
+    """Inference-only model object.  `state` holds four fp32 CPU state dicts (reference key names)."""
+
+    def __init__(self, device="cuda", init_seed=0, verbose=True):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise L.FFError("FreqFusionB200 runs on CUDA devices only: there is no CPU fallback")
+        L.load()
+        self.device = device
+        self.verbose = verbose
+        # random-init stand-ins (the reference keeps its random init when a checkpoint is missing)
+        self.state = {m: weights.make_state_dict(m, init_seed) for m in ("hat", "dat", "nafnet", "fusion")}
+        self._runners = None
+
+    # ---- checkpoint contract ------------------------------------------------------------------
+    def load_fusion_checkpoint(self, path):
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        sd = ckpt.get("model_state_dict", ckpt) if isinstance(ckpt, dict) else ckpt
+        n = _filtered_update(self.state["fusion"], sd, prefixes=("module.", "model."))
+        if self.verbose:
+            print(f"[team29_FreqFusion/b200] Loaded {n} fusion weight tensors from checkpoint")
+        self._runners = None
+        return n
+
+    def load_expert_checkpoint(self, name, path):
+        if not os.path.exists(path):
+            if self.verbose:
+                print(f"[team29_FreqFusion/b200] WARNING {name} checkpoint not found: {path} (random init kept)")
+            return 0
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        sd = _extract_state(ckpt, ("params_ema", "params", "state_dict", "model"))
+        n = _filtered_update(self.state[name], sd, replace_anywhere=True)
+        if self.verbose:
+            print(f"[team29_FreqFusion/b200] {name} loaded: {n}/{len(self.state[name])} tensors")
+        self._runners = None
+        return n
+
+    def state_dict(self):
+        """Reference-compatible flat view: fusion keys + expert_ensemble.<expert>.<key> (NAFNet under .nafnet.)."""
+        out = OrderedDict(self.state["fusion"])
+        for k, v in self.state["hat"].items():
+            out["expert_ensemble.hat." + k] = v
+        for k, v in self.state["dat"].items():
+            out["expert_ensemble.dat." + k] = v
+        for k, v in self.state["nafnet"].items():
+            out["expert_ensemble.nafnet.nafnet." + k] = v
+        return out
+
+    def load_state_dict(self, sd, strict=False):
+        n = _filtered_update(self.state["fusion"], sd, prefixes=("module.", "model."))
+        for name, pre in (("hat", "expert_ensemble.hat."), ("dat", "expert_ensemble.dat."), ("nafnet", "expert_ensemble.nafnet.nafnet.")):
+            n += _filtered_update(self.state[name], {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        self._runners = None
+        return n
+
+    # ---- execution ------------------------------------------------------------------------------
+    def runners(self):
+        if self._runners is None:
+            dev = self.device
+            self._runners = dict(hat=HATRunner(self.state["hat"], dev), dat=DATRunner(self.state["dat"], dev),
+                                 nafnet=NAFNetRunner(self.state["nafnet"], dev), head=HeadRunner(self.state["fusion"], dev))
+            self._stacks = {}
+        return self._runners
+
+    def _stack(self, B, S0, S1):
+        key = (B, S0, S1)
+        if key not in self._stacks:
+            self._stacks[key] = torch.zeros(B * 16 * S0 * S1, 12, dtype=torch.float32, device=self.device)
+        return self._stacks[key]
+
+    @torch.no_grad()
+    def forward_experts(self, lr):
+        """[B,3,S,S] fp32 on the device -> fp32 expert stack [B*4S*4S][12] (hat 0-2, dat 3-5, nafnet 6-8), each clamp(.,0,1)."""
+        r = self.runners()
+        B, _, h, w = lr.shape
+        stack = self._stack(B, h, w)
+        r["hat"].forward(lr, stack, 0)
+        r["dat"].forward(lr, stack, 3)
+        r["nafnet"].forward(lr, stack, 6)
+        return stack
+
+    @torch.no_grad()
+    def forward(self, lr, out=None, intermediates=None):
+        """lr: fp32 NCHW [B,3,S,S] in [0,1], S a multiple of 64 -> fp32 NCHW [B,3,4S,4S]."""
+        if not lr.is_cuda:
+            raise L.FFError("FreqFusionB200.forward needs a CUDA tensor (no CPU fallback)")
+        lr = lr.contiguous().float()
+        stack = self.forward_experts(lr)
+        return self.runners()["head"].forward(lr, stack, out=out, intermediates=intermediates)
+
+    __call__ = forward
+
+    def expert_outputs_nchw(self, lr):
+        """Testing helper: dict of NCHW expert outputs like ExpertEnsemble.forward_all(return_dict=True)."""
+        B, _, h, w = lr.shape
+        stack = self.forward_experts(lr.contiguous().float())
+        out = {}
+        for i, name in enumerate(("hat", "dat", "nafnet")):
+            t = torch.empty(B, 3, 4 * h, 4 * w, dtype=torch.float32, device=self.device)
+            ops.nhwc_to_nchw(stack, 3 * i, 3, t)
+            out[name] = t
+        return out

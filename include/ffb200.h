@@ -227,6 +227,18 @@ int ff_edge_merge(const void* feat, int ld_f, const float* att, int B, int Hl, i
 /* out_nchw = clamp(sr + gate * strength * edge, 0, 1)  (edge_enhancement.py:256-260); se = [P][8] (sr 0..2, edge 3..5). */
 int ff_edge_final(const float* se, const float* gate, int gate_ld, int B, int H, int W, float strength, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tile scheduler tail (csrc/stitch.cu)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Overlapped-tile stitch of io._tiled_forward (models/team29_FreqFusion/io.py:97-121): ramp-weighted accumulation in the
+ * reference's tile order with un-fused fp32 ops (bit-identical), normalisation by clamp(weight_map, 1e-8), and optionally
+ * io._save_image's quantisation (:71-76) round_half_even(clamp(x,0,1)*255) into an HWC uint8 image.
+ * tiles: fp32 [ny*nx][3][ts][ts] (y-major, x-minor); ty/tx: HR origin of each tile row / column; wy/wx: [ny][ts] / [nx][ts]
+ * 1-D blend weights; out: fp32 [3][H][W] or NULL; out_u8: uint8 [H][W][3] or NULL. */
+int ff_stitch(const float* tiles, const int* ty, const int* tx, const float* wy, const float* wx, int ny, int nx, int ts, int H, int W,
+              float* out, unsigned char* out_u8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

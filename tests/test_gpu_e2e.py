@@ -1,0 +1,103 @@
+"""End-to-end GPU parity: full model, tile stitching and the io.main plugin entry against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _lr(B, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(B, 3, h // 4, w // 4, generator=g)
+    x = F.interpolate(low, scale_factor=4, mode="bicubic", align_corners=False) + 0.03 * torch.randn(B, 3, h, w, generator=g)
+    return (x.clamp(0, 1) * 255).round() / 255
+
+
+def _psnr_y(a, b, crop=4):
+    """PSNR on the BT.601 Y channel with a 4-pixel border crop (reference src/utils/metrics.py:30-52, 76-126)."""
+    def y(t):
+        return (65.481 * t[:, 0] + 128.553 * t[:, 1] + 24.966 * t[:, 2] + 16.0) / 255.0
+    ya, yb = y(a)[..., crop:-crop, crop:-crop], y(b)[..., crop:-crop, crop:-crop]
+    mse = ((ya - yb) ** 2).mean().item()
+    return 100.0 if mse == 0 else 10 * np.log10(1.0 / mse)
+
+
+def test_full_model_vs_oracle():
+    from isr2_b200 import model as M
+    from oracle import full
+    lr = _lr(2, 64, 64, 21)
+    m = M.FreqFusionB200("cuda:0", init_seed=0, verbose=False)
+    ref, inter = full.forward(m.state, lr, True)
+    got_i = {}
+    out = m.forward(lr.cuda(), intermediates=got_i).cpu()
+    ex = m.expert_outputs_nchw(lr.cuda())
+    for i, name in enumerate(("hat", "dat", "nafnet")):
+        e = (ex[name].cpu() - inter["expert_outputs"][i]).abs().max().item()
+        assert e < TOL, f"{name}: {e}"
+    err = (out - ref).abs().max().item()
+    # delta-PSNR against a synthetic ground truth, as BASELINE.json states it (<= 0.02 dB)
+    hr = F.interpolate(lr, scale_factor=4, mode="bicubic", align_corners=False).clamp(0, 1)
+    dpsnr = abs(_psnr_y(out, hr) - _psnr_y(ref, hr))
+    print(f"full model: max-abs {err:.2e}, PSNR(ours, ref) {_psnr_y(out, ref):.1f} dB, dPSNR {dpsnr:.4f} dB")
+    assert err < TOL and dpsnr <= 0.02
+
+
+def test_batch_independence():
+    from isr2_b200 import model as M
+    lr = _lr(3, 64, 64, 22).cuda()
+    m = M.FreqFusionB200("cuda:0", init_seed=0, verbose=False)
+    a = m.forward(lr).clone()
+    b = torch.cat([m.forward(lr[i:i + 1]).clone() for i in range(3)])
+    assert (a - b).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("h,w,tile,ov", [(339, 510, 128, 32), (150, 170, 64, 8), (128, 128, 128, 32), (256, 300, 128, 32)])
+def test_stitch_bit_exact(h, w, tile, ov):
+    """Stitch kernel == the reference's sequential accumulation, bit for bit, incl. the uint8 quantisation."""
+    from isr2_b200 import tiling
+    from oracle import tiling as otil
+    g = torch.Generator().manual_seed(5)
+    pl = tiling.plan(h, w, tile, ov)
+    T = len(pl["ys"]) * len(pl["xs"])
+    ts = tile * 4
+    sr_tiles = torch.rand(T, 3, ts, ts, generator=g) * 1.2 - 0.1
+    it = iter(range(T))
+    ref, ys, xs = otil.tiled_forward(lambda t: sr_tiles[next(it)].unsqueeze(0), torch.zeros(1, 3, h, w), tile, ov)
+    assert ys == pl["ys"] and xs == pl["xs"]
+    st = tiling.Stitcher(pl, torch.device("cuda:0"))
+    out = torch.empty(3, 4 * h, 4 * w, device="cuda:0")
+    u8 = torch.empty(4 * h, 4 * w, 3, dtype=torch.uint8, device="cuda:0")
+    st(sr_tiles.cuda(), out=out, out_u8=u8)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref[0]), (out.cpu() - ref[0]).abs().max().item()
+    assert np.array_equal(u8.cpu().numpy(), otil.to_uint8(ref))
+
+
+def test_io_main_plugin(tmp_path):
+    """models.team29_FreqFusion.main(model_dir, input_path, output_path, device): same files out as the oracle pipeline."""
+    from PIL import Image
+    from isr2_b200 import weights
+    from oracle import full, tiling as otil
+    root = str(tmp_path)
+    fusion = weights.save_checkpoints(root, seed=3)
+    os.environ["FFB200_PRETRAINED_ROOT"] = root
+    inp, outp = os.path.join(root, "in"), os.path.join(root, "out")
+    os.makedirs(inp)
+    lr = _lr(1, 64, 96, 33)
+    Image.fromarray((lr[0].permute(1, 2, 0).numpy() * 255).round().astype("uint8")).save(os.path.join(inp, "a.PNG"))
+    from models.team29_FreqFusion import main
+    main(model_dir=fusion, input_path=inp, output_path=outp, device=torch.device("cuda"))
+    got = np.array(Image.open(os.path.join(outp, "a.PNG")))
+    assert got.shape == (256, 384, 3)
+    state = {m: weights.make_state_dict(m, 3) for m in ("hat", "dat", "nafnet", "fusion")}
+    ref, _, _ = otil.tiled_forward(lambda t: full.forward(state, t), lr, 64, 8)
+    refu8 = otil.to_uint8(ref)
+    diff = np.abs(got.astype(int) - refu8.astype(int))
+    print("io.main: max |diff| in gray levels", diff.max(), "mean", diff.mean())
+    assert diff.max() <= 5      # 2e-2 * 255
+    with pytest.raises(Exception):
+        main(model_dir=fusion, input_path=inp, output_path=outp, device=torch.device("cpu"))
