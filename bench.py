@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py -- FreqFusion x4 inference throughput on B200 (metric of BASELINE.json: x4 SR output Mpix/s, full FreqFusion).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--tile S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one forward of the full 3-expert FreqFusion (HAT-L + DAT + NAFNet-64 + fusion head) over a batch of
+16 synthetic 128x128 LR tiles per GPU (BASELINE.json configs[2]); weights are seeded synthetic ("random-init") because
+neither the fusion checkpoint nor the expert weights are available offline.  Tiles are independent, so ranks shard
+them with no data-path collective (weak scaling: per-GPU batch fixed).
+
+JSON keys follow the driver contract; `value` times the device-resident forward, `e2e` the public
+`FreqFusionB200.forward` call fed from pinned HOST memory with the H2D copy of the tiles and the D2H read of the SR
+result inside the timed region.  `roofline` is measured live (CUDA events around every ff_conv_gemm launch of one extra,
+untimed-for-`value` step) against MEASURED_PEAKS.json; `cpu_baseline` times the fp32 oracle port on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MFLOP_PER_OUT_PIXEL = 10.793      # BASELINE.md section 2 (2*MAC of matmul+conv, whole model)
+METRIC = "x4_sr_output_mpix_per_s"
+UNIT = "Mpix/s"
+
+
+def synth_tiles(B, S, seed):
+    """Image-like synthetic LR tiles: bicubic-upsampled noise + fine noise, quantised to 8 bit."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(B, 3, S // 4, S // 4, generator=g)
+    x = F.interpolate(low, scale_factor=4, mode="bicubic", align_corners=False) + 0.03 * torch.randn(B, 3, S, S, generator=g)
+    return ((x.clamp(0, 1) * 255).round() / 255).contiguous()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)), hbm=d.get("hbm_gbs", 6650.0), src="measured")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        import statistics
+        sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_sample(S, threads=None):
+    """Times the fp32 oracle port (oracle/full.py) on ONE SxS tile on the host cores; returns (Mpix/s, seconds, threads)."""
+    import torch
+    from isr2_b200 import weights
+    from oracle import full
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    state = {m: weights.make_state_dict(m, 0) for m in ("hat", "dat", "nafnet", "fusion")}
+    x = synth_tiles(1, S, 1234)
+    t0 = time.perf_counter()
+    full.forward(state, x)
+    dt = time.perf_counter() - t0
+    return 16 * S * S / 1e6 / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  /root/reference cannot travel to the GPU box, so
+    this arm times its fp32 port (oracle/, pinned to the reference by tests/golden) with all host threads; each step is
+    one 128x128 tile of the same workload (bounded sample)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from isr2_b200 import weights
+    from oracle import full
+    S = args.tile
+    torch.set_num_threads(os.cpu_count())
+    state = {m: weights.make_state_dict(m, 0) for m in ("hat", "dat", "nafnet", "fusion")}
+    x = synth_tiles(1, S, 1234)
+    steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    for _ in range(warm):
+        full.forward(state, x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        full.forward(state, x)
+    dt = (time.perf_counter() - t0) / steps
+    val = 16 * S * S / 1e6 / dt
+    sample = f"{steps} timed step(s) of 1 tile {S}x{S} (of the {args.batch}-tile batch), fp32 oracle port, {torch.get_num_threads()} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"full FreqFusion (HAT-L+DAT+NAFNet-64+fusion head), LR tile {S}x{S} -> {4*S}x{4*S}, CPU"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="LR tiles per GPU per step")
+    ap.add_argument("--tile", type=int, default=128, help="LR tile side")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from isr2_b200 import lib, ops
+    from isr2_b200.model import FreqFusionB200
+
+    B, S = args.batch, args.tile
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+    model = FreqFusionB200(dev, init_seed=0, verbose=False)
+    host_in = synth_tiles(B, S, 1000 + rank).pin_memory()           # this rank's shard of the tile stream
+    host_out = torch.empty(B, 3, 4 * S, 4 * S, dtype=torch.float32).pin_memory()
+    x_dev = host_in.to(dev)
+    out_dev = torch.empty(B, 3, 4 * S, 4 * S, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---------------- device-resident throughput (`value`)
+    for _ in range(W):
+        model.forward(x_dev, out=out_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        model.forward(x_dev, out=out_dev)
+    e1.record()
+    barrier()
+    launches = lib.launch_count() - n0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    sampler.stop_flag = True
+    mpix_step = world * B * 16 * S * S / 1e6
+    value = mpix_step * K / (ms_total / 1e3)
+
+    # ---------------- end-to-end through the public API with host buffers (`e2e`)
+    def e2e_step():
+        xd = host_in.to(dev, non_blocking=True)
+        y = model.forward(xd, out=out_dev)
+        host_out.copy_(y, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(K):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_val = mpix_step * K / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (ff_conv_gemm / conv_gemm_tc_kernel), one instrumented step
+    pk = peaks()
+    ops.PROFILE = ops.KernelProfile()
+    model.forward(x_dev, out=out_dev)
+    prof = ops.PROFILE.summary()
+    ops.PROFILE = None
+    achieved = prof["algo_flops"] / (prof["ms"] / 1e3) / 1e12
+    step_ms = ms_total / K
+    roofline = {
+        "kernel": "conv_gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear, all instances)",
+        "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+        "peak_source": pk["src"] + " (bf16 cuBLAS, sustained)", "traffic": None,
+        "launches_per_step": prof["launches"], "avg_launch_us": prof["ms"] * 1e3 / max(prof["launches"], 1),
+        "algorithmic_flops_per_step": prof["algo_flops"], "executed_flops_per_step": prof["exec_flops"],
+        "share_of_step": prof["ms"] / step_ms,
+        "whole_step": {"algorithmic_tflops": MFLOP_PER_OUT_PIXEL * B * 16 * S * S / 1e6 / (step_ms / 1e3), "note": "10.793 MFLOP per output pixel (BASELINE.md) / step time"},
+    }
+    roofline["whole_step"]["frac"] = roofline["whole_step"]["algorithmic_tflops"] / pk["tflops"]
+
+    # ---------------- CPU baseline: fp32 oracle port on the host cores, one tile (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, dt, th = cpu_oracle_sample(S)
+        cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port",
+               "sample": f"1 tile {S}x{S} of the {B}-tile batch, fp32 oracle port (oracle/full.py), {dt:.1f} s, scaled linearly (batch-independent path)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"full FreqFusion (HAT-L+DAT+NAFNet-64+fusion head), batch {B} of {S}x{S} LR tiles -> {4*S}x{4*S} per GPU, random-init weights",
+                   "tiles_per_gpu": B, "lr_tile": S, "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no explicit flush",
+                   "sharding": f"tiles sharded over {world} rank(s), no data-path collective"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / K},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

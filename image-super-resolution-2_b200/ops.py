@@ -14,6 +14,21 @@ _BF16 = torch.bfloat16
 _F32 = torch.float32
 
 
+class KernelProfile:
+    """Optional per-launch CUDA-event timing of ff_conv_gemm (bench.py's roofline leg; off on the hot path)."""
+
+    def __init__(self):
+        self.records = []   # (start_event, end_event, algorithmic_flops, executed_flops)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        ms = sum(s.elapsed_time(e) for s, e, _, _ in self.records)
+        return dict(launches=len(self.records), ms=ms, algo_flops=sum(r[2] for r in self.records), exec_flops=sum(r[3] for r in self.records))
+
+
+PROFILE = None   # set to a KernelProfile instance to record
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -61,6 +76,16 @@ def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_
         p.out_f32 = out_f32.data_ptr(); p.out_f32_ld = out_f32.stride(-2)
     p.pixel_shuffle = pixel_shuffle; p.gate_pairs = gate_pairs; p.w_batch_rows = w_batch_rows
     p.debug_simt = debug_simt
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.load().ff_conv_gemm(C.byref(p), _stream()), "ff_conv_gemm")
+        e1.record()
+        taps = {CONV_1X1: 1, CONV_3X3: 9, CONV_2X2S2: 4}[kind]
+        Mo = B * H * W // (4 if kind == CONV_2X2S2 else 1)
+        n_real, k_real = getattr(w, "ff_real", (p.n_pad, taps * cin))
+        PROFILE.records.append((e0, e1, 2.0 * Mo * n_real * k_real, 2.0 * Mo * p.n_pad * taps * cin))
+        return
     L.check(L.load().ff_conv_gemm(C.byref(p), _stream()), "ff_conv_gemm")
 
 

@@ -28,7 +28,9 @@ def pack_matrix(W, n_pad, k_pad, row_index=None, col_index=None, dtype=BF16, dev
     r = torch.arange(N) if row_index is None else row_index
     c = torch.arange(K) if col_index is None else col_index
     out[r[:, None], c[None, :]] = W.to(F32)
-    return out.to(dtype).to(device).contiguous()
+    t = out.to(dtype).to(device).contiguous()
+    t.ff_real = (N, K)      # un-padded (n, k): used only for FLOP accounting in bench.py
+    return t
 
 
 def pack_vector(v, n_pad, index=None, device="cuda", fill=0.0):
@@ -46,7 +48,9 @@ def pack_conv(W, n_pad, cin_pad, row_index=None, col_index=None, device="cuda", 
     c = torch.arange(Cin) if col_index is None else col_index
     Wt = W.to(F32).permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin)
     out[r[:, None], :, c[None, :]] = Wt.permute(0, 2, 1)
-    return out.reshape(n_pad, kh * kw * cin_pad).to(dtype).to(device).contiguous()
+    t = out.reshape(n_pad, kh * kw * cin_pad).to(dtype).to(device).contiguous()
+    t.ff_real = (Cout, kh * kw * Cin)
+    return t
 
 
 def pack_conv_direct(W, cout_pad, device="cuda"):
