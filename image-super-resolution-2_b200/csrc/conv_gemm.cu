@@ -14,22 +14,27 @@ constexpr int TILE_W = 16;
 constexpr int TILE_H = 8;
 constexpr int BLOCK_K = 64;   // bf16 elements per k-block = 128 B = one swizzle row
 constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 struct Args {
   FFConvGemm p;
   int Ho, Wo;
   int tiles_x, tiles_per_img, m_tiles, n_tiles;
   int ntaps, cchunks;
+  int vec_ok;   // every epilogue operand allows 16-byte fp32 / 8-byte bf16 vector access
 };
 
 template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+  static constexpr int CB = BN < 32 ? BN : 32;                    // epilogue column block
+  static constexpr int STG_PITCH = CB + 4;                        // floats; +4 keeps float4 accesses conflict-free
+  static constexpr int STG_BYTES = NUM_EPI_WARPS * 32 * STG_PITCH * 4;
+  static constexpr int STAGES_RAW = (225 * 1024 - STG_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -55,40 +60,16 @@ __device__ __forceinline__ void load_bf16x16(const bf16* ptr, float (&o)[16]) {
   }
 }
 
-// Fused epilogue for 16 consecutive output channels [n0, n0+16) of one output pixel.
-__device__ __forceinline__ void epilogue16(const Args& a, float (&v)[16], int b, int oy, int ox, int n0) {
+// ----------------------------------------------------------------------------------------------
+// Fused epilogue.
+//  * scalar flavour (`epilogue16`): 16 consecutive channels of one pixel -- used by the SIMT debug kernel and
+//    as the semantic reference of the vector flavour;
+//  * vector flavour (`epilogue_vec4`): 4 consecutive channels of one pixel, 16-byte fp32 / 8-byte bf16 accesses --
+//    used by the tcgen05 kernel after the accumulator tile has been transposed through shared memory so that
+//    consecutive lanes touch consecutive channels (coalesced global traffic).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void out_location(const Args& a, int b, int oy, int ox, int n0, long long& opix, int& oc) {
   const FFConvGemm& p = a.p;
-  if (n0 >= p.n_store) return;
-  if (p.bias) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n0 + i);
-  }
-  if (p.gate_pairs) {
-    const long long gpix = ((long long)(b * a.Ho + oy)) * a.Wo + ox;
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i] * v[2 * i + 8], v[2 * i + 1] * v[2 * i + 9]);
-      w[i] = *reinterpret_cast<uint32_t*>(&h);
-    }
-    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_bf16) + gpix * p.out_ld + (n0 >> 1)) = make_uint4(w[0], w[1], w[2], w[3]);
-    return;
-  }
-  if (p.act) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act);
-  }
-  if (p.alpha != 1.0f) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
-  }
-  if (p.col_scale) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] *= __ldg(p.col_scale + n0 + i);
-  }
-  // output location (optionally PixelShuffle(2): packed column n = (i*2+j)*Cq + c)
-  long long opix;
-  int oc;
   if (p.pixel_shuffle == 2) {
     const int cq = p.n_store >> 2;
     const int sub = n0 / cq;
@@ -98,89 +79,102 @@ __device__ __forceinline__ void epilogue16(const Args& a, float (&v)[16], int b,
     oc = n0;
     opix = ((long long)(b * a.Ho + oy)) * a.Wo + ox;
   }
-  const bool full = (oc + 16 <= ((p.pixel_shuffle == 2) ? (p.n_store >> 2) : p.n_store));
-  const int nvalid = full ? 16 : (((p.pixel_shuffle == 2) ? (p.n_store >> 2) : p.n_store) - oc);
-  if (p.mul) {
-    const bf16* q = reinterpret_cast<const bf16*>(p.mul) + opix * p.mul_ld + oc;
-    if (full) {
-      float m[16];
-      load_bf16x16(q, m);
+}
+
+__device__ __forceinline__ void epilogue16(const Args& a, float (&v)[16], int b, int oy, int ox, int n0) {
+  const FFConvGemm& p = a.p;
+  if (n0 >= p.n_store) return;
+  if (p.bias) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] *= m[i];
-    } else {
-      for (int i = 0; i < nvalid; ++i) v[i] *= __bfloat162float(q[i]);
-    }
+    for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n0 + i);
   }
-  if (p.aux) {
-    const bf16* q = reinterpret_cast<const bf16*>(p.aux) + opix * p.aux_ld + oc;
-    float m[16];
-    if (full) {
-      load_bf16x16(q, m);
-    } else {
+  if (p.gate_pairs) {
+    const long long gpix = ((long long)(b * a.Ho + oy)) * a.Wo + ox;
+    bf16* q = reinterpret_cast<bf16*>(p.out_bf16) + gpix * p.out_ld + (n0 >> 1);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) m[i] = (i < nvalid) ? __bfloat162float(q[i]) : 0.f;
-    }
-    if (p.aux_chan) {
-      const float* ch = p.aux_chan + (long long)b * p.aux_chan_ld + oc;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += p.aux_alpha * m[i] * ((i < nvalid) ? __ldg(ch + i) : 0.f);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += p.aux_alpha * m[i];
-    }
+    for (int i = 0; i < 8; ++i) q[i] = __float2bfloat16_rn(v[i] * v[i + 8]);
+    return;
   }
+  long long opix;
+  int oc;
+  out_location(a, b, oy, ox, n0, opix, oc);
+  const int width = (p.pixel_shuffle == 2) ? (p.n_store >> 2) : p.n_store;
+  const int nvalid = min(16, width - oc);
+  for (int i = 0; i < nvalid; ++i) {
+    float x = apply_act(v[i], p.act) * p.alpha;
+    if (p.col_scale) x *= __ldg(p.col_scale + n0 + i);
+    if (p.mul) x *= __bfloat162float(reinterpret_cast<const bf16*>(p.mul)[opix * p.mul_ld + oc + i]);
+    if (p.aux) {
+      const float m = __bfloat162float(reinterpret_cast<const bf16*>(p.aux)[opix * p.aux_ld + oc + i]);
+      x += p.aux_alpha * m * (p.aux_chan ? __ldg(p.aux_chan + (long long)b * p.aux_chan_ld + oc + i) : 1.f);
+    }
+    if (p.res) {
+      x += p.res_is_f32 ? reinterpret_cast<const float*>(p.res)[opix * p.res_ld + oc + i]
+                        : __bfloat162float(reinterpret_cast<const bf16*>(p.res)[opix * p.res_ld + oc + i]);
+    }
+    x = apply_act(x, p.post_act);
+    if (p.out_f32) p.out_f32[opix * p.out_f32_ld + oc + i] = x;
+    if (p.out_bf16) reinterpret_cast<bf16*>(p.out_bf16)[opix * p.out_ld + oc + i] = __float2bfloat16_rn(x);
+  }
+}
+
+struct Vec4Operands {   // global operands of one (pixel, 4 channels) item, loaded ahead of the math
+  float4 res;
+  uint2 mul, aux;
+};
+
+__device__ __forceinline__ void bf16x4_to_float(const uint2& q, float (&f)[4]) {
+  f[0] = __uint_as_float(q.x << 16); f[1] = __uint_as_float(q.x & 0xffff0000u);
+  f[2] = __uint_as_float(q.y << 16); f[3] = __uint_as_float(q.y & 0xffff0000u);
+}
+
+__device__ __forceinline__ void vec4_load(const FFConvGemm& p, long long opix, int oc, Vec4Operands& o) {
   if (p.res) {
     if (p.res_is_f32) {
-      const float* q = reinterpret_cast<const float*>(p.res) + opix * p.res_ld + oc;
-      if (full) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 r = __ldg(reinterpret_cast<const float4*>(q) + i);
-          v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
-        }
-      } else {
-        for (int i = 0; i < nvalid; ++i) v[i] += q[i];
-      }
+      o.res = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + opix * p.res_ld + oc));
     } else {
-      const bf16* q = reinterpret_cast<const bf16*>(p.res) + opix * p.res_ld + oc;
-      if (full) {
-        float m[16];
-        load_bf16x16(q, m);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += m[i];
-      } else {
-        for (int i = 0; i < nvalid; ++i) v[i] += __bfloat162float(q[i]);
-      }
+      const uint2 q = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.res) + opix * p.res_ld + oc));
+      float f[4];
+      bf16x4_to_float(q, f);
+      o.res = make_float4(f[0], f[1], f[2], f[3]);
     }
   }
+  if (p.mul) o.mul = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.mul) + opix * p.mul_ld + oc));
+  if (p.aux) o.aux = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.aux) + opix * p.aux_ld + oc));
+}
+
+// bias / col_scale / aux_chan for the 4 channels are loop-invariant per column block and passed in registers
+__device__ __forceinline__ void vec4_finish(const FFConvGemm& p, float4 acc, const Vec4Operands& o, const float (&bias)[4],
+                                            const float (&cscale)[4], const float (&achan)[4], long long opix, int oc) {
+  float v[4] = {acc.x + bias[0], acc.y + bias[1], acc.z + bias[2], acc.w + bias[3]};
+  if (p.act) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] *= cscale[i];    // alpha * col_scale folded by the caller
+  if (p.mul) {
+    float m[4];
+    bf16x4_to_float(o.mul, m);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] *= m[i];
+  }
+  if (p.aux) {
+    float m[4];
+    bf16x4_to_float(o.aux, m);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += p.aux_alpha * m[i] * achan[i];
+  }
+  if (p.res) { v[0] += o.res.x; v[1] += o.res.y; v[2] += o.res.z; v[3] += o.res.w; }
   if (p.post_act) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.post_act);
+    for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.post_act);
   }
-  if (p.out_f32) {
-    float* q = p.out_f32 + opix * p.out_f32_ld + oc;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        reinterpret_cast<float4*>(q)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    } else {
-      for (int i = 0; i < nvalid; ++i) q[i] = v[i];
-    }
-  }
+  if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + opix * p.out_f32_ld + oc) = make_float4(v[0], v[1], v[2], v[3]);
   if (p.out_bf16) {
-    bf16* q = reinterpret_cast<bf16*>(p.out_bf16) + opix * p.out_ld + oc;
-    if (full) {
-      uint32_t w[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        w[i] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      reinterpret_cast<uint4*>(q)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-      reinterpret_cast<uint4*>(q)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-    } else {
-      for (int i = 0; i < nvalid; ++i) q[i] = __float2bfloat16_rn(v[i]);
-    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out_bf16) + opix * p.out_ld + oc) =
+        make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
   }
 }
 
@@ -214,7 +208,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -292,8 +286,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ================= epilogue warps =================
+    // 8 warps: TMEM lane quadrant = warp % 4; the two warps of a quadrant alternate over CB-wide column blocks.
+    // Per column block: TMEM -> registers (one accumulator row per thread) -> per-warp smem staging (transpose) ->
+    // each lane owns 4 consecutive channels and walks the 32 rows, with all global operand loads issued up front.
+    constexpr int CB = C::CB;                 // columns per block
+    constexpr int LPR = CB / 4;               // lanes per row in the read-out phase
+    constexpr int RPI = 32 / LPR;             // rows per warp instruction
+    constexpr int ITERS = 32 / RPI;
+    const FFConvGemm& p = a.p;
+    const int ew = warp - 2;
     const int quad = warp & 3;
-    const int r = quad * 32 + lane;  // accumulator row == TMEM lane
+    const int half = ew >> 2;
+    float* stg = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES) + ew * (32 * C::STG_PITCH);
+    const int width = (p.pixel_shuffle == 2) ? (p.n_store >> 2) : (p.gate_pairs ? (p.n_store >> 1) : p.n_store);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -301,19 +306,138 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int b = m_tile / a.tiles_per_img;
       const int t = m_tile - b * a.tiles_per_img;
       const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
-      const int oy = ty * TILE_H + (r >> 4), ox = tx * TILE_W + (r & 15);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-      for (int j = 0; j < BN / 16; ++j) {
-        uint32_t raw[16];
-        tmem_ld16(taddr + j * 16, raw);
-        tc_wait_ld();
-        float v[16];
+      for (int cb = half; cb < BN / CB; cb += 2) {
+        const int n_blk = n_tile * BN + cb * CB;
+        if (n_blk >= p.n_store) break;
+        // ---- phase 1: TMEM -> smem staging, row `lane` of this quadrant
+        int cw = CB;      // staged columns per row
+        {
+          float v[CB];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
-        epilogue16(a, v, b, oy, ox, n_tile * BN + j * 16);
+          for (int j = 0; j < CB / 16; ++j) {
+            uint32_t raw[16];
+            tmem_ld16(taddr + cb * CB + j * 16, raw);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[j * 16 + i] = __uint_as_float(raw[i]);
+          }
+          float* dst = stg + lane * C::STG_PITCH;
+          if (p.gate_pairs) {
+            // SimpleGate folded: (acc+bias)[i] * (acc+bias)[i+8] within each 16-column chunk -> CB/2 staged columns
+            cw = CB / 2;
+#pragma unroll
+            for (int j = 0; j < CB / 16; ++j)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float x1 = v[j * 16 + i] + __ldg(p.bias + n_blk + j * 16 + i);
+                const float x2 = v[j * 16 + 8 + i] + __ldg(p.bias + n_blk + j * 16 + 8 + i);
+                dst[j * 8 + i] = x1 * x2;
+              }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CB / 4; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+        __syncwarp();
+        // ---- phase 2: coalesced read-out
+        const int lpr = cw / 4;                       // lanes per row (LPR, or LPR/2 with gate_pairs)
+        const int rpi = 32 / lpr;
+        const int c4 = (lane % lpr) * 4;
+        const int rsub = lane / lpr;
+        const int ncol = p.gate_pairs ? ((n_blk >> 1) + c4) : (n_blk + c4);     // column in the (logical) output row
+        long long opix0;
+        int oc;
+        {
+          // column-dependent part of the output location (pixel part added per row below)
+          if (p.pixel_shuffle == 2) {
+            const int cq = p.n_store >> 2;
+            oc = ncol % cq;
+          } else {
+            oc = ncol;
+          }
+          opix0 = 0;
+        }
+        const bool col_ok = (p.pixel_shuffle == 2) ? true : (ncol < width);
+        if (a.vec_ok && (ncol + 4 <= ((p.pixel_shuffle == 2) ? p.n_store : width) || p.pixel_shuffle == 2)) {
+          float bias[4] = {0.f, 0.f, 0.f, 0.f}, cscale[4], achan[4] = {1.f, 1.f, 1.f, 1.f};
+          if (!p.gate_pairs && p.bias) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bias[i] = __ldg(p.bias + ncol + i);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cscale[i] = p.alpha * (p.col_scale ? __ldg(p.col_scale + ncol + i) : 1.f);
+          if (p.aux && p.aux_chan) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) achan[i] = __ldg(p.aux_chan + (long long)b * p.aux_chan_ld + oc + i);
+          }
+          const int iters = 32 / rpi;
+          // two passes of up to ITERS/…: keep the unroll bounded -- process rows in groups of 4 iterations
+#pragma unroll 1
+          for (int it0 = 0; it0 < iters; it0 += 4) {
+            Vec4Operands ops[4];
+            long long opx[4];
+            float4 accv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int row = (it0 + u) * rpi + rsub;           // row within the quadrant
+              const int r = quad * 32 + row;
+              const int oy = ty * TILE_H + (r >> 4), ox = tx * TILE_W + (r & 15);
+              int dummy;
+              long long px;
+              if (p.pixel_shuffle == 2) out_location(a, b, oy, ox, ncol, px, dummy);
+              else px = ((long long)(b * a.Ho + oy)) * a.Wo + ox;
+              opx[u] = px;
+              vec4_load(p, px, oc, ops[u]);
+              accv[u] = *reinterpret_cast<const float4*>(stg + row * C::STG_PITCH + c4);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (p.gate_pairs) {
+                // only the bf16 store applies
+                __nv_bfloat162 lo = __floats2bfloat162_rn(accv[u].x, accv[u].y), hi = __floats2bfloat162_rn(accv[u].z, accv[u].w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out_bf16) + opx[u] * p.out_ld + oc) =
+                    make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+              } else {
+                vec4_finish(p, accv[u], ops[u], bias, cscale, achan, opx[u], oc);
+              }
+            }
+          }
+        } else if (col_ok) {
+          // scalar fallback (narrow / unaligned outputs, e.g. 3-channel image writes)
+          const int iters = 32 / rpi;
+          for (int it = 0; it < iters; ++it) {
+            const int row = it * rpi + rsub;
+            const int r = quad * 32 + row;
+            const int oy = ty * TILE_H + (r >> 4), ox = tx * TILE_W + (r & 15);
+            const long long px = ((long long)(b * a.Ho + oy)) * a.Wo + ox;
+            for (int i = 0; i < 4; ++i) {
+              const int n = ncol + i;
+              if (n >= width) break;
+              float x = stg[row * C::STG_PITCH + c4 + i];
+              if (p.bias) x += __ldg(p.bias + n);
+              x = apply_act(x, p.act) * p.alpha;
+              if (p.col_scale) x *= __ldg(p.col_scale + n);
+              if (p.mul) x *= __bfloat162float(reinterpret_cast<const bf16*>(p.mul)[px * p.mul_ld + n]);
+              if (p.aux) {
+                const float m = __bfloat162float(reinterpret_cast<const bf16*>(p.aux)[px * p.aux_ld + n]);
+                x += p.aux_alpha * m * (p.aux_chan ? __ldg(p.aux_chan + (long long)b * p.aux_chan_ld + n) : 1.f);
+              }
+              if (p.res) {
+                x += p.res_is_f32 ? reinterpret_cast<const float*>(p.res)[px * p.res_ld + n]
+                                  : __bfloat162float(reinterpret_cast<const bf16*>(p.res)[px * p.res_ld + n]);
+              }
+              x = apply_act(x, p.post_act);
+              if (p.out_f32) p.out_f32[px * p.out_f32_ld + n] = x;
+              if (p.out_bf16) reinterpret_cast<bf16*>(p.out_bf16)[px * p.out_ld + n] = __float2bfloat16_rn(x);
+            }
+          }
+        }
+        (void)opix0;
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -427,6 +551,7 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
     FF_CHECK_ARG(p.out_bf16 && !p.out_f32 && !p.act && !p.mul && !p.aux && !p.res && !p.pixel_shuffle && !p.col_scale && p.n_store % 16 == 0,
                  "ff_conv_gemm: gate_pairs supports bias + bf16 store only");
     FF_CHECK_ARG(p.out_ld >= p.n_store / 2 && p.out_ld % 8 == 0, "ff_conv_gemm: gate_pairs out_ld too small");
+    FF_CHECK_ARG(p.bias != nullptr && p.n_store >= 32, "ff_conv_gemm: gate_pairs needs a bias vector and n_store >= 32");
   }
   if (p.w_batch_rows) FF_CHECK_ARG(p.w_batch_rows >= p.n_pad, "ff_conv_gemm: w_batch_rows < n_pad");
   if (p.pixel_shuffle) {
@@ -435,6 +560,7 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   }
   const int width_ok = p.pixel_shuffle ? (p.n_store >> 2) : p.gate_pairs ? (p.n_store >> 1) : p.n_store;
   const bool vec = width_ok >= 16;  // narrower outputs take the scalar store path: no alignment requirement
+  a.vec_ok = vec ? 1 : 0;
   if (p.out_bf16) FF_CHECK_ARG(p.out_ld >= width_ok && (!vec || (p.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0)), "ff_conv_gemm: bad out_ld=%d", p.out_ld);
   if (p.out_f32) FF_CHECK_ARG(p.out_f32_ld >= width_ok && (!vec || (p.out_f32_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0)), "ff_conv_gemm: bad out_f32_ld=%d", p.out_f32_ld);
   if (p.mul) FF_CHECK_ARG(p.mul_ld >= width_ok && (!vec || (p.mul_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.mul) & 15) == 0)), "ff_conv_gemm: bad mul_ld");

@@ -1,0 +1,37 @@
+"""GPU path against golden outputs of the reference itself (tests/golden, made by oracle/make_golden.py) -- no oracle in between."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_experts_vs_reference_golden_64():
+    from isr2_b200 import model as M
+    g = torch.load(os.path.join(GOLD, "experts_64x64_fp16.pt"))
+    m = M.FreqFusionB200("cuda:0", init_seed=0, verbose=False)
+    ex = m.expert_outputs_nchw(g["x"].cuda())
+    for k in ("hat", "dat", "nafnet"):
+        err = (ex[k].cpu() - g[k].float()).abs().max().item()
+        assert err < 2e-2, f"{k}: {err}"
+
+
+def test_head_vs_reference_golden_64():
+    from isr2_b200 import head, weights
+    g = torch.load(os.path.join(GOLD, "head_64.pt"))
+    lr = g["lr"]
+    gen = torch.Generator().manual_seed(g["expert_seed"])
+    up = F.interpolate(lr, scale_factor=4, mode="bicubic", align_corners=False)
+    ex = [(up + s * torch.randn(1, 3, 256, 256, generator=gen)).clamp(0, 1) for s in (0.01, 0.02, 0.03)]
+    stack = torch.zeros(256 * 256, 12)
+    stack[:, :9] = torch.cat(ex, 1).permute(0, 2, 3, 1).reshape(-1, 9)
+    r = head.HeadRunner(weights.make_state_dict("fusion", 0), torch.device("cuda:0"))
+    inter = {}
+    out = r.forward(lr.cuda(), stack.cuda(), intermediates=inter).cpu()
+    nh = lambda t: t.permute(0, 2, 3, 1).reshape(-1, t.shape[1])
+    assert (inter["bands_raw"].cpu() - nh(g["raw_bands"])).abs().max() < 1e-4       # fp32 DCT/DWT/DFT kernels
+    assert (inter["band_features"].cpu() - nh(g["band_features"])).abs().max() < 2e-2
+    assert (out - g["out"]).abs().max() < 2e-2
