@@ -25,22 +25,45 @@ struct Args {
   int vec_ok;   // every epilogue operand allows 16-byte fp32 / 8-byte bf16 vector access
 };
 
-template <int BN>
+// EPI selects the epilogue at compile time:
+//   EPI_GENERIC    -- every fused operand, runtime flags, LSU loads/stores after an smem transpose
+//   EPI_STORE      -- out_bf16 = acc + bias        } rows converted to bf16, staged in 64B-swizzled smem, one TMA store per
+//   EPI_STORE_GELU -- out_bf16 = gelu(acc + bias)  } (warp, 32-column block)
+//   EPI_RES        -- out_f32 = (acc + bias) * (alpha * col_scale) + res_f32 (+ bf16 copy): the fp32 residual block is
+//                     TMA-loaded (prefetched one block ahead) into 128B-swizzled smem, updated in place and TMA-stored
+enum { EPI_GENERIC = 0, EPI_STORE = 1, EPI_STORE_GELU = 2, EPI_RES = 3 };
+
+template <int BN, int EPI>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int CB = BN < 32 ? BN : 32;                    // epilogue column block
-  static constexpr int STG_PITCH = CB + 4;                        // floats; +4 keeps float4 accesses conflict-free
-  static constexpr int STG_BYTES = NUM_EPI_WARPS * 32 * STG_PITCH * 4;
+  static constexpr int STG_PITCH = CB + 4;                        // floats; +4 keeps float4 accesses conflict-free (generic path)
+  static constexpr int STG_WARP_BYTES = EPI == EPI_RES ? 10240 : (EPI == EPI_GENERIC ? 32 * STG_PITCH * 4 : 4096);
+  static constexpr int STG_BYTES = NUM_EPI_WARPS * STG_WARP_BYTES;
   static constexpr int STAGES_RAW = (225 * 1024 - STG_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
+// erf-form GELU with the Abramowitz-Stegun 7.1.26 rational approximation of erf (|err| <= 1.5e-7, far below the bf16
+// rounding of the stored activations): 2 MUFU + ~12 FMA, branch free.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-az * az);
+  return 0.5f * x * (1.0f + copysignf(e, z));
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
-    case FF_ACT_GELU: return gelu_erf(v);
+    case FF_ACT_GELU: return gelu_fast(v);
     case FF_ACT_RELU: return fmaxf(v, 0.f);
     case FF_ACT_LRELU: return v > 0.f ? v : 0.01f * v;
     case FF_ACT_SIGMOID: return sigmoidf_(v);
@@ -181,17 +204,29 @@ __device__ __forceinline__ void vec4_finish(const FFConvGemm& p, float4 acc, con
 // ----------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ----------------------------------------------------------------------------------------------
-template <int BN>
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ Args a) {
-  using C = Cfg<BN>;
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+                    const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ Args a) {
+  using C = Cfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
   __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(8) uint64_t res_bar[NUM_EPI_WARPS][2];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5;
@@ -202,6 +237,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(&res_bar[w][0], 1); mbar_init(&res_bar[w][1], 1); }
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -286,6 +322,171 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ================= epilogue warps =================
+    if constexpr (EPI == EPI_RES) {
+      // ---------- residual epilogue: TMA-load res block -> in-place update in 128B-swizzled smem -> TMA store ----------
+      static_assert(C::CB == 32, "EPI_RES needs 32-column blocks");
+      const FFConvGemm& p = a.p;
+      const int ew = warp - 2;
+      const int quad = warp & 3;
+      const int half = ew >> 2;
+      uint8_t* wbase = smem + C::STAGES * C::STAGE_BYTES + ew * C::STG_WARP_BYTES;   // [R0 4K][R1 4K][O16 2K], 1024-B aligned
+      const int ncb = BN / 32;
+      int buf = 0;
+      uint32_t ph[2] = {0, 0};
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      if (lane == 0) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO32); if (p.out_bf16) tma_prefetch_desc(&tmO); }
+      // items of this warp: (tile, cb) with cb = half, half+2, ... while the block starts below n_store.  The residual
+      // block of the NEXT item (possibly in the next tile) is prefetched while the current one is processed.
+      auto valid = [&](int tl, int c) { return c < ncb && (tl % a.n_tiles) * BN + c * 32 < p.n_store; };
+      auto issue_load = [&](int tl, int c, int bsel) {
+        const int m_tile = tl / a.n_tiles, n_tile = tl - m_tile * a.n_tiles;
+        const int b = m_tile / a.tiles_per_img;
+        const int t = m_tile - b * a.tiles_per_img;
+        const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        mbar_arrive_expect_tx(&res_bar[ew][bsel], 4096);
+        tma_load_4d(wbase + bsel * 4096, &tmR, &res_bar[ew][bsel], n_tile * BN + c * 32, tx * TILE_W, ty * TILE_H + quad * 2, b);
+      };
+      {
+        int ft = blockIdx.x;
+        while (ft < num_tiles && !valid(ft, half)) ft += gridDim.x;
+        if (lane == 0 && ft < num_tiles) issue_load(ft, half, 0);
+      }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+        const int b = m_tile / a.tiles_per_img;
+        const int t = m_tile - b * a.tiles_per_img;
+        const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+        for (int cb = half; valid(tile, cb); cb += 2) {
+          const int n_blk = n_tile * BN + cb * 32;
+          // locate the next item and prefetch its residual block into the other buffer
+          int ntile = tile, ncb2 = cb + 2;
+          if (!valid(ntile, ncb2)) {
+            ncb2 = half;
+            ntile = tile + gridDim.x;
+            while (ntile < num_tiles && !valid(ntile, ncb2)) ntile += gridDim.x;
+          }
+          if (lane == 0) {
+            tma_store_wait_read<0>();      // the stores that read R[buf^1] / O16 (issued one item ago) have drained
+            if (ntile < num_tiles) issue_load(ntile, ncb2, buf ^ 1);
+          }
+          uint32_t raw[32];
+          tmem_ld16(taddr + cb * 32, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+          tmem_ld16(taddr + cb * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
+          tc_wait_ld();
+          mbar_wait(&res_bar[ew][buf], ph[buf]);
+          ph[buf] ^= 1;
+          __syncwarp();
+          uint8_t* rrow = wbase + buf * 4096 + lane * 128;
+          uint8_t* orow = wbase + 8192 + lane * 64;
+          const int sw7 = lane & 7, sw3 = (lane >> 1) & 3;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(p.alpha, p.alpha, p.alpha, p.alpha);
+            if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk + c * 4));
+            if (p.col_scale) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(p.col_scale + n_blk + c * 4));
+              cs.x *= q.x; cs.y *= q.y; cs.z *= q.z; cs.w *= q.w;
+            }
+            float4* rp = reinterpret_cast<float4*>(rrow + ((c ^ sw7) << 4));
+            float4 r = *rp;
+            r.x = fmaf(__uint_as_float(raw[4 * c]) + bb.x, cs.x, r.x);
+            r.y = fmaf(__uint_as_float(raw[4 * c + 1]) + bb.y, cs.y, r.y);
+            r.z = fmaf(__uint_as_float(raw[4 * c + 2]) + bb.z, cs.z, r.z);
+            r.w = fmaf(__uint_as_float(raw[4 * c + 3]) + bb.w, cs.w, r.w);
+            *rp = r;
+            if (p.out_bf16) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+              uint2* op = reinterpret_cast<uint2*>(orow + (((c >> 1) ^ sw3) << 4) + ((c & 1) << 3));
+              *op = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmO32, wbase + buf * 4096, n_blk, tx * TILE_W, ty * TILE_H + quad * 2, b);
+            if (p.out_bf16) tma_store_4d(&tmO, wbase + 8192, n_blk, tx * TILE_W, ty * TILE_H + quad * 2, b);
+            tma_store_commit();
+          }
+          buf ^= 1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else
+    if constexpr (EPI != EPI_GENERIC) {
+      // ---------- TMA-store epilogue: bias (+GELU) -> bf16 -> swizzled smem -> cp.async.bulk.tensor store ----------
+      static_assert(C::CB == 32, "TMA-store epilogue needs 32-column blocks");
+      const FFConvGemm& p = a.p;
+      const int ew = warp - 2;
+      const int quad = warp & 3;
+      const int half = ew >> 2;
+      uint8_t* stg_base = smem + C::STAGES * C::STAGE_BYTES + ew * C::STG_WARP_BYTES;   // 2 x 2 KB, 512-B aligned
+      int buf = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      if (lane == 0) tma_prefetch_desc(&tmO);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+        const int b = m_tile / a.tiles_per_img;
+        const int t = m_tile - b * a.tiles_per_img;
+        const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+        for (int cb = half; cb < BN / 32; cb += 2) {
+          const int n_blk = n_tile * BN + cb * 32;
+          if (n_blk >= p.n_store) break;
+          uint32_t raw[32];
+          tmem_ld16(taddr + cb * 32, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+          tmem_ld16(taddr + cb * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
+          // the staging buffer about to be overwritten must have been read by the TMA store issued two blocks ago
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          tc_wait_ld();
+          uint8_t* dst = stg_base + buf * 2048 + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w[4];
+            float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk + c * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk + c * 8) + 1);
+              bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float x0 = __uint_as_float(raw[c * 8 + 2 * i]) + bb[2 * i], x1 = __uint_as_float(raw[c * 8 + 2 * i + 1]) + bb[2 * i + 1];
+              if constexpr (EPI == EPI_STORE_GELU) { x0 = gelu_fast(x0); x1 = gelu_fast(x1); }
+              __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmO, stg_base + buf * 2048, n_blk, tx * TILE_W, ty * TILE_H + quad * 2, b);
+            tma_store_commit();
+          }
+          buf ^= 1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else {
     // 8 warps: TMEM lane quadrant = warp % 4; the two warps of a quadrant alternate over CB-wide column blocks.
     // Per column block: TMEM -> registers (one accumulator row per thread) -> per-warp smem staging (transpose) ->
     // each lane owns 4 consecutive channels and walks the 32 rows, with all global operand loads issued up front.
@@ -444,6 +645,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    }  // EPI_GENERIC
   }
 
   tc_fence_before();
@@ -508,12 +710,14 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <int BN>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a, cudaStream_t st) {
-  using C = Cfg<BN>;
+struct Maps { CUtensorMap A, B, O, R, O32; };
+
+template <int BN, int EPI>
+int launch_tc(const Maps& m, const Args& a, cudaStream_t st) {
+  using C = Cfg<BN, EPI>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) {
       ff_set_error("ff_conv_gemm: cudaFuncSetAttribute(%d) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
@@ -523,9 +727,19 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a, cud
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < ff_num_sms() ? tiles : ff_num_sms();
-  conv_gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, a);
+  conv_gemm_tc_kernel<BN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(m.A, m.B, m.O, m.R, m.O32, a);
   FF_CHECK_LAUNCH("ff_conv_gemm");
   return FF_OK;
+}
+
+template <int BN>
+int launch_bn(int epi, const Maps& m, const Args& a, cudaStream_t st) {
+  if constexpr (BN >= 32) {
+    if (epi == EPI_STORE) return launch_tc<BN, EPI_STORE>(m, a, st);
+    if (epi == EPI_STORE_GELU) return launch_tc<BN, EPI_STORE_GELU>(m, a, st);
+    if (epi == EPI_RES) return launch_tc<BN, EPI_RES>(m, a, st);
+  }
+  return launch_tc<BN, EPI_GENERIC>(m, a, st);
 }
 
 }  // namespace
@@ -625,13 +839,38 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
       return FF_ERR_DRIVER;
     }
   }
+  // epilogue selection: plain "bias (+GELU) -> bf16" layers and fp32-residual layers take the TMA epilogues
+  int epi = EPI_GENERIC;
+  Maps m;
+  m.A = tmA; m.B = tmB; m.O = tmA; m.R = tmA; m.O32 = tmA;
+  auto out_map = [&](CUtensorMap* tm, void* ptr, int ld, int esz, CUtensorMapDataType dt, CUtensorMapSwizzle sw) {
+    cuuint64_t dims[4] = {(cuuint64_t)p.n_store, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)p.B};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)ld * esz * a.Wo, (cuuint64_t)ld * esz * a.Wo * a.Ho};
+    cuuint32_t box[4] = {32, (cuuint32_t)TILE_W, 2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(tm, dt, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  const bool al16 = (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && (!p.col_scale || (reinterpret_cast<uintptr_t>(p.col_scale) & 15) == 0);
+  const bool bf16_ok = !p.out_bf16 || (p.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0);
+  const bool plain = !p.mul && !p.aux && !p.post_act && !p.pixel_shuffle && !p.gate_pairs && p.n_store % 8 == 0 && al16 && bf16_ok && BN >= 32;
+  if (plain && p.out_bf16 && !p.out_f32 && !p.res && !p.col_scale && p.alpha == 1.0f && (p.act == FF_ACT_NONE || p.act == FF_ACT_GELU)) {
+    if (out_map(&m.O, p.out_bf16, p.out_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B))
+      epi = (p.act == FF_ACT_GELU) ? EPI_STORE_GELU : EPI_STORE;
+  } else if (plain && p.res && p.res_is_f32 && p.out_f32 && p.act == FF_ACT_NONE && p.res_ld % 4 == 0 && p.out_f32_ld % 4 == 0 &&
+             (reinterpret_cast<uintptr_t>(p.res) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) {
+    bool ok = out_map(&m.R, const_cast<void*>(p.res), p.res_ld, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B) &&
+              out_map(&m.O32, p.out_f32, p.out_f32_ld, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (ok && p.out_bf16) ok = out_map(&m.O, p.out_bf16, p.out_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (ok) epi = EPI_RES;
+  }
   ++g_ff_launches;
   switch (BN) {
-    case 256: return launch_tc<256>(tmA, tmB, a, st);
-    case 192: return launch_tc<192>(tmA, tmB, a, st);
-    case 128: return launch_tc<128>(tmA, tmB, a, st);
-    case 64: return launch_tc<64>(tmA, tmB, a, st);
-    case 32: return launch_tc<32>(tmA, tmB, a, st);
-    default: return launch_tc<16>(tmA, tmB, a, st);
+    case 256: return launch_bn<256>(epi, m, a, st);
+    case 192: return launch_bn<192>(epi, m, a, st);
+    case 128: return launch_bn<128>(epi, m, a, st);
+    case 64: return launch_bn<64>(epi, m, a, st);
+    case 32: return launch_bn<32>(epi, m, a, st);
+    default: return launch_bn<16>(epi, m, a, st);
   }
 }

@@ -291,3 +291,31 @@ def test_dwconv_and_conv_direct():
     ops.nhwc_to_nchw(nh, 0, 3, back)
     torch.cuda.synchronize()
     assert (back.cpu() - (img - mean.view(1, 3, 1, 1))).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("cin,n,H,W,B,kind", [(384, 192, 32, 32, 2, 0), (64, 64, 16, 32, 1, 0), (192, 192, 32, 16, 1, 1), (256, 512, 16, 16, 2, 0), (128, 128, 8, 16, 1, 0)])
+def test_conv_gemm_residual_tma_epilogue(cin, n, H, W, B, kind):
+    """out_f32 = (acc + bias) * alpha * col_scale + res_f32, in place, with the bf16 copy (TMA load/store epilogue)."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(8)
+    k = 3 if kind == 1 else 1
+    x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
+    w = (torch.randn(n, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(BF16).float()
+    bias, cs = torch.randn(n, generator=g), torch.rand(n, generator=g) + 0.5
+    res = torch.randn(B * H * W, n, generator=g)
+    conv = _nhwc(F.conv2d(x, w, bias, padding=k // 2))
+    ref = conv * 0.7 * cs + res
+    d = _dev()
+    stream = res.clone().to(d)
+    o16 = torch.zeros(B * H * W, n, dtype=BF16, device=d)
+    ops.conv_gemm(_nhwc(x).to(d, BF16), B, H, W, cin, packing.pack_conv(w, n, cin, device=d), kind=kind, n_store=n, bias=bias.to(d), alpha=0.7,
+                  col_scale=cs.to(d), res=stream, out_f32=stream, out_bf16=o16)
+    torch.cuda.synchronize()
+    assert (stream.cpu() - ref).abs().max().item() < 3e-3
+    assert (o16.cpu().float() - ref).abs().max().item() < 3e-2
+    # separate output buffer, no bf16 copy, no col_scale
+    out = torch.zeros(B * H * W, n, device=d)
+    ops.conv_gemm(_nhwc(x).to(d, BF16), B, H, W, cin, packing.pack_conv(w, n, cin, device=d), kind=kind, n_store=n, bias=bias.to(d),
+                  res=res.to(d), out_f32=out)
+    torch.cuda.synchronize()
+    assert (out.cpu() - (conv + res)).abs().max().item() < 3e-3
