@@ -5,7 +5,7 @@
 //   -> + relative-position bias (table in smem, index computed arithmetically) + {0,-100} shift mask
 //   -> online softmax (fp32) -> O = P V -> normalise -> store at the un-shifted token position.
 // The logits never leave registers (the reference materialises [nW*B, heads, 256, 256|576] fp32 in HBM).
-// q is pre-scaled by head_dim^-0.5 through the packed qkv weights.
+// q is pre-scaled by head_dim^-0.5 * log2(e) through the packed qkv weights, so the softmax runs on exp2.
 #include "ff_common.cuh"
 #include "../../include/ffb200.h"
 
@@ -16,6 +16,8 @@ constexpr int ROWP = 40;     // smem row pitch (bf16) -> conflict-free ldmatrix
 constexpr int NQ = 256;
 constexpr int KCHUNK = 64;
 constexpr int NTHREADS = 512;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float MASKV = 100.0f * 1.4426950408889634f;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attention_kernel(const __g
       sKr[t] = (shifted && inside) ? (uint8_t)(region3(ys, p.H, p.wh, p.shift_y) * 3 + region3(xs, p.W, p.ww, p.shift_x)) : 0;
     }
   }
-  for (int i = tid; i < p.T; i += NTHREADS) sT[i] = __ldg(p.bias_table + (long long)i * p.bias_heads + p.bias_head_off + blockIdx.y);
+  for (int i = tid; i < p.T; i += NTHREADS) sT[i] = LOG2E * __ldg(p.bias_table + (long long)i * p.bias_heads + p.bias_head_off + blockIdx.y);
   __syncthreads();
 
   // ---- per-warp: 16 query rows ----
@@ -143,25 +145,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attention_kernel(const __g
         mma16816(s[2 * np + 1], qa[ks], kb[2], kb[3]);
       }
     }
-    // bias + mask, running max
+    // bias + mask, running max.  Each n8 tile holds 8 keys of one key-window row (kw is a multiple of 8), so the table
+    // index is affine in the in-tile key offset t = 2*(lane&3)+e:  idx = A_row(tile) - rel_sign * t.
     float cm0 = -1e30f, cm1 = -1e30f;
+    const int tq = 2 * (lane & 3);
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
+      const int kcd = sKc[kc + n * 8];                 // first key of the tile (warp-uniform)
+      const int ki = kcd >> 8, kj0 = kcd & 255;
+      const int a0 = (p.rel_sign * (qi0 - ki) + p.rel_off_y) * p.rel_stride + p.rel_sign * (qj0 - kj0 - tq) + p.rel_off_x;
+      const int a1 = (p.rel_sign * (qi1 - ki) + p.rel_off_y) * p.rel_stride + p.rel_sign * (qj1 - kj0 - tq) + p.rel_off_x;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int key = kc + n * 8 + 2 * (lane & 3) + e;
-        const int kcd = sKc[key];
-        const int ki = kcd >> 8, kj = kcd & 255;
-        const int kr = sKr[key];
-        int i0 = (p.rel_sign * (qi0 - ki) + p.rel_off_y) * p.rel_stride + p.rel_sign * (qj0 - kj) + p.rel_off_x;
-        int i1 = (p.rel_sign * (qi1 - ki) + p.rel_off_y) * p.rel_stride + p.rel_sign * (qj1 - kj) + p.rel_off_x;
-        if (i0 < 0) i0 += p.T;
-        if (i1 < 0) i1 += p.T;
+        int i0 = a0 - p.rel_sign * e, i1 = a1 - p.rel_sign * e;
+        i0 += (i0 >> 31) & p.T;
+        i1 += (i1 >> 31) & p.T;
         float v0 = s[n][e] + sT[i0];
         float v1 = s[n][2 + e] + sT[i1];
         if (shifted) {
-          if (kr != qr0) v0 -= 100.f;
-          if (kr != qr1) v1 -= 100.f;
+          const int kr = sKr[kc + n * 8 + tq + e];
+          if (kr != qr0) v0 -= MASKV;
+          if (kr != qr1) v1 -= MASKV;
         }
         s[n][e] = v0;
         s[n][2 + e] = v1;
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attention_kernel(const __g
     cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
     cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
     const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);
-    const float sc0 = __expf(m0 - nm0), sc1 = __expf(m1 - nm1);
+    const float sc0 = exp2f(m0 - nm0), sc1 = exp2f(m1 - nm1);
     m0 = nm0; m1 = nm1;
     l0 *= sc0; l1 *= sc1;
 #pragma unroll
@@ -183,10 +187,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attention_kernel(const __g
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {  // k16 steps over the 64 keys of the chunk
       uint32_t pa[4];
-      float e00 = __expf(s[2 * kk][0] - m0), e01 = __expf(s[2 * kk][1] - m0);
-      float e02 = __expf(s[2 * kk][2] - m1), e03 = __expf(s[2 * kk][3] - m1);
-      float e10 = __expf(s[2 * kk + 1][0] - m0), e11 = __expf(s[2 * kk + 1][1] - m0);
-      float e12 = __expf(s[2 * kk + 1][2] - m1), e13 = __expf(s[2 * kk + 1][3] - m1);
+      float e00 = exp2f(s[2 * kk][0] - m0), e01 = exp2f(s[2 * kk][1] - m0);
+      float e02 = exp2f(s[2 * kk][2] - m1), e03 = exp2f(s[2 * kk][3] - m1);
+      float e10 = exp2f(s[2 * kk + 1][0] - m0), e11 = exp2f(s[2 * kk + 1][1] - m0);
+      float e12 = exp2f(s[2 * kk + 1][2] - m1), e13 = exp2f(s[2 * kk + 1][3] - m1);
       l0 += e00 + e01 + e10 + e11;
       l1 += e02 + e03 + e12 + e13;
       pa[0] = pack_bf16(e00, e01);
@@ -243,6 +247,7 @@ extern "C" int ff_window_attention(const FFWinAttn* pp, void* stream) {
   FF_CHECK_ARG(p.wh < 256 && p.ww < 256 && p.kh < 256 && p.kw < 256, "ff_window_attention: window too large");
   const int NK = p.kh * p.kw;
   FF_CHECK_ARG(NK % KCHUNK == 0 && NK >= KCHUNK, "ff_window_attention: key window %dx%d not a multiple of 64 tokens", p.kh, p.kw);
+  FF_CHECK_ARG(p.kw % 8 == 0, "ff_window_attention: key window width must be a multiple of 8");
   FF_CHECK_ARG(p.H % p.wh == 0 && p.W % p.ww == 0, "ff_window_attention: image %dx%d not divisible by window %dx%d", p.H, p.W, p.wh, p.ww);
   FF_CHECK_ARG(p.ld % 8 == 0 && p.out_ld % 8 == 0 && p.q_off % 8 == 0 && p.k_off % 8 == 0 && p.v_off % 8 == 0 && p.out_off % 8 == 0, "ff_window_attention: offsets/pitches must be multiples of 8");
   FF_CHECK_ARG(p.heads > 0 && p.T > 0 && p.rel_stride > 0, "ff_window_attention: bad heads/T");

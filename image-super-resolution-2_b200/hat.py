@@ -53,7 +53,7 @@ class HATRunner:
         g = lambda k: sd[k].detach().to("cpu", F32)
         dev = device
         hp = head_pad_index(torch.arange(C))
-        scale = (C // HEADS) ** -0.5
+        scale = (C // HEADS) ** -0.5 * 1.4426950408889634   # q * head_dim^-0.5, and log2(e) for the exp2 softmax
         self.mean = torch.tensor(RGB_MEAN, dtype=F32, device=dev)
         self.conv_first_w = pack_conv_direct(g("conv_first.weight"), CP, dev)
         self.conv_first_b = pack_vector(g("conv_first.bias"), CP, device=dev)

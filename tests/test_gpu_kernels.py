@@ -143,12 +143,15 @@ def test_window_attention(mode):
     g = torch.Generator().manual_seed(5)
     B, H, W = 2, 32, 64
     heads, hd = 6, 30
-    q, k, v = [torch.randn(B, H, W, heads, hd, generator=g).to(BF16).float() for _ in range(3)]
+    qs, k, v = [torch.randn(B, H, W, heads, hd, generator=g).to(BF16).float() for _ in range(3)]
+    qs = qs * 0.3
+    q = qs / 1.4426950408889634          # the kernel receives q * log2(e) (bf16) and runs an exp2 softmax
     qkv = torch.zeros(B * H * W, 576, dtype=BF16)
-    for i, t in enumerate((q, k, v)):
+    for i, t in enumerate((qs.to(BF16).float(), k, v)):
         pad = torch.zeros(B, H, W, heads, 32)
-        pad[..., :hd] = t * (1.0 if i else 1.0)
+        pad[..., :hd] = t
         qkv[:, i * 192:(i + 1) * 192] = pad.reshape(B * H * W, 192).to(BF16)
+    q = qs.to(BF16).float() / 1.4426950408889634
     d = _dev()
     out = torch.zeros(B * H * W, 192, dtype=BF16, device=d)
 
