@@ -278,28 +278,42 @@ __global__ void __launch_bounds__(256) experts_resize_kernel(const float* __rest
 
 // SpatialGate (hierarchical_fusion.py:25-43): x *= sigmoid(w2 . gelu(W1 x + b1) + b2), per pixel, in place (bf16 rows).
 // One warp per pixel; C in {32, 64}, hidden = C/4.
-__global__ void __launch_bounds__(256) pixel_gate_kernel(bf16* __restrict__ x, int ld, long long P, int C, const float* __restrict__ w1,
+template <int C>
+__global__ void __launch_bounds__(256) pixel_gate_kernel(bf16* __restrict__ x, int ld, long long P, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, const float* __restrict__ w2, float b2) {
-  __shared__ float sW[16 * 64 + 32];
-  const int hid = C / 4;
-  for (int i = threadIdx.x; i < hid * C; i += 256) sW[i] = w1[i];
-  if (threadIdx.x < hid) { sW[16 * 64 + threadIdx.x] = b1[threadIdx.x]; sW[16 * 64 + 16 + threadIdx.x] = w2[threadIdx.x]; }
+  // one thread per pixel: C values in registers, weights broadcast from shared memory
+  constexpr int HID = C / 4;
+  __shared__ float sW[HID * C], sB[HID], sW2[HID];
+  for (int i = threadIdx.x; i < HID * C; i += 256) sW[i] = w1[i];
+  if (threadIdx.x < HID) { sB[threadIdx.x] = b1[threadIdx.x]; sW2[threadIdx.x] = w2[threadIdx.x]; }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long p = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
   if (p >= P) return;
-  const int per = C / 32;   // 1 or 2 channels per lane
-  float v[2] = {0.f, 0.f};
-  for (int i = 0; i < per; ++i) v[i] = __bfloat162float(x[p * ld + lane * per + i]);
+  float v[C];
+  uint4* row = reinterpret_cast<uint4*>(x + p * ld);
+#pragma unroll
+  for (int i = 0; i < C / 8; ++i) {
+    const uint4 q = row[i];
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[i * 8 + 2 * j] = __uint_as_float(w[j] << 16); v[i * 8 + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+  }
   float s = b2;
-  for (int h = 0; h < hid; ++h) {
-    float d = 0.f;
-    for (int i = 0; i < per; ++i) d += v[i] * sW[h * C + lane * per + i];
-    d = warp_sum(d) + sW[16 * 64 + h];
-    s += gelu_erf(d) * sW[16 * 64 + 16 + h];
+#pragma unroll 2
+  for (int h = 0; h < HID; ++h) {
+    float d = sB[h];
+#pragma unroll
+    for (int c = 0; c < C; ++c) d += v[c] * sW[h * C + c];
+    s += gelu_erf(d) * sW2[h];
   }
   const float g = sigmoidf_(s);
-  for (int i = 0; i < per; ++i) x[p * ld + lane * per + i] = __float2bfloat16_rn(v[i] * g);
+#pragma unroll
+  for (int i = 0; i < C / 8; ++i) {
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { __nv_bfloat162 hh = __floats2bfloat162_rn(v[i * 8 + 2 * j] * g, v[i * 8 + 2 * j + 1] * g); o[j] = *reinterpret_cast<uint32_t*>(&hh); }
+    row[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -509,7 +523,9 @@ extern "C" int ff_experts_resize(const float* stack, int ld, int B, int H, int W
 }
 extern "C" int ff_pixel_gate(void* x, int ld, long long P, int C, const float* w1, const float* b1, const float* w2, float b2, void* stream) {
   FF_CHECK_ARG(x && w1 && b1 && w2 && (C == 32 || C == 64), "ff_pixel_gate: C must be 32 or 64");
-  pixel_gate_kernel<<<ff_cdiv(P, 8), 256, 0, ST(stream)>>>(reinterpret_cast<bf16*>(x), ld, P, C, w1, b1, w2, b2);
+  FF_CHECK_ARG(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "ff_pixel_gate: rows must be 16-byte aligned");
+  if (C == 64) pixel_gate_kernel<64><<<ff_cdiv(P, 256), 256, 0, ST(stream)>>>(reinterpret_cast<bf16*>(x), ld, P, w1, b1, w2, b2);
+  else pixel_gate_kernel<32><<<ff_cdiv(P, 256), 256, 0, ST(stream)>>>(reinterpret_cast<bf16*>(x), ld, P, w1, b1, w2, b2);
   ++g_ff_launches; FF_CHECK_LAUNCH("ff_pixel_gate"); return FF_OK;
 }
 extern "C" int ff_blend(const float* stack, int ld_s, const float* hier, const float* guidance, const float* gates, const float* lr, int B, int h,

@@ -207,6 +207,86 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const __grid_constant__ DwA
   *reinterpret_cast<uint4*>(a.out + pix * a.out_ld + c0) = pack8(acc);
 }
 
+
+// 3x3 specialisation: one thread = 8 channels x 4 consecutive output pixels of one row; the 3x6 input patch and the 9 weight
+// vectors are loaded once (18 + 18 vector loads for 4 outputs instead of 36 + 72).
+template <int MODE>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const __grid_constant__ DwArgs a) {
+  const int cout = MODE == 1 ? a.C / 2 : a.C;
+  const int groups = cout >> 3;
+  const int wq = a.W >> 2;
+  const long long total = (long long)a.B * a.H * wq * groups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  long long r = idx / groups;
+  const int xq = (int)(r % wq);
+  r /= wq;
+  const int y = (int)(r % a.H), b = (int)(r / a.H);
+  const int x0 = xq * 4;
+  const int c0 = g * 8;
+  constexpr int NH = MODE == 1 ? 2 : 1;
+  float acc[NH][4][8];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const int cc = c0 + h * cout;
+    float bv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bv[i] = a.bias ? __ldg(a.bias + cc + i) : 0.f;
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[h][px][i] = bv[i];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      if (yy < 0 || yy >= a.H) continue;
+      float wv[3][8];
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float* wp = a.w + (long long)(dy * 3 + dx) * a.C + cc;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp) + 1);
+        wv[dx][0] = w0.x; wv[dx][1] = w0.y; wv[dx][2] = w0.z; wv[dx][3] = w0.w; wv[dx][4] = w1.x; wv[dx][5] = w1.y; wv[dx][6] = w1.z; wv[dx][7] = w1.w;
+      }
+      const bf16* rowp = a.x + ((long long)(b * a.H + yy) * a.W) * a.x_ld + cc;
+#pragma unroll
+      for (int col = 0; col < 6; ++col) {
+        const int xx = x0 + col - 1;
+        if (xx < 0 || xx >= a.W) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(rowp + (long long)xx * a.x_ld)), f);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const int dx = col - px;          // input column col contributes to output px with tap dx
+          if (dx >= 0 && dx < 3) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[h][px][i] += f[i] * wv[dx][i];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int px = 0; px < 4; ++px) {
+    const long long pix = (long long)(b * a.H + y) * a.W + x0 + px;
+    float o[8];
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = acc[0][px][i] * acc[NH - 1][px][i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = act_apply(acc[0][px][i], a.act);
+      if (a.mul) {
+        float m[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a.mul + pix * a.mul_ld + c0)), m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] *= m[i];
+      }
+    }
+    *reinterpret_cast<uint4*>(a.out + pix * a.out_ld + c0) = pack8(o);
+  }
+}
+
 // x[p][c] *= s[b][c]  (bf16 in place), 8 channels per thread
 __global__ void __launch_bounds__(256) scale_channels_kernel(bf16* __restrict__ x, int ld, long long P_per_b, int B, int C,
                                                             const float* __restrict__ s, int s_ld) {
@@ -268,13 +348,18 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant_
     sIn[pp * cs + c] = v;
   }
   const int KK = a.k * a.k * a.Cin;
-  const int n0 = blockIdx.y * 8;
+  const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
+  const long long opix = (long long)(b * a.H + ty * 8 + py) * a.W + tx * 16 + px;
+  // grid.y == 1: this block walks all output-channel groups (input patch staged once); else one group per block
+  const int g_begin = gridDim.y == 1 ? 0 : blockIdx.y, g_end = gridDim.y == 1 ? a.Cout_pad / 8 : blockIdx.y + 1;
+  for (int grp = g_begin; grp < g_end; ++grp) {
+  const int n0 = grp * 8;
+  __syncthreads();
   for (int i = threadIdx.x; i < KK * 8; i += 128) {
     const int o = i & 7, kk = i >> 3;
     sW[kk * 8 + o] = __ldg(a.w + (long long)(n0 + o) * KK + kk);
   }
   __syncthreads();
-  const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
   float acc[8];
 #pragma unroll
   for (int o = 0; o < 8; ++o) acc[o] = a.bias ? __ldg(a.bias + n0 + o) : 0.f;
@@ -290,7 +375,6 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant_
         acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
       }
     }
-  const long long opix = (long long)(b * a.H + ty * 8 + py) * a.W + tx * 16 + px;
 #pragma unroll
   for (int o = 0; o < 8; ++o) {
     const int n = n0 + o;
@@ -301,6 +385,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant_
       if (a.out_bf16) a.out_bf16[opix * a.out_ld + n] = __float2bfloat16_rn(v);
     }
   }
+  }  // output-channel groups
 }
 
 // NCHW fp32 image -> NHWC fp32 [pixels][ld] with per-channel offset subtraction (x - mean)
@@ -389,7 +474,12 @@ extern "C" int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, in
   FF_CHECK_ARG((kh & 1) && (kw & 1), "ff_dwconv: odd kernel sizes only");
   DwArgs a{reinterpret_cast<const bf16*>(x), x_ld, B, H, W, C, kh, kw, w, bias, act, mode, reinterpret_cast<const bf16*>(mul), mul_ld, reinterpret_cast<bf16*>(out), out_ld};
   const long long total = (long long)B * H * W * ((mode == 1 ? C / 2 : C) / 8);
-  dwconv_kernel<<<ff_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  if (kh == 3 && kw == 3 && W % 4 == 0) {
+    if (mode == 1) dwconv3x3_kernel<1><<<ff_cdiv(total / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    else dwconv3x3_kernel<0><<<ff_cdiv(total / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  } else {
+    dwconv_kernel<<<ff_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  }
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_dwconv");
   return FF_OK;
@@ -421,7 +511,8 @@ extern "C" int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int
     if (e != cudaSuccess) { ff_set_error("ff_conv_direct: smem %zu: %s", smem, cudaGetErrorString(e)); return FF_ERR_CUDA; }
     configured = smem;
   }
-  dim3 grid(B * (H / 8) * (W / 16), Cout_pad / 8);
+  // small input-channel counts: one block computes every output-channel group (the input patch is staged once)
+  dim3 grid(B * (H / 8) * (W / 16), (Cin <= 16) ? 1 : Cout_pad / 8);
   conv_direct_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_conv_direct");
