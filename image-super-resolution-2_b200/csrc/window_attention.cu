@@ -2,10 +2,16 @@
 // DAT rectangular-window spatial attention.  One CTA = one (window, head):
 //   gather Q/K/V rows (cyclic shift and OCAB zero padding resolved by index arithmetic, no roll/unfold copies)
 //   -> S = Q K^T on tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate)
-//   -> + relative-position bias (table in smem, index computed arithmetically) + {0,-100} shift mask
-//   -> online softmax (fp32) -> O = P V -> normalise -> store at the un-shifted token position.
+//   -> + relative-position bias (table in smem, index affine in the key offset) + {0,-100} shift mask
+//   -> online softmax (fp32, exp2) -> O = P V -> normalise -> store at the un-shifted token position.
 // The logits never leave registers (the reference materialises [nW*B, heads, 256, 256|576] fp32 in HBM).
 // q is pre-scaled by head_dim^-0.5 * log2(e) through the packed qkv weights, so the softmax runs on exp2.
+//
+// 8 warps per CTA, each owning 32 query rows (two passes of 16) -> <= 128 registers/thread and 2-3 resident CTAs
+// per SM, so the gather of one window overlaps the math of another.  The kernel is instruction-issue bound
+// (bias add + exp per logit), hence the template on the key-window width: every n8 key tile lies in one
+// key-window row, so the bias index of logit (row, tile n, in-tile offset t) is  A_row - rowmul*ki(n) - sign*(kj0(n)+t)
+// with ki(n), kj0(n) compile-time functions of n.
 #include "ff_common.cuh"
 #include "../../include/ffb200.h"
 
@@ -15,7 +21,7 @@ constexpr int HD = 32;       // padded head dim
 constexpr int ROWP = 40;     // smem row pitch (bf16) -> conflict-free ldmatrix
 constexpr int NQ = 256;
 constexpr int KCHUNK = 64;
-constexpr int NTHREADS = 512;
+constexpr int NTHREADS = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float MASKV = 100.0f * 1.4426950408889634f;
 
@@ -37,22 +43,33 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ int region3(int p, int size, int win, int shift) {
   return p < size - win ? 0 : (p < size - shift ? 1 : 2);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) window_attention_kernel(const __grid_constant__ FFWinAttn p) {
+// key-window row / first column of n8 tile `n` of the chunk starting at key kc
+template <int KW>
+__device__ __forceinline__ void tile_pos(int kc, int n, int& ki, int& kj0) {
+  if constexpr (KW == 16) { ki = (kc >> 4) + (n >> 1); kj0 = (n & 1) * 8; }
+  else if constexpr (KW == 32) { ki = (kc >> 5) + (n >> 2); kj0 = (n & 3) * 8; }
+  else if constexpr (KW == 8) { ki = (kc >> 3) + n; kj0 = 0; }
+  else { const int tg = (kc >> 3) + n; ki = tg / (KW / 8); kj0 = (tg - ki * (KW / 8)) * 8; }
+}
+
+template <int KW, bool WRAP>
+__global__ void __launch_bounds__(NTHREADS, 2) window_attention_kernel(const __grid_constant__ FFWinAttn p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int NK = p.kh * p.kw;
+  const int NK = p.kh * KW;
   bf16* sQ = reinterpret_cast<bf16*>(smem);
   bf16* sK = sQ + NQ * ROWP;
   bf16* sV = sK + NK * ROWP;
-  float* sT = reinterpret_cast<float*>(sV + NK * ROWP);       // bias column of this head, [T]
-  uint16_t* sQc = reinterpret_cast<uint16_t*>(sT + p.T);      // per query: (i<<8 | j)
-  uint16_t* sKc = sQc + NQ;                                    // per key:   (i<<8 | j)
-  uint8_t* sQr = reinterpret_cast<uint8_t*>(sKc + NK);         // per query region id
-  uint8_t* sKr = sQr + NQ;                                     // per key region id (255 = padded key)
+  float* sT = reinterpret_cast<float*>(sV + NK * ROWP);       // bias column of this head (x log2 e), [T]
+  uint8_t* sKr = reinterpret_cast<uint8_t*>(sT + p.T);         // per key region id
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = p.head_off + blockIdx.y;
@@ -64,25 +81,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attention_kernel(const __g
   const bf16* base = reinterpret_cast<const bf16*>(p.qkv);
   const long long img0 = (long long)b * p.H * p.W;
   const bool shifted = (p.shift_y | p.shift_x) != 0;
+  // only windows that touch the wrapped border hold more than one mask region
+  const bool need_mask = shifted && (wy == nwy - 1 || wx == nwx - 1);
 
   // ---- gather Q (4 x 16B per row) ----
   for (int idx = tid; idx < NQ * 4; idx += NTHREADS) {
     const int t = idx >> 2, part = idx & 3;
     const int i = t / p.ww, j = t - i * p.ww;
-    const int ys = wy * p.wh + i, xs = wx * p.ww + j;  // shifted-frame coordinates
-    int y = ys + p.shift_y; if (y >= p.H) y -= p.H;
-    int x = xs + p.shift_x; if (x >= p.W) x -= p.W;
+    int y = wy * p.wh + i + p.shift_y; if (y >= p.H) y -= p.H;
+    int x = wx * p.ww + j + p.shift_x; if (x >= p.W) x -= p.W;
     const bf16* src = base + (img0 + (long long)y * p.W + x) * p.ld + p.q_off + head * HD + part * 8;
     *reinterpret_cast<uint4*>(sQ + t * ROWP + part * 8) = __ldg(reinterpret_cast<const uint4*>(src));
-    if (part == 0) {
-      sQc[t] = (uint16_t)((i << 8) | j);
-      sQr[t] = shifted ? (uint8_t)(region3(ys, p.H, p.wh, p.shift_y) * 3 + region3(xs, p.W, p.ww, p.shift_x)) : 0;
-    }
   }
   // ---- gather K, V ----
   for (int idx = tid; idx < NK * 4; idx += NTHREADS) {
     const int t = idx >> 2, part = idx & 3;
-    const int i = t / p.kw, j = t - i * p.kw;
+    const int i = t / KW, j = t - i * KW;
     const int ys = wy * p.wh - p.kpad_y + i, xs = wx * p.ww - p.kpad_x + j;
     const bool inside = ys >= 0 && ys < p.H && xs >= 0 && xs < p.W;
     uint4 kq = make_uint4(0, 0, 0, 0), vq = kq;
@@ -95,144 +109,175 @@ __global__ void __launch_bounds__(NTHREADS, 1) window_attention_kernel(const __g
     }
     *reinterpret_cast<uint4*>(sK + t * ROWP + part * 8) = kq;
     *reinterpret_cast<uint4*>(sV + t * ROWP + part * 8) = vq;
-    if (part == 0) {
-      sKc[t] = (uint16_t)((i << 8) | j);
-      sKr[t] = (shifted && inside) ? (uint8_t)(region3(ys, p.H, p.wh, p.shift_y) * 3 + region3(xs, p.W, p.ww, p.shift_x)) : 0;
-    }
+    if (part == 0 && need_mask)
+      sKr[t] = inside ? (uint8_t)(region3(ys, p.H, p.wh, p.shift_y) * 3 + region3(xs, p.W, p.ww, p.shift_x)) : 0;
   }
-  for (int i = tid; i < p.T; i += NTHREADS) sT[i] = LOG2E * __ldg(p.bias_table + (long long)i * p.bias_heads + p.bias_head_off + blockIdx.y);
+  {
+    const float* tb = p.bias_table + (long long)(p.bias_head_off + blockIdx.y) * p.T;   // table is [heads][T]
+    for (int i = tid; i < p.T; i += NTHREADS) sT[i] = LOG2E * __ldg(tb + i);
+  }
   __syncthreads();
 
-  // ---- per-warp: 16 query rows ----
-  const int q0 = warp * 16;
-  uint32_t qa[2][4];
-  {
-    // A fragment (16x16) via ldmatrix.x4: matrices (rows 0-7,k 0-7), (rows 8-15,k 0-7), (rows 0-7,k 8-15), (rows 8-15,k 8-15)
-    const int row = q0 + (lane & 15);
-    const int kofs = (lane >> 4) * 8;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[ks], smem_u32(sQ + row * ROWP + ks * 16 + kofs));
-  }
-  const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
-  const int qc0 = sQc[r0], qc1 = sQc[r1];
-  const int qi0 = qc0 >> 8, qj0 = qc0 & 255, qi1 = qc1 >> 8, qj1 = qc1 & 255;
-  const int qr0 = sQr[r0], qr1 = sQr[r1];
-
-  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
-  float o[4][4];
-#pragma unroll
-  for (int n = 0; n < 4; ++n)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
-
-  for (int kc = 0; kc < NK; kc += KCHUNK) {
-    float s[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) s[n][i] = 0.f;
-    // S = Q K^T : B fragments (k16 x n8) come from K rows [key][dim] (non-transposed ldmatrix)
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {  // pairs of n8 tiles (16 keys)
-      // x4: (keys 0-7, dims 0-7), (keys 0-7, dims 8-15), (keys 8-15, dims 0-7), (keys 8-15, dims 8-15) for k-step ks
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        uint32_t kb[4];
-        const int key = kc + np * 16 + (lane & 7) + ((lane >> 4) << 3);
-        const int dofs = ks * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x4(kb, smem_u32(sK + key * ROWP + dofs));
-        mma16816(s[2 * np], qa[ks], kb[0], kb[1]);
-        mma16816(s[2 * np + 1], qa[ks], kb[2], kb[3]);
-      }
-    }
-    // bias + mask, running max.  Each n8 tile holds 8 keys of one key-window row (kw is a multiple of 8), so the table
-    // index is affine in the in-tile key offset t = 2*(lane&3)+e:  idx = A_row(tile) - rel_sign * t.
-    float cm0 = -1e30f, cm1 = -1e30f;
-    const int tq = 2 * (lane & 3);
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int kcd = sKc[kc + n * 8];                 // first key of the tile (warp-uniform)
-      const int ki = kcd >> 8, kj0 = kcd & 255;
-      const int a0 = (p.rel_sign * (qi0 - ki) + p.rel_off_y) * p.rel_stride + p.rel_sign * (qj0 - kj0 - tq) + p.rel_off_x;
-      const int a1 = (p.rel_sign * (qi1 - ki) + p.rel_off_y) * p.rel_stride + p.rel_sign * (qj1 - kj0 - tq) + p.rel_off_x;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        int i0 = a0 - p.rel_sign * e, i1 = a1 - p.rel_sign * e;
-        i0 += (i0 >> 31) & p.T;
-        i1 += (i1 >> 31) & p.T;
-        float v0 = s[n][e] + sT[i0];
-        float v1 = s[n][2 + e] + sT[i1];
-        if (shifted) {
-          const int kr = sKr[kc + n * 8 + tq + e];
-          if (kr != qr0) v0 -= MASKV;
-          if (kr != qr1) v1 -= MASKV;
-        }
-        s[n][e] = v0;
-        s[n][2 + e] = v1;
-        cm0 = fmaxf(cm0, v0);
-        cm1 = fmaxf(cm1, v1);
-      }
-    }
-    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
-    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
-    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
-    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
-    const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);
-    const float sc0 = exp2f(m0 - nm0), sc1 = exp2f(m1 - nm1);
-    m0 = nm0; m1 = nm1;
-    l0 *= sc0; l1 *= sc1;
-#pragma unroll
-    for (int n = 0; n < 4; ++n) { o[n][0] *= sc0; o[n][1] *= sc0; o[n][2] *= sc1; o[n][3] *= sc1; }
-    // P = exp(S - m), accumulate row sums, O += P V
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {  // k16 steps over the 64 keys of the chunk
-      uint32_t pa[4];
-      float e00 = exp2f(s[2 * kk][0] - m0), e01 = exp2f(s[2 * kk][1] - m0);
-      float e02 = exp2f(s[2 * kk][2] - m1), e03 = exp2f(s[2 * kk][3] - m1);
-      float e10 = exp2f(s[2 * kk + 1][0] - m0), e11 = exp2f(s[2 * kk + 1][1] - m0);
-      float e12 = exp2f(s[2 * kk + 1][2] - m1), e13 = exp2f(s[2 * kk + 1][3] - m1);
-      l0 += e00 + e01 + e10 + e11;
-      l1 += e02 + e03 + e12 + e13;
-      pa[0] = pack_bf16(e00, e01);
-      pa[1] = pack_bf16(e02, e03);
-      pa[2] = pack_bf16(e10, e11);
-      pa[3] = pack_bf16(e12, e13);
-      // B fragments of V (k16 keys x n8 dims) via transposed ldmatrix on V rows [key][dim]
-#pragma unroll
-      for (int dp = 0; dp < 2; ++dp) {  // pairs of n8 tiles (16 dims)
-        uint32_t vb[4];
-        const int key = kc + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int dofs = dp * 16 + (lane >> 4) * 8;
-        ldsm_x4_t(vb, smem_u32(sV + key * ROWP + dofs));
-        mma16816(o[2 * dp], pa, vb[0], vb[1]);
-        mma16816(o[2 * dp + 1], pa, vb[2], vb[3]);
-      }
-    }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-
-  // ---- store at the un-shifted token position ----
+  const int sgn = p.rel_sign;
+  const int rowmul = sgn * p.rel_stride;
+  const int tq = 2 * (lane & 3);
   bf16* outp = reinterpret_cast<bf16*>(p.out);
-  {
-    const int ys0 = wy * p.wh + qi0, xs0 = wx * p.ww + qj0;
-    int y = ys0 + p.shift_y; if (y >= p.H) y -= p.H;
-    int x = xs0 + p.shift_x; if (x >= p.W) x -= p.W;
-    bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + head * HD + 2 * (lane & 3);
+
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int q0 = warp * 32 + pass * 16;
+    uint32_t qa[2][4];
+    {
+      const int row = q0 + (lane & 15);
+      const int kofs = (lane >> 4) * 8;
 #pragma unroll
-    for (int n = 0; n < 4; ++n) *reinterpret_cast<uint32_t*>(dst + n * 8) = pack_bf16(o[n][0] * inv0, o[n][1] * inv0);
-  }
-  {
-    const int ys1 = wy * p.wh + qi1, xs1 = wx * p.ww + qj1;
-    int y = ys1 + p.shift_y; if (y >= p.H) y -= p.H;
-    int x = xs1 + p.shift_x; if (x >= p.W) x -= p.W;
-    bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + head * HD + 2 * (lane & 3);
+      for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[ks], smem_u32(sQ + row * ROWP + ks * 16 + kofs));
+    }
+    const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
+    const int qi0 = r0 / p.ww, qj0 = r0 - qi0 * p.ww, qi1 = r1 / p.ww, qj1 = r1 - qi1 * p.ww;
+    // bias index of (row, key (ki,kj)) = (sgn*(qi-ki)+offy)*stride + sgn*(qj-kj)+offx = A_row - rowmul*ki - sgn*kj
+    const int A0 = (sgn * qi0 + p.rel_off_y) * p.rel_stride + sgn * (qj0 - tq) + p.rel_off_x;
+    const int A1 = (sgn * qi1 + p.rel_off_y) * p.rel_stride + sgn * (qj1 - tq) + p.rel_off_x;
+    int qr0 = 0, qr1 = 0;
+    if (need_mask) {
+      qr0 = region3(wy * p.wh + qi0, p.H, p.wh, p.shift_y) * 3 + region3(wx * p.ww + qj0, p.W, p.ww, p.shift_x);
+      qr1 = region3(wy * p.wh + qi1, p.H, p.wh, p.shift_y) * 3 + region3(wx * p.ww + qj1, p.W, p.ww, p.shift_x);
+    }
+
+    float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
+    float o[4][4];
 #pragma unroll
-    for (int n = 0; n < 4; ++n) *reinterpret_cast<uint32_t*>(dst + n * 8) = pack_bf16(o[n][2] * inv1, o[n][3] * inv1);
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
+
+#pragma unroll 1
+    for (int kc = 0; kc < NK; kc += KCHUNK) {
+      float s[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[n][i] = 0.f;
+      // S = Q K^T : B fragments (k16 x n8) come from K rows [key][dim] (non-transposed ldmatrix)
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t kb[4];
+          const int key = kc + np * 16 + (lane & 7) + ((lane >> 4) << 3);
+          const int dofs = ks * 16 + ((lane >> 3) & 1) * 8;
+          ldsm_x4(kb, smem_u32(sK + key * ROWP + dofs));
+          mma16816(s[2 * np], qa[ks], kb[0], kb[1]);
+          mma16816(s[2 * np + 1], qa[ks], kb[2], kb[3]);
+        }
+      }
+      // bias (+ mask), running max
+      float cm0 = -1e30f, cm1 = -1e30f;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        int ki, kj0;
+        tile_pos<KW>(kc, n, ki, kj0);
+        const int off = rowmul * ki + sgn * kj0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          int i0 = A0 - off - sgn * e, i1 = A1 - off - sgn * e;
+          if constexpr (WRAP) {
+            i0 += (i0 >> 31) & p.T;
+            i1 += (i1 >> 31) & p.T;
+          }
+          s[n][e] += sT[i0];
+          s[n][2 + e] += sT[i1];
+        }
+      }
+      if (need_mask) {
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int kr = sKr[kc + n * 8 + tq + e];
+            if (kr != qr0) s[n][e] -= MASKV;
+            if (kr != qr1) s[n][2 + e] -= MASKV;
+          }
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        cm0 = fmaxf(cm0, fmaxf(s[n][0], s[n][1]));
+        cm1 = fmaxf(cm1, fmaxf(s[n][2], s[n][3]));
+      }
+      cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
+      cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+      cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
+      cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+      const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);
+      const float sc0 = ex2(m0 - nm0), sc1 = ex2(m1 - nm1);
+      m0 = nm0; m1 = nm1;
+      l0 *= sc0; l1 *= sc1;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) { o[n][0] *= sc0; o[n][1] *= sc0; o[n][2] *= sc1; o[n][3] *= sc1; }
+      // P = exp2(S - m), row sums, O += P V
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pa[4];
+        const float e00 = ex2(s[2 * kk][0] - m0), e01 = ex2(s[2 * kk][1] - m0);
+        const float e02 = ex2(s[2 * kk][2] - m1), e03 = ex2(s[2 * kk][3] - m1);
+        const float e10 = ex2(s[2 * kk + 1][0] - m0), e11 = ex2(s[2 * kk + 1][1] - m0);
+        const float e12 = ex2(s[2 * kk + 1][2] - m1), e13 = ex2(s[2 * kk + 1][3] - m1);
+        l0 += (e00 + e01) + (e10 + e11);
+        l1 += (e02 + e03) + (e12 + e13);
+        pa[0] = pack_bf16(e00, e01);
+        pa[1] = pack_bf16(e02, e03);
+        pa[2] = pack_bf16(e10, e11);
+        pa[3] = pack_bf16(e12, e13);
+#pragma unroll
+        for (int dp = 0; dp < 2; ++dp) {
+          uint32_t vb[4];
+          const int key = kc + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int dofs = dp * 16 + (lane >> 4) * 8;
+          ldsm_x4_t(vb, smem_u32(sV + key * ROWP + dofs));
+          mma16816(o[2 * dp], pa, vb[0], vb[1]);
+          mma16816(o[2 * dp + 1], pa, vb[2], vb[3]);
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+
+    // ---- store at the un-shifted token position ----
+    {
+      int y = wy * p.wh + qi0 + p.shift_y; if (y >= p.H) y -= p.H;
+      int x = wx * p.ww + qj0 + p.shift_x; if (x >= p.W) x -= p.W;
+      bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + head * HD + tq;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) *reinterpret_cast<uint32_t*>(dst + n * 8) = pack_bf16(o[n][0] * inv0, o[n][1] * inv0);
+    }
+    {
+      int y = wy * p.wh + qi1 + p.shift_y; if (y >= p.H) y -= p.H;
+      int x = wx * p.ww + qj1 + p.shift_x; if (x >= p.W) x -= p.W;
+      bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + head * HD + tq;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) *reinterpret_cast<uint32_t*>(dst + n * 8) = pack_bf16(o[n][2] * inv1, o[n][3] * inv1);
+    }
   }
+}
+
+template <int KW, bool WRAP>
+int launch(const FFWinAttn& p, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention_kernel<KW, WRAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      ff_set_error("ff_window_attention: smem %zu: %s", smem, cudaGetErrorString(e));
+      return FF_ERR_CUDA;
+    }
+    configured = smem;
+  }
+  dim3 grid(p.B * (p.H / p.wh) * (p.W / p.ww), p.heads);
+  window_attention_kernel<KW, WRAP><<<grid, NTHREADS, smem, st>>>(p);
+  FF_CHECK_LAUNCH("ff_window_attention");
+  return FF_OK;
 }
 
 }  // namespace
@@ -247,24 +292,22 @@ extern "C" int ff_window_attention(const FFWinAttn* pp, void* stream) {
   FF_CHECK_ARG(p.wh < 256 && p.ww < 256 && p.kh < 256 && p.kw < 256, "ff_window_attention: window too large");
   const int NK = p.kh * p.kw;
   FF_CHECK_ARG(NK % KCHUNK == 0 && NK >= KCHUNK, "ff_window_attention: key window %dx%d not a multiple of 64 tokens", p.kh, p.kw);
-  FF_CHECK_ARG(p.kw % 8 == 0, "ff_window_attention: key window width must be a multiple of 8");
+  FF_CHECK_ARG(p.kw == 8 || p.kw == 16 || p.kw == 24 || p.kw == 32, "ff_window_attention: key window width %d not in {8,16,24,32}", p.kw);
   FF_CHECK_ARG(p.H % p.wh == 0 && p.W % p.ww == 0, "ff_window_attention: image %dx%d not divisible by window %dx%d", p.H, p.W, p.wh, p.ww);
   FF_CHECK_ARG(p.ld % 8 == 0 && p.out_ld % 8 == 0 && p.q_off % 8 == 0 && p.k_off % 8 == 0 && p.v_off % 8 == 0 && p.out_off % 8 == 0, "ff_window_attention: offsets/pitches must be multiples of 8");
-  FF_CHECK_ARG(p.heads > 0 && p.T > 0 && p.rel_stride > 0, "ff_window_attention: bad heads/T");
+  FF_CHECK_ARG(p.heads > 0 && p.T > 0 && p.rel_stride > 0 && (p.rel_sign == 1 || p.rel_sign == -1), "ff_window_attention: bad heads/T/rel_sign");
   FF_CHECK_ARG(p.shift_y >= 0 && p.shift_y < p.wh && p.shift_x >= 0 && p.shift_x < p.ww, "ff_window_attention: bad shift");
-  size_t smem = (size_t)(NQ + 2 * NK) * ROWP * 2 + (size_t)p.T * 4 + (size_t)(NQ + NK) * 2 + (size_t)(NQ + NK) + 16;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      ff_set_error("ff_window_attention: smem %zu: %s", smem, cudaGetErrorString(e));
-      return FF_ERR_CUDA;
-    }
-    configured = smem;
-  }
-  dim3 grid(p.B * (p.H / p.wh) * (p.W / p.ww), p.heads);
-  window_attention_kernel<<<grid, NTHREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  // index range check: without wrap-around every index must already lie in [0, T)
+  const int lo_y = p.rel_sign > 0 ? -(p.kh - 1 - 0) : 0, hi_y = p.rel_sign > 0 ? p.wh - 1 : p.kh - 1;
+  (void)lo_y; (void)hi_y;
+  const size_t smem = (size_t)(NQ + 2 * NK) * ROWP * 2 + (size_t)p.T * 4 + (size_t)NK + 16;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ++g_ff_launches;
-  FF_CHECK_LAUNCH("ff_window_attention");
-  return FF_OK;
+  const bool wrap = p.rel_sign < 0;      // HAT's overlapping-window table is indexed with negative offsets
+  switch (p.kw) {
+    case 8: return wrap ? launch<8, true>(p, smem, st) : launch<8, false>(p, smem, st);
+    case 16: return wrap ? launch<16, true>(p, smem, st) : launch<16, false>(p, smem, st);
+    case 24: return wrap ? launch<24, true>(p, smem, st) : launch<24, false>(p, smem, st);
+    default: return wrap ? launch<32, true>(p, smem, st) : launch<32, false>(p, smem, st);
+  }
 }

@@ -69,8 +69,8 @@ class DATRunner:
                 if d["spatial"]:
                     wq[:C] *= scale
                     bq[:C] *= scale
-                    d["tables"] = [_dyn_pos_table(g, a + f"attns.{br}.pos.", *((SPLIT[0], SPLIT[1]) if br == 0 else (SPLIT[1], SPLIT[0]))).to(dev)
-                                   for br in range(2)]
+                    d["tables"] = [_dyn_pos_table(g, a + f"attns.{br}.pos.", *((SPLIT[0], SPLIT[1]) if br == 0 else (SPLIT[1], SPLIT[0]))).t().contiguous().to(dev)
+                                   for br in range(2)]   # [heads][T]
                 else:
                     d["temperature"] = g(a + "temperature").reshape(-1).to(dev).contiguous()
                 d["qkv_w"] = pack_matrix(wq, 3 * CP, CP, row_index=_qkv_rows(), device=dev)

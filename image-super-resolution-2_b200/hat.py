@@ -69,7 +69,7 @@ class HATRunner:
                 qkv_b=pack_vector(bq, 3 * CP, index=_qkv_rows(), device=dev),
                 proj_w=pack_matrix(g(prefix + "proj.weight"), CP, CP, col_index=hp, device=dev),
                 proj_b=pack_vector(g(prefix + "proj.bias"), CP, device=dev),
-                table=g(prefix + "relative_position_bias_table").to(dev).contiguous(),
+                table=g(prefix + "relative_position_bias_table").t().contiguous().to(dev),   # [heads][T]
             )
 
         def mlp_pack(prefix):

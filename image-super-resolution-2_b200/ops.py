@@ -103,7 +103,7 @@ def window_attention(qkv, B, H, W, out, *, bias_table, wh, ww, kh=None, kw=None,
     p.kpad_y, p.kpad_x = kpad
     p.shift_y, p.shift_x = shift
     p.heads, p.head_off = heads, head_off
-    p.bias_table = bias_table.data_ptr(); p.T = bias_table.shape[0]; p.bias_heads = bias_table.shape[1]
+    p.bias_table = bias_table.data_ptr(); p.T = bias_table.shape[1]; p.bias_heads = bias_table.shape[0]   # [heads][T]
     p.bias_head_off = bias_head_off
     p.rel_sign = rel_sign
     p.rel_off_y, p.rel_off_x = rel_off if rel_off is not None else (wh - 1, ww - 1)

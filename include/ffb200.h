@@ -95,7 +95,8 @@ int ff_conv_gemm(const FFConvGemm* p, void* stream);
  * kpad_{y,x} before the query window; keys outside the image are all-zero rows that still take softmax mass
  * (nn.Unfold zero padding, hat_arch.py:377).  Bias index for (query (qi,qj), key (ki,kj)) window coordinates:
  *   idx = (rel_sign*(qi-ki)+rel_off_y)*rel_stride + rel_sign*(qj-kj)+rel_off_x;  idx<0 -> idx+T  (HAT's OCA table
- *   relies on negative-index wrap-around, hat_arch.py:896-919);  bias = bias_table[idx*bias_heads + bias_head_off + h].
+ *   relies on negative-index wrap-around, hat_arch.py:896-919; applied when rel_sign < 0);  bias = bias_table[(bias_head_off + h)*T + idx]
+ *   (the table is stored transposed, [bias_heads][T]).  kw must be 8, 16, 24 or 32.
  * shift_{y,x} != 0 selects the cyclic shift and the {0,-100} region mask of hat_arch.py:921-940 / dat_arch.py:431-489.
  * Output token (un-shifted position) gets channels out_off + (head_off+h)*32 .. +32 of out (bf16 [B*H*W][out_ld]).
  */

@@ -179,7 +179,7 @@ def test_window_attention(mode):
         mask = ohat.shift_mask(H, W) if sh else None
         o = unpart(attend(part(roll(q), 16, 16), part(roll(k), 16, 16), part(roll(v), 16, 16), bias, mask), 16, 16)
         ref = torch.roll(o, (sh, sh), (1, 2)) if sh else o
-        ops.window_attention(qkv.to(d), B, H, W, out, bias_table=table.to(d), wh=16, ww=16, shift=(sh, sh))
+        ops.window_attention(qkv.to(d), B, H, W, out, bias_table=table.t().contiguous().to(d), wh=16, ww=16, shift=(sh, sh))
     elif mode == "oca":
         table = torch.randn(1521, heads, generator=g)
         bias = table[ohat.rpi_oca().reshape(-1)].view(256, 576, heads).permute(2, 0, 1)
@@ -190,7 +190,7 @@ def test_window_attention(mode):
             x = x.permute(0, 2, 3, 4, 5, 1).reshape(-1, 576, heads, hd).permute(0, 2, 1, 3)
             return x
         ref = unpart(attend(part(q, 16, 16), ext(k), ext(v), bias, None), 16, 16)
-        ops.window_attention(qkv.to(d), B, H, W, out, bias_table=table.to(d), wh=16, ww=16, kh=24, kw=24, kpad=(4, 4), rel_sign=-1,
+        ops.window_attention(qkv.to(d), B, H, W, out, bias_table=table.t().contiguous().to(d), wh=16, ww=16, kh=24, kw=24, kpad=(4, 4), rel_sign=-1,
                              rel_off=(-7, -7), rel_stride=39)
     else:
         from oracle import dat as odat
@@ -206,7 +206,7 @@ def test_window_attention(mode):
         o = torch.roll(o, sh, (1, 2)) if sh[0] else o
         ref = torch.zeros(B, H, W, heads, hd)
         ref[:, :, :, sl] = o
-        ops.window_attention(qkv.to(d), B, H, W, out, bias_table=table.to(d), wh=wh, ww=ww, shift=sh, heads=3, head_off=3 * br)
+        ops.window_attention(qkv.to(d), B, H, W, out, bias_table=table.t().contiguous().to(d), wh=wh, ww=ww, shift=sh, heads=3, head_off=3 * br)
     torch.cuda.synchronize()
     got = out.cpu().float().view(B, H, W, heads, 32)
     assert torch.all(got[..., 30:] == 0)
