@@ -21,8 +21,16 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 
 // ------------------------------------------------------------------------------------------
 // LayerNorm over the channel axis of [rows][ld]; one warp per row, values kept in registers.
+// Lanes own channel PAIRS (c = 2*lane + 64*i): 8-byte fp32 / 4-byte bf16 loads and 4-byte bf16x2 stores halve the
+// load/store instruction count of this issue-bound kernel.  C and out_cols must be even.
 // ------------------------------------------------------------------------------------------
-template <typename TIn, int MAXV>  // MAXV = ceil(C/32) upper bound
+__device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld_pair(const bf16* p) {
+  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(p);
+  return make_float2(__low2float(h), __high2float(h));
+}
+
+template <typename TIn, int NP>  // NP = pairs per lane = ceil(out_cols / 64)
 __global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ x, int in_ld, long long rows, int C,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, bf16* __restrict__ out_bf16, int out_ld, int out_cols,
@@ -31,31 +39,37 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ 
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const TIn* xr = x + row * in_ld;
-  float v[MAXV];
+  float2 v[NP];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = lane + i * 32;
-    v[i] = (c < C) ? (float)xr[c] : 0.f;
-    s += v[i];
+  for (int i = 0; i < NP; ++i) {
+    const int c = 2 * lane + 64 * i;
+    v[i] = (c < C) ? ld_pair(xr + c) : make_float2(0.f, 0.f);
+    s += v[i].x + v[i].y;
   }
   const float mean = warp_sum(s) / C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = lane + i * 32;
-    const float d = (c < C) ? v[i] - mean : 0.f;
-    q += d * d;
+  for (int i = 0; i < NP; ++i) {
+    const int c = 2 * lane + 64 * i;
+    if (c < C) {
+      const float d0 = v[i].x - mean, d1 = v[i].y - mean;
+      q += d0 * d0 + d1 * d1;
+    }
   }
   const float rstd = rsqrtf(warp_sum(q) / C + eps);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = lane + i * 32;
+  for (int i = 0; i < NP; ++i) {
+    const int c = 2 * lane + 64 * i;
     if (c < out_cols) {
-      float y = 0.f;
-      if (c < C) y = (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-      if (out_bf16) out_bf16[row * out_ld + c] = __float2bfloat16_rn(y);
-      if (out_f32) out_f32[row * out_f32_ld + c] = y;
+      float2 y = make_float2(0.f, 0.f);
+      if (c < C) {
+        const float2 g = __ldg(reinterpret_cast<const float2*>(gamma + c)), bb = __ldg(reinterpret_cast<const float2*>(beta + c));
+        y.x = (v[i].x - mean) * rstd * g.x + bb.x;
+        y.y = (v[i].y - mean) * rstd * g.y + bb.y;
+      }
+      if (out_bf16) *reinterpret_cast<__nv_bfloat162*>(out_bf16 + row * out_ld + c) = __floats2bfloat162_rn(y.x, y.y);
+      if (out_f32) *reinterpret_cast<float2*>(out_f32 + row * out_f32_ld + c) = y;
     }
   }
 }
@@ -424,13 +438,17 @@ extern "C" int ff_layernorm(const void* x, int x_is_bf16, int in_ld, long long r
   FF_CHECK_ARG(C > 0 && C <= 1024 && out_cols >= C && out_cols <= 1024, "ff_layernorm: C=%d out_cols=%d unsupported", C, out_cols);
   if (rows <= 0) return FF_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FF_CHECK_ARG(C % 2 == 0 && out_cols % 2 == 0 && in_ld % 2 == 0 && (!out_bf16 || out_ld % 2 == 0) && (!out_f32 || out_f32_ld % 2 == 0),
+               "ff_layernorm: C, out_cols and all pitches must be even");
+  FF_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 7) == 0 && (reinterpret_cast<uintptr_t>(beta) & 7) == 0,
+               "ff_layernorm: x / gamma / beta must be 8-byte aligned");
   const int grid = ff_cdiv(rows, 8);
-  const int maxv = ff_cdiv(out_cols, 32);
+  const int maxv = ff_cdiv(out_cols, 64);
 #define LN_LAUNCH(T, MV) layernorm_kernel<T, MV><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(x), in_ld, rows, C, gamma, beta, eps, reinterpret_cast<bf16*>(out_bf16), out_ld, out_cols, out_f32, out_f32_ld)
   if (x_is_bf16) {
-    if (maxv <= 2) LN_LAUNCH(bf16, 2); else if (maxv <= 4) LN_LAUNCH(bf16, 4); else if (maxv <= 8) LN_LAUNCH(bf16, 8); else if (maxv <= 16) LN_LAUNCH(bf16, 16); else LN_LAUNCH(bf16, 32);
+    if (maxv <= 1) LN_LAUNCH(bf16, 1); else if (maxv <= 2) LN_LAUNCH(bf16, 2); else if (maxv <= 3) LN_LAUNCH(bf16, 3); else if (maxv <= 4) LN_LAUNCH(bf16, 4); else if (maxv <= 6) LN_LAUNCH(bf16, 6); else if (maxv <= 8) LN_LAUNCH(bf16, 8); else LN_LAUNCH(bf16, 16);
   } else {
-    if (maxv <= 2) LN_LAUNCH(float, 2); else if (maxv <= 4) LN_LAUNCH(float, 4); else if (maxv <= 8) LN_LAUNCH(float, 8); else if (maxv <= 16) LN_LAUNCH(float, 16); else LN_LAUNCH(float, 32);
+    if (maxv <= 1) LN_LAUNCH(float, 1); else if (maxv <= 2) LN_LAUNCH(float, 2); else if (maxv <= 3) LN_LAUNCH(float, 3); else if (maxv <= 4) LN_LAUNCH(float, 4); else if (maxv <= 6) LN_LAUNCH(float, 6); else if (maxv <= 8) LN_LAUNCH(float, 8); else LN_LAUNCH(float, 16);
   }
 #undef LN_LAUNCH
   ++g_ff_launches;
