@@ -31,7 +31,9 @@ struct Args {
 //   EPI_STORE_GELU -- out_bf16 = gelu(acc + bias)  } (warp, 32-column block)
 //   EPI_RES        -- out_f32 = (acc + bias) * (alpha * col_scale) + res_f32 (+ bf16 copy): the fp32 residual block is
 //                     TMA-loaded (prefetched one block ahead) into 128B-swizzled smem, updated in place and TMA-stored
-enum { EPI_GENERIC = 0, EPI_STORE = 1, EPI_STORE_GELU = 2, EPI_RES = 3 };
+//   EPI_RES_AUX    -- EPI_RES + aux_alpha * aux_bf16[p,n] * aux_chan[b,n] (HAT: x = shortcut + proj(attn) + 0.01 * cab * se); no bf16 copy
+//   EPI_STORE_GATE -- SimpleGate folded: 64 accumulator columns -> 32 bf16 outputs, TMA store
+enum { EPI_GENERIC = 0, EPI_STORE = 1, EPI_STORE_GELU = 2, EPI_RES = 3, EPI_RES_AUX = 4, EPI_STORE_GATE = 5 };
 
 template <int BN, int EPI>
 struct Cfg {
@@ -39,7 +41,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int CB = BN < 32 ? BN : 32;                    // epilogue column block
   static constexpr int STG_PITCH = CB + 4;                        // floats; +4 keeps float4 accesses conflict-free (generic path)
-  static constexpr int STG_WARP_BYTES = EPI == EPI_RES ? 10240 : (EPI == EPI_GENERIC ? 32 * STG_PITCH * 4 : 4096);
+  static constexpr int STG_WARP_BYTES = EPI == EPI_RES ? 10240 : EPI == EPI_RES_AUX ? 12288 : (EPI == EPI_GENERIC ? 32 * STG_PITCH * 4 : 4096);
   static constexpr int STG_BYTES = NUM_EPI_WARPS * STG_WARP_BYTES;
   static constexpr int STAGES_RAW = (225 * 1024 - STG_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
@@ -322,7 +324,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ================= epilogue warps =================
-    if constexpr (EPI == EPI_RES) {
+    if constexpr (EPI == EPI_RES || EPI == EPI_RES_AUX) {
+      constexpr bool AUX = (EPI == EPI_RES_AUX);   // layout per warp: [R0 4K][R1 4K][O16 2K] or [R0 4K][R1 4K][X0 2K][X1 2K]
       // ---------- residual epilogue: TMA-load res block -> in-place update in 128B-swizzled smem -> TMA store ----------
       static_assert(C::CB == 32, "EPI_RES needs 32-column blocks");
       const FFConvGemm& p = a.p;
@@ -335,7 +338,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t ph[2] = {0, 0};
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (lane == 0) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO32); if (p.out_bf16) tma_prefetch_desc(&tmO); }
+      if (lane == 0) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO32); if (AUX || p.out_bf16) tma_prefetch_desc(&tmO); }
       // items of this warp: (tile, cb) with cb = half, half+2, ... while the block starts below n_store.  The residual
       // block of the NEXT item (possibly in the next tile) is prefetched while the current one is processed.
       auto valid = [&](int tl, int c) { return c < ncb && (tl % a.n_tiles) * BN + c * 32 < p.n_store; };
@@ -344,8 +347,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int b = m_tile / a.tiles_per_img;
         const int t = m_tile - b * a.tiles_per_img;
         const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
-        mbar_arrive_expect_tx(&res_bar[ew][bsel], 4096);
+        mbar_arrive_expect_tx(&res_bar[ew][bsel], AUX ? 6144 : 4096);
         tma_load_4d(wbase + bsel * 4096, &tmR, &res_bar[ew][bsel], n_tile * BN + c * 32, tx * TILE_W, ty * TILE_H + quad * 2, b);
+        if constexpr (AUX) tma_load_4d(wbase + 8192 + bsel * 2048, &tmO, &res_bar[ew][bsel], n_tile * BN + c * 32, tx * TILE_W, ty * TILE_H + quad * 2, b);
       };
       {
         int ft = blockIdx.x;
@@ -398,8 +402,20 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             r.y = fmaf(__uint_as_float(raw[4 * c + 1]) + bb.y, cs.y, r.y);
             r.z = fmaf(__uint_as_float(raw[4 * c + 2]) + bb.z, cs.z, r.z);
             r.w = fmaf(__uint_as_float(raw[4 * c + 3]) + bb.w, cs.w, r.w);
+            if constexpr (AUX) {
+              const uint2 q = *reinterpret_cast<const uint2*>(wbase + 8192 + buf * 2048 + lane * 64 + (((c >> 1) ^ sw3) << 4) + ((c & 1) << 3));
+              float4 ch = make_float4(p.aux_alpha, p.aux_alpha, p.aux_alpha, p.aux_alpha);
+              if (p.aux_chan) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(p.aux_chan + (long long)b * p.aux_chan_ld + n_blk + c * 4));
+                ch.x *= g.x; ch.y *= g.y; ch.z *= g.z; ch.w *= g.w;
+              }
+              r.x = fmaf(__uint_as_float(q.x << 16), ch.x, r.x);
+              r.y = fmaf(__uint_as_float(q.x & 0xffff0000u), ch.y, r.y);
+              r.z = fmaf(__uint_as_float(q.y << 16), ch.z, r.z);
+              r.w = fmaf(__uint_as_float(q.y & 0xffff0000u), ch.w, r.w);
+            }
             *rp = r;
-            if (p.out_bf16) {
+            if (!AUX && p.out_bf16) {
               __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
               uint2* op = reinterpret_cast<uint2*>(orow + (((c >> 1) ^ sw3) << 4) + ((c & 1) << 3));
               *op = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
@@ -409,7 +425,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0) {
             tma_store_4d(&tmO32, wbase + buf * 4096, n_blk, tx * TILE_W, ty * TILE_H + quad * 2, b);
-            if (p.out_bf16) tma_store_4d(&tmO, wbase + 8192, n_blk, tx * TILE_W, ty * TILE_H + quad * 2, b);
+            if (!AUX && p.out_bf16) tma_store_4d(&tmO, wbase + 8192, n_blk, tx * TILE_W, ty * TILE_H + quad * 2, b);
             tma_store_commit();
           }
           buf ^= 1;
@@ -421,7 +437,65 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (lane == 0) tma_store_wait_all();
     } else
-    if constexpr (EPI != EPI_GENERIC) {
+    if constexpr (EPI == EPI_STORE_GATE) {
+      // ---------- SimpleGate TMA-store epilogue: item = 64 accumulator columns (4 chunks of [8 x1 | 8 x2]) -> 32 bf16 outputs ----------
+      static_assert(BN % 64 == 0, "EPI_STORE_GATE needs BN % 64 == 0");
+      const FFConvGemm& p = a.p;
+      const int ew = warp - 2;
+      const int quad = warp & 3;
+      const int half = ew >> 2;
+      uint8_t* stg_base = smem + C::STAGES * C::STAGE_BYTES + ew * C::STG_WARP_BYTES;
+      int buf = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      if (lane == 0) tma_prefetch_desc(&tmO);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+        const int b = m_tile / a.tiles_per_img;
+        const int t = m_tile - b * a.tiles_per_img;
+        const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+        for (int it = half; it < BN / 64; it += 2) {
+          const int n_blk = n_tile * BN + it * 64;
+          if (n_blk >= p.n_store) break;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* dst = stg_base + buf * 2048 + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {      // chunk c: accumulator columns [16c, 16c+16) -> output columns [8c, 8c+8)
+            uint32_t raw[16];
+            tmem_ld16(taddr + it * 64 + c * 16, raw);
+            tc_wait_ld();
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = 2 * i;
+              const float x1a = __uint_as_float(raw[j]) + __ldg(p.bias + n_blk + c * 16 + j), x2a = __uint_as_float(raw[8 + j]) + __ldg(p.bias + n_blk + c * 16 + 8 + j);
+              const float x1b = __uint_as_float(raw[j + 1]) + __ldg(p.bias + n_blk + c * 16 + j + 1), x2b = __uint_as_float(raw[9 + j]) + __ldg(p.bias + n_blk + c * 16 + 9 + j);
+              __nv_bfloat162 h = __floats2bfloat162_rn(x1a * x2a, x1b * x2b);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmO, stg_base + buf * 2048, n_blk >> 1, tx * TILE_W, ty * TILE_H + quad * 2, b);
+            tma_store_commit();
+          }
+          buf ^= 1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else if constexpr (EPI != EPI_GENERIC) {
       // ---------- TMA-store epilogue: bias (+GELU) -> bf16 -> swizzled smem -> cp.async.bulk.tensor store ----------
       static_assert(C::CB == 32, "TMA-store epilogue needs 32-column blocks");
       const FFConvGemm& p = a.p;
@@ -738,6 +812,10 @@ int launch_bn(int epi, const Maps& m, const Args& a, cudaStream_t st) {
     if (epi == EPI_STORE) return launch_tc<BN, EPI_STORE>(m, a, st);
     if (epi == EPI_STORE_GELU) return launch_tc<BN, EPI_STORE_GELU>(m, a, st);
     if (epi == EPI_RES) return launch_tc<BN, EPI_RES>(m, a, st);
+    if (epi == EPI_RES_AUX) return launch_tc<BN, EPI_RES_AUX>(m, a, st);
+    if constexpr (BN % 64 == 0) {
+      if (epi == EPI_STORE_GATE) return launch_tc<BN, EPI_STORE_GATE>(m, a, st);
+    }
   }
   return launch_tc<BN, EPI_GENERIC>(m, a, st);
 }
@@ -853,16 +931,34 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   };
   const bool al16 = (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && (!p.col_scale || (reinterpret_cast<uintptr_t>(p.col_scale) & 15) == 0);
   const bool bf16_ok = !p.out_bf16 || (p.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0);
-  const bool plain = !p.mul && !p.aux && !p.post_act && !p.pixel_shuffle && !p.gate_pairs && p.n_store % 8 == 0 && al16 && bf16_ok && BN >= 32;
+  const bool base_ok = !p.mul && !p.post_act && !p.pixel_shuffle && p.n_store % 8 == 0 && al16 && bf16_ok && BN >= 32;
+  const bool plain = base_ok && !p.aux && !p.gate_pairs;
+  auto map_n = [&](CUtensorMap* tm, void* ptr, int ld, int esz, CUtensorMapDataType dt, CUtensorMapSwizzle sw, int ncols) {
+    cuuint64_t dims[4] = {(cuuint64_t)ncols, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)p.B};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)ld * esz * a.Wo, (cuuint64_t)ld * esz * a.Wo * a.Ho};
+    cuuint32_t box[4] = {32, (cuuint32_t)TILE_W, 2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(tm, dt, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  const bool res_ok = p.res && p.res_is_f32 && p.out_f32 && p.act == FF_ACT_NONE && p.res_ld % 4 == 0 && p.out_f32_ld % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.res) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0;
   if (plain && p.out_bf16 && !p.out_f32 && !p.res && !p.col_scale && p.alpha == 1.0f && (p.act == FF_ACT_NONE || p.act == FF_ACT_GELU)) {
     if (out_map(&m.O, p.out_bf16, p.out_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B))
       epi = (p.act == FF_ACT_GELU) ? EPI_STORE_GELU : EPI_STORE;
-  } else if (plain && p.res && p.res_is_f32 && p.out_f32 && p.act == FF_ACT_NONE && p.res_ld % 4 == 0 && p.out_f32_ld % 4 == 0 &&
-             (reinterpret_cast<uintptr_t>(p.res) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) {
+  } else if (base_ok && p.gate_pairs && BN % 64 == 0 && p.n_store % 64 == 0 && p.bias && !p.aux && !p.res && !p.out_f32 && !p.col_scale && p.alpha == 1.0f && p.act == FF_ACT_NONE) {
+    if (map_n(&m.O, p.out_bf16, p.out_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, p.n_store / 2)) epi = EPI_STORE_GATE;
+  } else if (plain && res_ok) {
     bool ok = out_map(&m.R, const_cast<void*>(p.res), p.res_ld, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B) &&
               out_map(&m.O32, p.out_f32, p.out_f32_ld, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (ok && p.out_bf16) ok = out_map(&m.O, p.out_bf16, p.out_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
     if (ok) epi = EPI_RES;
+  } else if (base_ok && res_ok && p.aux && !p.gate_pairs && !p.out_bf16 && p.aux_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0 &&
+             (!p.aux_chan || (p.aux_chan_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(p.aux_chan) & 15) == 0))) {
+    bool ok = out_map(&m.R, const_cast<void*>(p.res), p.res_ld, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B) &&
+              out_map(&m.O32, p.out_f32, p.out_f32_ld, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B) &&
+              out_map(&m.O, const_cast<void*>(p.aux), p.aux_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (ok) epi = EPI_RES_AUX;
   }
   ++g_ff_launches;
   switch (BN) {
