@@ -35,41 +35,65 @@ __global__ void __launch_bounds__(256) dat_aim_kernel(const __grid_constant__ Ai
   for (int i = threadIdx.x; i < a.hid * CP; i += 256) sW1[i] = a.w1[i];
   if (threadIdx.x < a.hid) { sB1[threadIdx.x] = a.b1[threadIdx.x]; sW2[threadIdx.x] = a.w2[threadIdx.x]; }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * 8;
-  for (long long p = warp0; p < a.M; p += nwarps) {
-    float av[6], cv[6];
+  // 8 lanes per pixel (4 pixels per warp): each lane owns 24 channels as 3 x 16-byte vectors (c = 64*i + 8*sub), so the
+  // hidden-unit reductions need 3 shuffles instead of 5 and every global access is a 16-byte vector.
+  const int lane = threadIdx.x & 31, sub = lane & 7;
+  const long long base0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;     // warp-uniform; M % 4 == 0 (checked on the host)
+  const long long stride = (long long)gridDim.x * 32;
+  for (long long base = base0; base < a.M; base += stride) {
+    const long long p = base + (lane >> 3);
+    float av[24], cv[24];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int c = i * 64 + lane * 2;
-      const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(a.att + p * a.att_ld + c);
-      const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(a.conv + p * a.conv_ld + c);
-      av[2 * i] = __low2float(x); av[2 * i + 1] = __high2float(x);
-      cv[2 * i] = __low2float(y); cv[2 * i + 1] = __high2float(y);
+      const int c = i * 64 + sub * 8;
+      const uint4 x = *reinterpret_cast<const uint4*>(a.att + p * a.att_ld + c);
+      const uint4 y = *reinterpret_cast<const uint4*>(a.conv + p * a.conv_ld + c);
+      const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        av[i * 8 + 2 * j] = __uint_as_float(xw[j] << 16); av[i * 8 + 2 * j + 1] = __uint_as_float(xw[j] & 0xffff0000u);
+        cv[i * 8 + 2 * j] = __uint_as_float(yw[j] << 16); cv[i * 8 + 2 * j + 1] = __uint_as_float(yw[j] & 0xffff0000u);
+      }
     }
-    const float* src = a.mode == 0 ? av : cv;
     float s = a.b2;
     for (int h = 0; h < a.hid; ++h) {
       float d = 0.f;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const int c = i * 64 + lane * 2;
-        d += src[2 * i] * sW1[h * CP + c] + src[2 * i + 1] * sW1[h * CP + c + 1];
+        const float4* w4 = reinterpret_cast<const float4*>(sW1 + h * CP + i * 64 + sub * 8);
+        const float4 w0 = w4[0], w1 = w4[1];
+        const float* src = (a.mode == 0 ? av : cv) + i * 8;
+        d += src[0] * w0.x + src[1] * w0.y + src[2] * w0.z + src[3] * w0.w + src[4] * w1.x + src[5] * w1.y + src[6] * w1.z + src[7] * w1.w;
       }
-      d = warp_sum(d) + sB1[h];
-      s += gelu_erf(d) * sW2[h];
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      s += gelu_erf(d + sB1[h]) * sW2[h];
     }
     const float sg = sigmoidf_(s);
     const int b = (int)(p / a.pixels_per_sample);
+    {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int c = i * 64 + lane * 2;
-      const float c0 = sigmoidf_(a.cmap[(long long)b * a.cmap_ld + c]), c1 = sigmoidf_(a.cmap[(long long)b * a.cmap_ld + c + 1]);
-      float o0, o1;
-      if (a.mode == 0) { o0 = av[2 * i] * c0 + sg * cv[2 * i]; o1 = av[2 * i + 1] * c1 + sg * cv[2 * i + 1]; }
-      else { o0 = av[2 * i] * sg + cv[2 * i] * c0; o1 = av[2 * i + 1] * sg + cv[2 * i + 1] * c1; }
-      *reinterpret_cast<__nv_bfloat162*>(a.out + p * a.out_ld + c) = __floats2bfloat162_rn(o0, o1);
+      for (int i = 0; i < 3; ++i) {
+        const int c = i * 64 + sub * 8;
+        const float4 m0 = *reinterpret_cast<const float4*>(a.cmap + (long long)b * a.cmap_ld + c);
+        const float4 m1 = *reinterpret_cast<const float4*>(a.cmap + (long long)b * a.cmap_ld + c + 4);
+        const float cm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float r[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float cg = sigmoidf_(cm[2 * j + e]);
+            const float xa = av[i * 8 + 2 * j + e], xc = cv[i * 8 + 2 * j + e];
+            r[e] = a.mode == 0 ? xa * cg + sg * xc : xa * sg + xc * cg;
+          }
+          __nv_bfloat162 hh = __floats2bfloat162_rn(r[0], r[1]);
+          o[j] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        *reinterpret_cast<uint4*>(a.out + p * a.out_ld + c) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 }
@@ -160,8 +184,9 @@ extern "C" int ff_dat_aim(const void* att, int att_ld, const void* conv, int con
                           int pixels_per_sample, void* out, int out_ld, void* stream) {
   FF_CHECK_ARG(att && conv && cmap && w1 && b1 && w2 && out, "ff_dat_aim: null buffer");
   FF_CHECK_ARG(hid > 0 && hid <= HID_MAX, "ff_dat_aim: hid=%d > %d", hid, HID_MAX);
+  FF_CHECK_ARG(M % 4 == 0 && att_ld % 8 == 0 && conv_ld % 8 == 0 && out_ld % 8 == 0 && cmap_ld % 4 == 0, "ff_dat_aim: M %% 4 and 16-byte rows required");
   AimArgs a{reinterpret_cast<const bf16*>(att), att_ld, reinterpret_cast<const bf16*>(conv), conv_ld, cmap, cmap_ld, w1, b1, w2, b2, hid, mode, M, pixels_per_sample, reinterpret_cast<bf16*>(out), out_ld};
-  int grid = ff_cdiv(M, 8);
+  int grid = ff_cdiv(M, 32);
   const int cap = ff_num_sms() * 16;
   if (grid > cap) grid = cap;
   dat_aim_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
@@ -175,7 +200,7 @@ extern "C" int ff_dat_channel_attention_weights(const void* qkv, int ld, int q_o
                                                 void* stream) {
   FF_CHECK_ARG(qkv && temperature && wout && scratch, "ff_dat_channel_attention_weights: null buffer");
   FF_CHECK_ARG(heads * 32 == CP && hd <= 32, "ff_dat_channel_attention_weights: expects 6 heads padded to 32 dims");
-  int chunk = 2048;
+  int chunk = 512;
   int nchunks = ff_cdiv(N, chunk);
   FF_CHECK_ARG(scratch_bytes >= (size_t)B * heads * nchunks * GRAM_STRIDE * sizeof(float), "ff_dat_channel_attention_weights: scratch too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

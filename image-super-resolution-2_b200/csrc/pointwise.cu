@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const __grid_constant__ DwA
 // 3x3 specialisation: one thread = 8 channels x 4 consecutive output pixels of one row; the 3x6 input patch and the 9 weight
 // vectors are loaded once (18 + 18 vector loads for 4 outputs instead of 36 + 72).
 template <int MODE>
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const __grid_constant__ DwArgs a) {
+__global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const __grid_constant__ DwArgs a) {
   const int cout = MODE == 1 ? a.C / 2 : a.C;
   const int groups = cout >> 3;
   const int wq = a.W >> 2;
@@ -335,6 +335,7 @@ struct DirectArgs {
   const float* mul_f32; int mul_ld;   // optional multiply by an fp32 NHWC tensor (same pixel, channel n) after act
   bf16* out_bf16; int out_ld;
   float* out_f32; int out_f32_ld;
+  int vec_bf16, vec_f32;   // 16-byte aligned rows: vector stores allowed
 };
 
 __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant__ DirectArgs a) {
@@ -342,8 +343,10 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant_
   const int pad = a.k >> 1;
   const int PW = 16 + 2 * pad, PH = 8 + 2 * pad;
   const int cs = a.Cin | 1;  // odd pitch -> conflict-free
+  const int KK = a.k * a.k * a.Cin;
+  const bool all_w = gridDim.y == 1;          // small Cin: every output-channel group's weights are staged once
   float* sIn = sm;                       // [PH*PW][cs]
-  float* sW = sm + PH * PW * cs;         // [k*k*Cin][8]
+  float* sW = sm + PH * PW * cs;         // [groups][KK][8]
   const int tiles_x = a.W / 16, tiles_y = a.H / 8;
   int t = blockIdx.x;
   const int b = t / (tiles_x * tiles_y);
@@ -361,45 +364,57 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant_
     }
     sIn[pp * cs + c] = v;
   }
-  const int KK = a.k * a.k * a.Cin;
+  const int g_begin = all_w ? 0 : blockIdx.y, g_end = all_w ? a.Cout_pad / 8 : blockIdx.y + 1;
+  for (int i = threadIdx.x; i < (g_end - g_begin) * KK * 8; i += 128) {
+    const int o = i & 7, kk = (i >> 3) % KK, g = (i >> 3) / KK;
+    sW[(g * KK + kk) * 8 + o] = __ldg(a.w + (long long)((g_begin + g) * 8 + o) * KK + kk);
+  }
+  __syncthreads();
   const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
   const long long opix = (long long)(b * a.H + ty * 8 + py) * a.W + tx * 16 + px;
-  // grid.y == 1: this block walks all output-channel groups (input patch staged once); else one group per block
-  const int g_begin = gridDim.y == 1 ? 0 : blockIdx.y, g_end = gridDim.y == 1 ? a.Cout_pad / 8 : blockIdx.y + 1;
   for (int grp = g_begin; grp < g_end; ++grp) {
-  const int n0 = grp * 8;
-  __syncthreads();
-  for (int i = threadIdx.x; i < KK * 8; i += 128) {
-    const int o = i & 7, kk = i >> 3;
-    sW[kk * 8 + o] = __ldg(a.w + (long long)(n0 + o) * KK + kk);
-  }
-  __syncthreads();
-  float acc[8];
+    const int n0 = grp * 8;
+    if (n0 >= a.n_store) break;
+    const float* wg = sW + (long long)(grp - g_begin) * KK * 8;
+    float acc[8];
 #pragma unroll
-  for (int o = 0; o < 8; ++o) acc[o] = a.bias ? __ldg(a.bias + n0 + o) : 0.f;
-  for (int dy = 0; dy < a.k; ++dy)
-    for (int dx = 0; dx < a.k; ++dx) {
-      const float* ip = sIn + ((py + dy) * PW + px + dx) * cs;
-      const float* wp = sW + (dy * a.k + dx) * a.Cin * 8;
-      for (int c = 0; c < a.Cin; ++c) {
-        const float xv = ip[c];
-        const float4 w0 = *reinterpret_cast<const float4*>(wp + c * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(wp + c * 8 + 4);
-        acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
-        acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+    for (int o = 0; o < 8; ++o) acc[o] = a.bias ? __ldg(a.bias + n0 + o) : 0.f;
+    for (int dy = 0; dy < a.k; ++dy)
+      for (int dx = 0; dx < a.k; ++dx) {
+        const float* ip = sIn + ((py + dy) * PW + px + dx) * cs;
+        const float* wp = wg + (dy * a.k + dx) * a.Cin * 8;
+        for (int c = 0; c < a.Cin; ++c) {
+          const float xv = ip[c];
+          const float4 w0 = *reinterpret_cast<const float4*>(wp + c * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + c * 8 + 4);
+          acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
+          acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+        }
       }
-    }
 #pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    const int n = n0 + o;
-    if (n < a.n_store) {
-      float v = act_apply(acc[o], a.act);
-      if (a.mul_f32) v *= a.mul_f32[opix * a.mul_ld + n];
-      if (a.out_f32) a.out_f32[opix * a.out_f32_ld + n] = v;
-      if (a.out_bf16) a.out_bf16[opix * a.out_ld + n] = __float2bfloat16_rn(v);
+    for (int o = 0; o < 8; ++o) acc[o] = act_apply(acc[o], a.act);
+    if (a.mul_f32) {
+      for (int o = 0; o < 8; ++o)
+        if (n0 + o < a.n_store) acc[o] *= a.mul_f32[opix * a.mul_ld + n0 + o];
+    }
+    const bool full = n0 + 8 <= a.n_store;
+    if (a.out_bf16) {
+      bf16* q = a.out_bf16 + opix * a.out_ld + n0;
+      if (full && a.vec_bf16) *reinterpret_cast<uint4*>(q) = pack8(acc);
+      else
+        for (int o = 0; o < 8; ++o)
+          if (n0 + o < a.n_store) q[o] = __float2bfloat16_rn(acc[o]);
+    }
+    if (a.out_f32) {
+      float* q = a.out_f32 + opix * a.out_f32_ld + n0;
+      if (full && a.vec_f32) {
+        reinterpret_cast<float4*>(q)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        reinterpret_cast<float4*>(q)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      } else
+        for (int o = 0; o < 8; ++o)
+          if (n0 + o < a.n_store) q[o] = acc[o];
     }
   }
-  }  // output-channel groups
 }
 
 // NCHW fp32 image -> NHWC fp32 [pixels][ld] with per-channel offset subtraction (x - mean)
@@ -520,17 +535,21 @@ extern "C" int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int
   FF_CHECK_ARG((k == 1 || k == 3) && Cin > 0 && Cin <= 192, "ff_conv_direct: k=%d Cin=%d unsupported", k, Cin);
   FF_CHECK_ARG(H % 8 == 0 && W % 16 == 0, "ff_conv_direct: %dx%d must be a multiple of 8x16", H, W);
   FF_CHECK_ARG(Cout_pad % 8 == 0 && n_store <= Cout_pad, "ff_conv_direct: Cout_pad must be a multiple of 8");
-  DirectArgs a{x, x_is_bf16, x_ld, B, H, W, Cin, k, w, bias, Cout_pad, n_store, act, mul_f32, mul_ld, reinterpret_cast<bf16*>(out_bf16), out_ld, out_f32, out_f32_ld};
+  const int vb = (out_bf16 && out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0) ? 1 : 0;
+  const int vf = (out_f32 && out_f32_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) ? 1 : 0;
+  DirectArgs a{x, x_is_bf16, x_ld, B, H, W, Cin, k, w, bias, Cout_pad, n_store, act, mul_f32, mul_ld, reinterpret_cast<bf16*>(out_bf16), out_ld, out_f32, out_f32_ld, vb, vf};
   const int pad = k / 2;
-  const size_t smem = ((size_t)(16 + 2 * pad) * (8 + 2 * pad) * (Cin | 1) + (size_t)k * k * Cin * 8) * sizeof(float);
+  // small input-channel counts: one block computes every output-channel group (input patch and all weights staged once)
+  const bool all_w = Cin <= 16 && (size_t)k * k * Cin * Cout_pad * sizeof(float) <= 96 * 1024;
+  const int wgroups = all_w ? Cout_pad / 8 : 1;
+  const size_t smem = ((size_t)(16 + 2 * pad) * (8 + 2 * pad) * (Cin | 1) + (size_t)k * k * Cin * 8 * wgroups) * sizeof(float);
   static size_t configured = 48 * 1024;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ff_set_error("ff_conv_direct: smem %zu: %s", smem, cudaGetErrorString(e)); return FF_ERR_CUDA; }
     configured = smem;
   }
-  // small input-channel counts: one block computes every output-channel group (the input patch is staged once)
-  dim3 grid(B * (H / 8) * (W / 16), (Cin <= 16) ? 1 : Cout_pad / 8);
+  dim3 grid(B * (H / 8) * (W / 16), all_w ? 1 : Cout_pad / 8);
   conv_direct_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_conv_direct");

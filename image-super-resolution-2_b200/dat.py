@@ -148,7 +148,7 @@ class DATRunner:
         gapv = ws.get("gap", B, CP, F32)
         ci_h = ws.get("ci_h", B, 24, F32)
         cmap = ws.get("cmap", B, CP, F32)
-        scratch = ws.get("scratch", 1, max(B * 64 * CP, B * HEADS * ((N + 2047) // 2048) * 1088), F32)
+        scratch = ws.get("scratch", 1, max(B * 64 * CP, B * HEADS * ((N + 511) // 512) * 1088), F32)
         wb = ws.get("chan_w", B * CP, CP, BF16)   # block-diagonal channel-attention weights (off-diagonal stays zero)
 
         ops.nchw_to_nhwc(x, img, sub=self.mean)

@@ -175,7 +175,7 @@ int ff_dat_aim(const void* att, int att_ld, const void* conv, int conv_ld, const
 /* Channel attention weights of AdaptiveChannelAttention (dat_arch.py:632-646): per (sample, head)
  * softmax_j( <q_i,k_j> / (max(|q_i|,1e-12) max(|k_j|,1e-12)) * temperature[h] ) with the contraction over all N tokens,
  * emitted as a block-diagonal bf16 [B*192][192] matrix so `attn @ v` runs through ff_conv_gemm (w_batch_rows=192).
- * scratch >= B*heads*ceil(N/2048)*1088 floats. */
+ * scratch >= B*heads*ceil(N/512)*1088 floats. */
 int ff_dat_channel_attention_weights(const void* qkv, int ld, int q_off, int k_off, int B, int N, int heads, int hd,
                                      const float* temperature, void* wout, float* scratch, size_t scratch_bytes, void* stream);
 
