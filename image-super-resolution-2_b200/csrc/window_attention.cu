@@ -61,8 +61,9 @@ __device__ __forceinline__ void tile_pos(int kc, int n, int& ki, int& kj0) {
   else { const int tg = (kc >> 3) + n; ki = tg / (KW / 8); kj0 = (tg - ki * (KW / 8)) * 8; }
 }
 
-template <int KW, bool WRAP>
-__global__ void __launch_bounds__(NTHREADS, 2) window_attention_kernel(const __grid_constant__ FFWinAttn p) {
+// SGN = rel_sign (compile time so key offsets become LDS immediates); SGN < 0 (HAT OCAB) also enables the negative-index wrap
+template <int KW, int SGN>
+__global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_kernel(const __grid_constant__ FFWinAttn p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int NK = p.kh * KW;
   bf16* sQ = reinterpret_cast<bf16*>(smem);
@@ -118,7 +119,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_kernel(const __g
   }
   __syncthreads();
 
-  const int sgn = p.rel_sign;
+  constexpr int sgn = SGN;
+  constexpr bool WRAP = SGN < 0;
   const int rowmul = sgn * p.rel_stride;
   const int tq = 2 * (lane & 3);
   bf16* outp = reinterpret_cast<bf16*>(p.out);
@@ -263,11 +265,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_kernel(const __g
   }
 }
 
-template <int KW, bool WRAP>
+template <int KW, int SGN>
 int launch(const FFWinAttn& p, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_kernel<KW, WRAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(window_attention_kernel<KW, SGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       ff_set_error("ff_window_attention: smem %zu: %s", smem, cudaGetErrorString(e));
       return FF_ERR_CUDA;
@@ -275,7 +277,7 @@ int launch(const FFWinAttn& p, size_t smem, cudaStream_t st) {
     configured = smem;
   }
   dim3 grid(p.B * (p.H / p.wh) * (p.W / p.ww), p.heads);
-  window_attention_kernel<KW, WRAP><<<grid, NTHREADS, smem, st>>>(p);
+  window_attention_kernel<KW, SGN><<<grid, NTHREADS, smem, st>>>(p);
   FF_CHECK_LAUNCH("ff_window_attention");
   return FF_OK;
 }
@@ -305,9 +307,9 @@ extern "C" int ff_window_attention(const FFWinAttn* pp, void* stream) {
   ++g_ff_launches;
   const bool wrap = p.rel_sign < 0;      // HAT's overlapping-window table is indexed with negative offsets
   switch (p.kw) {
-    case 8: return wrap ? launch<8, true>(p, smem, st) : launch<8, false>(p, smem, st);
-    case 16: return wrap ? launch<16, true>(p, smem, st) : launch<16, false>(p, smem, st);
-    case 24: return wrap ? launch<24, true>(p, smem, st) : launch<24, false>(p, smem, st);
-    default: return wrap ? launch<32, true>(p, smem, st) : launch<32, false>(p, smem, st);
+    case 8: return wrap ? launch<8, -1>(p, smem, st) : launch<8, 1>(p, smem, st);
+    case 16: return wrap ? launch<16, -1>(p, smem, st) : launch<16, 1>(p, smem, st);
+    case 24: return wrap ? launch<24, -1>(p, smem, st) : launch<24, 1>(p, smem, st);
+    default: return wrap ? launch<32, -1>(p, smem, st) : launch<32, 1>(p, smem, st);
   }
 }

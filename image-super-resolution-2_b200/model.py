@@ -125,9 +125,29 @@ class FreqFusionB200:
         r = self.runners()
         B, _, h, w = lr.shape
         stack = self._stack(B, h, w)
+        if os.environ.get("FFB200_EXPERT_STREAMS", "1") == "0":
+            r["hat"].forward(lr, stack, 0)
+            r["dat"].forward(lr, stack, 3)
+            r["nafnet"].forward(lr, stack, 6)
+            return stack
+        # the experts are independent (disjoint workspaces, disjoint channels of `stack`): run them on three streams so the
+        # small / low-occupancy kernels of one expert fill the gaps of the others
+        if not hasattr(self, "_streams"):
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        cur = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        done = []
+        for s, (name, off) in zip(self._streams, (("dat", 3), ("nafnet", 6))):
+            s.wait_event(ev)
+            with torch.cuda.stream(s):
+                r[name].forward(lr, stack, off)
+                e = torch.cuda.Event()
+                e.record(s)
+                done.append(e)
         r["hat"].forward(lr, stack, 0)
-        r["dat"].forward(lr, stack, 3)
-        r["nafnet"].forward(lr, stack, 6)
+        for e in done:
+            cur.wait_event(e)
         return stack
 
     @torch.no_grad()
