@@ -18,7 +18,9 @@
 namespace {
 
 constexpr int HD = 32;       // padded head dim
-constexpr int ROWP = 40;     // smem row pitch (bf16) -> conflict-free ldmatrix
+constexpr int ROWP = 32;     // dense 64-byte rows; the 16-byte chunk index is XOR-swizzled with (row>>1)&3 -> conflict-free ldmatrix
+// element offset of 16-byte chunk `chunk` (0..3) of row `row`
+__device__ __forceinline__ int swz(int row, int chunk) { return row * ROWP + ((chunk ^ ((row >> 1) & 3)) << 3); }
 constexpr int NQ = 256;
 constexpr int KCHUNK = 64;
 constexpr int NTHREADS = 256;
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
     int y = wy * p.wh + i + p.shift_y; if (y >= p.H) y -= p.H;
     int x = wx * p.ww + j + p.shift_x; if (x >= p.W) x -= p.W;
     const bf16* src = base + (img0 + (long long)y * p.W + x) * p.ld + p.q_off + head * HD + part * 8;
-    *reinterpret_cast<uint4*>(sQ + t * ROWP + part * 8) = __ldg(reinterpret_cast<const uint4*>(src));
+    *reinterpret_cast<uint4*>(sQ + swz(t, part)) = __ldg(reinterpret_cast<const uint4*>(src));
   }
   // ---- gather K, V ----
   for (int idx = tid; idx < NK * 4; idx += NTHREADS) {
@@ -108,8 +110,8 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
       kq = __ldg(reinterpret_cast<const uint4*>(src + p.k_off));
       vq = __ldg(reinterpret_cast<const uint4*>(src + p.v_off));
     }
-    *reinterpret_cast<uint4*>(sK + t * ROWP + part * 8) = kq;
-    *reinterpret_cast<uint4*>(sV + t * ROWP + part * 8) = vq;
+    *reinterpret_cast<uint4*>(sK + swz(t, part)) = kq;
+    *reinterpret_cast<uint4*>(sV + swz(t, part)) = vq;
     if (part == 0 && need_mask)
       sKr[t] = inside ? (uint8_t)(region3(ys, p.H, p.wh, p.shift_y) * 3 + region3(xs, p.W, p.ww, p.shift_x)) : 0;
   }
@@ -131,9 +133,8 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
     uint32_t qa[2][4];
     {
       const int row = q0 + (lane & 15);
-      const int kofs = (lane >> 4) * 8;
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[ks], smem_u32(sQ + row * ROWP + ks * 16 + kofs));
+      for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[ks], smem_u32(sQ + swz(row, ks * 2 + (lane >> 4))));
     }
     const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
     const int qi0 = r0 / p.ww, qj0 = r0 - qi0 * p.ww, qi1 = r1 / p.ww, qj1 = r1 - qi1 * p.ww;
@@ -167,8 +168,7 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
         for (int ks = 0; ks < 2; ++ks) {
           uint32_t kb[4];
           const int key = kc + np * 16 + (lane & 7) + ((lane >> 4) << 3);
-          const int dofs = ks * 16 + ((lane >> 3) & 1) * 8;
-          ldsm_x4(kb, smem_u32(sK + key * ROWP + dofs));
+          ldsm_x4(kb, smem_u32(sK + swz(key, ks * 2 + ((lane >> 3) & 1))));
           mma16816(s[2 * np], qa[ks], kb[0], kb[1]);
           mma16816(s[2 * np + 1], qa[ks], kb[2], kb[3]);
         }
@@ -234,8 +234,7 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
         for (int dp = 0; dp < 2; ++dp) {
           uint32_t vb[4];
           const int key = kc + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-          const int dofs = dp * 16 + (lane >> 4) * 8;
-          ldsm_x4_t(vb, smem_u32(sV + key * ROWP + dofs));
+          ldsm_x4_t(vb, smem_u32(sV + swz(key, dp * 2 + (lane >> 4))));
           mma16816(o[2 * dp], pa, vb[0], vb[1]);
           mma16816(o[2 * dp + 1], pa, vb[2], vb[3]);
         }
