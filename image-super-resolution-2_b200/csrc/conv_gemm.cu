@@ -65,6 +65,17 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(e, z));
 }
 
+// Hot GELU epilogue (fc1 / conv + GELU -> bf16): tanh form on the hardware tanh unit, 5 FP32 ops + 1 MUFU.
+// |gelu_tanh - gelu_erf| <= 4.8e-4 and tanh.approx adds <= 2.5e-4*|x|: both far below the bf16 rounding of the stored
+// activation (half ulp = 3.9e-3*|y|).  Measured effect on the HAT-L output: 3.4e-5 max-abs (tolerance 2e-2).
+__device__ __forceinline__ float gelu_tanh_hw(float x) {
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case FF_ACT_GELU: return gelu_fast(v);
@@ -542,7 +553,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float x0 = __uint_as_float(raw[c * 8 + 2 * i]) + bb[2 * i], x1 = __uint_as_float(raw[c * 8 + 2 * i + 1]) + bb[2 * i + 1];
-              if constexpr (EPI == EPI_STORE_GELU) { x0 = gelu_fast(x0); x1 = gelu_fast(x1); }
+              if constexpr (EPI == EPI_STORE_GELU) { x0 = gelu_tanh_hw(x0); x1 = gelu_tanh_hw(x1); }
               __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
               w[i] = *reinterpret_cast<uint32_t*>(&h);
             }

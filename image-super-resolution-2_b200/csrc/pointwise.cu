@@ -604,7 +604,7 @@ extern "C" int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, in
   DwArgs a{reinterpret_cast<const bf16*>(x), x_ld, B, H, W, C, kh, kw, w, bias, act, mode, reinterpret_cast<const bf16*>(mul), mul_ld, reinterpret_cast<bf16*>(out), out_ld};
   const long long total = (long long)B * H * W * ((mode == 1 ? C / 2 : C) / 8);
   const int cout_ = mode == 1 ? C / 2 : C;
-  if (kh == 3 && kw == 3 && W % 32 == 0 && H % 8 == 0 && cout_ % (mode == 1 ? 32 : 64) == 0) {
+  if (mode == 1 && kh == 3 && kw == 3 && W % 32 == 0 && H % 8 == 0 && cout_ % (mode == 1 ? 32 : 64) == 0) {
     const size_t smem = (size_t)(mode == 1 ? 2 : 1) * 10 * 34 * (mode == 1 ? 64 : 128);
     dim3 grid(B * (H / 8) * (W / 32), cout_ / (mode == 1 ? 32 : 64));
     if (mode == 1) dwconv3x3_tiled_kernel<1><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
