@@ -224,11 +224,20 @@ def main():
     ops.PROFILE = None
     os.environ.pop("FFB200_EXPERT_STREAMS", None)
     achieved = prof["algo_flops"] / (prof["ms"] / 1e3) / 1e12
+    traffic, traffic_note = None, "no ncu capture found under profiles/"
+    tpath = os.path.join(ROOT, "profiles", "r01_conv_gemm_traffic.json")
+    if os.path.exists(tpath) and B == 16 and S == 128:
+        tj = json.load(open(tpath))
+        traffic, traffic_note = tj["mean_dram_bytes_per_launch"], tj["source"]
     step_ms = ms_total / K
     roofline = {
         "kernel": "conv_gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear, all instances)",
         "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-        "peak_source": pk["src"] + " (bf16 cuBLAS, sustained)", "traffic": None,
+        "peak_source": pk["src"] + " (bf16 cuBLAS, sustained)", "traffic": traffic, "traffic_note": traffic_note,
+        "algorithmic_bytes_per_launch": prof["algo_bytes"] / max(prof["launches"], 1),
+        "hbm_view": {"achieved": prof["algo_bytes"] / (prof["ms"] / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                     "frac": prof["algo_bytes"] / (prof["ms"] / 1e3) / 1e9 / pk["hbm"],
+                     "note": "same launches, compulsory operand bytes / time: most K<=768 layers are HBM-bound, the 3x3 convs tensor/L2-bound"},
         "launches_per_step": prof["launches"], "avg_launch_us": prof["ms"] * 1e3 / max(prof["launches"], 1),
         "algorithmic_flops_per_step": prof["algo_flops"], "executed_flops_per_step": prof["exec_flops"],
         "share_of_step": prof["ms"] / step_ms,

@@ -18,12 +18,13 @@ class KernelProfile:
     """Optional per-launch CUDA-event timing of ff_conv_gemm (bench.py's roofline leg; off on the hot path)."""
 
     def __init__(self):
-        self.records = []   # (start_event, end_event, algorithmic_flops, executed_flops)
+        self.records = []   # (start_event, end_event, algorithmic_flops, executed_flops, algorithmic_bytes)
 
     def summary(self):
         torch.cuda.synchronize()
-        ms = sum(s.elapsed_time(e) for s, e, _, _ in self.records)
-        return dict(launches=len(self.records), ms=ms, algo_flops=sum(r[2] for r in self.records), exec_flops=sum(r[3] for r in self.records))
+        ms = sum(r[0].elapsed_time(r[1]) for r in self.records)
+        return dict(launches=len(self.records), ms=ms, algo_flops=sum(r[2] for r in self.records), exec_flops=sum(r[3] for r in self.records),
+                    algo_bytes=sum(r[4] for r in self.records))
 
 
 PROFILE = None   # set to a KernelProfile instance to record
@@ -84,7 +85,12 @@ def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_
         taps = {CONV_1X1: 1, CONV_3X3: 9, CONV_2X2S2: 4}[kind]
         Mo = B * H * W // (4 if kind == CONV_2X2S2 else 1)
         n_real, k_real = getattr(w, "ff_real", (p.n_pad, taps * cin))
-        PROFILE.records.append((e0, e1, 2.0 * Mo * n_real * k_real, 2.0 * Mo * p.n_pad * taps * cin))
+        # compulsory HBM bytes of this launch: A once (its real channels), weights, every epilogue operand / output at its dtype
+        cin_real = k_real // taps
+        width = n_real // (2 if gate_pairs else 1)
+        byts = B * H * W * cin_real * 2 + n_real * k_real * 2 + Mo * width * ((2 if out_bf16 is not None else 0) + (4 if out_f32 is not None else 0))
+        byts += Mo * width * ((4 if res.dtype == _F32 else 2) if res is not None else 0) + Mo * width * (2 if mul is not None else 0) + Mo * width * (2 if aux is not None else 0)
+        PROFILE.records.append((e0, e1, 2.0 * Mo * n_real * k_real, 2.0 * Mo * p.n_pad * taps * cin, float(byts)))
         return
     L.check(L.load().ff_conv_gemm(C.byref(p), _stream()), "ff_conv_gemm")
 
