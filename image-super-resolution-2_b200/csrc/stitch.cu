@@ -66,3 +66,55 @@ extern "C" int ff_stitch(const float* tiles, const int* ty, const int* tx, const
   FF_CHECK_LAUNCH("ff_stitch");
   return FF_OK;
 }
+
+// ----------------------------------------------------------------------------------------------
+// PSNR on the BT.601 luma channel with a border crop (reference src/utils/metrics.py:30-52, 76-126: rgb_to_y then
+// crop_border=4, MSE on [0,1] data).  Two-phase deterministic reduction: per-block partial sums of squared Y differences.
+// ----------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) sqdiff_y_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int crop,
+                                                      double* __restrict__ partial) {
+  __shared__ double red[256];
+  const int Hc = H - 2 * crop, Wc = W - 2 * crop;
+  const long long n = (long long)Hc * Wc;
+  const long long hw = (long long)H * W;
+  const float* pa = a + (long long)blockIdx.y * 3 * hw;
+  const float* pb = b + (long long)blockIdx.y * 3 * hw;
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int y = (int)(i / Wc) + crop, x = (int)(i % Wc) + crop;
+    const long long o = (long long)y * W + x;
+    const float ya = (65.481f * pa[o] + 128.553f * pa[hw + o] + 24.966f * pa[2 * hw + o] + 16.0f) / 255.0f;
+    const float yb = (65.481f * pb[o] + 128.553f * pb[hw + o] + 24.966f * pb[2 * hw + o] + 16.0f) / 255.0f;
+    const double d = (double)ya - (double)yb;
+    s += d * d;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(long long)blockIdx.y * gridDim.x + blockIdx.x] = red[0];
+}
+__global__ void psnr_final_kernel(const double* __restrict__ partial, int nblk, double n, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  double s = 0.0;
+  for (int i = 0; i < nblk; ++i) s += partial[(long long)b * nblk + i];
+  const double mse = s / n;
+  out[b] = mse <= 0.0 ? 100.0f : (float)(10.0 * log10(1.0 / mse));
+}
+}  // namespace
+
+extern "C" int ff_psnr_y(const float* a, const float* b, int B, int H, int W, int crop, float* out, double* scratch, size_t scratch_bytes,
+                         void* stream) {
+  FF_CHECK_ARG(a && b && out && scratch && H > 2 * crop && W > 2 * crop && crop >= 0, "ff_psnr_y: bad args");
+  const int nblk = 64;
+  FF_CHECK_ARG(scratch_bytes >= (size_t)B * nblk * sizeof(double), "ff_psnr_y: scratch too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  sqdiff_y_kernel<<<dim3(nblk, B), 256, 0, st>>>(a, b, H, W, crop, scratch);
+  psnr_final_kernel<<<B, 1, 0, st>>>(scratch, nblk, (double)(H - 2 * crop) * (W - 2 * crop), out);
+  g_ff_launches += 2;
+  FF_CHECK_LAUNCH("ff_psnr_y");
+  return FF_OK;
+}

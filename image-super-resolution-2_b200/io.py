@@ -85,10 +85,27 @@ def main(model_dir, input_path, output_path, device=None):
         input_imgs = sorted(glob.glob(os.path.join(input_path, "*.[jJ][pP]*[gG]")))
     print(f"[team29_FreqFusion/b200] Found {len(input_imgs)} images in {input_path}")
     os.makedirs(output_path, exist_ok=True)
-    for img_path in input_imgs:
-        lr_img = _load_image(img_path).to(device)
-        _, _, h, w = lr_img.shape
-        tile, ov = tiling.choose_tile(h, w)
-        u8 = tiled_forward(model, lr_img, tile_size=tile, overlap=ov, scale=4, return_u8=True)
-        Image.fromarray(u8.cpu().numpy()).save(os.path.join(output_path, os.path.basename(img_path)), format="PNG")
+    # Host I/O is overlapped with the GPU: the next image is decoded and the previous result is PNG-encoded on worker
+    # threads while the current image runs (test.py times the whole call, I/O included: reference test.py:46-53).
+    from concurrent.futures import ThreadPoolExecutor
+    workers = max(1, int(os.environ.get("FFB200_IO_THREADS", "4")))
+    pending = []
+
+    def _save(u8_host, path):
+        Image.fromarray(u8_host.numpy()).save(path, format="PNG")
+
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        nxt = pool.submit(_load_image, input_imgs[0]) if input_imgs else None
+        for i, img_path in enumerate(input_imgs):
+            lr_host = nxt.result()
+            nxt = pool.submit(_load_image, input_imgs[i + 1]) if i + 1 < len(input_imgs) else None
+            lr_img = lr_host.pin_memory().to(device, non_blocking=True)
+            _, _, h, w = lr_img.shape
+            tile, ov = tiling.choose_tile(h, w)
+            u8 = tiled_forward(model, lr_img, tile_size=tile, overlap=ov, scale=4, return_u8=True)
+            host = torch.empty(u8.shape, dtype=torch.uint8).pin_memory()
+            host.copy_(u8)                      # synchronous D2H: the result is complete before the encoder sees it
+            pending.append(pool.submit(_save, host, os.path.join(output_path, os.path.basename(img_path))))
+        for f in pending:
+            f.result()                          # every file is on disk before main() returns
     print(f"[team29_FreqFusion/b200] Done. {len(input_imgs)} images saved to {output_path}")

@@ -181,3 +181,14 @@ def nhwc_to_nchw(x, coff, C_, out):
     _req_cuda(x, out)
     B, _, H, W = out.shape
     L.check(L.load().ff_nhwc_to_nchw(_ptr(x), x.stride(-2), coff, B, C_, H, W, _ptr(out), _stream()), "ff_nhwc_to_nchw")
+
+
+def psnr_y(a, b, crop=4):
+    """PSNR on BT.601 Y, border crop (reference src/utils/metrics.py:76-126); a, b: fp32 NCHW [B,3,H,W] on the GPU -> fp32 [B]."""
+    _req_cuda(a, b)
+    B, _, H, W = a.shape
+    out = torch.empty(B, dtype=torch.float32, device=a.device)
+    scratch = torch.empty(B * 64, dtype=torch.float64, device=a.device)
+    L.check(L.load().ff_psnr_y(_ptr(a.contiguous()), _ptr(b.contiguous()), B, H, W, crop, _ptr(out), _ptr(scratch), C.c_size_t(scratch.numel() * 8), _stream()),
+            "ff_psnr_y")
+    return out

@@ -240,6 +240,10 @@ int ff_edge_final(const float* se, const float* gate, int gate_ld, int B, int H,
 int ff_stitch(const float* tiles, const int* ty, const int* tx, const float* wy, const float* wx, int ny, int nx, int ts, int H, int W,
               float* out, unsigned char* out_u8, void* stream);
 
+/* PSNR (dB) on the BT.601 Y channel with a `crop`-pixel border removed, per sample: a, b fp32 NCHW [B,3,H,W] in [0,1]
+ * (reference src/utils/metrics.py:30-52, 76-126).  out: fp32 [B]; scratch >= B*64 doubles.  Identical inputs give 100 dB. */
+int ff_psnr_y(const float* a, const float* b, int B, int H, int W, int crop, float* out, double* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

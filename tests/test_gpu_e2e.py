@@ -101,3 +101,14 @@ def test_io_main_plugin(tmp_path):
     assert diff.max() <= 5      # 2e-2 * 255
     with pytest.raises(Exception):
         main(model_dir=fusion, input_path=inp, output_path=outp, device=torch.device("cpu"))
+
+
+def test_psnr_y_kernel():
+    from isr2_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(2, 3, 96, 80, generator=g)
+    b = (a + 0.02 * torch.randn(2, 3, 96, 80, generator=g)).clamp(0, 1)
+    got = ops.psnr_y(a.cuda(), b.cuda()).cpu()
+    for i in range(2):
+        assert abs(got[i].item() - _psnr_y(a[i:i + 1], b[i:i + 1])) < 1e-3
+    assert ops.psnr_y(a.cuda(), a.cuda()).cpu()[0].item() == 100.0
