@@ -5,7 +5,8 @@
 //   -> + relative-position bias (table in smem, index affine in the key offset) + {0,-100} shift mask
 //   -> online softmax (fp32, exp2) -> O = P V -> normalise -> store at the un-shifted token position.
 // The logits never leave registers (the reference materialises [nW*B, heads, 256, 256|576] fp32 in HBM).
-// q is pre-scaled by head_dim^-0.5 * log2(e) through the packed qkv weights, so the softmax runs on exp2.
+// q is pre-scaled by head_dim^-0.5 * log2(e) through the packed qkv weights, so the softmax runs on exp2;
+// v carries 1.0 in padding dim 31 (bias of the packed projection) so the row sums come out of the P.V MMA.
 //
 // 8 warps per CTA, each owning 32 query rows (two passes of 16) -> <= 128 registers/thread and 2-3 resident CTAs
 // per SM, so the gather of one window overlaps the math of another.  The kernel is instruction-issue bound
@@ -49,6 +50,13 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ int region3(int p, int size, int win, int shift) {
   return p < size - win ? 0 : (p < size - shift ? 1 : 2);
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
     int y = wy * p.wh + i + p.shift_y; if (y >= p.H) y -= p.H;
     int x = wx * p.ww + j + p.shift_x; if (x >= p.W) x -= p.W;
     const bf16* src = base + (img0 + (long long)y * p.W + x) * p.ld + p.q_off + head * HD + part * 8;
-    *reinterpret_cast<uint4*>(sQ + swz(t, part)) = __ldg(reinterpret_cast<const uint4*>(src));
+    cp_async16(sQ + swz(t, part), src, 16);
   }
   // ---- gather K, V ----
   for (int idx = tid; idx < NK * 4; idx += NTHREADS) {
@@ -102,16 +110,16 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
     const int i = t / KW, j = t - i * KW;
     const int ys = wy * p.wh - p.kpad_y + i, xs = wx * p.ww - p.kpad_x + j;
     const bool inside = ys >= 0 && ys < p.H && xs >= 0 && xs < p.W;
-    uint4 kq = make_uint4(0, 0, 0, 0), vq = kq;
-    if (inside) {
-      int y = ys + p.shift_y; if (y >= p.H) y -= p.H;
-      int x = xs + p.shift_x; if (x >= p.W) x -= p.W;
-      const bf16* src = base + (img0 + (long long)y * p.W + x) * p.ld + head * HD + part * 8;
-      kq = __ldg(reinterpret_cast<const uint4*>(src + p.k_off));
-      vq = __ldg(reinterpret_cast<const uint4*>(src + p.v_off));
+    int y = ys + p.shift_y; if (y >= p.H) y -= p.H;
+    int x = xs + p.shift_x; if (x >= p.W) x -= p.W;
+    const bf16* src = inside ? base + (img0 + (long long)y * p.W + x) * p.ld + head * HD + part * 8 : base;
+    cp_async16(sK + swz(t, part), src + (inside ? p.k_off : 0), inside ? 16 : 0);
+    if (inside || part != 3) {
+      cp_async16(sV + swz(t, part), src + (inside ? p.v_off : 0), inside ? 16 : 0);
+    } else {
+      // zero-padded key (OCAB): V row is zero except the all-ones column (dim 31) that carries the softmax row sum
+      *reinterpret_cast<uint4*>(sV + swz(t, part)) = make_uint4(0, 0, 0, 0x3F800000u);
     }
-    *reinterpret_cast<uint4*>(sK + swz(t, part)) = kq;
-    *reinterpret_cast<uint4*>(sV + swz(t, part)) = vq;
     if (part == 0 && need_mask)
       sKr[t] = inside ? (uint8_t)(region3(ys, p.H, p.wh, p.shift_y) * 3 + region3(xs, p.W, p.ww, p.shift_x)) : 0;
   }
@@ -119,6 +127,7 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
     const float* tb = p.bias_table + (long long)(p.bias_head_off + blockIdx.y) * p.T;   // table is [heads][T]
     for (int i = tid; i < p.T; i += NTHREADS) sT[i] = LOG2E * __ldg(tb + i);
   }
+  cp_async_wait_all();
   __syncthreads();
 
   constexpr int sgn = SGN;
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
       qr1 = region3(wy * p.wh + qi1, p.H, p.wh, p.shift_y) * 3 + region3(wx * p.ww + qj1, p.W, p.ww, p.shift_x);
     }
 
-    float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
+    float m0 = -1e30f, m1 = -1e30f;
     float o[4][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n)
@@ -156,25 +165,8 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
 
 #pragma unroll 1
     for (int kc = 0; kc < NK; kc += KCHUNK) {
+      // accumulators start from the relative-position bias (x log2 e): S = bias + Q K^T comes out of the MMA directly
       float s[8][4];
-#pragma unroll
-      for (int n = 0; n < 8; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s[n][i] = 0.f;
-      // S = Q K^T : B fragments (k16 x n8) come from K rows [key][dim] (non-transposed ldmatrix)
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          uint32_t kb[4];
-          const int key = kc + np * 16 + (lane & 7) + ((lane >> 4) << 3);
-          ldsm_x4(kb, smem_u32(sK + swz(key, ks * 2 + ((lane >> 3) & 1))));
-          mma16816(s[2 * np], qa[ks], kb[0], kb[1]);
-          mma16816(s[2 * np + 1], qa[ks], kb[2], kb[3]);
-        }
-      }
-      // bias (+ mask), running max
-      float cm0 = -1e30f, cm1 = -1e30f;
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
         int ki, kj0;
@@ -187,10 +179,23 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
             i0 += (i0 >> 31) & p.T;
             i1 += (i1 >> 31) & p.T;
           }
-          s[n][e] += sT[i0];
-          s[n][2 + e] += sT[i1];
+          s[n][e] = sT[i0];
+          s[n][2 + e] = sT[i1];
         }
       }
+      // S += Q K^T : B fragments (k16 x n8) come from K rows [key][dim] (non-transposed ldmatrix)
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t kb[4];
+          const int key = kc + np * 16 + (lane & 7) + ((lane >> 4) << 3);
+          ldsm_x4(kb, smem_u32(sK + swz(key, ks * 2 + ((lane >> 3) & 1))));
+          mma16816(s[2 * np], qa[ks], kb[0], kb[1]);
+          mma16816(s[2 * np + 1], qa[ks], kb[2], kb[3]);
+        }
+      }
+      float cm0 = -1e30f, cm1 = -1e30f;
       if (need_mask) {
 #pragma unroll
         for (int n = 0; n < 8; ++n)
@@ -213,7 +218,6 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
       const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);
       const float sc0 = ex2(m0 - nm0), sc1 = ex2(m1 - nm1);
       m0 = nm0; m1 = nm1;
-      l0 *= sc0; l1 *= sc1;
 #pragma unroll
       for (int n = 0; n < 4; ++n) { o[n][0] *= sc0; o[n][1] *= sc0; o[n][2] *= sc1; o[n][3] *= sc1; }
       // P = exp2(S - m), row sums, O += P V
@@ -224,8 +228,6 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
         const float e02 = ex2(s[2 * kk][2] - m1), e03 = ex2(s[2 * kk][3] - m1);
         const float e10 = ex2(s[2 * kk + 1][0] - m0), e11 = ex2(s[2 * kk + 1][1] - m0);
         const float e12 = ex2(s[2 * kk + 1][2] - m1), e13 = ex2(s[2 * kk + 1][3] - m1);
-        l0 += (e00 + e01) + (e10 + e11);
-        l1 += (e02 + e03) + (e12 + e13);
         pa[0] = pack_bf16(e00, e01);
         pa[1] = pack_bf16(e02, e03);
         pa[2] = pack_bf16(e10, e11);
@@ -240,11 +242,10 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
         }
       }
     }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    // softmax denominators: V carries an all-ones column at dim 31 (bias of the packed v projection), so sum_k P[k]
+    // accumulates in O[:, 31] (lane quad member 3, second element of the last n8 tile) with the same bf16-rounded P
+    const float inv0 = 1.f / __shfl_sync(0xffffffffu, o[3][1], (lane & ~3) | 3);
+    const float inv1 = 1.f / __shfl_sync(0xffffffffu, o[3][3], (lane & ~3) | 3);
 
     // ---- store at the un-shifted token position ----
     {

@@ -12,7 +12,7 @@ import torch
 
 from . import lib as L
 from . import ops
-from .hat import CP, RGB_MEAN, Workspace, _qkv_rows
+from .hat import CP, RGB_MEAN, Workspace, _qkv_rows, pack_qkv_bias
 from .ops import ACT_CLAMP01, ACT_GELU, ACT_LRELU, ACT_NONE, CONV_3X3
 from .packing import (BF16, F32, fold_bn, head_pad_index, pack_conv, pack_conv_direct, pack_dw, pack_matrix,
                       pack_vector, pixel_shuffle_rows)
@@ -74,7 +74,7 @@ class DATRunner:
                 else:
                     d["temperature"] = g(a + "temperature").reshape(-1).to(dev).contiguous()
                 d["qkv_w"] = pack_matrix(wq, 3 * CP, CP, row_index=_qkv_rows(), device=dev)
-                d["qkv_b"] = pack_vector(bq, 3 * CP, index=_qkv_rows(), device=dev)
+                d["qkv_b"] = pack_qkv_bias(bq, dev)
                 d["proj_w"] = pack_matrix(g(a + "proj.weight"), CP, CP, col_index=hp, device=dev)
                 d["proj_b"] = pack_vector(g(a + "proj.bias"), CP, device=dev)
                 # depthwise conv branch on v: conv -> BN(eval) -> GELU, BN folded; head-padded channels

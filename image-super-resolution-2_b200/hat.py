@@ -45,6 +45,15 @@ def _qkv_rows():
     return (o // C) * CP + head_pad_index(o % C)
 
 
+def pack_qkv_bias(bq, device):
+    """qkv bias in the head-padded layout; padding dim 31 of every v head is set to 1.0 (its weight row is zero) so that
+    ff_window_attention gets the softmax row sums out of the P.V MMA (see csrc/window_attention.cu)."""
+    b = torch.zeros(3 * CP, dtype=F32)
+    b[_qkv_rows()] = bq.to(F32)
+    b[2 * CP + 31::32] = 1.0
+    return b.to(device).contiguous()
+
+
 class HATRunner:
     def __init__(self, sd, device="cuda", depths=12, blocks=6):
         self.device = device
@@ -66,7 +75,7 @@ class HATRunner:
             bq[:C] *= scale
             return dict(
                 qkv_w=pack_matrix(wq, 3 * CP, CP, row_index=_qkv_rows(), device=dev),
-                qkv_b=pack_vector(bq, 3 * CP, index=_qkv_rows(), device=dev),
+                qkv_b=pack_qkv_bias(bq, dev),
                 proj_w=pack_matrix(g(prefix + "proj.weight"), CP, CP, col_index=hp, device=dev),
                 proj_b=pack_vector(g(prefix + "proj.bias"), CP, device=dev),
                 table=g(prefix + "relative_position_bias_table").t().contiguous().to(dev),   # [heads][T]

@@ -91,7 +91,8 @@ int ff_conv_gemm(const FFConvGemm* p, void* stream);
  * copies of HAB.forward (hat_arch.py:279-303), OCAB's unfold + attention (hat_arch.py:398-435), and DAT's
  * SpatialAttention.forward (dat_arch.py:290-342) with the rolls of dat_arch.py:514-540.
  * Layout: qkv is bf16 [B*H*W][ld]; head h of q/k/v sits at channel {q,k,v}_off + (head_off+h)*32 (head dim 30
- * zero-padded to 32, q pre-scaled by head_dim^-0.5 * log2(e): the kernel's softmax uses exp2).  Query window wh x ww must hold 256 tokens.  Key window kh x kw starts
+ * zero-padded to 32, q pre-scaled by head_dim^-0.5 * log2(e): the kernel's softmax uses exp2; padding dim 31 of v must hold 1.0 --
+ * the softmax row sums are read from column 31 of P.V, so output channel 31 of every head comes out as 1.0 and dim 30 as 0).  Query window wh x ww must hold 256 tokens.  Key window kh x kw starts
  * kpad_{y,x} before the query window; keys outside the image are all-zero rows that still take softmax mass
  * (nn.Unfold zero padding, hat_arch.py:377).  Bias index for (query (qi,qj), key (ki,kj)) window coordinates:
  *   idx = (rel_sign*(qi-ki)+rel_off_y)*rel_stride + rel_sign*(qj-kj)+rel_off_x;  idx<0 -> idx+T  (HAT's OCA table
