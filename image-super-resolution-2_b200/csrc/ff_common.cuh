@@ -49,7 +49,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-form GELU; erf by Abramowitz-Stegun 7.1.28, erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |err| <= 3e-7 (fp32-grade for this
+// use), branch free: 6 FMA + 4 FMUL + one MUFU.RCP instead of the ~35-instruction branchy erff().
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  float p = fmaf(az, 0.0000430638f, 0.0002765672f);
+  p = fmaf(az, p, 0.0001520143f);
+  p = fmaf(az, p, 0.0092705272f);
+  p = fmaf(az, p, 0.0422820123f);
+  p = fmaf(az, p, 0.0705230784f);
+  p = fmaf(az, p, 1.0f);
+  p = p * p; p = p * p; p = p * p; p = p * p;
+  const float e = 1.0f - __fdividef(1.0f, p);
+  return 0.5f * x * (1.0f + copysignf(e, z));
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ bool elect_one() {

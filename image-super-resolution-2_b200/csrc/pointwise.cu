@@ -19,6 +19,15 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   }
 }
 
+// GELU on the hardware tanh unit for bf16-stored activations (see csrc/conv_gemm.cu: gelu_tanh_hw, |err| << bf16 rounding)
+__device__ __forceinline__ float gelu_tanh_hw(float x) {
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
 // ------------------------------------------------------------------------------------------
 // LayerNorm over the channel axis of [rows][ld]; one warp per row, values kept in registers.
 // Lanes own channel PAIRS (c = 2*lane + 64*i): 8-byte fp32 / 4-byte bf16 loads and 4-byte bf16x2 stores halve the
@@ -223,9 +232,18 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const __grid_constant__ DwA
 
 
 // 3x3 specialisation: one thread = 8 channels x 4 consecutive output pixels of one row; the 3x6 input patch and the 9 weight
-// vectors are loaded once (18 + 18 vector loads for 4 outputs instead of 36 + 72).
-template <int MODE>
-__global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const __grid_constant__ DwArgs a) {
+// vectors are loaded once (18 + 18 vector loads for 4 outputs instead of 36 + 72) and the MACs run as packed fp32x2 FMAs
+// (FFMA2, sm_100): 144 FFMA2 per thread instead of 288 FFMA -- the kernel is instruction-issue bound, not HBM bound.
+__device__ __forceinline__ void unpack8_f2(const uint4& q, float2 (&f)[4]) {
+  f[0] = make_float2(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u));
+  f[1] = make_float2(__uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+  f[2] = make_float2(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xffff0000u));
+  f[3] = make_float2(__uint_as_float(q.w << 16), __uint_as_float(q.w & 0xffff0000u));
+}
+
+// ACT: 0 none, 1 GELU (hardware tanh form), 2 runtime a.act
+template <int MODE, int ACT>
+__global__ void __launch_bounds__(128, MODE == 1 ? 2 : 3) dwconv3x3_kernel(const __grid_constant__ DwArgs a) {
   const int cout = MODE == 1 ? a.C / 2 : a.C;
   const int groups = cout >> 3;
   const int wq = a.W >> 2;
@@ -240,41 +258,59 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const __grid_constant
   const int x0 = xq * 4;
   const int c0 = g * 8;
   constexpr int NH = MODE == 1 ? 2 : 1;
-  float acc[NH][4][8];
+  float2 acc[NH][4][4];
 #pragma unroll
   for (int h = 0; h < NH; ++h) {
     const int cc = c0 + h * cout;
-    float bv[8];
+    float2 bv[4];
+    if (a.bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + cc)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + cc) + 1);
+      bv[0] = make_float2(b0.x, b0.y); bv[1] = make_float2(b0.z, b0.w); bv[2] = make_float2(b1.x, b1.y); bv[3] = make_float2(b1.z, b1.w);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) bv[i] = a.bias ? __ldg(a.bias + cc + i) : 0.f;
+      for (int i = 0; i < 4; ++i) bv[i] = make_float2(0.f, 0.f);
+    }
 #pragma unroll
     for (int px = 0; px < 4; ++px)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[h][px][i] = bv[i];
+      for (int i = 0; i < 4; ++i) acc[h][px][i] = bv[i];
+    // all 18 input vectors are requested before any math (branch-free clamped addresses; out-of-image taps are zeroed
+    // afterwards) so each warp keeps 18 x 512 B in flight -- this kernel lives or dies by memory-level parallelism
+    uint4 in[3][6];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = min(max(y + dy - 1, 0), a.H - 1);
+      const bf16* rowp = a.x + ((long long)(b * a.H + yy) * a.W) * a.x_ld + cc;
+#pragma unroll
+      for (int col = 0; col < 6; ++col) {
+        const int xx = min(max(x0 + col - 1, 0), a.W - 1);
+        in[dy][col] = __ldg(reinterpret_cast<const uint4*>(rowp + (long long)xx * a.x_ld));
+      }
+    }
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
       const int yy = y + dy - 1;
-      if (yy < 0 || yy >= a.H) continue;
-      float wv[3][8];
+      const bool yok = yy >= 0 && yy < a.H;
+      float2 wv[3][4];
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
         const float* wp = a.w + (long long)(dy * 3 + dx) * a.C + cc;
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp) + 1);
-        wv[dx][0] = w0.x; wv[dx][1] = w0.y; wv[dx][2] = w0.z; wv[dx][3] = w0.w; wv[dx][4] = w1.x; wv[dx][5] = w1.y; wv[dx][6] = w1.z; wv[dx][7] = w1.w;
+        wv[dx][0] = make_float2(w0.x, w0.y); wv[dx][1] = make_float2(w0.z, w0.w); wv[dx][2] = make_float2(w1.x, w1.y); wv[dx][3] = make_float2(w1.z, w1.w);
       }
-      const bf16* rowp = a.x + ((long long)(b * a.H + yy) * a.W) * a.x_ld + cc;
 #pragma unroll
       for (int col = 0; col < 6; ++col) {
         const int xx = x0 + col - 1;
-        if (xx < 0 || xx >= a.W) continue;
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(rowp + (long long)xx * a.x_ld)), f);
+        const bool ok = yok && xx >= 0 && xx < a.W;
+        const uint4 q = ok ? in[dy][col] : make_uint4(0, 0, 0, 0);
+        float2 f[4];
+        unpack8_f2(q, f);
 #pragma unroll
         for (int px = 0; px < 4; ++px) {
           const int dx = col - px;          // input column col contributes to output px with tap dx
           if (dx >= 0 && dx < 3) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[h][px][i] += f[i] * wv[dx][i];
+            for (int i = 0; i < 4; ++i) acc[h][px][i] = __ffma2_rn(f[i], wv[dx][i], acc[h][px][i]);
           }
         }
       }
@@ -286,10 +322,15 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const __grid_constant
     float o[8];
     if (MODE == 1) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = acc[0][px][i] * acc[NH - 1][px][i];
+      for (int i = 0; i < 4; ++i) { o[2 * i] = acc[0][px][i].x * acc[NH - 1][px][i].x; o[2 * i + 1] = acc[0][px][i].y * acc[NH - 1][px][i].y; }
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = act_apply(acc[0][px][i], a.act);
+      for (int i = 0; i < 4; ++i) {
+        float v0 = acc[0][px][i].x, v1 = acc[0][px][i].y;
+        if constexpr (ACT == 1) { v0 = gelu_tanh_hw(v0); v1 = gelu_tanh_hw(v1); }
+        else if constexpr (ACT == 2) { v0 = act_apply(v0, a.act); v1 = act_apply(v1, a.act); }
+        o[2 * i] = v0; o[2 * i + 1] = v1;
+      }
       if (a.mul) {
         float m[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(a.mul + pix * a.mul_ld + c0)), m);
@@ -300,7 +341,6 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const __grid_constant
     *reinterpret_cast<uint4*>(a.out + pix * a.out_ld + c0) = pack8(o);
   }
 }
-
 
 // Shared-memory tiled 3x3 depthwise conv: block = 8 x 32 output pixels x one channel block; the (8+2) x (32+2) halo tile is
 // staged once (coalesced 16-byte loads, zero fill outside the image), each thread keeps its 9 x CH weights in registers and walks
@@ -336,47 +376,53 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tiled_kernel(const __grid_co
       v = __ldg(reinterpret_cast<const uint4*>(a.x + ((long long)(b * a.H + yy) * a.W + xx) * a.x_ld + h * cout + cb * CW + k * 8));
     *reinterpret_cast<uint4*>(dsm + ((h * HH_ + hy) * HW_ + hx) * PIXB + k * 16) = v;
   }
-  // ---- per-thread weights / bias
+  // ---- per-thread weights / bias (as fp32 pairs for packed FFMA2)
   const int c = threadIdx.x & 7, x = threadIdx.x >> 3;     // channel chunk, column
-  float w[NH][9][CH], bv[NH][CH];
+  constexpr int CP2 = CH / 2;
+  float2 w[NH][9][CP2], bv[NH][CP2];
 #pragma unroll
   for (int h = 0; h < NH; ++h) {
     const int cc = h * cout + cb * CW + c * CH;
 #pragma unroll
     for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
-      for (int i = 0; i < CH; ++i) w[h][tp][i] = __ldg(a.w + (long long)tp * a.C + cc + i);
+      for (int i = 0; i < CP2; ++i) w[h][tp][i] = __ldg(reinterpret_cast<const float2*>(a.w + (long long)tp * a.C + cc) + i);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) bv[h][i] = a.bias ? __ldg(a.bias + cc + i) : 0.f;
+    for (int i = 0; i < CP2; ++i) bv[h][i] = a.bias ? __ldg(reinterpret_cast<const float2*>(a.bias + cc) + i) : make_float2(0.f, 0.f);
   }
   __syncthreads();
 #pragma unroll 1
   for (int y = 0; y < 8; ++y) {
-    float acc[NH][CH];
+    float2 acc2[NH][CP2];
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
 #pragma unroll
-      for (int i = 0; i < CH; ++i) acc[h][i] = bv[h][i];
+      for (int i = 0; i < CP2; ++i) acc2[h][i] = bv[h][i];
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           const uint8_t* sp = dsm + ((h * HH_ + y + dy) * HW_ + x + dx) * PIXB + c * (CH * 2);
-          float f[CH];
+          float2 f[CP2];
           if constexpr (CH == 8) {
             const uint4 q = *reinterpret_cast<const uint4*>(sp);
             const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(qq[i] << 16); f[2 * i + 1] = __uint_as_float(qq[i] & 0xffff0000u); }
+            for (int i = 0; i < 4; ++i) f[i] = make_float2(__uint_as_float(qq[i] << 16), __uint_as_float(qq[i] & 0xffff0000u));
           } else {
             const uint2 q = *reinterpret_cast<const uint2*>(sp);
-            f[0] = __uint_as_float(q.x << 16); f[1] = __uint_as_float(q.x & 0xffff0000u);
-            f[2] = __uint_as_float(q.y << 16); f[3] = __uint_as_float(q.y & 0xffff0000u);
+            f[0] = make_float2(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u));
+            f[1] = make_float2(__uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
           }
 #pragma unroll
-          for (int i = 0; i < CH; ++i) acc[h][i] = fmaf(f[i], w[h][dy * 3 + dx][i], acc[h][i]);
+          for (int i = 0; i < CP2; ++i) acc2[h][i] = __ffma2_rn(f[i], w[h][dy * 3 + dx][i], acc2[h][i]);
         }
     }
+    float acc[NH][CH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+      for (int i = 0; i < CP2; ++i) { acc[h][2 * i] = acc2[h][i].x; acc[h][2 * i + 1] = acc2[h][i].y; }
     const long long pix = (long long)(b * a.H + y0 + y) * a.W + x0 + x;
     if constexpr (MODE == 1) {
       __nv_bfloat162 lo = __floats2bfloat162_rn(acc[0][0] * acc[1][0], acc[0][1] * acc[1][1]);
@@ -610,8 +656,12 @@ extern "C" int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, in
     if (mode == 1) dwconv3x3_tiled_kernel<1><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     else dwconv3x3_tiled_kernel<0><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   } else if (kh == 3 && kw == 3 && W % 4 == 0) {
-    if (mode == 1) dwconv3x3_kernel<1><<<ff_cdiv(total / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
-    else dwconv3x3_kernel<0><<<ff_cdiv(total / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+    const int nb = ff_cdiv(total / 4, 128);
+    if (mode == 1) dwconv3x3_kernel<1, 0><<<nb, 128, 0, st_>>>(a);
+    else if (act == FF_ACT_NONE) dwconv3x3_kernel<0, 0><<<nb, 128, 0, st_>>>(a);
+    else if (act == FF_ACT_GELU) dwconv3x3_kernel<0, 1><<<nb, 128, 0, st_>>>(a);
+    else dwconv3x3_kernel<0, 2><<<nb, 128, 0, st_>>>(a);
   } else {
     dwconv_kernel<<<ff_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   }
