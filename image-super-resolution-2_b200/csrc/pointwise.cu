@@ -83,6 +83,51 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ 
   }
 }
 
+__device__ __forceinline__ uint4 ln_pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Narrow rows (C = 64 or 128, fp32 in, bf16 out, no padding): LPR lanes per row, each lane owns 8 contiguous channels
+// (two 16-byte loads, one 16-byte bf16 store), 32/LPR rows per warp, log2(LPR) shuffle steps.  NAFNet's high-resolution levels.
+template <int LPR>
+__global__ void __launch_bounds__(256) layernorm_narrow_kernel(const float* __restrict__ x, int in_ld, long long rows,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                              bf16* __restrict__ out, int out_ld) {
+  constexpr int C = LPR * 8;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const long long row = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool ok = row < rows;
+  const float* xr = x + (ok ? row : 0) * in_ld + sub * 8;
+  const float4 a = *reinterpret_cast<const float4*>(xr), b = *reinterpret_cast<const float4*>(xr + 4);
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.f / C) + eps);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + sub * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + sub * 8) + 1);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + sub * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + sub * 8) + 1);
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float o8[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o8[i] = v[i] * rstd * gg[i] + bb[i];
+  if (ok) *reinterpret_cast<uint4*>(out + row * out_ld + sub * 8) = ln_pack8(o8);
+}
+
 // ------------------------------------------------------------------------------------------
 // Global average pool over pixels: x [B][P][ld] -> partial sums [B][nsplit][C] -> mean [B][out_ld]
 // (two phases, fixed summation order => deterministic).
@@ -342,107 +387,6 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 2 : 3) dwconv3x3_kernel(const
   }
 }
 
-// Shared-memory tiled 3x3 depthwise conv: block = 8 x 32 output pixels x one channel block; the (8+2) x (32+2) halo tile is
-// staged once (coalesced 16-byte loads, zero fill outside the image), each thread keeps its 9 x CH weights in registers and walks
-// a column strip.  MODE 0: CH = 8 channels/thread, 64-channel blocks; MODE 1 (SimpleGate): CH = 4, 32 output channels per block
-// computed from the two matching 32-channel input slices.  Global traffic = 1.33 x the compulsory read + the write.
-template <int MODE>
-__global__ void __launch_bounds__(256, 2) dwconv3x3_tiled_kernel(const __grid_constant__ DwArgs a) {
-  constexpr int CH = MODE ? 4 : 8;
-  constexpr int NH = MODE ? 2 : 1;
-  constexpr int CW = 8 * CH;                 // channels per block per half
-  constexpr int PIXB = CW * 2;               // bytes per halo pixel per half
-  constexpr int HW_ = 34, HH_ = 10;
-  extern __shared__ __align__(16) uint8_t dsm[];
-  const int cout = MODE ? a.C / 2 : a.C;
-  const int tiles_x = a.W / 32, tiles_y = a.H / 8;
-  int t = blockIdx.x;
-  const int b = t / (tiles_x * tiles_y);
-  t -= b * tiles_x * tiles_y;
-  const int ty = t / tiles_x, tx = t - ty * tiles_x;
-  const int y0 = ty * 8, x0 = tx * 32;
-  const int cb = blockIdx.y;
-  // ---- stage the halo tile(s)
-  constexpr int CPP = PIXB / 16;             // 16-byte chunks per pixel per half
-  for (int i = threadIdx.x; i < NH * HH_ * HW_ * CPP; i += 256) {
-    const int k = i % CPP;
-    int r = i / CPP;
-    const int hx = r % HW_;
-    r /= HW_;
-    const int hy = r % HH_, h = r / HH_;
-    const int yy = y0 - 1 + hy, xx = x0 - 1 + hx;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W)
-      v = __ldg(reinterpret_cast<const uint4*>(a.x + ((long long)(b * a.H + yy) * a.W + xx) * a.x_ld + h * cout + cb * CW + k * 8));
-    *reinterpret_cast<uint4*>(dsm + ((h * HH_ + hy) * HW_ + hx) * PIXB + k * 16) = v;
-  }
-  // ---- per-thread weights / bias (as fp32 pairs for packed FFMA2)
-  const int c = threadIdx.x & 7, x = threadIdx.x >> 3;     // channel chunk, column
-  constexpr int CP2 = CH / 2;
-  float2 w[NH][9][CP2], bv[NH][CP2];
-#pragma unroll
-  for (int h = 0; h < NH; ++h) {
-    const int cc = h * cout + cb * CW + c * CH;
-#pragma unroll
-    for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-      for (int i = 0; i < CP2; ++i) w[h][tp][i] = __ldg(reinterpret_cast<const float2*>(a.w + (long long)tp * a.C + cc) + i);
-#pragma unroll
-    for (int i = 0; i < CP2; ++i) bv[h][i] = a.bias ? __ldg(reinterpret_cast<const float2*>(a.bias + cc) + i) : make_float2(0.f, 0.f);
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int y = 0; y < 8; ++y) {
-    float2 acc2[NH][CP2];
-#pragma unroll
-    for (int h = 0; h < NH; ++h) {
-#pragma unroll
-      for (int i = 0; i < CP2; ++i) acc2[h][i] = bv[h][i];
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const uint8_t* sp = dsm + ((h * HH_ + y + dy) * HW_ + x + dx) * PIXB + c * (CH * 2);
-          float2 f[CP2];
-          if constexpr (CH == 8) {
-            const uint4 q = *reinterpret_cast<const uint4*>(sp);
-            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) f[i] = make_float2(__uint_as_float(qq[i] << 16), __uint_as_float(qq[i] & 0xffff0000u));
-          } else {
-            const uint2 q = *reinterpret_cast<const uint2*>(sp);
-            f[0] = make_float2(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u));
-            f[1] = make_float2(__uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
-          }
-#pragma unroll
-          for (int i = 0; i < CP2; ++i) acc2[h][i] = __ffma2_rn(f[i], w[h][dy * 3 + dx][i], acc2[h][i]);
-        }
-    }
-    float acc[NH][CH];
-#pragma unroll
-    for (int h = 0; h < NH; ++h)
-#pragma unroll
-      for (int i = 0; i < CP2; ++i) { acc[h][2 * i] = acc2[h][i].x; acc[h][2 * i + 1] = acc2[h][i].y; }
-    const long long pix = (long long)(b * a.H + y0 + y) * a.W + x0 + x;
-    if constexpr (MODE == 1) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(acc[0][0] * acc[1][0], acc[0][1] * acc[1][1]);
-      __nv_bfloat162 hi = __floats2bfloat162_rn(acc[0][2] * acc[1][2], acc[0][3] * acc[1][3]);
-      *reinterpret_cast<uint2*>(a.out + pix * a.out_ld + cb * CW + c * CH) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-    } else {
-      float o[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = act_apply(acc[0][i], a.act);
-      if (a.mul) {
-        float m[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(a.mul + pix * a.mul_ld + cb * CW + c * CH)), m);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] *= m[i];
-      }
-      *reinterpret_cast<uint4*>(a.out + pix * a.out_ld + cb * CW + c * CH) = pack8(o);
-    }
-  }
-}
-
 // x[p][c] *= s[b][c]  (bf16 in place), 8 channels per thread
 __global__ void __launch_bounds__(256) scale_channels_kernel(bf16* __restrict__ x, int ld, long long P_per_b, int B, int C,
                                                             const float* __restrict__ s, int s_ld) {
@@ -599,6 +543,15 @@ extern "C" int ff_layernorm(const void* x, int x_is_bf16, int in_ld, long long r
                "ff_layernorm: C, out_cols and all pitches must be even");
   FF_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 7) == 0 && (reinterpret_cast<uintptr_t>(beta) & 7) == 0,
                "ff_layernorm: x / gamma / beta must be 8-byte aligned");
+  if (!x_is_bf16 && out_bf16 && !out_f32 && out_cols == C && (C == 64 || C == 128) && in_ld % 4 == 0 && out_ld % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(beta) & 15) == 0) {
+    if (C == 64) layernorm_narrow_kernel<8><<<ff_cdiv(rows, 32), 256, 0, st>>>(reinterpret_cast<const float*>(x), in_ld, rows, gamma, beta, eps, reinterpret_cast<bf16*>(out_bf16), out_ld);
+    else layernorm_narrow_kernel<16><<<ff_cdiv(rows, 16), 256, 0, st>>>(reinterpret_cast<const float*>(x), in_ld, rows, gamma, beta, eps, reinterpret_cast<bf16*>(out_bf16), out_ld);
+    ++g_ff_launches;
+    FF_CHECK_LAUNCH("ff_layernorm");
+    return FF_OK;
+  }
   const int grid = ff_cdiv(rows, 8);
   const int maxv = ff_cdiv(out_cols, 64);
 #define LN_LAUNCH(T, MV) layernorm_kernel<T, MV><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(x), in_ld, rows, C, gamma, beta, eps, reinterpret_cast<bf16*>(out_bf16), out_ld, out_cols, out_f32, out_f32_ld)
@@ -649,13 +602,7 @@ extern "C" int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, in
   FF_CHECK_ARG((kh & 1) && (kw & 1), "ff_dwconv: odd kernel sizes only");
   DwArgs a{reinterpret_cast<const bf16*>(x), x_ld, B, H, W, C, kh, kw, w, bias, act, mode, reinterpret_cast<const bf16*>(mul), mul_ld, reinterpret_cast<bf16*>(out), out_ld};
   const long long total = (long long)B * H * W * ((mode == 1 ? C / 2 : C) / 8);
-  const int cout_ = mode == 1 ? C / 2 : C;
-  if (mode == 1 && kh == 3 && kw == 3 && W % 32 == 0 && H % 8 == 0 && cout_ % (mode == 1 ? 32 : 64) == 0) {
-    const size_t smem = (size_t)(mode == 1 ? 2 : 1) * 10 * 34 * (mode == 1 ? 64 : 128);
-    dim3 grid(B * (H / 8) * (W / 32), cout_ / (mode == 1 ? 32 : 64));
-    if (mode == 1) dwconv3x3_tiled_kernel<1><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
-    else dwconv3x3_tiled_kernel<0><<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
-  } else if (kh == 3 && kw == 3 && W % 4 == 0) {
+  if (kh == 3 && kw == 3 && W % 4 == 0) {
     cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
     const int nb = ff_cdiv(total / 4, 128);
     if (mode == 1) dwconv3x3_kernel<1, 0><<<nb, 128, 0, st_>>>(a);
