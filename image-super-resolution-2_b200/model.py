@@ -161,6 +161,29 @@ class FreqFusionB200:
 
     __call__ = forward
 
+    @torch.no_grad()
+    def forward_with_precomputed(self, lr, expert_outputs, out=None, intermediates=None):
+        """Fusion head only, on pre-computed expert SR outputs (reference CompleteEnhancedFusionSR.forward_with_precomputed,
+        src/models/enhanced_fusion.py:756-812, eval path; BASELINE.json configs[0]).
+        expert_outputs: dict with keys 'hat', 'dat', 'nafnet' (the cached-dataset aliases 'drct' -> hat and 'grl' / 'mambair' -> dat
+        of src/data/cached_dataset.py are accepted), each fp32 NCHW [B,3,4h,4w] on the device."""
+        alias = {"drct": "hat", "grl": "dat", "mambair": "dat"}
+        ex = {alias.get(k, k): v for k, v in expert_outputs.items()}
+        missing = [k for k in ("hat", "dat", "nafnet") if k not in ex]
+        if missing:
+            raise KeyError(f"forward_with_precomputed: missing expert outputs {missing}")
+        lr = lr.contiguous().float()
+        B, _, h, w = lr.shape
+        self.runners()
+        stack = self._stack(B, h, w)
+        for i, k in enumerate(("hat", "dat", "nafnet")):
+            t = ex[k]
+            if not t.is_cuda or tuple(t.shape) != (B, 3, 4 * h, 4 * w):
+                raise L.FFError(f"forward_with_precomputed: expert output '{k}' must be a CUDA tensor of shape {(B, 3, 4 * h, 4 * w)}")
+            # NCHW -> channels 3i..3i+2 of the NHWC expert stack (layout plumbing; no arithmetic)
+            stack.view(B, 4 * h, 4 * w, 12)[..., 3 * i:3 * i + 3].copy_(t.float().permute(0, 2, 3, 1))
+        return self.runners()["head"].forward(lr, stack, out=out, intermediates=intermediates)
+
     def expert_outputs_nchw(self, lr):
         """Testing helper: dict of NCHW expert outputs like ExpertEnsemble.forward_all(return_dict=True)."""
         B, _, h, w = lr.shape

@@ -35,3 +35,18 @@ def test_head_vs_reference_golden_64():
     assert (inter["bands_raw"].cpu() - nh(g["raw_bands"])).abs().max() < 1e-4       # fp32 DCT/DWT/DFT kernels
     assert (inter["band_features"].cpu() - nh(g["band_features"])).abs().max() < 2e-2
     assert (out - g["out"]).abs().max() < 2e-2
+
+
+def test_forward_with_precomputed_vs_reference_golden_64():
+    """BASELINE.json configs[0]: fusion head alone on synthetic expert outputs, public API."""
+    from isr2_b200 import model as M
+    g = torch.load(os.path.join(GOLD, "head_64.pt"))
+    lr = g["lr"]
+    gen = torch.Generator().manual_seed(g["expert_seed"])
+    up = F.interpolate(lr, scale_factor=4, mode="bicubic", align_corners=False)
+    ex = {k: (up + s * torch.randn(1, 3, 256, 256, generator=gen)).clamp(0, 1).cuda() for k, s in (("hat", 0.01), ("grl", 0.02), ("nafnet", 0.03))}
+    m = M.FreqFusionB200("cuda:0", init_seed=0, verbose=False)
+    out = m.forward_with_precomputed(lr.cuda(), ex).cpu()
+    assert (out - g["out"]).abs().max() < 2e-2
+    with pytest.raises(KeyError):
+        m.forward_with_precomputed(lr.cuda(), {"hat": ex["hat"]})
