@@ -16,6 +16,15 @@ constexpr int BLOCK_K = 64;   // bf16 elements per k-block = 128 B = one swizzle
 constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 2;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+// HALO variant (3x3 convs with few output channels, where the A operand re-read per tap is the L2 bottleneck):
+// output tile = 16 rows x 8 cols; per 64-channel chunk the producer loads three column-shifted halo slabs
+// [18 rows][8 px][64 ch] (dx = -1, 0, +1) ONCE and the nine taps address them with a row offset (dy * 1024 B), so A
+// moves 55 KB per chunk instead of 9 x 16 KB.  Each slab is a standard 128B-swizzled K-major operand (8-pixel row =
+// one 1024-B swizzle atom), so the UMMA descriptor is the same as in the plain variant.
+constexpr int HALO_TW = 8, HALO_TH = 16;
+constexpr int HALO_SLAB_BYTES = 18 * 8 * 128;
+constexpr int HALO_A_BYTES = 3 * HALO_SLAB_BYTES;
+constexpr int HALO_A_STAGES = 2;
 
 struct Args {
   FFConvGemm p;
@@ -35,17 +44,24 @@ struct Args {
 //   EPI_STORE_GATE -- SimpleGate folded: 64 accumulator columns -> 32 bf16 outputs, TMA store
 enum { EPI_GENERIC = 0, EPI_STORE = 1, EPI_STORE_GELU = 2, EPI_RES = 3, EPI_RES_AUX = 4, EPI_STORE_GATE = 5 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool HALO = false>
 struct Cfg {
+  static constexpr int TW = HALO ? HALO_TW : TILE_W;              // output tile geometry (TW x TH = 128 pixels)
+  static constexpr int TH = HALO ? HALO_TH : TILE_H;
+  static constexpr int QR = 32 / TW;                              // tile rows per TMEM lane quadrant
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGE_BYTES = HALO ? B_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int HALO_BYTES = HALO ? HALO_A_STAGES * HALO_A_BYTES : 0;
   static constexpr int CB = BN < 32 ? BN : 32;                    // epilogue column block
   static constexpr int STG_PITCH = CB + 4;                        // floats; +4 keeps float4 accesses conflict-free (generic path)
   static constexpr int STG_WARP_BYTES = EPI == EPI_RES ? 10240 : EPI == EPI_RES_AUX ? 12288 : (EPI == EPI_GENERIC ? 32 * STG_PITCH * 4 : 4096);
   static constexpr int STG_BYTES = NUM_EPI_WARPS * STG_WARP_BYTES;
-  static constexpr int STAGES_RAW = (225 * 1024 - STG_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;  // + alignment slack
+  static constexpr int STAGES_RAW = (225 * 1024 - STG_BYTES - HALO_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_MAX = HALO ? 9 : 6;
+  static constexpr int STAGES = STAGES_RAW > STAGES_MAX ? STAGES_MAX : STAGES_RAW;
+  static constexpr int RING_BYTES = HALO_BYTES + STAGES * STAGE_BYTES;        // [halo A stages][ring]; staging follows
+  static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + 1024;            // + alignment slack
+  static constexpr int THREADS = NUM_THREADS + (HALO ? 32 : 0);               // HALO: warp 10 = A-slab producer
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -229,15 +245,18 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int EPI, bool HALO>
+__global__ void __launch_bounds__(NUM_THREADS + (HALO ? 32 : 0), 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                     const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ Args a) {
-  using C = Cfg<BN, EPI>;
+  using C = Cfg<BN, EPI, HALO>;
+  constexpr int TW = C::TW, TH = C::TH, QR = C::QR;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
   __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t halo_full[HALO_A_STAGES];
+  __shared__ __align__(8) uint64_t halo_empty[HALO_A_STAGES];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ uint32_t tmem_base_smem;
@@ -261,6 +280,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
     }
+    for (int s = 0; s < HALO_A_STAGES; ++s) {
+      mbar_init(&halo_full[s], 1);
+      mbar_init(&halo_empty[s], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -272,23 +295,43 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
+  // The producer and MMA warps stay converged: every lane runs the loops and polls the barriers, one elected lane issues
+  // the TMA / tcgen05 instructions.  (Issuing from a divergent `lane == 0` branch makes ptxas wrap every tcgen05.mma in a
+  // per-thread election loop and recompute the descriptors through a long dependent chain: ~150 cycles per MMA instead of
+  // the ~50 of back-to-back UTCHMMA, which capped every N <= 192 GEMM.)
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
-        const int b = m_tile / a.tiles_per_img;
-        const int t = m_tile - b * a.tiles_per_img;
-        const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
-        const int y0 = ty * TILE_H, x0 = tx * TILE_W;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+      const int b = m_tile / a.tiles_per_img;
+      const int t = m_tile - b * a.tiles_per_img;
+      const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+      const int y0 = ty * TH, x0 = tx * TW;
+      const int brow = b * a.p.w_batch_rows + n_tile * BN;
+      if constexpr (HALO) {
+        // weights only, chunk-major k order; the A slabs come from warp 10
+        uint8_t* ring = smem + C::HALO_BYTES;
+        for (int cc = 0; cc < a.cchunks; ++cc) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[stage], C::B_STAGE_BYTES);
+              tma_load_2d(ring + stage * C::STAGE_BYTES, &tmB, &full_bar[stage], (tap * a.cchunks + cc) * BLOCK_K, brow);
+            }
+            __syncwarp();
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else {
+        int tap = 0, cc = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
-          const int tap = kb / a.cchunks, cc = kb - tap * a.cchunks;
           int cx, cy;
           if (a.p.kind == FF_CONV_3X3) {
-            cx = x0 + (tap % 3) - 1;
-            cy = y0 + (tap / 3) - 1;
+            const int dy = (tap * 11) >> 5;       // tap / 3 for tap in [0, 9)
+            cx = x0 + (tap - 3 * dy) - 1;
+            cy = y0 + dy - 1;
           } else if (a.p.kind == FF_CONV_2X2S2) {
             cx = 2 * x0 + (tap & 1);
             cy = 2 * y0 + (tap >> 1);
@@ -297,43 +340,97 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             cy = y0;
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * C::STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_4d(sa, &tmA, &full_bar[stage], cc * BLOCK_K, cx, cy, b);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, b * a.p.w_batch_rows + n_tile * BN);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_4d(sa, &tmA, &full_bar[stage], cc * BLOCK_K, cx, cy, b);
+            tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, brow);
+          }
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (++cc == a.cchunks) { cc = 0; ++tap; }
         }
+      }
+    }
+  } else if (HALO && warp == 2 + NUM_EPI_WARPS) {
+    // ================= HALO A-slab producer =================
+    int hs = 0;
+    uint32_t hphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / a.n_tiles;
+      const int b = m_tile / a.tiles_per_img;
+      const int t = m_tile - b * a.tiles_per_img;
+      const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+      for (int cc = 0; cc < a.cchunks; ++cc) {
+        mbar_wait(&halo_empty[hs], hphase ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + hs * HALO_A_BYTES;
+          mbar_arrive_expect_tx(&halo_full[hs], HALO_A_BYTES);
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            tma_load_4d(sa + j * HALO_SLAB_BYTES, &tmA, &halo_full[hs], cc * BLOCK_K, tx * TW - 1 + j, ty * TH - 1, b);
+        }
+        __syncwarp();
+        if (++hs == HALO_A_STAGES) { hs = 0; hphase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+    // descriptors advance by plain adds on the 14-bit (address >> 4) field: +2 per 16-element k step, +bytes/16 per stage / slab
+    const uint64_t desc_ring = umma_desc_k_sw128(smem_u32(smem + C::HALO_BYTES));
+    const uint64_t desc_halo = umma_desc_k_sw128(smem_u32(smem));
+    (void)desc_halo;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int hs = 0;
+    uint32_t hphase = 0;
+    (void)hs; (void)hphase;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      if constexpr (HALO) {
+        for (int cc = 0; cc < a.cchunks; ++cc) {
+          mbar_wait(&halo_full[hs], hphase);
+          const uint64_t dslab = desc_halo + (uint64_t)(hs * (HALO_A_BYTES >> 4));
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t da = dslab + (uint64_t)((tap % 3) * (HALO_SLAB_BYTES >> 4) + (tap / 3) * (1024 >> 4));   // dx slab, dy row offset
+              const uint64_t db = desc_ring + (uint64_t)(stage * (C::STAGE_BYTES >> 4));
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k) tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
+              tc_commit(&empty_bar[stage]);
+              if (tap == 8) tc_commit(&halo_empty[hs]);
+            }
+            __syncwarp();
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++hs == HALO_A_STAGES) { hs = 0; hphase ^= 1; }
+        }
+      } else {
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          if (elect_one()) {
+            const uint64_t da = desc_ring + (uint64_t)(stage * (C::STAGE_BYTES >> 4));
+            const uint64_t db = da + (A_STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            tc_mma_bf16(d_tmem, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit(&empty_bar[stage]);
           }
-          tc_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (elect_one()) tc_commit(&tmem_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ================= epilogue warps =================
@@ -345,7 +442,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int ew = warp - 2;
       const int quad = warp & 3;
       const int half = ew >> 2;
-      uint8_t* wbase = smem + C::STAGES * C::STAGE_BYTES + ew * C::STG_WARP_BYTES;   // [R0 4K][R1 4K][O16 2K], 1024-B aligned
+      uint8_t* wbase = smem + C::RING_BYTES + ew * C::STG_WARP_BYTES;   // [R0 4K][R1 4K][O16 2K], 1024-B aligned
       const int ncb = BN / 32;
       int buf = 0;
       uint32_t ph[2] = {0, 0};
@@ -361,8 +458,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int t = m_tile - b * a.tiles_per_img;
         const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
         mbar_arrive_expect_tx(&res_bar[ew][bsel], AUX ? 6144 : 4096);
-        tma_load_4d(wbase + bsel * 4096, &tmR, &res_bar[ew][bsel], n_tile * BN + c * 32, tx * TILE_W, ty * TILE_H + quad * 2, b);
-        if constexpr (AUX) tma_load_4d(wbase + 8192 + bsel * 2048, &tmO, &res_bar[ew][bsel], n_tile * BN + c * 32, tx * TILE_W, ty * TILE_H + quad * 2, b);
+        tma_load_4d(wbase + bsel * 4096, &tmR, &res_bar[ew][bsel], n_tile * BN + c * 32, tx * TW, ty * TH + quad * QR, b);
+        if constexpr (AUX) tma_load_4d(wbase + 8192 + bsel * 2048, &tmO, &res_bar[ew][bsel], n_tile * BN + c * 32, tx * TW, ty * TH + quad * QR, b);
       };
       {
         int ft = blockIdx.x;
@@ -437,8 +534,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&tmO32, wbase + buf * 4096, n_blk, tx * TILE_W, ty * TILE_H + quad * 2, b);
-            if (!AUX && p.out_bf16) tma_store_4d(&tmO, wbase + 8192, n_blk, tx * TILE_W, ty * TILE_H + quad * 2, b);
+            tma_store_4d(&tmO32, wbase + buf * 4096, n_blk, tx * TW, ty * TH + quad * QR, b);
+            if (!AUX && p.out_bf16) tma_store_4d(&tmO, wbase + 8192, n_blk, tx * TW, ty * TH + quad * QR, b);
             tma_store_commit();
           }
           buf ^= 1;
@@ -457,7 +554,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int ew = warp - 2;
       const int quad = warp & 3;
       const int half = ew >> 2;
-      uint8_t* stg_base = smem + C::STAGES * C::STAGE_BYTES + ew * C::STG_WARP_BYTES;
+      uint8_t* stg_base = smem + C::RING_BYTES + ew * C::STG_WARP_BYTES;
       int buf = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
@@ -497,7 +594,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&tmO, stg_base + buf * 2048, n_blk >> 1, tx * TILE_W, ty * TILE_H + quad * 2, b);
+            tma_store_4d(&tmO, stg_base + buf * 2048, n_blk >> 1, tx * TW, ty * TH + quad * QR, b);
             tma_store_commit();
           }
           buf ^= 1;
@@ -515,7 +612,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int ew = warp - 2;
       const int quad = warp & 3;
       const int half = ew >> 2;
-      uint8_t* stg_base = smem + C::STAGES * C::STAGE_BYTES + ew * C::STG_WARP_BYTES;   // 2 x 2 KB, 512-B aligned
+      uint8_t* stg_base = smem + C::RING_BYTES + ew * C::STG_WARP_BYTES;   // 2 x 2 KB, 512-B aligned
       int buf = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
@@ -562,7 +659,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&tmO, stg_base + buf * 2048, n_blk, tx * TILE_W, ty * TILE_H + quad * 2, b);
+            tma_store_4d(&tmO, stg_base + buf * 2048, n_blk, tx * TW, ty * TH + quad * QR, b);
             tma_store_commit();
           }
           buf ^= 1;
@@ -585,7 +682,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ew = warp - 2;
     const int quad = warp & 3;
     const int half = ew >> 2;
-    float* stg = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES) + ew * (32 * C::STG_PITCH);
+    float* stg = reinterpret_cast<float*>(smem + C::RING_BYTES) + ew * (32 * C::STG_PITCH);
     const int width = (p.pixel_shuffle == 2) ? (p.n_store >> 2) : (p.gate_pairs ? (p.n_store >> 1) : p.n_store);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -673,7 +770,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int u = 0; u < 4; ++u) {
               const int row = (it0 + u) * rpi + rsub;           // row within the quadrant
               const int r = quad * 32 + row;
-              const int oy = ty * TILE_H + (r >> 4), ox = tx * TILE_W + (r & 15);
+              const int oy = ty * TH + r / TW, ox = tx * TW + r % TW;
               int dummy;
               long long px;
               if (p.pixel_shuffle == 2) out_location(a, b, oy, ox, ncol, px, dummy);
@@ -700,7 +797,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int it = 0; it < iters; ++it) {
             const int row = it * rpi + rsub;
             const int r = quad * 32 + row;
-            const int oy = ty * TILE_H + (r >> 4), ox = tx * TILE_W + (r & 15);
+            const int oy = ty * TH + r / TW, ox = tx * TW + r % TW;
             const long long px = ((long long)(b * a.Ho + oy)) * a.Wo + ox;
             for (int i = 0; i < 4; ++i) {
               const int n = ncol + i;
@@ -799,12 +896,13 @@ EncodeTiledFn get_encode() {
 
 struct Maps { CUtensorMap A, B, O, R, O32; };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool HALO = false>
 int launch_tc(const Maps& m, const Args& a, cudaStream_t st) {
-  using C = Cfg<BN, EPI>;
+  using C = Cfg<BN, EPI, HALO>;
+  static_assert(C::STAGES >= (HALO ? 3 : 2), "ff_conv_gemm: smem ring too shallow");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, EPI, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) {
       ff_set_error("ff_conv_gemm: cudaFuncSetAttribute(%d) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
@@ -814,13 +912,25 @@ int launch_tc(const Maps& m, const Args& a, cudaStream_t st) {
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < ff_num_sms() ? tiles : ff_num_sms();
-  conv_gemm_tc_kernel<BN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(m.A, m.B, m.O, m.R, m.O32, a);
+  conv_gemm_tc_kernel<BN, EPI, HALO><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(m.A, m.B, m.O, m.R, m.O32, a);
   FF_CHECK_LAUNCH("ff_conv_gemm");
   return FF_OK;
 }
 
+constexpr int HALO_MAX_BN = 64;   // wider tiles are MMA-bound already and would not leave room for the slabs
+
 template <int BN>
-int launch_bn(int epi, const Maps& m, const Args& a, cudaStream_t st) {
+int launch_bn(int epi, const Maps& m, const Args& a, cudaStream_t st, bool halo) {
+  if constexpr (BN <= HALO_MAX_BN) {
+    if (halo) {
+      if constexpr (BN >= 32) {
+        if (epi == EPI_STORE) return launch_tc<BN, EPI_STORE, true>(m, a, st);
+        if (epi == EPI_STORE_GELU) return launch_tc<BN, EPI_STORE_GELU, true>(m, a, st);
+        if (epi == EPI_RES) return launch_tc<BN, EPI_RES, true>(m, a, st);
+      }
+      return launch_tc<BN, EPI_GENERIC, true>(m, a, st);
+    }
+  }
   if constexpr (BN >= 32) {
     if (epi == EPI_STORE) return launch_tc<BN, EPI_STORE>(m, a, st);
     if (epi == EPI_STORE_GELU) return launch_tc<BN, EPI_STORE_GELU>(m, a, st);
@@ -852,6 +962,10 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   a.Ho = (p.kind == FF_CONV_2X2S2) ? p.H / 2 : p.H;
   a.Wo = (p.kind == FF_CONV_2X2S2) ? p.W / 2 : p.W;
   FF_CHECK_ARG(a.Ho % TILE_H == 0 && a.Wo % TILE_W == 0 && a.Ho > 0, "ff_conv_gemm: output %dx%d must be a multiple of %dx%d", a.Ho, a.Wo, TILE_H, TILE_W);
+  static const bool halo_enabled = []() { const char* e = getenv("FFB200_CONV_HALO"); return !(e && e[0] == '0'); }();
+  const bool halo = halo_enabled && !p.debug_simt && p.kind == FF_CONV_3X3 && p.n_pad % 128 != 0 && p.n_pad % 192 != 0 && p.n_pad <= 4 * HALO_MAX_BN &&
+                    a.Ho % HALO_TH == 0 && a.Wo % HALO_TW == 0;
+  const int TW = halo ? HALO_TW : TILE_W, TH = halo ? HALO_TH : TILE_H;
   if (p.gate_pairs) {
     FF_CHECK_ARG(p.out_bf16 && !p.out_f32 && !p.act && !p.mul && !p.aux && !p.res && !p.pixel_shuffle && !p.col_scale && p.n_store % 16 == 0,
                  "ff_conv_gemm: gate_pairs supports bias + bf16 store only");
@@ -872,8 +986,8 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   if (p.aux) FF_CHECK_ARG(p.aux_ld >= width_ok && (!vec || (p.aux_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)), "ff_conv_gemm: bad aux_ld");
   if (p.res) FF_CHECK_ARG(p.res_ld >= width_ok && (!vec || (p.res_ld % (p.res_is_f32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0)), "ff_conv_gemm: bad res_ld");
 
-  a.tiles_x = a.Wo / TILE_W;
-  a.tiles_per_img = a.tiles_x * (a.Ho / TILE_H);
+  a.tiles_x = a.Wo / TW;
+  a.tiles_per_img = a.tiles_x * (a.Ho / TH);
   a.m_tiles = a.tiles_per_img * p.B;
   a.ntaps = (p.kind == FF_CONV_3X3) ? 9 : (p.kind == FF_CONV_2X2S2) ? 4 : 1;
   a.cchunks = p.cin / BLOCK_K;
@@ -907,6 +1021,7 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
     cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
     cuuint64_t strides[3] = {(cuuint64_t)p.x_ld * 2, (cuuint64_t)p.x_ld * 2 * p.W, (cuuint64_t)p.x_ld * 2 * p.W * p.H};
     cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(TILE_W * es), (cuuint32_t)(TILE_H * es), 1};
+    if (halo) { box[1] = HALO_TW; box[2] = HALO_TH + 2; }
     cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.x), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -937,7 +1052,7 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   auto out_map = [&](CUtensorMap* tm, void* ptr, int ld, int esz, CUtensorMapDataType dt, CUtensorMapSwizzle sw) {
     cuuint64_t dims[4] = {(cuuint64_t)p.n_store, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)p.B};
     cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)ld * esz * a.Wo, (cuuint64_t)ld * esz * a.Wo * a.Ho};
-    cuuint32_t box[4] = {32, (cuuint32_t)TILE_W, 2, 1};
+    cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)(32 / TW), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(tm, dt, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -949,7 +1064,7 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   auto map_n = [&](CUtensorMap* tm, void* ptr, int ld, int esz, CUtensorMapDataType dt, CUtensorMapSwizzle sw, int ncols) {
     cuuint64_t dims[4] = {(cuuint64_t)ncols, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)p.B};
     cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)ld * esz * a.Wo, (cuuint64_t)ld * esz * a.Wo * a.Ho};
-    cuuint32_t box[4] = {32, (cuuint32_t)TILE_W, 2, 1};
+    cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)(32 / TW), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(tm, dt, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -975,11 +1090,11 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   }
   ++g_ff_launches;
   switch (BN) {
-    case 256: return launch_bn<256>(epi, m, a, st);
-    case 192: return launch_bn<192>(epi, m, a, st);
-    case 128: return launch_bn<128>(epi, m, a, st);
-    case 64: return launch_bn<64>(epi, m, a, st);
-    case 32: return launch_bn<32>(epi, m, a, st);
-    default: return launch_bn<16>(epi, m, a, st);
+    case 256: return launch_bn<256>(epi, m, a, st, false);
+    case 192: return launch_bn<192>(epi, m, a, st, false);
+    case 128: return launch_bn<128>(epi, m, a, st, false);
+    case 64: return launch_bn<64>(epi, m, a, st, halo);
+    case 32: return launch_bn<32>(epi, m, a, st, halo);
+    default: return launch_bn<16>(epi, m, a, st, halo);
   }
 }

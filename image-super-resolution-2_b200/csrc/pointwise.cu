@@ -2,6 +2,7 @@
 // layer norm, global average pool, tiny per-sample linear layers (SE / SCA / AIM heads), depthwise
 // convolutions with fused gates, direct small-channel convolutions (fp32), layout conversion.
 #include "ff_common.cuh"
+#include <type_traits>
 #include "../../include/ffb200.h"
 
 extern long long g_ff_launches;
@@ -387,6 +388,171 @@ __global__ void __launch_bounds__(128, MODE == 1 ? 2 : 3) dwconv3x3_kernel(const
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// 3x3 depthwise conv, TMA-staged.  The register kernel above is latency bound (a warp issues its loads, waits a full
+// memory round trip, computes, and only then asks for more: ~1.5-2.4 TB/s).  Here persistent CTAs stream halo tiles
+// [10 rows][34 px][64 ch] (hardware zero fill = the conv padding), plus the [8][32][64] tile of the fused multiplier when
+// there is one, through a shared-memory ring filled by TMA, so the next tiles are in flight while one is consumed.
+// 512 threads: a thread owns one pixel column x 4 channels and slides down the 8 output rows with the unpacked 3x3
+// window and its 36 weights in registers.
+// MODE 1 = SimpleGate pair (NAFNet): the tile holds 32 channels of each half; partner lanes meet through a shuffle.
+// ------------------------------------------------------------------------------------------
+constexpr int DWT_TX = 32, DWT_TY = 8;
+constexpr int DWT_THREADS = 512;
+constexpr int DWT_TILE_BYTES = (DWT_TY + 2) * (DWT_TX + 2) * 64 * 2;      // 43520
+constexpr int DWT_HALF_BYTES = DWT_TILE_BYTES / 2;                        // MODE 1: one 32-channel box per half (21760 = 170 * 128)
+constexpr int DWT_MUL_BYTES = DWT_TY * DWT_TX * 64 * 2;                   // 32768
+__device__ __forceinline__ void unpack4_f2(const uint2& q, float2 (&f)[2]) {
+  f[0] = make_float2(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u));
+  f[1] = make_float2(__uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+}
+template <bool MUL> struct DwtCfg {
+  static constexpr int STAGES = MUL ? 2 : 3;
+  static constexpr int STAGE_BYTES = DWT_TILE_BYTES + (MUL ? DWT_MUL_BYTES : 0);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 128;
+};
+
+template <int MODE, int ACT, bool MUL>
+__global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM,
+                                                                       const __grid_constant__ DwArgs a, int tiles_x, int tiles_y, int ctiles) {
+  using Cf = DwtCfg<MUL>;
+  extern __shared__ uint8_t dw_smem_raw[];
+  __shared__ __align__(8) uint64_t full[Cf::STAGES];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~(uintptr_t)127);
+  const int tid = threadIdx.x;
+  const int cout = MODE == 1 ? a.C / 2 : a.C;
+  const int num_tiles = a.B * tiles_y * tiles_x * ctiles;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    if (MUL) tma_prefetch_desc(&tmM);
+    for (int s = 0; s < Cf::STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int s) {     // one thread
+    const int ct = tile % ctiles;
+    int r = tile / ctiles;
+    const int tx = r % tiles_x;
+    r /= tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    uint8_t* dst = smem + s * Cf::STAGE_BYTES;
+    mbar_arrive_expect_tx(&full[s], Cf::STAGE_BYTES);
+    if constexpr (MODE == 1) {
+      tma_load_4d(dst, &tmX, &full[s], ct * 32, tx * DWT_TX - 1, ty * DWT_TY - 1, b);
+      tma_load_4d(dst + DWT_HALF_BYTES, &tmX, &full[s], cout + ct * 32, tx * DWT_TX - 1, ty * DWT_TY - 1, b);
+    } else {
+      tma_load_4d(dst, &tmX, &full[s], ct * 64, tx * DWT_TX - 1, ty * DWT_TY - 1, b);
+    }
+    if constexpr (MUL) tma_load_4d(dst + DWT_TILE_BYTES, &tmM, &full[s], ct * 64, tx * DWT_TX, ty * DWT_TY, b);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < Cf::STAGES - 1; ++s) {
+      const int t = blockIdx.x + s * gridDim.x;
+      if (t < num_tiles) issue(t, s);
+    }
+  }
+  // thread -> (pixel column, 4-channel group).  MODE 0: 16 groups per pixel (128-B pixel pitch), a half warp reads one pixel.
+  // MODE 1: lane = sub(3 bits) | px&1 << 3 | half << 4, so that a half warp reads two adjacent 64-B pixels of ONE half
+  // (no bank conflicts) and the SimpleGate partner is lane ^ 16.
+  int px, sub, half;
+  if constexpr (MODE == 1) {
+    sub = tid & 7; half = (tid >> 4) & 1; px = ((tid >> 3) & 1) | ((tid >> 5) << 1);
+  } else {
+    sub = tid & 15; half = 0; px = tid >> 4;
+  }
+  constexpr int PP = MODE == 1 ? 64 : 128;
+  const int toff = half * DWT_HALF_BYTES + px * PP + sub * 8;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int ct = tile % ctiles;
+    int r = tile / ctiles;
+    const int tx = r % tiles_x;
+    r /= tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    const int cin0 = MODE == 1 ? half * cout + ct * 32 + sub * 4 : ct * 64 + sub * 4;     // input channel of this thread
+    const int co0 = MODE == 1 ? ct * 32 + sub * 4 : cin0;                                   // output channel
+    float2 w[9][2], bv[2];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(a.w + (long long)t * a.C + cin0));
+      w[t][0] = make_float2(q.x, q.y); w[t][1] = make_float2(q.z, q.w);
+    }
+    if (a.bias) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(a.bias + cin0));
+      bv[0] = make_float2(q.x, q.y); bv[1] = make_float2(q.z, q.w);
+    } else {
+      bv[0] = bv[1] = make_float2(0.f, 0.f);
+    }
+    // refill the stage consumed in the previous iteration (every thread passed the barrier at its end)
+    if (tid == 0) {
+      const int t2 = tile + (Cf::STAGES - 1) * gridDim.x;
+      if (t2 < num_tiles) issue(t2, (stage + Cf::STAGES - 1) % Cf::STAGES);
+    }
+    mbar_wait(&full[stage], phase);
+    const uint8_t* base = smem + stage * Cf::STAGE_BYTES + toff;
+    const uint8_t* mbase = smem + stage * Cf::STAGE_BYTES + DWT_TILE_BYTES + px * 128 + sub * 8;
+    (void)mbase;
+    float2 win[3][3][2];      // [row slot][column][channel pair], unpacked
+    auto load_row = [&](int slot, int hr) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) unpack4_f2(*reinterpret_cast<const uint2*>(base + (hr * (DWT_TX + 2) + c) * PP), win[slot][c]);
+    };
+    load_row(0, 0);
+    load_row(1, 1);
+    bf16* op = a.out + ((long long)(b * a.H + ty * DWT_TY) * a.W + tx * DWT_TX + px) * a.out_ld + co0;
+#pragma unroll
+    for (int row = 0; row < DWT_TY; ++row) {
+      load_row((row + 2) % 3, row + 2);
+      float2 acc[2] = {bv[0], bv[1]};
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          acc[0] = __ffma2_rn(win[(row + dy) % 3][dx][0], w[dy * 3 + dx][0], acc[0]);
+          acc[1] = __ffma2_rn(win[(row + dy) % 3][dx][1], w[dy * 3 + dx][1], acc[1]);
+        }
+      float o[4] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y};
+      bool writer = true;
+      if constexpr (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] *= __shfl_xor_sync(0xffffffffu, o[i], 16);
+        writer = half == 0;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if constexpr (ACT == 1) o[i] = gelu_tanh_hw(o[i]);
+          else if constexpr (ACT == 2) o[i] = act_apply(o[i], a.act);
+        }
+        if constexpr (MUL) {
+          float2 m[2];
+          unpack4_f2(*reinterpret_cast<const uint2*>(mbase + row * (DWT_TX * 128)), m);
+          o[0] *= m[0].x; o[1] *= m[0].y; o[2] *= m[1].x; o[3] *= m[1].y;
+        }
+      }
+      if (writer) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+        *reinterpret_cast<uint2*>(op + (long long)row * a.W * a.out_ld) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      }
+    }
+    __syncthreads();      // everyone is done with this stage before it is refilled in the next iteration
+    if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
+  }
+}
+
+template <int MODE, int ACT, bool MUL>
+static int launch_dw_tma(const CUtensorMap& tx_, const CUtensorMap& tm_, const DwArgs& a, int tiles_x, int tiles_y, int ctiles, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_tma_kernel<MODE, ACT, MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwtCfg<MUL>::SMEM);
+    if (e != cudaSuccess) { ff_set_error("ff_dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FF_ERR_CUDA; }
+    configured = true;
+  }
+  dwconv3x3_tma_kernel<MODE, ACT, MUL><<<grid, DWT_THREADS, DwtCfg<MUL>::SMEM, st>>>(tx_, tm_, a, tiles_x, tiles_y, ctiles);
+  return FF_OK;
+}
+
 // x[p][c] *= s[b][c]  (bf16 in place), 8 channels per thread
 __global__ void __launch_bounds__(256) scale_channels_kernel(bf16* __restrict__ x, int ld, long long P_per_b, int B, int C,
                                                             const float* __restrict__ s, int s_ld) {
@@ -604,6 +770,51 @@ extern "C" int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, in
   const long long total = (long long)B * H * W * ((mode == 1 ? C / 2 : C) / 8);
   if (kh == 3 && kw == 3 && W % 4 == 0) {
     cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+    static const bool tma_enabled = []() { const char* e = getenv("FFB200_DW_TMA"); return !(e && e[0] == '0'); }();
+    const int cout_ = mode == 1 ? C / 2 : C;
+    if (tma_enabled && W % DWT_TX == 0 && H % DWT_TY == 0 && cout_ % (mode == 1 ? 32 : 64) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!mul || (mode != 1 && (reinterpret_cast<uintptr_t>(mul) & 15) == 0 && mul_ld % 8 == 0))) {
+      typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      static EncodeTiledFn enc = []() -> EncodeTiledFn {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+          return reinterpret_cast<EncodeTiledFn>(ptr);
+        return nullptr;
+      }();
+      if (!enc) { ff_set_error("ff_dwconv: cuTensorMapEncodeTiled entry point unavailable"); return FF_ERR_DRIVER; }
+      CUtensorMap tm, tmm;
+      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+      cuuint64_t strides[3] = {(cuuint64_t)x_ld * 2, (cuuint64_t)x_ld * 2 * W, (cuuint64_t)x_ld * 2 * W * H};
+      cuuint32_t box[4] = {(cuuint32_t)(mode == 1 ? 32 : 64), DWT_TX + 2, DWT_TY + 2, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { ff_set_error("ff_dwconv: cuTensorMapEncodeTiled failed with %d", (int)r); return FF_ERR_DRIVER; }
+      tmm = tm;
+      if (mul) {
+        cuuint64_t mstr[3] = {(cuuint64_t)mul_ld * 2, (cuuint64_t)mul_ld * 2 * W, (cuuint64_t)mul_ld * 2 * W * H};
+        cuuint32_t mbox[4] = {64, DWT_TX, DWT_TY, 1};
+        r = enc(&tmm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(mul), dims, mstr, mbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { ff_set_error("ff_dwconv: cuTensorMapEncodeTiled(mul) failed with %d", (int)r); return FF_ERR_DRIVER; }
+      }
+      const int tiles_x = W / DWT_TX, tiles_y = H / DWT_TY, ctiles = cout_ / (mode == 1 ? 32 : 64);
+      const long long ntiles = (long long)B * tiles_x * tiles_y * ctiles;
+      const int grid = (int)(ntiles < ff_num_sms() ? ntiles : ff_num_sms());
+      int rc;
+      if (mode == 1) rc = launch_dw_tma<1, 0, false>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_);
+      else if (mul) rc = act == FF_ACT_NONE ? launch_dw_tma<0, 0, true>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_)
+                                            : launch_dw_tma<0, 2, true>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_);
+      else if (act == FF_ACT_NONE) rc = launch_dw_tma<0, 0, false>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_);
+      else if (act == FF_ACT_GELU) rc = launch_dw_tma<0, 1, false>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_);
+      else rc = launch_dw_tma<0, 2, false>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_);
+      if (rc != FF_OK) return rc;
+      ++g_ff_launches;
+      FF_CHECK_LAUNCH("ff_dwconv");
+      return FF_OK;
+    }
     const int nb = ff_cdiv(total / 4, 128);
     if (mode == 1) dwconv3x3_kernel<1, 0><<<nb, 128, 0, st_>>>(a);
     else if (act == FF_ACT_NONE) dwconv3x3_kernel<0, 0><<<nb, 128, 0, st_>>>(a);

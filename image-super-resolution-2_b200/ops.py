@@ -90,7 +90,8 @@ def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_
         width = n_real // (2 if gate_pairs else 1)
         byts = B * H * W * cin_real * 2 + n_real * k_real * 2 + Mo * width * ((2 if out_bf16 is not None else 0) + (4 if out_f32 is not None else 0))
         byts += Mo * width * ((4 if res.dtype == _F32 else 2) if res is not None else 0) + Mo * width * (2 if mul is not None else 0) + Mo * width * (2 if aux is not None else 0)
-        PROFILE.records.append((e0, e1, 2.0 * Mo * n_real * k_real, 2.0 * Mo * p.n_pad * taps * cin, float(byts)))
+        PROFILE.records.append((e0, e1, 2.0 * Mo * n_real * k_real, 2.0 * Mo * p.n_pad * taps * cin, float(byts),
+                                (kind, cin, p.n_pad, B, H, W, act, res is not None, aux is not None, mul is not None, gate_pairs, pixel_shuffle, out_f32 is not None)))
         return
     L.check(L.load().ff_conv_gemm(C.byref(p), _stream()), "ff_conv_gemm")
 

@@ -340,3 +340,72 @@ def test_layernorm_narrow_rows(C_):
     torch.cuda.synchronize()
     err = (out.cpu().float() - ref).abs()
     assert (err <= 4e-3 * ref.abs() + 1e-3).all(), err.max().item()     # bf16 output rounding only
+
+
+@pytest.mark.parametrize("cin,n,H,W,B", [(192, 64, 128, 128, 2), (64, 64, 48, 32, 1), (128, 32, 32, 48, 3), (64, 16, 64, 64, 2), (192, 48, 16, 16, 1), (64, 160, 32, 32, 1)])
+@pytest.mark.parametrize("epi", ["store", "gelu", "res", "generic"])
+def test_conv_gemm_halo_3x3(cin, n, H, W, B, epi):
+    """3x3 convs with <= 64-wide N tiles take the halo-slab variant (A loaded once per 64-channel chunk, nine taps address it):
+    every epilogue flavour against F.conv2d on the same bf16 operands, multi-chunk K, multi-tile persistent loops, non-square images."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
+    w = (torch.randn(n, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(BF16).float()
+    bias = torch.randn(n, generator=g)
+    conv = _nhwc(F.conv2d(x, w, bias, padding=1))
+    d = _dev()
+    n_pad = (n + 15) // 16 * 16
+    xd, wd, bd = _nhwc(x).to(d, BF16), packing.pack_conv(w, n_pad, cin, device=d), packing.pack_vector(bias, n_pad, device=d)
+    P = B * H * W
+    if epi == "store":
+        out = torch.zeros(P, n_pad, dtype=BF16, device=d)
+        ops.conv_gemm(xd, B, H, W, cin, wd, kind=1, n_store=n, bias=bd, out_bf16=out)
+        got, ref, tol = out.float().cpu()[:, :n], conv, 3e-2
+    elif epi == "gelu":
+        out = torch.zeros(P, n_pad, dtype=BF16, device=d)
+        ops.conv_gemm(xd, B, H, W, cin, wd, kind=1, n_store=n, bias=bd, act=ops.ACT_GELU, out_bf16=out)
+        got, ref, tol = out.float().cpu()[:, :n], F.gelu(conv), 3e-2
+    elif epi == "res":
+        res = torch.randn(P, n_pad, generator=g)
+        stream = res.clone().to(d)
+        ops.conv_gemm(xd, B, H, W, cin, wd, kind=1, n_store=n, bias=bd, res=stream, out_f32=stream)
+        got, ref, tol = stream.cpu()[:, :n], conv + res[:, :n], 3e-3
+    else:
+        res = torch.randn(P, n_pad, generator=g).to(BF16)
+        out = torch.zeros(P, n_pad, device=d)
+        ops.conv_gemm(xd, B, H, W, cin, wd, kind=1, n_store=n, bias=bd, act=ops.ACT_LRELU, res=res.to(d), post_act=ops.ACT_CLAMP01, out_f32=out)
+        got, ref, tol = out.cpu()[:, :n], (F.leaky_relu(conv, 0.01) + res.float()[:, :n]).clamp(0, 1), 3e-3
+    torch.cuda.synchronize()
+    err = (got - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("B,H,W,C_", [(2, 16, 32, 64), (1, 24, 64, 192), (3, 8, 32, 128), (2, 40, 96, 64), (1, 13, 20, 192), (3, 8, 4, 32), (1, 41, 36, 48)])
+def test_dwconv3x3_variants(B, H, W, C_):
+    """3x3 depthwise conv, both code paths (TMA-staged tiles when W % 32 == 0, H % 8 == 0 and the channels tile by 64 / 32+32;
+    the register kernel otherwise): image borders, multi-tile persistent loops, channel offset in a wider buffer, every
+    activation flavour, the fused multiplier and the SimpleGate pair mode, against F.conv2d."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(21)
+    d = _dev()
+    xw = torch.randn(B, C_ + 16, H, W, generator=g).to(BF16).float()      # the conv reads channels [8, 8 + C_)
+    x = xw[:, 8:8 + C_]
+    w = torch.randn(C_, 1, 3, 3, generator=g) / 3
+    b = torch.randn(C_, generator=g)
+    y = F.conv2d(x, w, b, padding=1, groups=C_)
+    xd, wd, bd = _nhwc(xw).to(d, BF16), packing.pack_dw(w, C_, device=d), b.to(d)
+    mul = torch.randn(B * H * W, C_, generator=g).to(BF16)
+    for act, fn in ((ops.ACT_NONE, lambda t: t), (ops.ACT_GELU, F.gelu), (ops.ACT_RELU, F.relu)):
+        for m in (None, mul):
+            out = torch.zeros(B * H * W, C_, dtype=BF16, device=d)
+            ops.dwconv(xd, B, H, W, C_, 3, 3, wd, bd, out, act=act, mul=m.to(d) if m is not None else None, x_off=8)
+            torch.cuda.synchronize()
+            ref = _nhwc(fn(y)) * (m.float() if m is not None else 1.0)
+            err = (out.cpu().float() - ref).abs().max().item()
+            assert err < 2e-2 * max(1.0, ref.abs().max().item()), f"act={act} mul={m is not None}: {err}"
+    ref = _nhwc(y[:, :C_ // 2] * y[:, C_ // 2:])
+    out = torch.zeros(B * H * W, C_ // 2, dtype=BF16, device=d)
+    ops.dwconv(xd, B, H, W, C_, 3, 3, wd, bd, out, mode=1, x_off=8)
+    torch.cuda.synchronize()
+    err = (out.cpu().float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), f"gate: {err}"
