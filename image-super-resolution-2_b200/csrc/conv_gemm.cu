@@ -42,7 +42,13 @@ struct Args {
 //                     TMA-loaded (prefetched one block ahead) into 128B-swizzled smem, updated in place and TMA-stored
 //   EPI_RES_AUX    -- EPI_RES + aux_alpha * aux_bf16[p,n] * aux_chan[b,n] (HAT: x = shortcut + proj(attn) + 0.01 * cab * se); no bf16 copy
 //   EPI_STORE_GATE -- SimpleGate folded: 64 accumulator columns -> 32 bf16 outputs, TMA store
-enum { EPI_GENERIC = 0, EPI_STORE = 1, EPI_STORE_GELU = 2, EPI_RES = 3, EPI_RES_AUX = 4, EPI_STORE_GATE = 5 };
+//   EPI_NARROW     -- n_store <= 4 (image-space outputs): one accumulator row per thread straight from TMEM to global, fp32 / bf16
+//                     residual prefetched before the accumulator wait (BN = 16 only)
+//   EPI_OPS1..3    -- bf16 output with up to three bf16 operand tiles (res / mul / aux) of the same [pixels, n] shape:
+//                     out = post(act(acc + bias) * alpha * col_scale * mul + aux_alpha * aux * aux_chan + res); the operand
+//                     blocks are TMA-loaded one item ahead into 64B-swizzled smem, the result leaves through a TMA store
+enum { EPI_GENERIC = 0, EPI_STORE = 1, EPI_STORE_GELU = 2, EPI_RES = 3, EPI_RES_AUX = 4, EPI_STORE_GATE = 5, EPI_NARROW = 6,
+       EPI_OPS1 = 7, EPI_OPS2 = 8, EPI_OPS3 = 9 };
 
 template <int BN, int EPI, bool HALO = false>
 struct Cfg {
@@ -54,7 +60,7 @@ struct Cfg {
   static constexpr int HALO_BYTES = HALO ? HALO_A_STAGES * HALO_A_BYTES : 0;
   static constexpr int CB = BN < 32 ? BN : 32;                    // epilogue column block
   static constexpr int STG_PITCH = CB + 4;                        // floats; +4 keeps float4 accesses conflict-free (generic path)
-  static constexpr int STG_WARP_BYTES = EPI == EPI_RES ? 10240 : EPI == EPI_RES_AUX ? 12288 : (EPI == EPI_GENERIC ? 32 * STG_PITCH * 4 : 4096);
+  static constexpr int STG_WARP_BYTES = EPI == EPI_RES ? 10240 : EPI == EPI_RES_AUX ? 12288 : EPI == EPI_NARROW ? 0 : EPI >= EPI_OPS1 ? (2 * (EPI - EPI_OPS1 + 1) + 2) * 2048 : (EPI == EPI_GENERIC ? 32 * STG_PITCH * 4 : 4096);
   static constexpr int STG_BYTES = NUM_EPI_WARPS * STG_WARP_BYTES;
   static constexpr int STAGES_RAW = (225 * 1024 - STG_BYTES - HALO_BYTES) / STAGE_BYTES;
   static constexpr int STAGES_MAX = HALO ? 9 : 6;
@@ -100,6 +106,34 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case FF_ACT_SIGMOID: return sigmoidf_(v);
     case FF_ACT_CLAMP01: return fminf(fmaxf(v, 0.f), 1.f);
     default: return v;
+  }
+}
+
+// one uniform switch for a vector of values (the per-element switch of apply_act costs a branch per value)
+template <int N>
+__device__ __forceinline__ void apply_act_n(float (&v)[N], int act) {
+  switch (act) {
+    case FF_ACT_GELU:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = gelu_fast(v[i]);
+      break;
+    case FF_ACT_RELU:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.f);
+      break;
+    case FF_ACT_LRELU:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
+      break;
+    case FF_ACT_SIGMOID:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = sigmoidf_(v[i]);
+      break;
+    case FF_ACT_CLAMP01:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i], 0.f), 1.f);
+      break;
+    default: break;
   }
 }
 
@@ -249,7 +283,7 @@ template <int BN, int EPI, bool HALO>
 __global__ void __launch_bounds__(NUM_THREADS + (HALO ? 32 : 0), 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
-                    const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ Args a) {
+                    const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Args a) {
   using C = Cfg<BN, EPI, HALO>;
   constexpr int TW = C::TW, TH = C::TH, QR = C::QR;
   extern __shared__ uint8_t smem_raw[];
@@ -536,6 +570,197 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (lane == 0) {
             tma_store_4d(&tmO32, wbase + buf * 4096, n_blk, tx * TW, ty * TH + quad * QR, b);
             if (!AUX && p.out_bf16) tma_store_4d(&tmO, wbase + 8192, n_blk, tx * TW, ty * TH + quad * QR, b);
+            tma_store_commit();
+          }
+          buf ^= 1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else
+    if constexpr (EPI == EPI_NARROW) {
+      // ---------- narrow epilogue: <= 4 output channels, thread = pixel, no staging ----------
+      static_assert(BN == 16, "EPI_NARROW is the BN = 16 tile");
+      const FFConvGemm& p = a.p;
+      const int quad = warp & 3;
+      const bool worker = ((warp - 2) >> 2) == 0;      // the second warp of each quadrant only takes part in the TMEM handshake
+      float bias_r[4], cs_r[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        bias_r[n] = (p.bias && n < p.n_store) ? __ldg(p.bias + n) : 0.f;
+        cs_r[n] = p.alpha * ((p.col_scale && n < p.n_store) ? __ldg(p.col_scale + n) : 1.f);
+      }
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles;
+        const int b = m_tile / a.tiles_per_img;
+        const int t = m_tile - b * a.tiles_per_img;
+        const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        const int r = quad * 32 + lane;
+        const long long px = ((long long)(b * a.Ho + ty * TH + r / TW)) * a.Wo + tx * TW + r % TW;
+        float resv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (worker && p.res) {      // requested before the accumulator wait: the round trip hides behind the main loop
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+            if (n < p.n_store)
+              resv[n] = p.res_is_f32 ? __ldg(reinterpret_cast<const float*>(p.res) + px * p.res_ld + n)
+                                     : __bfloat162float(reinterpret_cast<const bf16*>(p.res)[px * p.res_ld + n]);
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        if (worker) {
+          uint32_t raw[16];
+          tmem_ld16(tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16), raw);
+          tc_wait_ld();
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            if (n < p.n_store) {
+              float x = __uint_as_float(raw[n]) + bias_r[n];
+              if (p.act) x = apply_act(x, p.act);
+              x = fmaf(x, cs_r[n], resv[n]);
+              if (p.post_act) x = apply_act(x, p.post_act);
+              if (p.out_f32) p.out_f32[px * p.out_f32_ld + n] = x;
+              if (p.out_bf16) reinterpret_cast<bf16*>(p.out_bf16)[px * p.out_ld + n] = __float2bfloat16_rn(x);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else
+    if constexpr (EPI >= EPI_OPS1) {
+      // ---------- bf16 operand epilogue: TMA-load res / mul / aux blocks (one item ahead) -> math -> bf16 -> TMA store ----------
+      static_assert(C::CB == 32, "EPI_OPS needs 32-column blocks");
+      constexpr int NOPS = EPI - EPI_OPS1 + 1;
+      const FFConvGemm& p = a.p;
+      const int ew = warp - 2;
+      const int quad = warp & 3;
+      const int half = ew >> 2;
+      uint8_t* wbase = smem + C::RING_BYTES + ew * C::STG_WARP_BYTES;   // [slot0 b0|b1][slot1 b0|b1]..[out b0|b1], 2 KB each
+      uint8_t* obase = wbase + NOPS * 4096;
+      // operand slots in the order res, mul, aux (maps tmR, tmO32, tmX)
+      const int s_res = 0, s_mul = p.res ? 1 : 0, s_aux = (p.res ? 1 : 0) + (p.mul ? 1 : 0);
+      const uint32_t tx_bytes = 2048u * ((p.res ? 1 : 0) + (p.mul ? 1 : 0) + (p.aux ? 1 : 0));
+      const int ncb = BN / 32;
+      int buf = 0;
+      uint32_t ph[2] = {0, 0};
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      if (lane == 0) { tma_prefetch_desc(&tmO); if (p.res) tma_prefetch_desc(&tmR); if (p.mul) tma_prefetch_desc(&tmO32); if (p.aux) tma_prefetch_desc(&tmX); }
+      auto valid = [&](int tl, int c) { return c < ncb && (tl % a.n_tiles) * BN + c * 32 < p.n_store; };
+      auto issue_load = [&](int tl, int c, int bsel) {
+        const int m_tile = tl / a.n_tiles, n_tile = tl - m_tile * a.n_tiles;
+        const int b = m_tile / a.tiles_per_img;
+        const int t = m_tile - b * a.tiles_per_img;
+        const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        const int n0 = n_tile * BN + c * 32, x0 = tx * TW, y0 = ty * TH + quad * QR;
+        mbar_arrive_expect_tx(&res_bar[ew][bsel], tx_bytes);
+        if (p.res) tma_load_4d(wbase + s_res * 4096 + bsel * 2048, &tmR, &res_bar[ew][bsel], n0, x0, y0, b);
+        if (p.mul) tma_load_4d(wbase + s_mul * 4096 + bsel * 2048, &tmO32, &res_bar[ew][bsel], n0, x0, y0, b);
+        if (p.aux) tma_load_4d(wbase + s_aux * 4096 + bsel * 2048, &tmX, &res_bar[ew][bsel], n0, x0, y0, b);
+      };
+      {
+        int ft = blockIdx.x;
+        while (ft < num_tiles && !valid(ft, half)) ft += gridDim.x;
+        if (lane == 0 && ft < num_tiles) issue_load(ft, half, 0);
+      }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+        const int b = m_tile / a.tiles_per_img;
+        const int t = m_tile - b * a.tiles_per_img;
+        const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+        for (int cb = half; valid(tile, cb); cb += 2) {
+          const int n_blk = n_tile * BN + cb * 32;
+          int ntile = tile, ncb2 = cb + 2;
+          if (!valid(ntile, ncb2)) {
+            ncb2 = half;
+            ntile = tile + gridDim.x;
+            while (ntile < num_tiles && !valid(ntile, ncb2)) ntile += gridDim.x;
+          }
+          if (lane == 0) {
+            tma_store_wait_read<1>();      // the store that read out[buf] two items ago has drained
+            if (ntile < num_tiles) issue_load(ntile, ncb2, buf ^ 1);   // operand buffers [buf^1] were consumed (generic reads) one item ago
+          }
+          uint32_t raw[32];
+          tmem_ld16(taddr + cb * 32, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+          tmem_ld16(taddr + cb * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
+          tc_wait_ld();
+          mbar_wait(&res_bar[ew][buf], ph[buf]);
+          ph[buf] ^= 1;
+          __syncwarp();
+          const int sw = (lane >> 1) & 3;
+          const uint8_t* rrow = wbase + s_res * 4096 + buf * 2048 + lane * 64;
+          const uint8_t* mrow = wbase + s_mul * 4096 + buf * 2048 + lane * 64;
+          const uint8_t* xrow = wbase + s_aux * 4096 + buf * 2048 + lane * 64;
+          uint8_t* orow = obase + buf * 2048 + lane * 64;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {          // 8 channels per 16-byte chunk
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[c * 8 + i]);
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk + c * 8) + 1);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (p.act) apply_act_n(v, p.act);
+            float cs[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cs[i] = p.alpha;
+            if (p.col_scale) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) cs[i] *= __ldg(p.col_scale + n_blk + c * 8 + i);
+            }
+            const int off = (c ^ sw) << 4;
+            if (p.mul) {
+              float m[8];
+              const uint4 q = *reinterpret_cast<const uint4*>(mrow + off);
+              m[0] = __uint_as_float(q.x << 16); m[1] = __uint_as_float(q.x & 0xffff0000u); m[2] = __uint_as_float(q.y << 16); m[3] = __uint_as_float(q.y & 0xffff0000u);
+              m[4] = __uint_as_float(q.z << 16); m[5] = __uint_as_float(q.z & 0xffff0000u); m[6] = __uint_as_float(q.w << 16); m[7] = __uint_as_float(q.w & 0xffff0000u);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) cs[i] *= m[i];
+            }
+            float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (p.res) {
+              const uint4 q = *reinterpret_cast<const uint4*>(rrow + off);
+              r[0] = __uint_as_float(q.x << 16); r[1] = __uint_as_float(q.x & 0xffff0000u); r[2] = __uint_as_float(q.y << 16); r[3] = __uint_as_float(q.y & 0xffff0000u);
+              r[4] = __uint_as_float(q.z << 16); r[5] = __uint_as_float(q.z & 0xffff0000u); r[6] = __uint_as_float(q.w << 16); r[7] = __uint_as_float(q.w & 0xffff0000u);
+            }
+            if (p.aux) {
+              float x[8];
+              const uint4 q = *reinterpret_cast<const uint4*>(xrow + off);
+              x[0] = __uint_as_float(q.x << 16); x[1] = __uint_as_float(q.x & 0xffff0000u); x[2] = __uint_as_float(q.y << 16); x[3] = __uint_as_float(q.y & 0xffff0000u);
+              x[4] = __uint_as_float(q.z << 16); x[5] = __uint_as_float(q.z & 0xffff0000u); x[6] = __uint_as_float(q.w << 16); x[7] = __uint_as_float(q.w & 0xffff0000u);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float ch = p.aux_chan ? __ldg(p.aux_chan + (long long)b * p.aux_chan_ld + n_blk + c * 8 + i) : 1.f;
+                r[i] = fmaf(p.aux_alpha * ch, x[i], r[i]);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], cs[i], r[i]);
+            if (p.post_act) apply_act_n(v, p.post_act);
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(orow + off) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmO, obase + buf * 2048, n_blk, tx * TW, ty * TH + quad * QR, b);
             tma_store_commit();
           }
           buf ^= 1;
@@ -894,7 +1119,7 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-struct Maps { CUtensorMap A, B, O, R, O32; };
+struct Maps { CUtensorMap A, B, O, R, O32, X; };
 
 template <int BN, int EPI, bool HALO = false>
 int launch_tc(const Maps& m, const Args& a, cudaStream_t st) {
@@ -912,7 +1137,7 @@ int launch_tc(const Maps& m, const Args& a, cudaStream_t st) {
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < ff_num_sms() ? tiles : ff_num_sms();
-  conv_gemm_tc_kernel<BN, EPI, HALO><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(m.A, m.B, m.O, m.R, m.O32, a);
+  conv_gemm_tc_kernel<BN, EPI, HALO><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(m.A, m.B, m.O, m.R, m.O32, m.X, a);
   FF_CHECK_LAUNCH("ff_conv_gemm");
   return FF_OK;
 }
@@ -928,8 +1153,19 @@ int launch_bn(int epi, const Maps& m, const Args& a, cudaStream_t st, bool halo)
         if (epi == EPI_STORE_GELU) return launch_tc<BN, EPI_STORE_GELU, true>(m, a, st);
         if (epi == EPI_RES) return launch_tc<BN, EPI_RES, true>(m, a, st);
       }
+      if constexpr (BN == 16) {
+        if (epi == EPI_NARROW) return launch_tc<BN, EPI_NARROW, true>(m, a, st);
+      }
       return launch_tc<BN, EPI_GENERIC, true>(m, a, st);
     }
+  }
+  if constexpr (BN == 16) {
+    if (epi == EPI_NARROW) return launch_tc<BN, EPI_NARROW, false>(m, a, st);
+  }
+  if constexpr (BN == 64) {
+    if (epi == EPI_OPS1) return launch_tc<BN, EPI_OPS1, false>(m, a, st);
+    if (epi == EPI_OPS2) return launch_tc<BN, EPI_OPS2, false>(m, a, st);
+    if (epi == EPI_OPS3) return launch_tc<BN, EPI_OPS3, false>(m, a, st);
   }
   if constexpr (BN >= 32) {
     if (epi == EPI_STORE) return launch_tc<BN, EPI_STORE>(m, a, st);
@@ -963,8 +1199,15 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   a.Wo = (p.kind == FF_CONV_2X2S2) ? p.W / 2 : p.W;
   FF_CHECK_ARG(a.Ho % TILE_H == 0 && a.Wo % TILE_W == 0 && a.Ho > 0, "ff_conv_gemm: output %dx%d must be a multiple of %dx%d", a.Ho, a.Wo, TILE_H, TILE_W);
   static const bool halo_enabled = []() { const char* e = getenv("FFB200_CONV_HALO"); return !(e && e[0] == '0'); }();
+  // bf16-operand TMA epilogue (EPI_OPS*): N tile 64, bf16 output, 1..3 bf16 operand tensors among res / mul / aux
+  auto al16p = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  int n_ops = 0;
+  if (p.n_pad % 64 == 0 && p.n_pad % 128 != 0 && p.n_pad % 192 != 0 && p.out_bf16 && !p.out_f32 && !p.pixel_shuffle && !p.gate_pairs && p.n_store % 8 == 0 &&
+      (!p.bias || al16p(p.bias)) && p.out_ld % 8 == 0 && al16p(p.out_bf16) && (!p.res || (!p.res_is_f32 && p.res_ld % 8 == 0 && al16p(p.res))) &&
+      (!p.mul || (p.mul_ld % 8 == 0 && al16p(p.mul))) && (!p.aux || (p.aux_ld % 8 == 0 && al16p(p.aux))))
+    n_ops = (p.res ? 1 : 0) + (p.mul ? 1 : 0) + (p.aux ? 1 : 0);
   const bool halo = halo_enabled && !p.debug_simt && p.kind == FF_CONV_3X3 && p.n_pad % 128 != 0 && p.n_pad % 192 != 0 && p.n_pad <= 4 * HALO_MAX_BN &&
-                    a.Ho % HALO_TH == 0 && a.Wo % HALO_TW == 0;
+                    a.Ho % HALO_TH == 0 && a.Wo % HALO_TW == 0 && n_ops == 0;   // the operand rings and the halo slabs do not fit together (and measured slower at one ring)
   const int TW = halo ? HALO_TW : TILE_W, TH = halo ? HALO_TH : TILE_H;
   if (p.gate_pairs) {
     FF_CHECK_ARG(p.out_bf16 && !p.out_f32 && !p.act && !p.mul && !p.aux && !p.res && !p.pixel_shuffle && !p.col_scale && p.n_store % 16 == 0,
@@ -1048,7 +1291,7 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   // epilogue selection: plain "bias (+GELU) -> bf16" layers and fp32-residual layers take the TMA epilogues
   int epi = EPI_GENERIC;
   Maps m;
-  m.A = tmA; m.B = tmB; m.O = tmA; m.R = tmA; m.O32 = tmA;
+  m.A = tmA; m.B = tmB; m.O = tmA; m.R = tmA; m.O32 = tmA; m.X = tmA;
   auto out_map = [&](CUtensorMap* tm, void* ptr, int ld, int esz, CUtensorMapDataType dt, CUtensorMapSwizzle sw) {
     cuuint64_t dims[4] = {(cuuint64_t)p.n_store, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)p.B};
     cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)ld * esz * a.Wo, (cuuint64_t)ld * esz * a.Wo * a.Ho};
@@ -1071,7 +1314,14 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   };
   const bool res_ok = p.res && p.res_is_f32 && p.out_f32 && p.act == FF_ACT_NONE && p.res_ld % 4 == 0 && p.out_f32_ld % 4 == 0 &&
                       (reinterpret_cast<uintptr_t>(p.res) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0;
-  if (plain && p.out_bf16 && !p.out_f32 && !p.res && !p.col_scale && p.alpha == 1.0f && (p.act == FF_ACT_NONE || p.act == FF_ACT_GELU)) {
+  if (n_ops > 0) {
+    bool ok = out_map(&m.O, p.out_bf16, p.out_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (ok && p.res) ok = out_map(&m.R, const_cast<void*>(p.res), p.res_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (ok && p.mul) ok = out_map(&m.O32, const_cast<void*>(p.mul), p.mul_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (ok && p.aux) ok = out_map(&m.X, const_cast<void*>(p.aux), p.aux_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+    FF_CHECK_ARG(ok, "ff_conv_gemm: cuTensorMapEncodeTiled failed for an epilogue operand");
+    epi = EPI_OPS1 + n_ops - 1;
+  } else if (plain && p.out_bf16 && !p.out_f32 && !p.res && !p.col_scale && p.alpha == 1.0f && (p.act == FF_ACT_NONE || p.act == FF_ACT_GELU)) {
     if (out_map(&m.O, p.out_bf16, p.out_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B))
       epi = (p.act == FF_ACT_GELU) ? EPI_STORE_GELU : EPI_STORE;
   } else if (base_ok && p.gate_pairs && BN % 64 == 0 && p.n_store % 64 == 0 && p.bias && !p.aux && !p.res && !p.out_f32 && !p.col_scale && p.alpha == 1.0f && p.act == FF_ACT_NONE) {
@@ -1088,6 +1338,7 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
               out_map(&m.O, const_cast<void*>(p.aux), p.aux_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
     if (ok) epi = EPI_RES_AUX;
   }
+  if (BN == 16 && p.n_store <= 4 && !p.mul && !p.aux && !p.pixel_shuffle && !p.gate_pairs) epi = EPI_NARROW;
   ++g_ff_launches;
   switch (BN) {
     case 256: return launch_bn<256>(epi, m, a, st, false);

@@ -64,7 +64,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float e = 1.0f - __fdividef(1.0f, p);
   return 0.5f * x * (1.0f + copysignf(e, z));
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// fast-division sigmoid (ex2.approx + rcp.approx, ~2 ulp): the IEEE divide costs more than the rest of an epilogue
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;

@@ -27,7 +27,7 @@ def _nchw(x2d, b, h, w):
 @pytest.mark.parametrize("kind,cin,cout,H,W,B", [
     ("1x1", 192, 576, 16, 16, 1), ("1x1", 384, 192, 32, 48, 2), ("3x3", 192, 64, 32, 32, 2), ("3x3", 64, 192, 16, 32, 1),
     ("3x3", 64, 256, 32, 32, 1), ("3x3", 64, 16, 32, 32, 1), ("1x1", 1024, 2048, 16, 16, 1), ("2x2s2", 64, 128, 32, 64, 2),
-    ("3x3", 128, 32, 64, 64, 1), ("1x1", 64, 128, 8, 16, 3),
+    ("3x3", 128, 32, 64, 64, 1), ("1x1", 64, 128, 8, 16, 3), ("1x1", 64, 3, 16, 32, 2), ("2x2s2", 64, 2, 32, 32, 1),
 ])
 @pytest.mark.parametrize("simt", [0, 1])
 def test_conv_gemm_plain(kind, cin, cout, H, W, B, simt):
@@ -44,8 +44,9 @@ def test_conv_gemm_plain(kind, cin, cout, H, W, B, simt):
     else:
         ref = F.conv2d(x, w, bias, padding=k // 2)
     xd = _nhwc(x).to(_dev(), BF16)
-    wd = packing.pack_conv(w, cout, cin, device=_dev())
-    bd = bias.to(_dev())
+    n_pad = (cout + 15) // 16 * 16
+    wd = packing.pack_conv(w, n_pad, cin, device=_dev())
+    bd = packing.pack_vector(bias, n_pad, device=_dev())
     Ho, Wo = ref.shape[-2:]
     out = torch.zeros(B * Ho * Wo, cout, dtype=F32, device=_dev())
     ops.conv_gemm(xd, B, H, W, cin, wd, kind={"1x1": 0, "3x3": 1, "2x2s2": 2}[kind], n_store=cout, bias=bd, out_f32=out, debug_simt=simt)
@@ -342,7 +343,7 @@ def test_layernorm_narrow_rows(C_):
     assert (err <= 4e-3 * ref.abs() + 1e-3).all(), err.max().item()     # bf16 output rounding only
 
 
-@pytest.mark.parametrize("cin,n,H,W,B", [(192, 64, 128, 128, 2), (64, 64, 48, 32, 1), (128, 32, 32, 48, 3), (64, 16, 64, 64, 2), (192, 48, 16, 16, 1), (64, 160, 32, 32, 1)])
+@pytest.mark.parametrize("cin,n,H,W,B", [(192, 64, 128, 128, 2), (64, 64, 48, 32, 1), (128, 32, 32, 48, 3), (64, 16, 64, 64, 2), (192, 48, 16, 16, 1), (64, 160, 32, 32, 1), (64, 3, 32, 32, 2), (128, 4, 16, 48, 1)])
 @pytest.mark.parametrize("epi", ["store", "gelu", "res", "generic"])
 def test_conv_gemm_halo_3x3(cin, n, H, W, B, epi):
     """3x3 convs with <= 64-wide N tiles take the halo-slab variant (A loaded once per 64-channel chunk, nine taps address it):
@@ -409,3 +410,37 @@ def test_dwconv3x3_variants(B, H, W, C_):
     torch.cuda.synchronize()
     err = (out.cpu().float() - ref).abs().max().item()
     assert err < 2e-2 * max(1.0, ref.abs().max().item()), f"gate: {err}"
+
+
+@pytest.mark.parametrize("kind,cin,H,W,B", [(0, 64, 16, 32, 2), (1, 64, 32, 32, 2), (0, 128, 128, 144, 1), (1, 128, 48, 16, 3)])
+@pytest.mark.parametrize("ops_", ["res", "mul", "aux", "res+mul", "res+aux", "res+mul+aux"])
+def test_conv_gemm_bf16_operand_epilogue(kind, cin, H, W, B, ops_):
+    """out_bf16 = post(act(acc + bias) * alpha * col_scale * mul + aux_alpha * aux * aux_chan + res) with bf16 operand tensors:
+    the TMA-operand epilogue (N tile 64), 1x1 and 3x3 (halo and plain main loops), multi-tile persistent loops."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(31)
+    n, k = 64, (3 if kind == 1 else 1)
+    x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
+    w = (torch.randn(n, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(BF16).float()
+    bias, cs = torch.randn(n, generator=g), torch.rand(n, generator=g) + 0.5
+    P = B * H * W
+    res = torch.randn(P, n, generator=g).to(BF16)
+    mul = torch.randn(P, n, generator=g).to(BF16)
+    aux = torch.randn(P, 80, generator=g).to(BF16)       # wider buffer: pitch 80, the first 64 columns are the operand
+    chan = torch.rand(B, n, generator=g)
+    v = torch.sigmoid(_nhwc(F.conv2d(x, w, bias, padding=k // 2))) * 0.7 * cs
+    kw = {}
+    if "mul" in ops_:
+        v = v * mul.float(); kw["mul"] = mul.to(_dev())
+    if "aux" in ops_:
+        v = v + 0.3 * aux[:, :n].float() * chan.repeat_interleave(H * W, 0); kw.update(aux=aux.to(_dev()), aux_chan=chan.to(_dev()), aux_alpha=0.3)
+    if "res" in ops_:
+        v = v + res.float(); kw["res"] = res.to(_dev())
+    ref = v.clamp(-1.5, 1.5) if False else F.leaky_relu(v, 0.01)
+    d = _dev()
+    out = torch.zeros(P, n, dtype=BF16, device=d)
+    ops.conv_gemm(_nhwc(x).to(d, BF16), B, H, W, cin, packing.pack_conv(w, n, cin, device=d), kind=kind, n_store=n, bias=bias.to(d), act=ops.ACT_SIGMOID,
+                  alpha=0.7, col_scale=cs.to(d), post_act=ops.ACT_LRELU, out_bf16=out, **kw)
+    torch.cuda.synchronize()
+    err = (out.cpu().float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
