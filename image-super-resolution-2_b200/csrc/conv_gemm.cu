@@ -274,6 +274,35 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// One [rows x pixels x 32 channels] epilogue block of the output-shaped tensors.  With PixelShuffle(2) folded into the layer the
+// tensor map is 5-D (channel, sub-x, x, sub-y, image row): GEMM column n = sub * cq + c lands at pixel (2y + sub / 2, 2x + sub % 2).
+__device__ __forceinline__ void tma_store_blk(const CUtensorMap* m, const void* src, const Args& a, int n_blk, int x, int y, int b) {
+  if (a.p.pixel_shuffle) {
+    const int cq = a.p.n_store >> 2, sub = n_blk / cq;
+    tma_store_5d(m, src, n_blk - sub * cq, sub & 1, x, sub >> 1, b * a.Ho + y);
+  } else {
+    tma_store_4d(m, src, n_blk, x, y, b);
+  }
+}
+__device__ __forceinline__ void tma_load_blk(void* dst, const CUtensorMap* m, uint64_t* bar, const Args& a, int n_blk, int x, int y, int b) {
+  if (a.p.pixel_shuffle) {
+    const int cq = a.p.n_store >> 2, sub = n_blk / cq;
+    tma_load_5d(dst, m, bar, n_blk - sub * cq, sub & 1, x, sub >> 1, b * a.Ho + y);
+  } else {
+    tma_load_4d(dst, m, bar, n_blk, x, y, b);
+  }
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -492,7 +521,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int t = m_tile - b * a.tiles_per_img;
         const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
         mbar_arrive_expect_tx(&res_bar[ew][bsel], AUX ? 6144 : 4096);
-        tma_load_4d(wbase + bsel * 4096, &tmR, &res_bar[ew][bsel], n_tile * BN + c * 32, tx * TW, ty * TH + quad * QR, b);
+        tma_load_blk(wbase + bsel * 4096, &tmR, &res_bar[ew][bsel], a, n_tile * BN + c * 32, tx * TW, ty * TH + quad * QR, b);
         if constexpr (AUX) tma_load_4d(wbase + 8192 + bsel * 2048, &tmO, &res_bar[ew][bsel], n_tile * BN + c * 32, tx * TW, ty * TH + quad * QR, b);
       };
       {
@@ -568,8 +597,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&tmO32, wbase + buf * 4096, n_blk, tx * TW, ty * TH + quad * QR, b);
-            if (!AUX && p.out_bf16) tma_store_4d(&tmO, wbase + 8192, n_blk, tx * TW, ty * TH + quad * QR, b);
+            tma_store_blk(&tmO32, wbase + buf * 4096, a, n_blk, tx * TW, ty * TH + quad * QR, b);
+            if (!AUX && p.out_bf16) tma_store_blk(&tmO, wbase + 8192, a, n_blk, tx * TW, ty * TH + quad * QR, b);
             tma_store_commit();
           }
           buf ^= 1;
@@ -876,6 +905,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int i = 0; i < 4; ++i) {
               float x0 = __uint_as_float(raw[c * 8 + 2 * i]) + bb[2 * i], x1 = __uint_as_float(raw[c * 8 + 2 * i + 1]) + bb[2 * i + 1];
               if constexpr (EPI == EPI_STORE_GELU) { x0 = gelu_tanh_hw(x0); x1 = gelu_tanh_hw(x1); }
+              else if (p.act) { x0 = apply_act(x0, p.act) * p.alpha; x1 = apply_act(x1, p.act) * p.alpha; }
               __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
               w[i] = *reinterpret_cast<uint32_t*>(&h);
             }
@@ -884,7 +914,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&tmO, stg_base + buf * 2048, n_blk, tx * TW, ty * TH + quad * QR, b);
+            tma_store_blk(&tmO, stg_base + buf * 2048, a, n_blk, tx * TW, ty * TH + quad * QR, b);
             tma_store_commit();
           }
           buf ^= 1;
@@ -1293,6 +1323,15 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   Maps m;
   m.A = tmA; m.B = tmB; m.O = tmA; m.R = tmA; m.O32 = tmA; m.X = tmA;
   auto out_map = [&](CUtensorMap* tm, void* ptr, int ld, int esz, CUtensorMapDataType dt, CUtensorMapSwizzle sw) {
+    if (p.pixel_shuffle) {
+      const cuuint64_t e = (cuuint64_t)ld * esz;
+      cuuint64_t dims[5] = {(cuuint64_t)(p.n_store >> 2), 2, (cuuint64_t)a.Wo, 2, (cuuint64_t)p.B * a.Ho};
+      cuuint64_t strides[4] = {e, 2 * e, 2 * e * a.Wo, 4 * e * a.Wo};
+      cuuint32_t box[5] = {32, 1, (cuuint32_t)TW, 1, (cuuint32_t)(32 / TW)};
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      return enc(tm, dt, 5, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
     cuuint64_t dims[4] = {(cuuint64_t)p.n_store, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)p.B};
     cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)ld * esz * a.Wo, (cuuint64_t)ld * esz * a.Wo * a.Ho};
     cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)(32 / TW), 1};
@@ -1302,7 +1341,9 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   };
   const bool al16 = (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) && (!p.col_scale || (reinterpret_cast<uintptr_t>(p.col_scale) & 15) == 0);
   const bool bf16_ok = !p.out_bf16 || (p.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0);
+  const bool ps_ok = !p.pixel_shuffle || (p.n_store % 128 == 0);     // 32-column blocks must not straddle a sub-pixel group
   const bool base_ok = !p.mul && !p.post_act && !p.pixel_shuffle && p.n_store % 8 == 0 && al16 && bf16_ok && BN >= 32;
+  const bool plain_ps = !p.mul && !p.post_act && ps_ok && p.n_store % 8 == 0 && al16 && bf16_ok && BN >= 32 && !p.aux && !p.gate_pairs;
   const bool plain = base_ok && !p.aux && !p.gate_pairs;
   auto map_n = [&](CUtensorMap* tm, void* ptr, int ld, int esz, CUtensorMapDataType dt, CUtensorMapSwizzle sw, int ncols) {
     cuuint64_t dims[4] = {(cuuint64_t)ncols, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)p.B};
@@ -1321,12 +1362,12 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
     if (ok && p.aux) ok = out_map(&m.X, const_cast<void*>(p.aux), p.aux_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
     FF_CHECK_ARG(ok, "ff_conv_gemm: cuTensorMapEncodeTiled failed for an epilogue operand");
     epi = EPI_OPS1 + n_ops - 1;
-  } else if (plain && p.out_bf16 && !p.out_f32 && !p.res && !p.col_scale && p.alpha == 1.0f && (p.act == FF_ACT_NONE || p.act == FF_ACT_GELU)) {
+  } else if (plain_ps && p.out_bf16 && !p.out_f32 && !p.res && !p.col_scale && (p.alpha == 1.0f || (p.act != FF_ACT_NONE && p.act != FF_ACT_GELU))) {
     if (out_map(&m.O, p.out_bf16, p.out_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B))
       epi = (p.act == FF_ACT_GELU) ? EPI_STORE_GELU : EPI_STORE;
   } else if (base_ok && p.gate_pairs && BN % 64 == 0 && p.n_store % 64 == 0 && p.bias && !p.aux && !p.res && !p.out_f32 && !p.col_scale && p.alpha == 1.0f && p.act == FF_ACT_NONE) {
     if (map_n(&m.O, p.out_bf16, p.out_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, p.n_store / 2)) epi = EPI_STORE_GATE;
-  } else if (plain && res_ok) {
+  } else if (plain_ps && res_ok) {
     bool ok = out_map(&m.R, const_cast<void*>(p.res), p.res_ld, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B) &&
               out_map(&m.O32, p.out_f32, p.out_f32_ld, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (ok && p.out_bf16) ok = out_map(&m.O, p.out_bf16, p.out_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);

@@ -1,6 +1,6 @@
 // DAT-specific kernels:
-//  * ff_dat_aim         -- Adaptive Interaction Module tail (dat_arch.py:544-560 / :650-664): per-pixel
-//                          spatial-interaction MLP (C -> C/16 -> 1, BN folded, GELU) + both sigmoid gates + sum.
+//  * ff_dat_aim         -- Adaptive Interaction Module tail (dat_arch.py:544-560 / :650-664): second layer of the
+//                          spatial-interaction MLP (the first, C -> C/16 + BN + GELU, is an ff_conv_gemm) + both gates + sum.
 //  * ff_dat_chan_gram   -- channel attention statistics (dat_arch.py:636-646): per (sample, head) Gram matrix
 //                          q^T k over all tokens plus the squared L2 norms of the q / k channels, split over
 //                          token chunks (deterministic two-phase reduction).
@@ -15,85 +15,64 @@ extern long long g_ff_launches;
 namespace {
 
 constexpr int CP = 192;
-constexpr int HID_MAX = 16;
+constexpr int HID_MAX = 32;
 
 struct AimArgs {
   const bf16* att; int att_ld;
   const bf16* conv; int conv_ld;
-  const float* cmap; int cmap_ld;   // [B][192] pre-sigmoid channel map
-  const float* w1; const float* b1; // [hid][192], [hid]
-  const float* w2; float b2;        // [hid]
-  int hid;
-  int mode;                         // 0: spatial block, 1: channel block
+  const float* cgate; int cgate_ld;   // [B][192] sigmoid(channel_interaction)
+  const bf16* hid; int hid_ld;        // [M][>= 32] gelu(W1 x + b1), columns >= nhid ignored
+  const float* w2; float b2; int nhid;
+  int mode;                           // 0: spatial block, 1: channel block
   long long M; int pixels_per_sample;
   bf16* out; int out_ld;
 };
 
+// Memory-bound gate: 8 lanes per pixel (4 pixels per warp), each lane owns 24 channels as 3 x 16-byte vectors
+// (c = 64*i + 8*sub) and 4 of the 32 hidden units of the spatial-interaction MLP (whose first layer ran on the tensor cores).
 __global__ void __launch_bounds__(256) dat_aim_kernel(const __grid_constant__ AimArgs a) {
-  __shared__ float sW1[HID_MAX * CP];
-  __shared__ float sB1[HID_MAX], sW2[HID_MAX];
-  for (int i = threadIdx.x; i < a.hid * CP; i += 256) sW1[i] = a.w1[i];
-  if (threadIdx.x < a.hid) { sB1[threadIdx.x] = a.b1[threadIdx.x]; sW2[threadIdx.x] = a.w2[threadIdx.x]; }
-  __syncthreads();
-  // 8 lanes per pixel (4 pixels per warp): each lane owns 24 channels as 3 x 16-byte vectors (c = 64*i + 8*sub), so the
-  // hidden-unit reductions need 3 shuffles instead of 5 and every global access is a 16-byte vector.
   const int lane = threadIdx.x & 31, sub = lane & 7;
+  float w2r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w2r[i] = (sub * 4 + i < a.nhid) ? __ldg(a.w2 + sub * 4 + i) : 0.f;
   const long long base0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;     // warp-uniform; M % 4 == 0 (checked on the host)
   const long long stride = (long long)gridDim.x * 32;
   for (long long base = base0; base < a.M; base += stride) {
     const long long p = base + (lane >> 3);
-    float av[24], cv[24];
+    uint4 x[3], y[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int c = i * 64 + sub * 8;
-      const uint4 x = *reinterpret_cast<const uint4*>(a.att + p * a.att_ld + c);
-      const uint4 y = *reinterpret_cast<const uint4*>(a.conv + p * a.conv_ld + c);
-      const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+      x[i] = __ldg(reinterpret_cast<const uint4*>(a.att + p * a.att_ld + c));
+      y[i] = __ldg(reinterpret_cast<const uint4*>(a.conv + p * a.conv_ld + c));
+    }
+    const uint2 hq = __ldg(reinterpret_cast<const uint2*>(a.hid + p * a.hid_ld + sub * 4));
+    float s = __uint_as_float(hq.x << 16) * w2r[0] + __uint_as_float(hq.x & 0xffff0000u) * w2r[1] + __uint_as_float(hq.y << 16) * w2r[2] +
+              __uint_as_float(hq.y & 0xffff0000u) * w2r[3];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float sg = sigmoidf_(s + a.b2);
+    const int b = (int)(p / a.pixels_per_sample);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int c = i * 64 + sub * 8;
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(a.cgate + (long long)b * a.cgate_ld + c));
+      const float4 m1 = __ldg(reinterpret_cast<const float4*>(a.cgate + (long long)b * a.cgate_ld + c + 4));
+      const float cg[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      const uint32_t xw[4] = {x[i].x, x[i].y, x[i].z, x[i].w}, yw[4] = {y[i].x, y[i].y, y[i].z, y[i].w};
+      uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        av[i * 8 + 2 * j] = __uint_as_float(xw[j] << 16); av[i * 8 + 2 * j + 1] = __uint_as_float(xw[j] & 0xffff0000u);
-        cv[i * 8 + 2 * j] = __uint_as_float(yw[j] << 16); cv[i * 8 + 2 * j + 1] = __uint_as_float(yw[j] & 0xffff0000u);
+        const float xa0 = __uint_as_float(xw[j] << 16), xa1 = __uint_as_float(xw[j] & 0xffff0000u);
+        const float xc0 = __uint_as_float(yw[j] << 16), xc1 = __uint_as_float(yw[j] & 0xffff0000u);
+        float r0, r1;
+        if (a.mode == 0) { r0 = fmaf(xa0, cg[2 * j], sg * xc0); r1 = fmaf(xa1, cg[2 * j + 1], sg * xc1); }
+        else { r0 = fmaf(xc0, cg[2 * j], sg * xa0); r1 = fmaf(xc1, cg[2 * j + 1], sg * xa1); }
+        __nv_bfloat162 hh = __floats2bfloat162_rn(r0, r1);
+        o[j] = *reinterpret_cast<uint32_t*>(&hh);
       }
-    }
-    float s = a.b2;
-    for (int h = 0; h < a.hid; ++h) {
-      float d = 0.f;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const float4* w4 = reinterpret_cast<const float4*>(sW1 + h * CP + i * 64 + sub * 8);
-        const float4 w0 = w4[0], w1 = w4[1];
-        const float* src = (a.mode == 0 ? av : cv) + i * 8;
-        d += src[0] * w0.x + src[1] * w0.y + src[2] * w0.z + src[3] * w0.w + src[4] * w1.x + src[5] * w1.y + src[6] * w1.z + src[7] * w1.w;
-      }
-      d += __shfl_xor_sync(0xffffffffu, d, 1);
-      d += __shfl_xor_sync(0xffffffffu, d, 2);
-      d += __shfl_xor_sync(0xffffffffu, d, 4);
-      s += gelu_erf(d + sB1[h]) * sW2[h];
-    }
-    const float sg = sigmoidf_(s);
-    const int b = (int)(p / a.pixels_per_sample);
-    {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c = i * 64 + sub * 8;
-        const float4 m0 = *reinterpret_cast<const float4*>(a.cmap + (long long)b * a.cmap_ld + c);
-        const float4 m1 = *reinterpret_cast<const float4*>(a.cmap + (long long)b * a.cmap_ld + c + 4);
-        const float cm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-        uint32_t o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float r[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float cg = sigmoidf_(cm[2 * j + e]);
-            const float xa = av[i * 8 + 2 * j + e], xc = cv[i * 8 + 2 * j + e];
-            r[e] = a.mode == 0 ? xa * cg + sg * xc : xa * sg + xc * cg;
-          }
-          __nv_bfloat162 hh = __floats2bfloat162_rn(r[0], r[1]);
-          o[j] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-        *reinterpret_cast<uint4*>(a.out + p * a.out_ld + c) = make_uint4(o[0], o[1], o[2], o[3]);
-      }
+      *reinterpret_cast<uint4*>(a.out + p * a.out_ld + c) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -179,13 +158,14 @@ __global__ void __launch_bounds__(1024) dat_chan_softmax_kernel(const float* __r
 
 }  // namespace
 
-extern "C" int ff_dat_aim(const void* att, int att_ld, const void* conv, int conv_ld, const float* cmap, int cmap_ld,
-                          const float* w1, const float* b1, const float* w2, float b2, int hid, int mode, long long M,
+extern "C" int ff_dat_aim(const void* att, int att_ld, const void* conv, int conv_ld, const float* cgate, int cgate_ld,
+                          const void* hid, int hid_ld, const float* w2, float b2, int nhid, int mode, long long M,
                           int pixels_per_sample, void* out, int out_ld, void* stream) {
-  FF_CHECK_ARG(att && conv && cmap && w1 && b1 && w2 && out, "ff_dat_aim: null buffer");
-  FF_CHECK_ARG(hid > 0 && hid <= HID_MAX, "ff_dat_aim: hid=%d > %d", hid, HID_MAX);
-  FF_CHECK_ARG(M % 4 == 0 && att_ld % 8 == 0 && conv_ld % 8 == 0 && out_ld % 8 == 0 && cmap_ld % 4 == 0, "ff_dat_aim: M %% 4 and 16-byte rows required");
-  AimArgs a{reinterpret_cast<const bf16*>(att), att_ld, reinterpret_cast<const bf16*>(conv), conv_ld, cmap, cmap_ld, w1, b1, w2, b2, hid, mode, M, pixels_per_sample, reinterpret_cast<bf16*>(out), out_ld};
+  FF_CHECK_ARG(att && conv && cgate && hid && w2 && out, "ff_dat_aim: null buffer");
+  FF_CHECK_ARG(nhid > 0 && nhid <= HID_MAX && hid_ld >= HID_MAX && hid_ld % 4 == 0, "ff_dat_aim: nhid=%d (max %d), hid_ld=%d", nhid, HID_MAX, hid_ld);
+  FF_CHECK_ARG(M % 4 == 0 && att_ld % 8 == 0 && conv_ld % 8 == 0 && out_ld % 8 == 0 && cgate_ld % 4 == 0, "ff_dat_aim: M %% 4 and 16-byte rows required");
+  AimArgs a{reinterpret_cast<const bf16*>(att), att_ld, reinterpret_cast<const bf16*>(conv), conv_ld, cgate, cgate_ld, reinterpret_cast<const bf16*>(hid), hid_ld,
+            w2, b2, nhid, mode, M, pixels_per_sample, reinterpret_cast<bf16*>(out), out_ld};
   int grid = ff_cdiv(M, 32);
   const int cap = ff_num_sms() * 16;
   if (grid > cap) grid = cap;

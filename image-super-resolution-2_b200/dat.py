@@ -13,7 +13,7 @@ import torch
 from . import lib as L
 from . import ops
 from .hat import CP, RGB_MEAN, Workspace, _qkv_rows, pack_qkv_bias
-from .ops import ACT_CLAMP01, ACT_GELU, ACT_LRELU, ACT_NONE, CONV_3X3
+from .ops import ACT_CLAMP01, ACT_GELU, ACT_LRELU, ACT_NONE, ACT_SIGMOID, CONV_3X3
 from .packing import (BF16, F32, fold_bn, head_pad_index, pack_conv, pack_conv_direct, pack_dw, pack_matrix,
                       pack_vector, pixel_shuffle_rows)
 
@@ -93,8 +93,8 @@ class DATRunner:
                 w, b = fold_bn(g(a + "spatial_interaction.0.weight"), g(a + "spatial_interaction.0.bias"), g(a + "spatial_interaction.1.weight"),
                                g(a + "spatial_interaction.1.bias"), g(a + "spatial_interaction.1.running_mean"), g(a + "spatial_interaction.1.running_var"))
                 d["si_hid"] = w.shape[0]
-                d["si1_w"] = pack_matrix(w.reshape(w.shape[0], C), w.shape[0], CP, col_index=hp, dtype=F32, device=dev)
-                d["si1_b"] = b.to(dev).contiguous()
+                d["si1_w"] = pack_matrix(w.reshape(w.shape[0], C), 32, CP, col_index=hp, device=dev)     # tensor-core layer, rows >= hid zero
+                d["si1_b"] = pack_vector(b, 32, device=dev)
                 d["si2_w"] = g(a + "spatial_interaction.3.weight").reshape(-1).to(dev).contiguous()
                 d["si2_b"] = float(g(a + "spatial_interaction.3.bias").item())
                 # SGFN: fc1 (180 -> 720) split into two 360-wide halves, each padded to 384
@@ -148,6 +148,7 @@ class DATRunner:
         gapv = ws.get("gap", B, CP, F32)
         ci_h = ws.get("ci_h", B, 24, F32)
         cmap = ws.get("cmap", B, CP, F32)
+        sih = ws.get("si_hid", M, 32, BF16)
         scratch = ws.get("scratch", 1, max(B * 64 * CP, B * HEADS * ((N + 511) // 512) * 1088), F32)
         wb = ws.get("chan_w", B * CP, CP, BF16)   # block-diagonal channel-attention weights (off-diagonal stays zero)
 
@@ -179,9 +180,11 @@ class DATRunner:
                     gap_src, mode = att, 1
                 ops.gap(gap_src, B, N, CP, gapv, scratch)
                 ops.vec_linear(gapv, B, CP, d["ci1_w"], d["ci1_b"], 24, ACT_GELU, ci_h, y_cols=24)
-                ops.vec_linear(ci_h, B, 24, d["ci2_w"], d["ci2_b"], CP, ACT_NONE, cmap, y_cols=CP)
+                ops.vec_linear(ci_h, B, 24, d["ci2_w"], d["ci2_b"], CP, ACT_SIGMOID, cmap, y_cols=CP)
+                # spatial interaction: first layer (C -> C/16, BN folded, GELU) on the tensor cores, second layer inside the gate kernel
+                ops.conv_gemm(convx if mode else att, B, H, W, CP, d["si1_w"], n_store=32, bias=d["si1_b"], act=ACT_GELU, out_bf16=sih)
                 L.check(lib.ff_dat_aim(C_.c_void_p(att.data_ptr()), CP, C_.c_void_p(convx.data_ptr()), CP, C_.c_void_p(cmap.data_ptr()), CP,
-                                       C_.c_void_p(d["si1_w"].data_ptr()), C_.c_void_p(d["si1_b"].data_ptr()), C_.c_void_p(d["si2_w"].data_ptr()),
+                                       C_.c_void_p(sih.data_ptr()), 32, C_.c_void_p(d["si2_w"].data_ptr()),
                                        C_.c_float(d["si2_b"]), d["si_hid"], mode, C_.c_longlong(M), N, C_.c_void_p(mix.data_ptr()), CP, st()),
                         "ff_dat_aim")
                 ops.conv_gemm(mix, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], res=src, out_f32=X)

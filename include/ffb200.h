@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FFB200_ABI_VERSION 1
+#define FFB200_ABI_VERSION 2
 
 int ff_abi_version(void);
 const char* ff_last_error(void);
@@ -166,11 +166,12 @@ int ff_bicubic_up(const float* x, int B, int C, int h, int w, int scale, float* 
  * ------------------------------------------------------------------------------------------------ */
 
 /* Adaptive Interaction Module tail, dat_arch.py:544-560 (mode 0, spatial block) / :650-664 (mode 1, channel block):
- *   s = w2 . gelu(W1 . (mode ? conv : att)[p] + b1) + b2     (spatial_interaction, BN folded into W1/b1)
- *   mode 0: out = att * sigmoid(cmap[b]) + sigmoid(s) * conv;   mode 1: out = att * sigmoid(s) + conv * sigmoid(cmap[b])
- * att / conv / out are bf16 [M][192]; cmap is the pre-sigmoid channel_interaction output [B][192]. */
-int ff_dat_aim(const void* att, int att_ld, const void* conv, int conv_ld, const float* cmap, int cmap_ld, const float* w1,
-               const float* b1, const float* w2, float b2, int hid, int mode, long long M, int pixels_per_sample, void* out,
+ *   s = w2 . hid[p] + b2, with hid = gelu(W1 . (mode ? conv : att)[p] + b1) computed beforehand by ff_conv_gemm
+ *       (spatial_interaction, BN folded into W1/b1; bf16 [M][hid_ld >= 32], columns >= nhid ignored)
+ *   mode 0: out = att * cgate[b] + sigmoid(s) * conv;   mode 1: out = att * sigmoid(s) + conv * cgate[b]
+ * att / conv / out are bf16 [M][192]; cgate = sigmoid(channel_interaction output) [B][192] fp32. */
+int ff_dat_aim(const void* att, int att_ld, const void* conv, int conv_ld, const float* cgate, int cgate_ld, const void* hid,
+               int hid_ld, const float* w2, float b2, int nhid, int mode, long long M, int pixels_per_sample, void* out,
                int out_ld, void* stream);
 
 /* Channel attention weights of AdaptiveChannelAttention (dat_arch.py:632-646): per (sample, head)

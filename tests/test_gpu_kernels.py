@@ -444,3 +444,34 @@ def test_conv_gemm_bf16_operand_epilogue(kind, cin, H, W, B, ops_):
     torch.cuda.synchronize()
     err = (out.cpu().float() - ref).abs().max().item()
     assert err < 2e-2 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("kind,cin,n,H,W,B", [(0, 128, 256, 32, 32, 2), (1, 64, 256, 16, 48, 1), (0, 256, 512, 16, 16, 1)])
+def test_conv_gemm_pixel_shuffle_tma_epilogues(kind, cin, n, H, W, B):
+    """PixelShuffle(2) folded into the layer through 5-D tensor maps: bf16 store (+LeakyReLU) and the fp32 residual epilogue
+    (out = shuffle(conv) + res, in place, with the bf16 copy) against F.pixel_shuffle."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(41)
+    k = 3 if kind == 1 else 1
+    x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
+    w = (torch.randn(n, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(BF16).float()
+    bias = torch.randn(n, generator=g)
+    ref = F.pixel_shuffle(F.conv2d(x, w, bias, padding=k // 2), 2)
+    d = _dev()
+    rows = packing.pixel_shuffle_rows(n)
+    wd, bd = packing.pack_conv(w, n, cin, row_index=rows, device=d), packing.pack_vector(bias, n, index=rows, device=d)
+    xd = _nhwc(x).to(d, BF16)
+    P4, cq = B * 4 * H * W, n // 4
+    out = torch.zeros(P4, cq, dtype=BF16, device=d)
+    ops.conv_gemm(xd, B, H, W, cin, wd, kind=kind, n_store=n, bias=bd, act=ops.ACT_LRELU, pixel_shuffle=2, out_bf16=out)
+    torch.cuda.synchronize()
+    r1 = F.leaky_relu(ref, 0.01)
+    assert (_nchw(out.cpu().float(), B, 2 * H, 2 * W) - r1).abs().max().item() < 2e-2 * max(1.0, r1.abs().max().item())
+    res = torch.randn(P4, cq, generator=g)
+    stream = res.clone().to(d)
+    o16 = torch.zeros(P4, cq, dtype=BF16, device=d)
+    ops.conv_gemm(xd, B, H, W, cin, wd, kind=kind, n_store=n, bias=bd, pixel_shuffle=2, res=stream, out_f32=stream, out_bf16=o16)
+    torch.cuda.synchronize()
+    r2 = ref + _nchw(res, B, 2 * H, 2 * W)
+    assert (_nchw(stream.cpu(), B, 2 * H, 2 * W) - r2).abs().max().item() < 3e-3 * max(1.0, r2.abs().max().item())
+    assert (_nchw(o16.cpu().float(), B, 2 * H, 2 * W) - r2).abs().max().item() < 2e-2 * max(1.0, r2.abs().max().item())
