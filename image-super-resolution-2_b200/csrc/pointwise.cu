@@ -129,6 +129,55 @@ __global__ void __launch_bounds__(256) layernorm_narrow_kernel(const float* __re
   if (ok) *reinterpret_cast<uint4*>(out + row * out_ld + sub * 8) = ln_pack8(o8);
 }
 
+// The residual-stream LayerNorm of HAT / DAT (fp32 [rows][>=192] -> bf16 / fp32, out_cols = 192, C <= 192, C % 4 == 0):
+// 16 lanes per row, two rows per warp, lanes own channel QUADS (c = 4*sub + 64*i): three 16-byte loads and three 8-byte bf16
+// stores per lane -- twice the bytes in flight per warp and half the memory instructions of the pair kernel above.
+__global__ void __launch_bounds__(256) layernorm_w192_kernel(const float* __restrict__ x, int in_ld, long long rows, int C,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                            bf16* __restrict__ out_bf16, int out_ld, float* __restrict__ out_f32, int out_f32_ld) {
+  const int lane = threadIdx.x & 31, sub = lane & 15;
+  const long long row = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+  const bool ok = row < rows;
+  const float* xr = x + (ok ? row : 0) * in_ld;
+  float4 v[3];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c = 4 * sub + 64 * i;
+    v[i] = (c < C) ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (4 * sub + 64 * i < C) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  if (!ok) return;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c = 4 * sub + 64 * i;
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c)), bb = __ldg(reinterpret_cast<const float4*>(beta + c));
+      y.x = v[i].x * rstd * g.x + bb.x; y.y = v[i].y * rstd * g.y + bb.y; y.z = v[i].z * rstd * g.z + bb.z; y.w = v[i].w * rstd * g.w + bb.w;
+    }
+    if (out_bf16) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+      *reinterpret_cast<uint2*>(out_bf16 + row * out_ld + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * out_f32_ld + c) = y;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Global average pool over pixels: x [B][P][ld] -> partial sums [B][nsplit][C] -> mean [B][out_ld]
 // (two phases, fixed summation order => deterministic).
@@ -590,21 +639,24 @@ struct DirectArgs {
   int vec_bf16, vec_f32;   // 16-byte aligned rows: vector stores allowed
 };
 
+// R = output rows per thread (tile = 16 x 8R pixels).  R = 4 for the small-Cin layers that run at HR resolution: the weight
+// staging is amortised over four times the pixels and every weight vector read from smem feeds four pixels.
+template <int R>
 __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant__ DirectArgs a) {
   extern __shared__ float sm[];
   const int pad = a.k >> 1;
-  const int PW = 16 + 2 * pad, PH = 8 + 2 * pad;
+  const int PW = 16 + 2 * pad, PH = 8 * R + 2 * pad;
   const int cs = a.Cin | 1;  // odd pitch -> conflict-free
   const int KK = a.k * a.k * a.Cin;
   const bool all_w = gridDim.y == 1;          // small Cin: every output-channel group's weights are staged once
   float* sIn = sm;                       // [PH*PW][cs]
   float* sW = sm + PH * PW * cs;         // [groups][KK][8]
-  const int tiles_x = a.W / 16, tiles_y = a.H / 8;
+  const int tiles_x = a.W / 16, tiles_y = a.H / (8 * R);
   int t = blockIdx.x;
   const int b = t / (tiles_x * tiles_y);
   t -= b * tiles_x * tiles_y;
   const int ty = t / tiles_x, tx = t - ty * tiles_x;
-  const int y0 = ty * 8 - pad, x0 = tx * 16 - pad;
+  const int y0 = ty * 8 * R - pad, x0 = tx * 16 - pad;
   for (int i = threadIdx.x; i < PH * PW * a.Cin; i += 128) {
     const int c = i % a.Cin, pp = i / a.Cin;
     const int py = pp / PW, px = pp - py * PW;
@@ -623,26 +675,36 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant_
   }
   __syncthreads();
   const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
-  const long long opix = (long long)(b * a.H + ty * 8 + py) * a.W + tx * 16 + px;
   for (int grp = g_begin; grp < g_end; ++grp) {
     const int n0 = grp * 8;
     if (n0 >= a.n_store) break;
     const float* wg = sW + (long long)(grp - g_begin) * KK * 8;
-    float acc[8];
+    float accr[R][8];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = a.bias ? __ldg(a.bias + n0 + o) : 0.f;
+    for (int o = 0; o < 8; ++o) {
+      const float bvv = a.bias ? __ldg(a.bias + n0 + o) : 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) accr[r][o] = bvv;
+    }
     for (int dy = 0; dy < a.k; ++dy)
       for (int dx = 0; dx < a.k; ++dx) {
         const float* ip = sIn + ((py + dy) * PW + px + dx) * cs;
         const float* wp = wg + (dy * a.k + dx) * a.Cin * 8;
         for (int c = 0; c < a.Cin; ++c) {
-          const float xv = ip[c];
           const float4 w0 = *reinterpret_cast<const float4*>(wp + c * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(wp + c * 8 + 4);
-          acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
-          acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float xv = ip[r * 8 * PW * cs + c];
+            accr[r][0] += xv * w0.x; accr[r][1] += xv * w0.y; accr[r][2] += xv * w0.z; accr[r][3] += xv * w0.w;
+            accr[r][4] += xv * w1.x; accr[r][5] += xv * w1.y; accr[r][6] += xv * w1.z; accr[r][7] += xv * w1.w;
+          }
         }
       }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+    float (&acc)[8] = accr[r];
+    const long long opix = (long long)(b * a.H + ty * 8 * R + r * 8 + py) * a.W + tx * 16 + px;
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = act_apply(acc[o], a.act);
     if (a.mul_f32) {
@@ -665,6 +727,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant_
       } else
         for (int o = 0; o < 8; ++o)
           if (n0 + o < a.n_store) q[o] = acc[o];
+    }
     }
   }
 }
@@ -714,6 +777,15 @@ extern "C" int ff_layernorm(const void* x, int x_is_bf16, int in_ld, long long r
       (reinterpret_cast<uintptr_t>(beta) & 15) == 0) {
     if (C == 64) layernorm_narrow_kernel<8><<<ff_cdiv(rows, 32), 256, 0, st>>>(reinterpret_cast<const float*>(x), in_ld, rows, gamma, beta, eps, reinterpret_cast<bf16*>(out_bf16), out_ld);
     else layernorm_narrow_kernel<16><<<ff_cdiv(rows, 16), 256, 0, st>>>(reinterpret_cast<const float*>(x), in_ld, rows, gamma, beta, eps, reinterpret_cast<bf16*>(out_bf16), out_ld);
+    ++g_ff_launches;
+    FF_CHECK_LAUNCH("ff_layernorm");
+    return FF_OK;
+  }
+  auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!x_is_bf16 && out_cols == 192 && C % 4 == 0 && in_ld % 4 == 0 && a16(x) && a16(gamma) && a16(beta) && (!out_bf16 || (out_ld % 4 == 0 && a16(out_bf16))) &&
+      (!out_f32 || (out_f32_ld % 4 == 0 && a16(out_f32)))) {
+    layernorm_w192_kernel<<<ff_cdiv(rows, 16), 256, 0, st>>>(reinterpret_cast<const float*>(x), in_ld, rows, C, gamma, beta, eps,
+                                                              reinterpret_cast<bf16*>(out_bf16), out_ld, out_f32, out_f32_ld);
     ++g_ff_launches;
     FF_CHECK_LAUNCH("ff_layernorm");
     return FF_OK;
@@ -852,15 +924,19 @@ extern "C" int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int
   // small input-channel counts: one block computes every output-channel group (input patch and all weights staged once)
   const bool all_w = Cin <= 16 && (size_t)k * k * Cin * Cout_pad * sizeof(float) <= 96 * 1024;
   const int wgroups = all_w ? Cout_pad / 8 : 1;
-  const size_t smem = ((size_t)(16 + 2 * pad) * (8 + 2 * pad) * (Cin | 1) + (size_t)k * k * Cin * 8 * wgroups) * sizeof(float);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // four rows per thread when the whole problem is large and the weights are staged once per block
+  const int R = (all_w && H % 32 == 0 && (long long)B * H * W >= (1 << 18)) ? 4 : 1;
+  const size_t smem = ((size_t)(16 + 2 * pad) * (8 * R + 2 * pad) * (Cin | 1) + (size_t)k * k * Cin * 8 * wgroups) * sizeof(float);
+  static size_t configured[2] = {48 * 1024, 48 * 1024};
+  if (smem > configured[R == 4]) {
+    cudaError_t e = R == 4 ? cudaFuncSetAttribute(conv_direct_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(conv_direct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ff_set_error("ff_conv_direct: smem %zu: %s", smem, cudaGetErrorString(e)); return FF_ERR_CUDA; }
-    configured = smem;
+    configured[R == 4] = smem;
   }
-  dim3 grid(B * (H / 8) * (W / 16), all_w ? 1 : Cout_pad / 8);
-  conv_direct_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  dim3 grid(B * (H / (8 * R)) * (W / 16), all_w ? 1 : Cout_pad / 8);
+  if (R == 4) conv_direct_kernel<4><<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  else conv_direct_kernel<1><<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_conv_direct");
   return FF_OK;

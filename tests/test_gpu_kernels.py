@@ -221,7 +221,7 @@ def test_layernorm_gap_vec_linear():
     from isr2_b200 import ops
     g = torch.Generator().manual_seed(6)
     d = _dev()
-    rows, C_ = 1000, 180
+    rows, C_ = 1001, 180
     x = torch.randn(rows, 192, generator=g) * 3 + 1
     gam, bet = torch.randn(C_, generator=g), torch.randn(C_, generator=g)
     ref = F.layer_norm(x[:, :C_], (C_,), gam, bet, 1e-5)
@@ -231,7 +231,7 @@ def test_layernorm_gap_vec_linear():
     torch.cuda.synchronize()
     assert (o32.cpu()[:, :C_] - ref).abs().max().item() < 1e-4
     assert torch.all(o32.cpu()[:, C_:] == 0) and torch.all(o16.cpu()[:, C_:] == 0)
-    assert (o16.cpu().float()[:, :C_] - ref).abs().max().item() < 3e-2
+    assert (o16.cpu().float()[:, :C_] - ref).abs().max().item() < 4e-3 * max(1.0, ref.abs().max().item())     # bf16 half ulp = 2^-9 relative
     # bf16 input with channel offset (DAT SpatialGate norm) and wide rows (NAFNet 1024)
     xb = torch.randn(64, 2048, generator=g).to(BF16)
     g2, b2 = torch.randn(1024, generator=g), torch.randn(1024, generator=g)
@@ -475,3 +475,25 @@ def test_conv_gemm_pixel_shuffle_tma_epilogues(kind, cin, n, H, W, B):
     r2 = ref + _nchw(res, B, 2 * H, 2 * W)
     assert (_nchw(stream.cpu(), B, 2 * H, 2 * W) - r2).abs().max().item() < 3e-3 * max(1.0, r2.abs().max().item())
     assert (_nchw(o16.cpu().float(), B, 2 * H, 2 * W) - r2).abs().max().item() < 2e-2 * max(1.0, r2.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,k,H,W", [(3, 64, 3, 512, 512), (6, 16, 3, 512, 544), (16, 1, 3, 544, 512), (3, 64, 1, 512, 512)])
+def test_conv_direct_large_images(cin, cout, k, H, W):
+    """fp32 direct conv on HR-sized images (the four-rows-per-thread variant): borders, partial channel groups, bf16 and fp32 stores."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(51)
+    d = _dev()
+    x = torch.rand(1, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g)
+    ref = _nhwc(F.gelu(F.conv2d(x, w, b, padding=k // 2)))
+    cpad = (cout + 7) // 8 * 8
+    xin = torch.zeros(H * W, cin + 1, device=d)
+    xin[:, :cin] = _nhwc(x).to(d)
+    o32 = torch.zeros(H * W, cpad, device=d)
+    o16 = torch.zeros(H * W, cpad, device=d, dtype=BF16)
+    ops.conv_direct(xin, 1, H, W, cin, k, packing.pack_conv_direct(w, cpad, d), packing.pack_vector(b, cpad, device=d), n_store=cout, act=ops.ACT_GELU, out_f32=o32)
+    ops.conv_direct(xin, 1, H, W, cin, k, packing.pack_conv_direct(w, cpad, d), packing.pack_vector(b, cpad, device=d), n_store=cout, act=ops.ACT_GELU, out_bf16=o16)
+    torch.cuda.synchronize()
+    assert (o32.cpu()[:, :cout] - ref).abs().max().item() < 1e-4
+    assert (o16.cpu().float()[:, :cout] - ref).abs().max().item() < 2e-2
