@@ -892,6 +892,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_wait_ld();
           uint8_t* dst = stg_base + buf * 2048 + lane * 64;
           const int sw = (lane >> 1) & 3;
+          float cs_v[EPI == EPI_STORE ? 32 : 1];      // this lane's row of the block, kept for the column sums (EPI_STORE only)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t w[4];
@@ -906,10 +907,27 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               float x0 = __uint_as_float(raw[c * 8 + 2 * i]) + bb[2 * i], x1 = __uint_as_float(raw[c * 8 + 2 * i + 1]) + bb[2 * i + 1];
               if constexpr (EPI == EPI_STORE_GELU) { x0 = gelu_tanh_hw(x0); x1 = gelu_tanh_hw(x1); }
               else if (p.act) { x0 = apply_act(x0, p.act) * p.alpha; x1 = apply_act(x1, p.act) * p.alpha; }
+              if constexpr (EPI == EPI_STORE) { cs_v[c * 8 + 2 * i] = x0; cs_v[c * 8 + 2 * i + 1] = x1; }
               __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
               w[i] = *reinterpret_cast<uint32_t*>(&h);
             }
             *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          if constexpr (EPI == EPI_STORE) {
+            if (p.col_sums) {
+              // transpose-reduce: after the five halving steps lane c holds the sum of column c over the warp's 32 rows
+#pragma unroll
+              for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int j = 0; j < off; ++j) {
+                  const float send = up ? cs_v[j] : cs_v[j + off];
+                  const float keep = up ? cs_v[j + off] : cs_v[j];
+                  cs_v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+              if (n_blk + lane < p.n_store) p.col_sums[((long long)m_tile * 4 + quad) * p.n_store + n_blk + lane] = cs_v[0];
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -1380,6 +1398,7 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
     if (ok) epi = EPI_RES_AUX;
   }
   if (BN == 16 && p.n_store <= 4 && !p.mul && !p.aux && !p.pixel_shuffle && !p.gate_pairs) epi = EPI_NARROW;
+  FF_CHECK_ARG(!p.col_sums || (epi == EPI_STORE && !p.pixel_shuffle), "ff_conv_gemm: col_sums needs the plain bf16-store epilogue (bias, optional non-GELU act)");
   ++g_ff_launches;
   switch (BN) {
     case 256: return launch_bn<256>(epi, m, a, st, false);

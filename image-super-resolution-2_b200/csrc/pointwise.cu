@@ -822,6 +822,14 @@ extern "C" int ff_gap(const void* x, int x_is_bf16, int ld, int B, int P, int C,
   return FF_OK;
 }
 
+extern "C" int ff_gap_finalize(const float* partial, int B, int nsplit, int C, float inv, float* out, int out_ld, void* stream) {
+  FF_CHECK_ARG(partial && out && B > 0 && nsplit > 0 && out_ld >= C, "ff_gap_finalize: bad args");
+  gap_final_kernel<<<dim3(ff_cdiv(out_ld, 128), B), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, C, nsplit, inv, out, out_ld);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_gap_finalize");
+  return FF_OK;
+}
+
 extern "C" int ff_vec_linear(const float* x, int x_ld, int R, int K, const float* W, const float* bias, int N, int act,
                              float* y, int y_ld, int y_cols, void* stream) {
   FF_CHECK_ARG(x && W && y, "ff_vec_linear: null buffer");

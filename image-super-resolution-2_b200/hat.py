@@ -158,6 +158,7 @@ class HATRunner:
         h = ws.get("h", M, 2 * CP, BF16)
         Xb = ws.get("Xb", M, CP, BF16)
         gapv = ws.get("gap", B, CP, F32)
+        gpart = ws.get("gap_part", B * (H * W // 32), CP, F32)
         se_h = ws.get("se_h", B, 8, F32)
         se = ws.get("se", B, CP, F32)
         scratch = ws.get("gap_scratch", 1, B * 64 * CP, F32)
@@ -173,8 +174,9 @@ class HATRunner:
                 ops.layernorm(src, M, C, d["norm1"][0], d["norm1"][1], 1e-5, out_bf16=t, out_cols=CP)
                 # CAB on the LN1 output (hat_arch.py:272-277)
                 ops.conv_gemm(t, B, H, W, CP, d["cab1_w"], kind=CONV_3X3, n_store=64, bias=d["cab1_b"], act=ACT_GELU, out_bf16=cab1)
-                ops.conv_gemm(cab1, B, H, W, 64, d["cab2_w"], kind=CONV_3X3, n_store=CP, bias=d["cab2_b"], out_bf16=cab2)
-                ops.gap(cab2, B, H * W, C, gapv, scratch)
+                # the conv's store epilogue also emits the per-tile column sums of the squeeze-excite average pool
+                ops.conv_gemm(cab1, B, H, W, 64, d["cab2_w"], kind=CONV_3X3, n_store=CP, bias=d["cab2_b"], out_bf16=cab2, col_sums=gpart)
+                ops.gap_finalize(gpart, B, H * W // 32, CP, 1.0 / (H * W), gapv)
                 ops.vec_linear(gapv, B, C, d["se1_w"], d["se1_b"], 6, ACT_RELU, se_h, y_cols=8)
                 ops.vec_linear(se_h, B, 6, d["se2_w"], d["se2_b"], C, ACT_SIGMOID, se, y_cols=CP)
                 # (S)W-MSA

@@ -19,7 +19,7 @@ class FFConvGemm(C.Structure):
         ("aux_alpha", C.c_float), ("res", C.c_void_p), ("res_ld", C.c_int), ("res_is_f32", C.c_int),
         ("post_act", C.c_int), ("out_bf16", C.c_void_p), ("out_ld", C.c_int), ("out_f32", C.c_void_p),
         ("out_f32_ld", C.c_int), ("pixel_shuffle", C.c_int), ("gate_pairs", C.c_int), ("w_batch_rows", C.c_int),
-        ("debug_simt", C.c_int),
+        ("debug_simt", C.c_int), ("col_sums", C.c_void_p),
     ]
 
 

@@ -46,7 +46,7 @@ def _req_cuda(*ts):
 
 def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_NONE, alpha=1.0, col_scale=None,
               mul=None, aux=None, aux_chan=None, aux_alpha=1.0, res=None, post_act=ACT_NONE, out_bf16=None,
-              out_f32=None, pixel_shuffle=0, gate_pairs=0, w_batch_rows=0, x_ld=None, debug_simt=0):
+              out_f32=None, pixel_shuffle=0, gate_pairs=0, w_batch_rows=0, x_ld=None, debug_simt=0, col_sums=None):
     """Implicit-GEMM conv / linear on tcgen05 (see ff_conv_gemm in include/ffb200.h).
 
     x: bf16 tensor whose last dim is the channel pitch (or pass x_ld); w: packed bf16 [n_pad, taps*cin].
@@ -77,6 +77,9 @@ def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_
         p.out_f32 = out_f32.data_ptr(); p.out_f32_ld = out_f32.stride(-2)
     p.pixel_shuffle = pixel_shuffle; p.gate_pairs = gate_pairs; p.w_batch_rows = w_batch_rows
     p.debug_simt = debug_simt
+    if col_sums is not None:
+        _req_cuda(col_sums)
+        p.col_sums = col_sums.data_ptr()
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -136,6 +139,12 @@ def gap(x, B, P, C_, out, scratch, *, x_off=0):
     esz = 2 if is_bf16 else 4
     L.check(L.load().ff_gap(C.c_void_p(x.data_ptr() + x_off * esz), is_bf16, x.stride(-2), B, P, C_, _ptr(out), out.stride(0), _ptr(scratch),
                             C.c_size_t(scratch.numel() * 4), _stream()), "ff_gap")
+
+
+def gap_finalize(partial, B, nsplit, C_, inv, out):
+    """out[b][c] = inv * sum_s partial[b][s][c] (second phase of the pool; partials from conv_gemm(col_sums=...))."""
+    _req_cuda(partial, out)
+    L.check(L.load().ff_gap_finalize(_ptr(partial), B, nsplit, C_, C.c_float(inv), _ptr(out), out.stride(0), _stream()), "ff_gap_finalize")
 
 
 def vec_linear(x, R, K, W, bias, N, act, y, y_cols=None):

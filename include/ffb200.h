@@ -82,6 +82,9 @@ typedef struct FFConvGemm {
                           out[p, n0/2 + i] = (acc+bias)[n0+i] * (acc+bias)[n0+8+i]; only bias + bf16 store apply */
   int w_batch_rows;    /* 0, or rows of w per sample: sample b uses weight rows [b*w_batch_rows, +n_pad) */
   int debug_simt;      /* 1: run the slow SIMT reference main loop (same epilogue) -- testing only */
+  float* col_sums;     /* optional (plain bf16-store layers only): per-(128-pixel tile, 32-row quadrant) column sums of the stored
+                        * values before bf16 rounding, [B][Ho*Wo/32][n_store] fp32 -- the global-average-pool partials of a
+                        * squeeze-excite block, finished by ff_gap_finalize (deterministic two-phase sum) */
 } FFConvGemm;
 int ff_conv_gemm(const FFConvGemm* p, void* stream);
 
@@ -130,6 +133,8 @@ int ff_layernorm(const void* x, int x_is_bf16, int in_ld, long long rows, int C,
  * dat_arch.py:411,603, nafnet_arch.py:86. */
 int ff_gap(const void* x, int x_is_bf16, int ld, int B, int P, int C, float* out, int out_ld, float* scratch,
            size_t scratch_bytes, void* stream);
+/* Second phase of the pool on its own: out[b][c] = inv * sum_s partial[b][s][c] (partials from FFConvGemm.col_sums). */
+int ff_gap_finalize(const float* partial, int B, int nsplit, int C, float inv, float* out, int out_ld, void* stream);
 
 /* y[r][n] = act(x[r][:K] . W[n][:K] + bias[n]) for per-sample vectors (SE / SCA / channel-interaction heads);
  * columns N..y_cols-1 are written as zero. */

@@ -497,3 +497,28 @@ def test_conv_direct_large_images(cin, cout, k, H, W):
     torch.cuda.synchronize()
     assert (o32.cpu()[:, :cout] - ref).abs().max().item() < 1e-4
     assert (o16.cpu().float()[:, :cout] - ref).abs().max().item() < 2e-2
+
+
+def test_conv_gemm_col_sums_and_gap_finalize():
+    """Squeeze-excite pool fused into the conv's store epilogue: per-tile column sums + ff_gap_finalize == mean over pixels
+    of the fp32 conv output (3x3 halo-free N=192 layer and a 1x1 layer with two N tiles), deterministic across runs."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(61)
+    d = _dev()
+    for kind, cin, n, B, H, W in ((1, 64, 192, 3, 32, 48), (0, 128, 384, 2, 16, 32)):
+        k = 3 if kind == 1 else 1
+        x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
+        w = (torch.randn(n, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(BF16).float()
+        bias = torch.randn(n, generator=g)
+        conv = F.conv2d(x, w, bias, padding=k // 2)
+        ref = conv.mean(dim=(2, 3))
+        out = torch.zeros(B * H * W, n, dtype=BF16, device=d)
+        part = torch.zeros(B * (H * W // 32), n, device=d)
+        pooled = [torch.zeros(B, n, device=d) for _ in range(2)]
+        for it in range(2):
+            ops.conv_gemm(_nhwc(x).to(d, BF16), B, H, W, cin, packing.pack_conv(w, n, cin, device=d), kind=kind, n_store=n, bias=bias.to(d), out_bf16=out, col_sums=part)
+            ops.gap_finalize(part, B, H * W // 32, n, 1.0 / (H * W), pooled[it])
+        torch.cuda.synchronize()
+        assert (pooled[0].cpu() - ref).abs().max().item() < 1e-3
+        assert torch.equal(pooled[0], pooled[1])
+        assert (_nchw(out.cpu().float(), B, H, W) - conv).abs().max().item() < 3e-2 * max(1.0, conv.abs().max().item())
