@@ -14,8 +14,7 @@ constexpr int TILE_W = 16;
 constexpr int TILE_H = 8;
 constexpr int BLOCK_K = 64;   // bf16 elements per k-block = 128 B = one swizzle row
 constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 2;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int NUM_EPI_WARPS = 8;    // epilogue warps of every variant except the TMA-store ones (see Cfg::EPI_WARPS)
 // HALO variant (3x3 convs with few output channels, where the A operand re-read per tap is the L2 bottleneck):
 // output tile = 16 rows x 8 cols; per 64-channel chunk the producer loads three column-shifted halo slabs
 // [18 rows][8 px][64 ch] (dx = -1, 0, +1) ONCE and the nine taps address them with a row offset (dy * 1024 B), so A
@@ -61,13 +60,16 @@ struct Cfg {
   static constexpr int CB = BN < 32 ? BN : 32;                    // epilogue column block
   static constexpr int STG_PITCH = CB + 4;                        // floats; +4 keeps float4 accesses conflict-free (generic path)
   static constexpr int STG_WARP_BYTES = EPI == EPI_RES ? 10240 : EPI == EPI_RES_AUX ? 12288 : EPI == EPI_NARROW ? 0 : EPI >= EPI_OPS1 ? (2 * (EPI - EPI_OPS1 + 1) + 2) * 2048 : (EPI == EPI_GENERIC ? 32 * STG_PITCH * 4 : 4096);
-  static constexpr int STG_BYTES = NUM_EPI_WARPS * STG_WARP_BYTES;
+  // The plain TMA-store epilogues are latency bound per warp (tcgen05.ld -> cvt -> st.shared -> proxy fence -> TMA store is one
+  // dependent chain per 32-column block), so they run four warps per TMEM lane quadrant instead of two.
+  static constexpr int EPI_WARPS = (EPI == 1 || EPI == 2) ? 16 : NUM_EPI_WARPS;
+  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
   static constexpr int STAGES_RAW = (225 * 1024 - STG_BYTES - HALO_BYTES) / STAGE_BYTES;
   static constexpr int STAGES_MAX = HALO ? 9 : 6;
   static constexpr int STAGES = STAGES_RAW > STAGES_MAX ? STAGES_MAX : STAGES_RAW;
   static constexpr int RING_BYTES = HALO_BYTES + STAGES * STAGE_BYTES;        // [halo A stages][ring]; staging follows
   static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + 1024;            // + alignment slack
-  static constexpr int THREADS = NUM_THREADS + (HALO ? 32 : 0);               // HALO: warp 10 = A-slab producer
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + (HALO ? 32 : 0);       // HALO: the last warp = A-slab producer
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -309,7 +311,7 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int BN, int EPI, bool HALO>
-__global__ void __launch_bounds__(NUM_THREADS + (HALO ? 32 : 0), 1)
+__global__ void __launch_bounds__(Cfg<BN, EPI, HALO>::THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                     const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Args a) {
@@ -341,7 +343,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[s], C::EPI_WARPS);
     }
     for (int s = 0; s < HALO_A_STAGES; ++s) {
       mbar_init(&halo_full[s], 1);
@@ -415,7 +417,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (HALO && warp == 2 + NUM_EPI_WARPS) {
+  } else if (HALO && warp == 2 + C::EPI_WARPS) {
     // ================= HALO A-slab producer =================
     int hs = 0;
     uint32_t hphase = 0;
@@ -865,7 +867,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const FFConvGemm& p = a.p;
       const int ew = warp - 2;
       const int quad = warp & 3;
-      const int half = ew >> 2;
+      const int half = ew >> 2;                 // position among the warps of this lane quadrant
+      constexpr int CB_STEP = C::EPI_WARPS / 4;
       uint8_t* stg_base = smem + C::RING_BYTES + ew * C::STG_WARP_BYTES;   // 2 x 2 KB, 512-B aligned
       int buf = 0;
       int acc = 0;
@@ -880,7 +883,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-        for (int cb = half; cb < BN / 32; cb += 2) {
+        for (int cb = half; cb < BN / 32; cb += CB_STEP) {
           const int n_blk = n_tile * BN + cb * 32;
           if (n_blk >= p.n_store) break;
           uint32_t raw[32];
