@@ -619,6 +619,157 @@ static int launch_dw_tma(const CUtensorMap& tx_, const CUtensorMap& tm_, const D
   return FF_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Large-kernel depthwise conv (the 5x5 / 1x21 / 21x1 chain of the fusion head's large-kernel attention), TMA-staged.
+// Persistent CTAs stream zero-filled halo tiles [TY+KH-1][TX+KW-1][64 ch] through a two-stage shared-memory ring.
+// A warp owns whole pixels: lane = channel pair, so one LDS.32 per lane reads a 128-byte pixel chunk conflict-free and
+// the store of a pixel is one 128-byte line.  A thread slides along a run of 16 outputs on the long axis of the kernel
+// with its K x Kc weights (float2 per tap) in registers: every staged input is read once per cross tap and feeds up to K
+// packed FFMA2, so the kernel needs ~28 (21 taps) / ~44 (5x5) issue slots per output pair and stays under the HBM time.
+// ------------------------------------------------------------------------------------------
+constexpr int DWL_THREADS = 512;
+constexpr int DWL_R = 16;
+template <int KH, int KW, int TY, int TX>
+struct DwlCfg {
+  static constexpr bool ALONG_X = KW >= KH;
+  static constexpr int HH = TY + KH - 1, HW = TX + KW - 1;
+  static constexpr int TILE_BYTES = HH * HW * 128;
+  static constexpr int STAGES = 2;
+  static constexpr int SMEM = STAGES * TILE_BYTES + 128;
+  static constexpr int K = ALONG_X ? KW : KH;     // taps along the run
+  static constexpr int KC = ALONG_X ? KH : KW;    // taps across it
+  static constexpr int RUNS = TY * TX / DWL_R;
+  static_assert((ALONG_X ? TX : TY) % DWL_R == 0, "tile must hold whole runs");
+  static_assert(SMEM <= 227 * 1024, "halo ring exceeds shared memory");
+};
+
+template <int KH, int KW, int TY, int TX>
+__global__ void __launch_bounds__(DWL_THREADS, 1) dwconv_large_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ DwArgs a,
+                                                                          int tiles_x, int tiles_y, int ctiles) {
+  using Cf = DwlCfg<KH, KW, TY, TX>;
+  constexpr int K = Cf::K, KC = Cf::KC, R = DWL_R;
+  extern __shared__ uint8_t dwl_smem_raw[];
+  __shared__ __align__(8) uint64_t full[Cf::STAGES];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dwl_smem_raw) + 127) & ~(uintptr_t)127);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int num_tiles = a.B * tiles_y * tiles_x * ctiles;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < Cf::STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int s) {     // one thread
+    const int ct = tile % ctiles;
+    int r = tile / ctiles;
+    const int tx = r % tiles_x;
+    r /= tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    mbar_arrive_expect_tx(&full[s], Cf::TILE_BYTES);
+    tma_load_4d(smem + s * Cf::TILE_BYTES, &tmX, &full[s], ct * 64, tx * TX - (KW >> 1), ty * TY - (KH >> 1), b);
+  };
+  if (tid == 0 && (int)blockIdx.x < num_tiles) issue(blockIdx.x, 0);
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int ct = tile % ctiles;
+    int r = tile / ctiles;
+    const int tx = r % tiles_x;
+    r /= tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    const int c0 = ct * 64 + lane * 2;
+    // the other stage was released by the barrier that ended the previous iteration
+    if (tid == 0) {
+      const int t2 = tile + gridDim.x;
+      if (t2 < num_tiles) issue(t2, stage ^ 1);
+    }
+    float2 w[KC][K];
+#pragma unroll
+    for (int c = 0; c < KC; ++c)
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int tap = Cf::ALONG_X ? c * KW + k : k * KW + c;
+        w[c][k] = __ldg(reinterpret_cast<const float2*>(a.w + (long long)tap * a.C + c0));
+      }
+    const float2 bv = a.bias ? __ldg(reinterpret_cast<const float2*>(a.bias + c0)) : make_float2(0.f, 0.f);
+    mbar_wait(&full[stage], phase);
+    const uint32_t base = smem_u32(smem) + stage * Cf::TILE_BYTES + lane * 4;
+#pragma unroll 1
+    for (int run = warp; run < Cf::RUNS; run += DWL_THREADS / 32) {
+      int oy, ox;           // first output pixel of the run (tile coordinates)
+      if constexpr (Cf::ALONG_X) { oy = run / (TX / R); ox = (run - oy * (TX / R)) * R; }
+      else { oy = (run / TX) * R; ox = run - (run / TX) * TX; }
+      float2 acc[R];
+#pragma unroll
+      for (int o = 0; o < R; ++o) acc[o] = bv;
+      const uint32_t rbase = base + (oy * Cf::HW + ox) * 128;      // halo pixel of (first output, tap 0); the rest are immediates
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+#pragma unroll
+        for (int i = 0; i < R + K - 1; ++i) {
+          const int off = (Cf::ALONG_X ? c * Cf::HW + i : i * Cf::HW + c) * 128;
+          uint32_t q;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"(rbase + off));
+          const float2 v = make_float2(__uint_as_float(q << 16), __uint_as_float(q & 0xffff0000u));
+#pragma unroll
+          for (int o = 0; o < R; ++o) {
+            if (i - o >= 0 && i - o < K) acc[o] = __ffma2_rn(v, w[c][i - o], acc[o]);
+          }
+        }
+      }
+      bf16* op = a.out + ((long long)(b * a.H + ty * TY + oy) * a.W + tx * TX + ox) * a.out_ld + c0;
+      const long long step = Cf::ALONG_X ? (long long)a.out_ld : (long long)a.W * a.out_ld;
+#pragma unroll
+      for (int o = 0; o < R; ++o) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(acc[o].x, acc[o].y);
+        *reinterpret_cast<uint32_t*>(op + o * step) = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    }
+    __syncthreads();      // everyone is done with this stage before it is refilled in the next iteration
+    stage ^= 1;
+    if (stage == 0) phase ^= 1;
+  }
+}
+
+typedef CUresult (*DwEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static DwEncodeTiledFn dw_encode_fn() {
+  static DwEncodeTiledFn enc = []() -> DwEncodeTiledFn {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<DwEncodeTiledFn>(ptr);
+    return nullptr;
+  }();
+  return enc;
+}
+
+template <int KH, int KW, int TY, int TX>
+static int launch_dw_large(const DwArgs& a, cudaStream_t st) {
+  using Cf = DwlCfg<KH, KW, TY, TX>;
+  DwEncodeTiledFn enc = dw_encode_fn();
+  if (!enc) { ff_set_error("ff_dwconv: cuTensorMapEncodeTiled entry point unavailable"); return FF_ERR_DRIVER; }
+  CUtensorMap tm;
+  cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+  cuuint64_t strides[3] = {(cuuint64_t)a.x_ld * 2, (cuuint64_t)a.x_ld * 2 * a.W, (cuuint64_t)a.x_ld * 2 * a.W * a.H};
+  cuuint32_t box[4] = {64, (cuuint32_t)Cf::HW, (cuuint32_t)Cf::HH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ff_set_error("ff_dwconv: cuTensorMapEncodeTiled failed with %d", (int)r); return FF_ERR_DRIVER; }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_large_tma_kernel<KH, KW, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM);
+    if (e != cudaSuccess) { ff_set_error("ff_dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FF_ERR_CUDA; }
+    configured = true;
+  }
+  const int tiles_x = a.W / TX, tiles_y = a.H / TY, ctiles = a.C / 64;
+  const long long ntiles = (long long)a.B * tiles_x * tiles_y * ctiles;
+  const int grid = (int)(ntiles < ff_num_sms() ? ntiles : ff_num_sms());
+  dwconv_large_tma_kernel<KH, KW, TY, TX><<<grid, DWL_THREADS, Cf::SMEM, st>>>(tm, a, tiles_x, tiles_y, ctiles);
+  return FF_OK;
+}
+
 // x[p][c] *= s[b][c]  (bf16 in place), 8 channels per thread
 __global__ void __launch_bounds__(256) scale_channels_kernel(bf16* __restrict__ x, int ld, long long P_per_b, int B, int C,
                                                             const float* __restrict__ s, int s_ld) {
@@ -918,7 +1069,16 @@ extern "C" int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, in
     else if (act == FF_ACT_GELU) dwconv3x3_kernel<0, 1><<<nb, 128, 0, st_>>>(a);
     else dwconv3x3_kernel<0, 2><<<nb, 128, 0, st_>>>(a);
   } else {
-    dwconv_kernel<<<ff_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+    // large-kernel chain of the fusion head: plain depthwise conv (optional bias), 64-channel chunks, tile-aligned images
+    const bool plain = mode == 0 && act == FF_ACT_NONE && !mul && C % 64 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(out) & 3) == 0 && out_ld % 2 == 0;
+    int rc = 1;            // > 0: no fast path for this shape
+    if (plain && kh == 5 && kw == 5 && H % 16 == 0 && W % 32 == 0) rc = launch_dw_large<5, 5, 16, 32>(a, st_);
+    else if (plain && kh == 1 && kw == 21 && H % 8 == 0 && W % 64 == 0) rc = launch_dw_large<1, 21, 8, 64>(a, st_);
+    else if (plain && kh == 21 && kw == 1 && H % 64 == 0 && W % 8 == 0) rc = launch_dw_large<21, 1, 64, 8>(a, st_);
+    if (rc < 0) return rc;
+    if (rc > 0) dwconv_kernel<<<ff_cdiv(total, 256), 256, 0, st_>>>(a);
   }
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_dwconv");

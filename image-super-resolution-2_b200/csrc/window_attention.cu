@@ -83,9 +83,12 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
   uint8_t* sKr = reinterpret_cast<uint8_t*>(sT + p.T);         // per key region id
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int head = p.head_off + blockIdx.y;
+  // heads are the fast grid index: the CTAs that share a window run together, so the 64-byte head slices of one token row
+  // (one 128-byte line holds two heads) are fetched from DRAM once instead of once per head pass
+  const int head_l = blockIdx.x % p.heads;
+  const int head = p.head_off + head_l;
   const int nwx = p.W / p.ww, nwy = p.H / p.wh;
-  int win = blockIdx.x;
+  int win = blockIdx.x / p.heads;
   const int b = win / (nwx * nwy);
   win -= b * nwx * nwy;
   const int wy = win / nwx, wx = win - wy * nwx;
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
       sKr[t] = inside ? (uint8_t)(region3(ys, p.H, p.wh, p.shift_y) * 3 + region3(xs, p.W, p.ww, p.shift_x)) : 0;
   }
   {
-    const float* tb = p.bias_table + (long long)(p.bias_head_off + blockIdx.y) * p.T;   // table is [heads][T]
+    const float* tb = p.bias_table + (long long)(p.bias_head_off + head_l) * p.T;   // table is [heads][T]
     for (int i = tid; i < p.T; i += NTHREADS) sT[i] = LOG2E * __ldg(tb + i);
   }
   cp_async_wait_all();
@@ -276,7 +279,7 @@ int launch(const FFWinAttn& p, size_t smem, cudaStream_t st) {
     }
     configured = smem;
   }
-  dim3 grid(p.B * (p.H / p.wh) * (p.W / p.ww), p.heads);
+  dim3 grid((unsigned)(p.B * (p.H / p.wh) * (p.W / p.ww) * p.heads));
   window_attention_kernel<KW, SGN><<<grid, NTHREADS, smem, st>>>(p);
   FF_CHECK_LAUNCH("ff_window_attention");
   return FF_OK;

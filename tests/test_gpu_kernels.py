@@ -412,6 +412,28 @@ def test_dwconv3x3_variants(B, H, W, C_):
     assert err < 2e-2 * max(1.0, ref.abs().max().item()), f"gate: {err}"
 
 
+@pytest.mark.parametrize("B,H,W,C_", [(2, 64, 64, 128), (1, 128, 64, 576), (3, 64, 128, 64)])
+@pytest.mark.parametrize("kh,kw", [(5, 5), (1, 21), (21, 1)])
+def test_dwconv_large_kernel(B, H, W, C_, kh, kw):
+    """The fusion head's large-kernel-attention depthwise chain (5x5, 1x21, 21x1; reference
+    src/models/enhanced_fusion.py LKA block) on the TMA-staged sliding-run kernel: image borders on every side, several
+    spatial and channel tiles per CTA, with and without bias, against F.conv2d on the same bf16-rounded input."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(100 * kh + kw)
+    d = _dev()
+    x = torch.randn(B, C_, H, W, generator=g).to(BF16).float()
+    w = torch.randn(C_, 1, kh, kw, generator=g) / math.sqrt(kh * kw)
+    b = torch.randn(C_, generator=g)
+    xd, wd = _nhwc(x).to(d, BF16), packing.pack_dw(w, C_, device=d)
+    for bias in (None, b):
+        ref = _nhwc(F.conv2d(x, w, bias, padding=(kh // 2, kw // 2), groups=C_))
+        out = torch.zeros(B * H * W, C_, dtype=BF16, device=d)
+        ops.dwconv(xd, B, H, W, C_, kh, kw, wd, bias.to(d) if bias is not None else None, out)
+        torch.cuda.synchronize()
+        err = (out.cpu().float() - ref).abs().max().item()
+        assert err < 1e-2 * max(1.0, ref.abs().max().item()), f"{kh}x{kw} bias={bias is not None}: {err}"
+
+
 @pytest.mark.parametrize("kind,cin,H,W,B", [(0, 64, 16, 32, 2), (1, 64, 32, 32, 2), (0, 128, 128, 144, 1), (1, 128, 48, 16, 3)])
 @pytest.mark.parametrize("ops_", ["res", "mul", "aux", "res+mul", "res+aux", "res+mul+aux"])
 def test_conv_gemm_bf16_operand_epilogue(kind, cin, H, W, B, ops_):
