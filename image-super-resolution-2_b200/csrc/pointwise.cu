@@ -268,6 +268,7 @@ struct DwArgs {
   int act; int mode;
   const bf16* mul; int mul_ld;
   bf16* out; int out_ld;
+  float* col_sums;      // optional (TMA-staged 3x3 path): per-tile column sums of the stored values, [B][tiles_y*tiles_x][cout]
 };
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
@@ -484,6 +485,7 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3x3_tma_kernel(const __g
   using Cf = DwtCfg<MUL>;
   extern __shared__ uint8_t dw_smem_raw[];
   __shared__ __align__(8) uint64_t full[Cf::STAGES];
+  __shared__ float4 pool_red[2][DWT_THREADS / 32][16];      // per-warp column sums of a tile (global-average-pool partials), by tile parity
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~(uintptr_t)127);
   const int tid = threadIdx.x;
   const int cout = MODE == 1 ? a.C / 2 : a.C;
@@ -568,6 +570,7 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3x3_tma_kernel(const __g
     load_row(0, 0);
     load_row(1, 1);
     bf16* op = a.out + ((long long)(b * a.H + ty * DWT_TY) * a.W + tx * DWT_TX + px) * a.out_ld + co0;
+    float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int row = 0; row < DWT_TY; ++row) {
       load_row((row + 2) % 3, row + 2);
@@ -597,12 +600,35 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3x3_tma_kernel(const __g
           o[0] *= m[0].x; o[1] *= m[0].y; o[2] *= m[1].x; o[3] *= m[1].y;
         }
       }
+      psum.x += o[0]; psum.y += o[1]; psum.z += o[2]; psum.w += o[3];
       if (writer) {
         const __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
         *reinterpret_cast<uint2*>(op + (long long)row * a.W * a.out_ld) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
       }
     }
+    const int par = ((tile - (int)blockIdx.x) / (int)gridDim.x) & 1;
+    if (a.col_sums) {
+      // a warp holds two pixel columns of every channel group: fold them, then leave one float4 per (warp, channel group)
+      constexpr int XOR = MODE == 1 ? 8 : 16;
+      psum.x += __shfl_xor_sync(0xffffffffu, psum.x, XOR); psum.y += __shfl_xor_sync(0xffffffffu, psum.y, XOR);
+      psum.z += __shfl_xor_sync(0xffffffffu, psum.z, XOR); psum.w += __shfl_xor_sync(0xffffffffu, psum.w, XOR);
+      const int lane = tid & 31;
+      if (lane < (MODE == 1 ? 8 : 16)) pool_red[par][tid >> 5][lane] = psum;
+    }
     __syncthreads();      // everyone is done with this stage before it is refilled in the next iteration
+    if (a.col_sums) {
+      constexpr int GROUPS = MODE == 1 ? 8 : 16;             // 4-channel groups per tile
+      if (tid < GROUPS) {
+        float4 t = pool_red[par][0][tid];
+#pragma unroll
+        for (int w2 = 1; w2 < DWT_THREADS / 32; ++w2) {
+          const float4 q = pool_red[par][w2][tid];
+          t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+        }
+        const long long prow = ((long long)b * tiles_y + ty) * tiles_x + tx;
+        *reinterpret_cast<float4*>(a.col_sums + prow * cout + ct * (MODE == 1 ? 32 : 64) + tid * 4) = t;
+      }
+    }
     if (++stage == Cf::STAGES) { stage = 0; phase ^= 1; }
   }
 }
@@ -1008,19 +1034,42 @@ extern "C" int ff_vec_linear(const float* x, int x_ld, int R, int K, const float
   return FF_OK;
 }
 
+static int dwconv_impl(const void* x, int x_ld, int B, int H, int W, int C, int kh, int kw, const float* w,
+                       const float* bias, int act, int mode, const void* mul, int mul_ld, void* out, int out_ld,
+                       float* col_sums, void* stream);
+
 extern "C" int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, int kh, int kw, const float* w,
                          const float* bias, int act, int mode, const void* mul, int mul_ld, void* out, int out_ld,
                          void* stream) {
+  return dwconv_impl(x, x_ld, B, H, W, C, kh, kw, w, bias, act, mode, mul, mul_ld, out, out_ld, nullptr, stream);
+}
+
+extern "C" int ff_dwconv_pool(const void* x, int x_ld, int B, int H, int W, int C, const float* w, const float* bias, int act, int mode,
+                              const void* mul, int mul_ld, void* out, int out_ld, float* col_sums, void* stream) {
+  FF_CHECK_ARG(col_sums != nullptr, "ff_dwconv_pool: null col_sums");
+  FF_CHECK_ARG(ff_dwconv_pool_rows(H, W, mode == 1 ? C / 2 : C, mode) > 0 && (reinterpret_cast<uintptr_t>(col_sums) & 15) == 0,
+               "ff_dwconv_pool: %dx%d x %d channels does not tile (need H %% 8 == 0, W %% 32 == 0, 64-channel (gate: 32) chunks)", H, W, C);
+  return dwconv_impl(x, x_ld, B, H, W, C, 3, 3, w, bias, act, mode, mul, mul_ld, out, out_ld, col_sums, stream);
+}
+
+extern "C" int ff_dwconv_pool_rows(int H, int W, int cout, int mode) {
+  if (H <= 0 || W <= 0 || W % DWT_TX || H % DWT_TY || cout % (mode == 1 ? 32 : 64)) return 0;
+  return (H / DWT_TY) * (W / DWT_TX);
+}
+
+static int dwconv_impl(const void* x, int x_ld, int B, int H, int W, int C, int kh, int kw, const float* w,
+                       const float* bias, int act, int mode, const void* mul, int mul_ld, void* out, int out_ld,
+                       float* col_sums, void* stream) {
   FF_CHECK_ARG(x && w && out, "ff_dwconv: null buffer");
   FF_CHECK_ARG(C % 8 == 0 && x_ld % 8 == 0 && out_ld % 8 == 0 && (mode != 1 || C % 16 == 0), "ff_dwconv: channels/pitches must be multiples of 8");
   FF_CHECK_ARG((kh & 1) && (kw & 1), "ff_dwconv: odd kernel sizes only");
-  DwArgs a{reinterpret_cast<const bf16*>(x), x_ld, B, H, W, C, kh, kw, w, bias, act, mode, reinterpret_cast<const bf16*>(mul), mul_ld, reinterpret_cast<bf16*>(out), out_ld};
+  DwArgs a{reinterpret_cast<const bf16*>(x), x_ld, B, H, W, C, kh, kw, w, bias, act, mode, reinterpret_cast<const bf16*>(mul), mul_ld, reinterpret_cast<bf16*>(out), out_ld, col_sums};
   const long long total = (long long)B * H * W * ((mode == 1 ? C / 2 : C) / 8);
   if (kh == 3 && kw == 3 && W % 4 == 0) {
     cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
     static const bool tma_enabled = []() { const char* e = getenv("FFB200_DW_TMA"); return !(e && e[0] == '0'); }();
     const int cout_ = mode == 1 ? C / 2 : C;
-    if (tma_enabled && W % DWT_TX == 0 && H % DWT_TY == 0 && cout_ % (mode == 1 ? 32 : 64) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+    if ((tma_enabled || col_sums) && W % DWT_TX == 0 && H % DWT_TY == 0 && cout_ % (mode == 1 ? 32 : 64) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!mul || (mode != 1 && (reinterpret_cast<uintptr_t>(mul) & 15) == 0 && mul_ld % 8 == 0))) {
       typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1063,6 +1112,7 @@ extern "C" int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, in
       FF_CHECK_LAUNCH("ff_dwconv");
       return FF_OK;
     }
+    FF_CHECK_ARG(!col_sums, "ff_dwconv_pool: operands are not 16-byte aligned for the TMA-staged path");
     const int nb = ff_cdiv(total / 4, 128);
     if (mode == 1) dwconv3x3_kernel<1, 0><<<nb, 128, 0, st_>>>(a);
     else if (act == FF_ACT_NONE) dwconv3x3_kernel<0, 0><<<nb, 128, 0, st_>>>(a);
@@ -1082,6 +1132,29 @@ extern "C" int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, in
   }
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_dwconv");
+  return FF_OK;
+}
+
+// out[b][n][k] = bf16(w[n][k] * s[b][k]): per-sample copies of a small 1x1-conv weight with the channel-attention scale of
+// sample b folded into its input columns, so  conv(x * s_b) = conv_b(x)  and the activation tensor is not rewritten.
+__global__ void __launch_bounds__(256) scale_weight_cols_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ s, int s_ld,
+                                                               int B, bf16* __restrict__ out, int n_pad, int k_pad) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)B * n_pad * k_pad;
+  if (idx >= total) return;
+  const int k = (int)(idx % k_pad);
+  const int n = (int)((idx / k_pad) % n_pad);
+  const int b = (int)(idx / ((long long)k_pad * n_pad));
+  const float v = (n < N && k < K) ? __ldg(w + (long long)n * K + k) * __ldg(s + (long long)b * s_ld + k) : 0.f;
+  out[idx] = __float2bfloat16_rn(v);
+}
+
+extern "C" int ff_scale_weight_cols(const float* w, int N, int K, const float* s, int s_ld, int B, void* out, int n_pad, int k_pad, void* stream) {
+  FF_CHECK_ARG(w && s && out && N > 0 && K > 0 && B > 0 && n_pad >= N && k_pad >= K, "ff_scale_weight_cols: bad args");
+  const long long total = (long long)B * n_pad * k_pad;
+  scale_weight_cols_kernel<<<ff_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, N, K, s, s_ld, B, reinterpret_cast<bf16*>(out), n_pad, k_pad);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_scale_weight_cols");
   return FF_OK;
 }
 

@@ -163,7 +163,13 @@ class DATRunner:
                 ops.layernorm(src, M, C, d["norm1"][0], d["norm1"][1], 1e-5, out_bf16=t, out_cols=CP)
                 ops.conv_gemm(t, B, H, W, CP, d["qkv_w"], n_store=3 * CP, bias=d["qkv_b"], out_bf16=qkv)
                 # conv branch on v (image form of v: channels 384..575 of qkv)
-                ops.dwconv(qkv, B, H, W, CP, 3, 3, d["dw_w"], d["dw_b"], convx, act=ACT_GELU, x_off=2 * CP)
+                pool_rows = ops.dwconv_pool_rows(H, W, CP, 0) if d["spatial"] else 0
+                if pool_rows:
+                    # spatial blocks pool the conv branch: the depthwise kernel emits the per-tile sums
+                    gpart = ws.get("gpart_dw", B * pool_rows, CP, F32)
+                    ops.dwconv_pool(qkv, B, H, W, CP, d["dw_w"], d["dw_b"], convx, gpart, act=ACT_GELU, x_off=2 * CP)
+                else:
+                    ops.dwconv(qkv, B, H, W, CP, 3, 3, d["dw_w"], d["dw_b"], convx, act=ACT_GELU, x_off=2 * CP)
                 if d["spatial"]:
                     for br in range(2):
                         wh, ww = (SPLIT[0], SPLIT[1]) if br == 0 else (SPLIT[1], SPLIT[0])
@@ -176,9 +182,15 @@ class DATRunner:
                                                                  C_.c_void_p(scratch.data_ptr()), C_.c_size_t(scratch.numel() * 4), st()),
                             "ff_dat_channel_attention_weights")
                     # attn @ v with per-sample block-diagonal weights; A = v (channels 384.. of qkv)
-                    ops.conv_gemm(qkv[:, 2 * CP:], B, H, W, CP, wb, n_store=CP, w_batch_rows=CP, out_bf16=att, x_ld=3 * CP)
+                    # the store epilogue emits the pool partials of the attention branch
+                    gpart = ws.get("gpart_att", B * (N // 32), CP, F32)
+                    pool_rows = N // 32
+                    ops.conv_gemm(qkv[:, 2 * CP:], B, H, W, CP, wb, n_store=CP, w_batch_rows=CP, out_bf16=att, x_ld=3 * CP, col_sums=gpart)
                     gap_src, mode = att, 1
-                ops.gap(gap_src, B, N, CP, gapv, scratch)
+                if pool_rows:
+                    ops.gap_finalize(gpart, B, pool_rows, CP, 1.0 / N, gapv)
+                else:
+                    ops.gap(gap_src, B, N, CP, gapv, scratch)
                 ops.vec_linear(gapv, B, CP, d["ci1_w"], d["ci1_b"], 24, ACT_GELU, ci_h, y_cols=24)
                 ops.vec_linear(ci_h, B, 24, d["ci2_w"], d["ci2_b"], CP, ACT_SIGMOID, cmap, y_cols=CP)
                 # spatial interaction: first layer (C -> C/16, BN folded, GELU) on the tensor cores, second layer inside the gate kernel

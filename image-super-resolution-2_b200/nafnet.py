@@ -46,6 +46,7 @@ class NAFNetRunner:
                 w1=pack_matrix(g(p + "conv1.weight").reshape(2 * c, c), 2 * c, c, device=dev), b1=g(p + "conv1.bias").to(dev),
                 dw=pack_dw(g(p + "conv2.weight"), 2 * c, device=dev), dwb=g(p + "conv2.bias").to(dev),
                 w3=pack_matrix(g(p + "conv3.weight").reshape(c, c), c, c, device=dev), b3=g(p + "conv3.bias").to(dev),
+                w3_f32=g(p + "conv3.weight").reshape(c, c).to(dev).contiguous(),
                 sca_w=g(p + "sca.1.weight").reshape(c, c).to(dev).contiguous(), sca_b=g(p + "sca.1.bias").to(dev),
                 w4=pack_matrix(g(p + "conv4.weight").reshape(2 * c, c)[perm], 2 * c, c, device=dev), b4=g(p + "conv4.bias")[perm].contiguous().to(dev),
                 w5=pack_matrix(g(p + "conv5.weight").reshape(c, c), c, c, device=dev), b5=g(p + "conv5.bias").to(dev),
@@ -77,11 +78,24 @@ class NAFNetRunner:
         t, a, gt, gapv, sca, scratch = bufs
         ops.layernorm(S, P, c, d["n1"][0], d["n1"][1], 1e-6, out_bf16=t, out_cols=c)
         ops.conv_gemm(t, B, H, W, c, d["w1"], n_store=2 * c, bias=d["b1"], out_bf16=a)
-        ops.dwconv(a, B, H, W, 2 * c, 3, 3, d["dw"], d["dwb"], gt, mode=1)
-        ops.gap(gt, B, H * W, c, gapv, scratch)
+        rows = ops.dwconv_pool_rows(H, W, c, 1)
+        if rows:
+            # the SimpleGate depthwise kernel also emits the per-tile sums of the SCA average pool
+            gpart = self.ws.get(f"gpart{c}", B * rows, c, F32)
+            ops.dwconv_pool(a, B, H, W, 2 * c, d["dw"], d["dwb"], gt, gpart, mode=1)
+            ops.gap_finalize(gpart, B, rows, c, 1.0 / (H * W), gapv)
+        else:
+            ops.dwconv(a, B, H, W, 2 * c, 3, 3, d["dw"], d["dwb"], gt, mode=1)
+            ops.gap(gt, B, H * W, c, gapv, scratch)
         ops.vec_linear(gapv, B, c, d["sca_w"], d["sca_b"], c, ACT_NONE, sca)
-        ops.scale_channels(gt, B, H * W, c, sca)
-        ops.conv_gemm(gt, B, H, W, c, d["w3"], n_store=c, bias=d["b3"], col_scale=d["beta"], res=S, out_f32=S)
+        if c < H * W:
+            # x * sca folded into per-sample conv3 weights (c*c per sample instead of a pass over H*W*c activations)
+            w3b = self.ws.get(f"w3b{c}", B * c, c, BF16)
+            ops.scale_weight_cols(d["w3_f32"], sca, w3b.view(B, c, c))
+            ops.conv_gemm(gt, B, H, W, c, w3b, n_store=c, w_batch_rows=c, bias=d["b3"], col_scale=d["beta"], res=S, out_f32=S)
+        else:
+            ops.scale_channels(gt, B, H * W, c, sca)
+            ops.conv_gemm(gt, B, H, W, c, d["w3"], n_store=c, bias=d["b3"], col_scale=d["beta"], res=S, out_f32=S)
         ops.layernorm(S, P, c, d["n2"][0], d["n2"][1], 1e-6, out_bf16=t, out_cols=c)
         ops.conv_gemm(t, B, H, W, c, d["w4"], n_store=2 * c, bias=d["b4"], gate_pairs=1, out_bf16=gt)
         ops.conv_gemm(gt, B, H, W, c, d["w5"], n_store=c, bias=d["b5"], col_scale=d["gamma"], res=S, out_f32=S,

@@ -161,10 +161,31 @@ def dwconv(x, B, H, W, C_, kh, kw, w, bias, out, *, act=ACT_NONE, mode=0, mul=No
                                mul.stride(-2) if mul is not None else 0, _ptr(out), out.stride(-2), _stream()), "ff_dwconv")
 
 
+def dwconv_pool_rows(H, W, cout, mode=0):
+    """Partial rows per sample of dwconv_pool, 0 when the shape does not tile for the fused pool."""
+    return int(L.load().ff_dwconv_pool_rows(H, W, cout, mode))
+
+
+def dwconv_pool(x, B, H, W, C_, w, bias, out, col_sums, *, act=ACT_NONE, mode=0, mul=None, x_off=0, x_ld=None):
+    """3x3 depthwise conv + per-tile column sums of its output (finish with gap_finalize)."""
+    _req_cuda(x, w, bias, out, mul, col_sums)
+    L.check(L.load().ff_dwconv_pool(C.c_void_p(x.data_ptr() + 2 * x_off), x_ld if x_ld is not None else x.stride(-2), B, H, W, C_,
+                                    _ptr(w), _ptr(bias), act, mode, _ptr(mul), mul.stride(-2) if mul is not None else 0,
+                                    _ptr(out), out.stride(-2), _ptr(col_sums), _stream()), "ff_dwconv_pool")
+
+
 def scale_channels(x, B, pixels_per_sample, C_, s):
     _req_cuda(x, s)
     L.check(L.load().ff_scale_channels(_ptr(x), x.stride(-2), B, C.c_longlong(pixels_per_sample), C_, _ptr(s), s.stride(0), _stream()),
             "ff_scale_channels")
+
+
+def scale_weight_cols(w_f32, s, out):
+    """out[b] = bf16(w * s[b][None, :]) -- see ff_scale_weight_cols."""
+    _req_cuda(w_f32, s, out)
+    N, K = w_f32.shape
+    B, n_pad, k_pad = out.shape
+    L.check(L.load().ff_scale_weight_cols(_ptr(w_f32), N, K, _ptr(s), s.stride(0), B, _ptr(out), n_pad, k_pad, _stream()), "ff_scale_weight_cols")
 
 
 def conv_direct(x, B, H, W, Cin, k, w, bias, *, n_store, act=ACT_NONE, mul_f32=None, out_bf16=None, out_f32=None,

@@ -148,8 +148,23 @@ int ff_vec_linear(const float* x, int x_ld, int R, int K, const float* W, const 
 int ff_dwconv(const void* x, int x_ld, int B, int H, int W, int C, int kh, int kw, const float* w, const float* bias,
               int act, int mode, const void* mul, int mul_ld, void* out, int out_ld, void* stream);
 
+/* 3x3 depthwise conv (same operands as ff_dwconv) that also emits the global-average-pool partials of its output:
+ * col_sums [B][rows][cout] fp32 with rows = ff_dwconv_pool_rows(H, W, cout, mode) tile sums of the stored values before
+ * bf16 rounding; ff_gap_finalize(col_sums, B, rows, cout, 1/(H*W), ...) finishes the pool.  Fuses the AdaptiveAvgPool2d(1)
+ * of nafnet_arch.py:86,117 (SCA on the SimpleGate output) and dat_arch.py:411 (channel interaction on the conv branch)
+ * into the producer.  ff_dwconv_pool_rows returns 0 when the shape does not tile (use ff_dwconv + ff_gap then). */
+int ff_dwconv_pool(const void* x, int x_ld, int B, int H, int W, int C, const float* w, const float* bias, int act, int mode,
+                   const void* mul, int mul_ld, void* out, int out_ld, float* col_sums, void* stream);
+int ff_dwconv_pool_rows(int H, int W, int cout, int mode);
+
 /* x[p][c] *= s[b][c] in place (bf16): NAFNet simplified channel attention, nafnet_arch.py:118. */
 int ff_scale_channels(void* x, int ld, int B, long long pixels_per_sample, int C, const float* s, int s_ld, void* stream);
+
+/* Per-sample weights with a channel-attention scale folded into the input columns: out[b][n][k] = bf16(w[n][k] * s[b][k]),
+ * zero outside [N) x [K), laid out [B][n_pad][k_pad] for FFConvGemm.w_batch_rows = n_pad.  Replaces the in-place
+ * `x * sca(x)` of nafnet_arch.py:118 when the weight is smaller than the activation (conv3(x * s_b) = conv3_b(x)). */
+int ff_scale_weight_cols(const float* w, int N, int K, const float* s, int s_ld, int B, void* out, int n_pad, int k_pad,
+                         void* stream);
 
 /* Direct fp32 convolution (k = 1 or 3, zero pad) for small channel counts: image-space first/last layers and
  * the fp32 routing path of the fusion head (fusion_network.py:167-236,543-607).  w is fp32 [Cout_pad][k*k*Cin]. */

@@ -544,3 +544,86 @@ def test_conv_gemm_col_sums_and_gap_finalize():
         assert (pooled[0].cpu() - ref).abs().max().item() < 1e-3
         assert torch.equal(pooled[0], pooled[1])
         assert (_nchw(out.cpu().float(), B, H, W) - conv).abs().max().item() < 3e-2 * max(1.0, conv.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H,W,ld", [(2, 32, 48, 8), (1, 64, 64, 4), (1, 6, 10, 5)])
+def test_gauss_down(B, H, W, ld):
+    """Laplacian-pyramid down step (5x5 Gaussian blur with zero padding, then 2x2 mean; reference
+    src/models/fusion_network.py LaplacianPyramidRefinement) as one 6x6 stencil, against F.conv2d + avg_pool2d."""
+    import ctypes as C_
+    from isr2_b200 import lib as L
+    g = torch.Generator().manual_seed(5)
+    d = _dev()
+    x = torch.rand(B, 3, H, W, generator=g)
+    k1 = torch.tensor([1.0, 4.0, 6.0, 4.0, 1.0]) / 16.0
+    k2 = (k1[:, None] * k1[None, :]).expand(3, 1, 5, 5).contiguous()
+    ref = F.avg_pool2d(F.conv2d(x, k2, padding=2, groups=3), 2)
+    cur = torch.zeros(B * H * W, ld)
+    cur[:, :3] = x.permute(0, 2, 3, 1).reshape(-1, 3)
+    cur, k1d = cur.to(d), k1.to(d)
+    down = torch.full((B * (H // 2) * (W // 2), 4), 7.0, device=d)
+    L.check(L.load().ff_gauss_down(C_.c_void_p(cur.data_ptr()), ld, B, H, W, C_.c_void_p(k1d.data_ptr()), C_.c_void_p(down.data_ptr()), 4, None), "ff_gauss_down")
+    torch.cuda.synchronize()
+    got = down.cpu()
+    assert (got[:, :3] - ref.permute(0, 2, 3, 1).reshape(-1, 3)).abs().max().item() < 1e-6
+    assert torch.all(got[:, 3] == 0)
+
+
+def test_scale_weight_cols_matches_scaled_input():
+    """conv(x * s_b) == conv_b(x) with the per-sample weights of ff_scale_weight_cols (NAFNet SCA, nafnet_arch.py:118)."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(9)
+    d = _dev()
+    B, H, W, c = 3, 16, 32, 64
+    x = torch.randn(B * H * W, c, generator=g).to(BF16)
+    w = torch.randn(c, c, generator=g) / 8
+    s = torch.rand(B, c, generator=g) + 0.5
+    wb = torch.zeros(B, c, c, dtype=BF16, device=d)
+    ops.scale_weight_cols(w.to(d), s.to(d), wb)
+    torch.cuda.synchronize()
+    assert torch.equal(wb.cpu(), (w[None] * s[:, None, :]).to(BF16))
+    out = torch.zeros(B * H * W, c, dtype=BF16, device=d)
+    ops.conv_gemm(x.to(d), B, H, W, c, wb.view(B * c, c), n_store=c, w_batch_rows=c, out_bf16=out)
+    torch.cuda.synchronize()
+    ref = torch.einsum("bpk,bnk->bpn", x.float().view(B, H * W, c), (w[None] * s[:, None, :]).to(BF16).float()).reshape(-1, c)
+    assert (out.cpu().float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("mode,act,with_mul", [(0, 1, False), (1, 0, False), (0, 0, True)])
+def test_dwconv_pool(mode, act, with_mul):
+    """3x3 depthwise conv with the average-pool partials fused in (NAFNet SCA on the SimpleGate output, DAT channel
+    interaction on the conv branch): outputs identical to ff_dwconv, pooled mean == mean of the fp32 result, deterministic."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(77 + mode)
+    d = _dev()
+    B, H, W, C_ = 3, 24, 64, 128
+    cout = C_ // 2 if mode == 1 else C_
+    x = torch.randn(B, C_, H, W, generator=g).to(BF16).float()
+    w = torch.randn(C_, 1, 3, 3, generator=g) / 3
+    b = torch.randn(C_, generator=g)
+    y = F.conv2d(x, w, b, padding=1, groups=C_)
+    mul = torch.randn(B * H * W, cout, generator=g).to(BF16) if with_mul else None
+    if mode == 1:
+        full = _nhwc(y[:, :cout] * y[:, cout:])
+    else:
+        full = _nhwc(F.gelu(y) if act == 1 else y) * (mul.float() if with_mul else 1.0)
+    ref_mean = full.view(B, H * W, cout).mean(1)
+    rows = ops.dwconv_pool_rows(H, W, cout, mode)
+    assert rows == (H // 8) * (W // 32)
+    assert ops.dwconv_pool_rows(H, W + 8, cout, mode) == 0
+    xd, wd, bd = _nhwc(x).to(d, BF16), packing.pack_dw(w, C_, device=d), b.to(d)
+    md = mul.to(d) if with_mul else None
+    plain = torch.zeros(B * H * W, cout, dtype=BF16, device=d)
+    ops.dwconv(xd, B, H, W, C_, 3, 3, wd, bd, plain, act=act, mode=mode, mul=md)
+    pooled = []
+    for _ in range(2):
+        out = torch.zeros(B * H * W, cout, dtype=BF16, device=d)
+        part = torch.full((B * rows, cout), 3.0, device=d)
+        mean = torch.zeros(B, cout, device=d)
+        ops.dwconv_pool(xd, B, H, W, C_, wd, bd, out, part, act=act, mode=mode, mul=md)
+        ops.gap_finalize(part, B, rows, cout, 1.0 / (H * W), mean)
+        torch.cuda.synchronize()
+        assert torch.equal(out, plain)
+        pooled.append(mean)
+    assert torch.equal(pooled[0], pooled[1])
+    assert (pooled[0].cpu() - ref_mean).abs().max().item() < 2e-3 * max(1.0, ref_mean.abs().max().item())
