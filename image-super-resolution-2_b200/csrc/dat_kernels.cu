@@ -79,54 +79,106 @@ __global__ void __launch_bounds__(256) dat_aim_kernel(const __grid_constant__ Ai
 
 // partial[b*heads+h][chunk][0..1023] = G (i*32+j), [1024..1055] = |q_i|^2, [1056..1087] = |k_j|^2
 constexpr int GRAM_STRIDE = 1088;
-constexpr int GRAM_TOK = 64;
+
+// Tensor-core Gram matrix: G = Q^T K over a chunk of 512 tokens.  Each of the 8 warps copies its own 64 tokens (q and k rows
+// of this head, 64 B each) into a private XOR-swizzled staging area with cp.async, runs 4 k-steps of mma.sync m16n8k16
+// (A = Q^T and B = K both come out of [token][dim] rows through ldmatrix.trans, fp32 accumulation of exact bf16 products)
+// and the squared channel norms on the side; the warps' 32x32 partials are then summed through shared memory.
+constexpr int GRAM_WARP_TOK = 64;
+constexpr int GRAM_WARP_BYTES = 2 * GRAM_WARP_TOK * 64;                 // q + k rows of one warp
+constexpr int GRAM_SMEM = 8 * GRAM_WARP_BYTES;
+__device__ __forceinline__ int gram_swz(int row, int chunk) { return row * 32 + ((chunk ^ ((row >> 1) & 3)) << 3); }   // bf16 element offset
 
 __global__ void __launch_bounds__(256) dat_chan_gram_kernel(const bf16* __restrict__ qkv, int ld, int q_off, int k_off, int N,
                                                            int heads, int chunk_tokens, float* __restrict__ partial, int nchunks) {
-  __shared__ float sq[GRAM_TOK][33], sk[GRAM_TOK][33];
+  extern __shared__ __align__(16) uint8_t gram_smem[];
   const int bh = blockIdx.x, chunk = blockIdx.y;
   const int b = bh / heads, h = bh - b * heads;
-  const int t0 = chunk * chunk_tokens, t1 = min(N, t0 + chunk_tokens);
-  const int tid = threadIdx.x;
-  const int i0 = (tid >> 4) * 2, j0 = (tid & 15) * 2;   // 2x2 sub-block of the 32x32 Gram matrix
-  float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f, nq = 0.f, nk = 0.f;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t1 = min(N, (chunk + 1) * chunk_tokens);
+  const int tw = chunk * chunk_tokens + warp * GRAM_WARP_TOK;          // first token of this warp
+  bf16* sQ = reinterpret_cast<bf16*>(gram_smem + warp * GRAM_WARP_BYTES);
+  bf16* sK = sQ + GRAM_WARP_TOK * 32;
   const bf16* base = qkv + ((long long)b * N) * ld + h * 32;
-  for (int t = t0; t < t1; t += GRAM_TOK) {
-    // load 64 tokens x 32 dims of q and k (each thread: 8 q + 8 k values)
-    {
-      const int tok = tid >> 2, part = (tid & 3) * 8;
-      float fq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (t + tok < t1) {
-        const bf16* row = base + (long long)(t + tok) * ld + part;
-        const uint4 uq = *reinterpret_cast<const uint4*>(row + q_off);
-        const uint4 uk = *reinterpret_cast<const uint4*>(row + k_off);
-        const uint32_t wq[4] = {uq.x, uq.y, uq.z, uq.w}, wk[4] = {uk.x, uk.y, uk.z, uk.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          fq[2 * e] = __uint_as_float(wq[e] << 16); fq[2 * e + 1] = __uint_as_float(wq[e] & 0xffff0000u);
-          fk[2 * e] = __uint_as_float(wk[e] << 16); fk[2 * e + 1] = __uint_as_float(wk[e] & 0xffff0000u);
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { sq[tok][part + e] = fq[e]; sk[tok][part + e] = fk[e]; }
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int n = 0; n < GRAM_TOK; ++n) {
-      const float a0 = sq[n][i0], a1 = sq[n][i0 + 1], b0 = sk[n][j0], b1 = sk[n][j0 + 1];
-      g00 += a0 * b0; g01 += a0 * b1; g10 += a1 * b0; g11 += a1 * b1;
-    }
-    if (tid < 32) {
-      for (int n = 0; n < GRAM_TOK; ++n) nq += sq[n][tid] * sq[n][tid];
-    } else if (tid < 64) {
-      for (int n = 0; n < GRAM_TOK; ++n) nk += sk[n][tid - 32] * sk[n][tid - 32];
-    }
-    __syncthreads();
+  for (int it = 0; it < 8; ++it) {
+    const int idx = it * 32 + lane, r = idx >> 2, part = idx & 3;
+    const bool ok = tw + r < t1;
+    const bf16* row = ok ? base + (long long)(tw + r) * ld + part * 8 : base;
+    const uint32_t dq = smem_u32(sQ + gram_swz(r, part)), dk = smem_u32(sK + gram_swz(r, part));
+    const int nb = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dq), "l"(row + (ok ? q_off : 0)), "r"(nb) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dk), "l"(row + (ok ? k_off : 0)), "r"(nb) : "memory");
   }
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  float acc[2][4][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mi][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < GRAM_WARP_TOK / 16; ++ks) {
+    uint32_t a[2][4], bq[2][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      // matrices: (dims 16mi..+7, tok 0-7), (dims +8..+15, tok 0-7), (dims ..+7, tok 8-15), (dims +8.., tok 8-15)
+      const int tok = ks * 16 + (lane & 7) + ((lane >> 4) << 3);
+      const uint32_t addr = smem_u32(sQ + gram_swz(tok, mi * 2 + ((lane >> 3) & 1)));
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(a[mi][0]), "=r"(a[mi][1]), "=r"(a[mi][2]), "=r"(a[mi][3]) : "r"(addr));
+    }
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp) {
+      const int tok = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const uint32_t addr = smem_u32(sK + gram_swz(tok, dp * 2 + (lane >> 4)));
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(bq[dp][0]), "=r"(bq[dp][1]), "=r"(bq[dp][2]), "=r"(bq[dp][3]) : "r"(addr));
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float (&d)[4] = acc[mi][nt];
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[mi][0]), "r"(a[mi][1]), "r"(a[mi][2]), "r"(a[mi][3]), "r"(bq[nt >> 1][(nt & 1) * 2]), "r"(bq[nt >> 1][(nt & 1) * 2 + 1]));
+      }
+  }
+  // squared norms of dim `lane` over this warp's tokens (a 64-byte row is one wavefront whatever the swizzle)
+  float nq = 0.f, nk = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < GRAM_WARP_TOK; ++r) {
+    const int off = gram_swz(r, lane >> 3) + (lane & 7);
+    const float vq = __bfloat162float(sQ[off]), vk = __bfloat162float(sK[off]);
+    nq = fmaf(vq, vq, nq); nk = fmaf(vk, vk, nk);
+  }
+  __syncwarp();
+  // this warp's partial over its own staging area: [1024 G][32 |q|^2][32 |k|^2] floats (4352 B <= 8 KB)
+  float* red = reinterpret_cast<float*>(gram_smem + warp * GRAM_WARP_BYTES);
+  {
+    const int g = lane >> 2, q2 = (lane & 3) * 2;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int i = mi * 16 + g, j = nt * 8 + q2;
+        red[i * 32 + j] = acc[mi][nt][0]; red[i * 32 + j + 1] = acc[mi][nt][1];
+        red[(i + 8) * 32 + j] = acc[mi][nt][2]; red[(i + 8) * 32 + j + 1] = acc[mi][nt][3];
+      }
+    red[1024 + lane] = nq;
+    red[1056 + lane] = nk;
+  }
+  __syncthreads();
   float* out = partial + ((long long)bh * nchunks + chunk) * GRAM_STRIDE;
-  out[i0 * 32 + j0] = g00; out[i0 * 32 + j0 + 1] = g01; out[(i0 + 1) * 32 + j0] = g10; out[(i0 + 1) * 32 + j0 + 1] = g11;
-  if (tid < 32) out[1024 + tid] = nq;
-  else if (tid < 64) out[1056 + tid - 32] = nk;
+  for (int e = tid; e < GRAM_STRIDE; e += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += reinterpret_cast<const float*>(gram_smem + w * GRAM_WARP_BYTES)[e];
+    out[e] = t;
+  }
 }
 
 __global__ void __launch_bounds__(1024) dat_chan_softmax_kernel(const float* __restrict__ partial, int nchunks, int heads, int hd,
@@ -184,7 +236,13 @@ extern "C" int ff_dat_channel_attention_weights(const void* qkv, int ld, int q_o
   int nchunks = ff_cdiv(N, chunk);
   FF_CHECK_ARG(scratch_bytes >= (size_t)B * heads * nchunks * GRAM_STRIDE * sizeof(float), "ff_dat_channel_attention_weights: scratch too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dat_chan_gram_kernel<<<dim3(B * heads, nchunks), 256, 0, st>>>(reinterpret_cast<const bf16*>(qkv), ld, q_off, k_off, N, heads, chunk, scratch, nchunks);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dat_chan_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
+    if (e != cudaSuccess) { ff_set_error("ff_dat_channel_attention_weights: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FF_ERR_CUDA; }
+    configured = true;
+  }
+  dat_chan_gram_kernel<<<dim3(B * heads, nchunks), 256, GRAM_SMEM, st>>>(reinterpret_cast<const bf16*>(qkv), ld, q_off, k_off, N, heads, chunk, scratch, nchunks);
   dat_chan_softmax_kernel<<<B * heads, 1024, 0, st>>>(scratch, nchunks, heads, hd, temperature, reinterpret_cast<bf16*>(wout));
   g_ff_launches += 2;
   FF_CHECK_LAUNCH("ff_dat_channel_attention_weights");
