@@ -62,7 +62,7 @@ struct Cfg {
   static constexpr int STG_WARP_BYTES = EPI == EPI_RES ? 10240 : EPI == EPI_RES_AUX ? 12288 : EPI == EPI_NARROW ? 0 : EPI >= EPI_OPS1 ? (2 * (EPI - EPI_OPS1 + 1) + 2) * 2048 : (EPI == EPI_GENERIC ? 32 * STG_PITCH * 4 : 4096);
   // The plain TMA-store epilogues are latency bound per warp (tcgen05.ld -> cvt -> st.shared -> proxy fence -> TMA store is one
   // dependent chain per 32-column block), so they run four warps per TMEM lane quadrant instead of two.
-  static constexpr int EPI_WARPS = (EPI == 1 || EPI == 2) ? 16 : NUM_EPI_WARPS;
+  static constexpr int EPI_WARPS = ((EPI == 1 || EPI == 2) && !HALO) ? 16 : NUM_EPI_WARPS;   // HALO tiles hold <= 2 column blocks; the smaller staging area leaves room for a 9-stage weight ring (417 vs 463 us on the HR 64->64 layers)
   static constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
   static constexpr int STAGES_RAW = (225 * 1024 - STG_BYTES - HALO_BYTES) / STAGE_BYTES;
   static constexpr int STAGES_MAX = HALO ? 9 : 6;
@@ -376,7 +376,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int y0 = ty * TH, x0 = tx * TW;
       const int brow = b * a.p.w_batch_rows + n_tile * BN;
       if constexpr (HALO) {
-        // weights only, chunk-major k order; the A slabs come from warp 10
+        // weights only, chunk-major k order; the A slabs come from the last warp
         uint8_t* ring = smem + C::HALO_BYTES;
         for (int cc = 0; cc < a.cchunks; ++cc) {
           for (int tap = 0; tap < 9; ++tap) {

@@ -343,11 +343,13 @@ def test_layernorm_narrow_rows(C_):
     assert (err <= 4e-3 * ref.abs() + 1e-3).all(), err.max().item()     # bf16 output rounding only
 
 
-@pytest.mark.parametrize("cin,n,H,W,B", [(192, 64, 128, 128, 2), (64, 64, 48, 32, 1), (128, 32, 32, 48, 3), (64, 16, 64, 64, 2), (192, 48, 16, 16, 1), (64, 160, 32, 32, 1), (64, 3, 32, 32, 2), (128, 4, 16, 48, 1)])
+@pytest.mark.parametrize("cin,n,H,W,B", [(192, 64, 128, 128, 2), (64, 64, 48, 32, 1), (128, 32, 32, 48, 3), (64, 16, 64, 64, 2), (192, 48, 16, 16, 1), (64, 160, 32, 32, 1), (64, 3, 32, 32, 2), (128, 4, 16, 48, 1),
+                                            (64, 64, 192, 128, 1), (64, 16, 256, 128, 2), (64, 32, 128, 160, 1)])
 @pytest.mark.parametrize("epi", ["store", "gelu", "res", "generic"])
 def test_conv_gemm_halo_3x3(cin, n, H, W, B, epi):
     """3x3 convs with <= 64-wide N tiles take the halo-slab variant (A loaded once per 64-channel chunk, nine taps address it):
-    every epilogue flavour against F.conv2d on the same bf16 operands, multi-chunk K, multi-tile persistent loops, non-square images."""
+    every epilogue flavour against F.conv2d on the same bf16 operands, multi-chunk K, multi-tile persistent loops, non-square images;
+    the last three cases give every persistent CTA several tiles."""
     from isr2_b200 import ops, packing
     g = torch.Generator().manual_seed(11)
     x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
