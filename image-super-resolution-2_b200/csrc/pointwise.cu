@@ -1158,6 +1158,70 @@ extern "C" int ff_scale_weight_cols(const float* w, int N, int K, const float* s
   return FF_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// fp32 -> split-bf16 operand packing for the tensor-core path of fp32 layers.
+//   out[p][(t*K*K + tap)*CIN + c] = term_t(x[p + tap offset][c])  (zero outside the image, zero in the padding columns)
+//   term 0 = hi = bf16(x), term 1 = lo = bf16(x - hi), term 2 = hi again.
+// With the weight rows laid out [w_hi ; w_hi ; w_lo] (TERMS = 3) the bf16 GEMM accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in
+// fp32, i.e. ~16 mantissa bits on both operands; TERMS = 2 keeps the activation at 16 bits against bf16 weights.  K = 3 also
+// gathers the 3x3 neighbourhood (im2col of a <= 7-channel image into one 64-wide k-block), so the conv runs as a 1x1 GEMM.
+// 8 lanes per pixel, one 16-byte store per lane.
+// ------------------------------------------------------------------------------------------
+template <int CIN, int K, int TERMS>
+__global__ void __launch_bounds__(256) pack_taps_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, bf16* __restrict__ out,
+                                                        int out_ld, int out_cols) {
+  constexpr int KK = K * K, TOT = KK * CIN * TERMS;
+  const int groups = out_cols >> 3;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)B * H * W * groups;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const long long pix = idx / groups;
+  const int px = (int)(pix % W), py = (int)((pix / W) % H);
+  uint32_t wout[4];
+#pragma unroll
+  for (int e2 = 0; e2 < 4; ++e2) {
+    float v[2];
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int kidx = g * 8 + e2 * 2 + h2;
+      float val = 0.f;
+      if (kidx < TOT) {
+        const int t = kidx / (KK * CIN), r = kidx - t * (KK * CIN);
+        const int tap = r / CIN, c = r - tap * CIN;
+        const int dy = tap / K - K / 2, dx = tap - (tap / K) * K - K / 2;
+        const int yy = py + dy, xx = px + dx;
+        float xv = 0.f;
+        if (K == 1 || (yy >= 0 && yy < H && xx >= 0 && xx < W)) xv = __ldg(x + (pix + (long long)dy * W + dx) * x_ld + c);
+        const float hi = __bfloat162float(__float2bfloat16_rn(xv));
+        val = (t == 1) ? (xv - hi) : hi;
+      }
+      v[h2] = val;
+    }
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[0], v[1]);
+    wout[e2] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  *reinterpret_cast<uint4*>(out + pix * out_ld + g * 8) = make_uint4(wout[0], wout[1], wout[2], wout[3]);
+}
+
+extern "C" int ff_pack_taps(const float* x, int x_ld, int B, int H, int W, int Cin, int k, int terms, void* out, int out_ld, void* stream) {
+  FF_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0, "ff_pack_taps: bad args");
+  const int tot = k * k * Cin * terms;
+  const int out_cols = (tot + 63) / 64 * 64;
+  FF_CHECK_ARG(out_ld >= out_cols && out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && x_ld >= Cin, "ff_pack_taps: out_ld=%d < %d or unaligned", out_ld, out_cols);
+  const long long total = (long long)B * H * W * (out_cols / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nb = ff_cdiv(total, 256);
+  bf16* o = reinterpret_cast<bf16*>(out);
+  if (Cin == 3 && k == 3 && terms == 2) pack_taps_kernel<3, 3, 2><<<nb, 256, 0, st>>>(x, x_ld, B, H, W, o, out_ld, out_cols);
+  else if (Cin == 64 && k == 1 && terms == 3) pack_taps_kernel<64, 1, 3><<<nb, 256, 0, st>>>(x, x_ld, B, H, W, o, out_ld, out_cols);
+  else if (Cin == 32 && k == 1 && terms == 3) pack_taps_kernel<32, 1, 3><<<nb, 256, 0, st>>>(x, x_ld, B, H, W, o, out_ld, out_cols);
+  else { ff_set_error("ff_pack_taps: (Cin=%d, k=%d, terms=%d) is not an instantiated combination", Cin, k, terms); return FF_ERR_ARG; }
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_pack_taps");
+  return FF_OK;
+}
+
 extern "C" int ff_scale_channels(void* x, int ld, int B, long long pixels_per_sample, int C, const float* s, int s_ld,
                                  void* stream) {
   FF_CHECK_ARG(x && s && C % 8 == 0 && ld % 8 == 0, "ff_scale_channels: bad args");

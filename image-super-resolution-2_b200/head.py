@@ -17,8 +17,9 @@ import torch.nn.functional as F
 from . import lib as L
 from . import ops
 from .hat import Workspace
-from .ops import ACT_CLAMP01, ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, CONV_3X3
-from .packing import BF16, F32, pack_conv, pack_conv_direct, pack_dw, pack_matrix, pack_vector
+from .ops import ACT_CLAMP01, ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, CONV_1X1, CONV_3X3
+from .packing import (BF16, F32, pack_conv, pack_conv_direct, pack_conv_im2col2, pack_conv_split3, pack_dw, pack_matrix,
+                      pack_vector)
 
 DB4_LO = [-0.010597401784997278, 0.032883011666982945, 0.030841381835986965, -0.18703481171888114,
           -0.027983769416983849, 0.63088076792959036, 0.71484657055291582, 0.23037781330885523]
@@ -127,6 +128,10 @@ class HeadRunner:
                    for i, co in ((0, 64), (2, 32), (4, 8))]
         self.eg0 = (pack_conv_direct(g(p + "expert_gate.0.weight"), 64, dev), d(g(p + "expert_gate.0.bias")))
         self.eg2 = (pack_conv_direct(g(p + "expert_gate.2.weight"), 8, dev), pack_vector(g(p + "expert_gate.2.bias"), 8, device=dev))
+        # the two 64-channel 3x3 layers of the selector run on the tensor cores with split-bf16 operands (hi/lo terms of the fp32
+        # activations and weights, fp32 accumulation: ~16 mantissa bits, the hard >= 0.99*max mask downstream stays stable)
+        self.de1_tc = (pack_conv_split3(g(p + "difficulty_estimator.2.weight"), 32, device=dev), pack_vector(g(p + "difficulty_estimator.2.bias"), 32, device=dev))
+        self.eg0_tc = (pack_conv_split3(g(p + "expert_gate.0.weight"), 64, device=dev), d(g(p + "expert_gate.0.bias")))
         # ---- hierarchical fusion
         p = "multi_res_fusion."
         self.hier = []
@@ -143,7 +148,8 @@ class HeadRunner:
         self.rgb0_w, self.rgb0_b = pack_conv(g(p + "to_rgb.0.weight"), 64, 64, device=dev), pack_vector(g(p + "to_rgb.0.bias"), 64, device=dev)
         self.rgb2_w, self.rgb2_b = pack_conv(g(p + "to_rgb.2.weight"), 16, 64, device=dev), pack_vector(g(p + "to_rgb.2.bias"), 16, device=dev)
         # ---- refine net
-        self.rf0 = (pack_conv_direct(g("refine_net.0.weight"), 64, dev), d(g("refine_net.0.bias")))
+        # 3 -> 64 first layers at HR: im2col of the 3x3 neighbourhood with split-bf16 activations (54 of one 64-wide k-block)
+        self.rf0 = (pack_conv_im2col2(g("refine_net.0.weight"), 64, device=dev), d(g("refine_net.0.bias")))
         self.rf2 = (pack_conv(g("refine_net.2.weight"), 64, 64, device=dev), d(g("refine_net.2.bias")))
         self.rf4 = (pack_conv(g("refine_net.4.weight"), 64, 64, device=dev), d(g("refine_net.4.bias")))
         self.rf6 = (pack_conv(g("refine_net.6.weight"), 16, 64, device=dev), pack_vector(g("refine_net.6.bias"), 16, device=dev))
@@ -157,7 +163,7 @@ class HeadRunner:
         for l in range(3):
             q = p + f"edge_refiners.{l}."
             self.edge_levels.append(dict(
-                c1=(pack_conv_direct(g(q + "conv1.weight"), 64, dev), pack_vector(g(q + "conv1.bias"), 64, device=dev)),
+                c1=(pack_conv_im2col2(g(q + "conv1.weight"), 64, device=dev), pack_vector(g(q + "conv1.bias"), 64, device=dev)),
                 pj=(pack_conv_direct(g(q + "proj.weight"), 64, dev), pack_vector(g(q + "proj.bias"), 64, device=dev)),
                 c2=(pack_conv(g(q + "conv2.weight"), 64, 64, device=dev), pack_vector(g(q + "conv2.bias"), 64, device=dev)),
                 c3=(pack_conv(g(q + "conv3.weight"), 64, 64, device=dev), pack_vector(g(q + "conv3.bias"), 64, device=dev)),
@@ -253,9 +259,12 @@ class HeadRunner:
         t64 = ws.get("sel64", P, 64, F32)
         t32 = ws.get("sel32", P, 32, F32)
         ops.conv_direct(lrn, B, h, w, 3, 3, self.de[0][0], self.de[0][1], n_store=64, act=ACT_RELU, out_f32=t64)
-        ops.conv_direct(t64, B, h, w, 64, 3, self.de[1][0], self.de[1][1], n_store=32, act=ACT_RELU, out_f32=t32)
+        sp = ws.get("split192", P, 192, BF16)
+        ops.pack_taps(t64, B, h, w, 64, 1, 3, sp)
+        ops.conv_gemm(sp, B, h, w, 192, self.de1_tc[0], kind=CONV_3X3, n_store=32, bias=self.de1_tc[1], act=ACT_RELU, out_f32=t32)
         ops.conv_direct(t32, B, h, w, 32, 3, self.de[2][0], self.de[2][1], n_store=1, act=ACT_SIGMOID, out_f32=gd, out_f32_off=3)
-        ops.conv_direct(ms, B, h, w, 64, 3, self.eg0[0], self.eg0[1], n_store=64, act=ACT_RELU, out_f32=t64)
+        ops.pack_taps(ms, B, h, w, 64, 1, 3, sp)
+        ops.conv_gemm(sp, B, h, w, 192, self.eg0_tc[0], kind=CONV_3X3, n_store=64, bias=self.eg0_tc[1], act=ACT_RELU, out_f32=t64)
         ops.conv_direct(t64, B, h, w, 64, 1, self.eg2[0], self.eg2[1], n_store=3, act=ACT_SIGMOID, out_f32=gd)
         ck(lib.ff_selector_tail(_ptr(gd), C_.c_longlong(P), st()), "ff_selector_tail")
         # ---------------- hierarchical multi-resolution fusion (1/4 -> 1/2 -> 1x)
@@ -298,7 +307,9 @@ class HeadRunner:
         ra = ws.get("rf_a", PH, 64, BF16)
         rb = ws.get("rf_b", PH, 64, BF16)
         se = ws.get("se", PH, 8, F32)
-        ops.conv_direct(fused, B, H, W, 3, 3, self.rf0[0], self.rf0[1], n_store=64, act=ACT_GELU, out_bf16=ra)
+        im = ws.get("im2col", PH, 64, BF16)
+        ops.pack_taps(fused, B, H, W, 3, 3, 2, im)
+        ops.conv_gemm(im, B, H, W, 64, self.rf0[0], kind=CONV_1X1, n_store=64, bias=self.rf0[1], act=ACT_GELU, out_bf16=ra)
         ops.conv_gemm(ra, B, H, W, 64, self.rf2[0], kind=CONV_3X3, n_store=64, bias=self.rf2[1], act=ACT_GELU, out_bf16=rb)
         ops.conv_gemm(rb, B, H, W, 64, self.rf4[0], kind=CONV_3X3, n_store=64, bias=self.rf4[1], act=ACT_GELU, out_bf16=ra)
         ops.conv_gemm(ra, B, H, W, 64, self.rf6[0], kind=CONV_3X3, n_store=3, bias=self.rf6[1], alpha=0.1, res=base, post_act=ACT_CLAMP01, out_f32=se)
@@ -320,7 +331,8 @@ class HeadRunner:
             c2 = ws.get(f"e_c2_{l}", Pl, 64, BF16)
             a8 = ws.get(f"e_a8_{l}", Pl, 8, F32)
             am = ws.get(f"e_am_{l}", Pl, 1, F32)
-            ops.conv_direct(lap, B, Hl, Wl, 3, 3, e["c1"][0], e["c1"][1], n_store=64, act=ACT_GELU, out_bf16=c1)
+            ops.pack_taps(lap, B, Hl, Wl, 3, 3, 2, im)
+            ops.conv_gemm(im, B, Hl, Wl, 64, e["c1"][0], kind=CONV_1X1, n_store=64, bias=e["c1"][1], act=ACT_GELU, out_bf16=c1)
             ops.conv_direct(lap, B, Hl, Wl, 3, 1, e["pj"][0], e["pj"][1], n_store=64, out_bf16=idn)
             ops.conv_gemm(c1, B, Hl, Wl, 64, e["c2"][0], kind=CONV_3X3, n_store=64, bias=e["c2"][1], act=ACT_GELU, out_bf16=c2)
             ops.conv_gemm(c2, B, Hl, Wl, 64, e["c3"][0], kind=CONV_3X3, n_store=64, bias=e["c3"][1], res=idn, out_bf16=c1)

@@ -16,7 +16,7 @@ from . import lib as L
 from . import ops
 from .hat import Workspace
 from .ops import ACT_CLAMP01, ACT_NONE, CONV_1X1, CONV_2X2S2, CONV_3X3
-from .packing import BF16, F32, pack_conv, pack_conv_direct, pack_dw, pack_matrix, pack_vector, pixel_shuffle_rows
+from .packing import BF16, F32, pack_conv, pack_conv_im2col2, pack_dw, pack_matrix, pack_vector, pixel_shuffle_rows
 
 WIDTH = 64
 ENC = (2, 2, 4, 8)
@@ -53,7 +53,7 @@ class NAFNetRunner:
                 beta=g(p + "beta").reshape(-1).to(dev).contiguous(), gamma=g(p + "gamma").reshape(-1).to(dev).contiguous(),
             )
 
-        self.intro_w = pack_conv_direct(g("intro.weight"), WIDTH, dev)
+        self.intro_w = pack_conv_im2col2(g("intro.weight"), WIDTH, device=dev)      # 3 -> 64 3x3 as an im2col GEMM (ops.pack_taps)
         self.intro_b = g("intro.bias").to(dev)
         self.end_w = pack_conv(g("ending.weight"), 16, WIDTH, device=dev)
         self.end_b = pack_vector(g("ending.bias"), 16, device=dev)
@@ -122,7 +122,9 @@ class NAFNetRunner:
                                  ws.get(f"gap{c}", B, c, F32), ws.get(f"sca{c}", B, c, F32), ws.get("gscratch", 1, B * 64 * 1024, F32))))
             c, Hc, Wc = 2 * c, Hc // 2, Wc // 2
         l0 = lv[0]
-        ops.conv_direct(up, B, H, W, 3, 3, self.intro_w, self.intro_b, n_store=WIDTH, out_f32=l0["S"])
+        im = l0["bufs"][0]        # [P, 64] bf16 scratch of level 0 (free until the first block's LayerNorm)
+        ops.pack_taps(up, B, H, W, 3, 3, 2, im)
+        ops.conv_gemm(im, B, H, W, 64, self.intro_w, n_store=WIDTH, bias=self.intro_b, out_f32=l0["S"])
         for s in range(nlev):
             l = lv[s]
             blks = self.encoders[s]

@@ -188,6 +188,12 @@ def scale_weight_cols(w_f32, s, out):
     L.check(L.load().ff_scale_weight_cols(_ptr(w_f32), N, K, _ptr(s), s.stride(0), B, _ptr(out), n_pad, k_pad, _stream()), "ff_scale_weight_cols")
 
 
+def pack_taps(x, B, H, W, Cin, k, terms, out):
+    """fp32 NHWC rows -> split-bf16 (hi, lo, hi) operand rows, optionally with the 3x3 neighbourhood gathered (ff_pack_taps)."""
+    _req_cuda(x, out)
+    L.check(L.load().ff_pack_taps(_ptr(x), x.stride(-2), B, H, W, Cin, k, terms, _ptr(out), out.stride(-2), _stream()), "ff_pack_taps")
+
+
 def conv_direct(x, B, H, W, Cin, k, w, bias, *, n_store, act=ACT_NONE, mul_f32=None, out_bf16=None, out_f32=None,
                 x_ld=None, x_off=0, out_f32_off=0, out_bf16_off=0):
     _req_cuda(x, w, bias, mul_f32, out_bf16, out_f32)

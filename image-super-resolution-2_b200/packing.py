@@ -53,6 +53,34 @@ def pack_conv(W, n_pad, cin_pad, row_index=None, col_index=None, device="cuda", 
     return t
 
 
+def _split_bf16(W):
+    hi = W.to(F32).to(BF16).to(F32)
+    lo = (W.to(F32) - hi).to(BF16).to(F32)
+    return hi, lo
+
+
+def pack_conv_split3(W, n_pad, device="cuda"):
+    """fp32 conv weight [Cout, Cin, k, k] for the split-bf16 tensor-core path: input channels become [hi | lo | hi] blocks
+    (ops.pack_taps with terms = 3), so the weight channels are [w_hi ; w_hi ; w_lo] -> [n_pad, k*k*3*Cin]."""
+    hi, lo = _split_bf16(W)
+    t = pack_conv(torch.cat([hi, hi, lo], dim=1), n_pad, 3 * W.shape[1], device=device)
+    t.ff_real = (W.shape[0], W.shape[2] * W.shape[3] * W.shape[1])
+    return t
+
+
+def pack_conv_im2col2(W, n_pad, device="cuda"):
+    """fp32 conv weight [Cout, Cin, 3, 3] (Cin * 18 <= 64) for ops.pack_taps(k=3, terms=2): K index (t*9 + tap)*Cin + c holds
+    bf16(W[:, c, tap]) for both activation terms -> [n_pad, 64]."""
+    Cout, Cin, kh, kw = W.shape
+    hi, _ = _split_bf16(W)
+    row = hi.permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin)
+    out = torch.zeros(n_pad, 64, dtype=F32)
+    out[:Cout, :2 * kh * kw * Cin] = torch.cat([row, row], dim=1)
+    t = out.to(BF16).to(device).contiguous()
+    t.ff_real = (Cout, kh * kw * Cin)
+    return t
+
+
 def pack_conv_direct(W, cout_pad, device="cuda"):
     """Conv weight [Cout, Cin, k, k] -> fp32 [cout_pad, k*k*Cin] for ff_conv_direct."""
     Cout, Cin, kh, kw = W.shape

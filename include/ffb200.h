@@ -166,6 +166,14 @@ int ff_scale_channels(void* x, int ld, int B, long long pixels_per_sample, int C
 int ff_scale_weight_cols(const float* w, int N, int K, const float* s, int s_ld, int B, void* out, int n_pad, int k_pad,
                          void* stream);
 
+/* fp32 -> split-bf16 operand packing, so fp32 layers of the routing path / image-space first layers run on ff_conv_gemm:
+ * out[p][(t*k*k + tap)*Cin + c] = term_t(x[p + tap][c]), terms (hi, lo, hi) with hi = bf16(x), lo = bf16(x - hi); zero outside
+ * the image and in the padding up to the next multiple of 64 columns.  Pair with weight rows [w_hi; w_hi; w_lo] (terms = 3,
+ * ~16-bit mantissas on both operands, fp32 accumulation) or [w_hi; w_hi] (terms = 2).  k = 3 gathers the 3x3 neighbourhood
+ * (im2col) so a 3-channel 3x3 conv becomes one 64-wide k-block.  Instantiated: (Cin,k,terms) = (3,3,2), (64,1,3), (32,1,3).
+ * Replaces the fp32 nn.Conv2d evaluation of fusion_network.py:167-236 (difficulty / gate heads) and the 3->64 first layers. */
+int ff_pack_taps(const float* x, int x_ld, int B, int H, int W, int Cin, int k, int terms, void* out, int out_ld, void* stream);
+
 /* Direct fp32 convolution (k = 1 or 3, zero pad) for small channel counts: image-space first/last layers and
  * the fp32 routing path of the fusion head (fusion_network.py:167-236,543-607).  w is fp32 [Cout_pad][k*k*Cin]. */
 int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int H, int W, int Cin, int k, const float* w,

@@ -629,3 +629,51 @@ def test_dwconv_pool(mode, act, with_mul):
         pooled.append(mean)
     assert torch.equal(pooled[0], pooled[1])
     assert (pooled[0].cpu() - ref_mean).abs().max().item() < 2e-3 * max(1.0, ref_mean.abs().max().item())
+
+
+def test_pack_taps_and_split_bf16_convs():
+    """fp32 layers on the tensor cores through split-bf16 operands (ff_pack_taps): the packed rows hold exactly (hi, lo, hi)
+    terms / the zero-padded 3x3 neighbourhood, and the resulting convs track fp32 F.conv2d far below bf16 precision."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(123)
+    d = _dev()
+    # (a) 64 -> 32 3x3 fp32 layer: terms = 3 split, conv_gemm does the 3x3
+    B, H, W, cin, n = 2, 32, 48, 64, 32
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(n, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    bias = torch.randn(n, generator=g)
+    xr = _nhwc(x).contiguous()
+    sp = torch.zeros(B * H * W, 192, dtype=BF16, device=d)
+    ops.pack_taps(xr.to(d), B, H, W, cin, 1, 3, sp)
+    torch.cuda.synchronize()
+    hi = xr.to(BF16)
+    lo = (xr - hi.float()).to(BF16)
+    assert torch.equal(sp.cpu(), torch.cat([hi, lo, hi], 1))
+    out = torch.zeros(B * H * W, n, device=d)
+    ops.conv_gemm(sp, B, H, W, 192, packing.pack_conv_split3(w, n, device=d), kind=1, n_store=n, bias=bias.to(d), act=ops.ACT_RELU, out_f32=out)
+    torch.cuda.synchronize()
+    ref = _nhwc(F.relu(F.conv2d(x.double(), w.double(), bias.double(), padding=1))).float()
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
+    # (b) 3 -> 64 3x3 image layer: im2col (k = 3) with terms = 2, conv_gemm is a 1x1 over one 64-wide k-block
+    B, H, W = 2, 24, 48
+    img = torch.rand(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 3, 3, generator=g) / math.sqrt(27)
+    bias = torch.randn(64, generator=g)
+    rows = torch.zeros(B * H * W, 4)
+    rows[:, :3] = _nhwc(img)
+    im = torch.full((B * H * W, 64), 5.0, dtype=BF16, device=d)
+    ops.pack_taps(rows.to(d), B, H, W, 3, 3, 2, im)
+    torch.cuda.synchronize()
+    cols = F.unfold(img, 3, padding=1).view(B, 3, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 27)     # [p][tap][c]
+    chi = cols.to(BF16)
+    clo = (cols - chi.float()).to(BF16)
+    exp = torch.cat([chi, clo, torch.zeros(B * H * W, 10, dtype=BF16)], 1)
+    assert torch.equal(im.cpu(), exp)
+    out = torch.zeros(B * H * W, 64, device=d)
+    ops.conv_gemm(im, B, H, W, 64, packing.pack_conv_im2col2(w, 64, device=d), n_store=64, bias=bias.to(d), out_f32=out)
+    torch.cuda.synchronize()
+    ref = _nhwc(F.conv2d(img, w.to(BF16).float(), bias, padding=1))
+    assert (out.cpu() - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+    ref32 = _nhwc(F.conv2d(img, w, bias, padding=1))
+    assert (out.cpu() - ref32).abs().max().item() < 1e-2
