@@ -289,6 +289,62 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// bf16 rows wider than the residual stream (DAT's SGFN norm over the gated half, 360 of 384 columns): 16 lanes per row, two rows
+// per warp, lanes own channel OCTETS (c = 8*sub + 128*i): NV 16-byte loads and NV 16-byte stores per lane instead of the
+// 4-byte accesses of the generic pair kernel.  C % 8 == 0, out_cols <= 128*NV, padding columns are written as zero.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bf16_wide_kernel(const bf16* __restrict__ x, int in_ld, long long rows, int C,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                                 bf16* __restrict__ out, int out_ld, int out_cols) {
+  const int lane = threadIdx.x & 31, sub = lane & 15;
+  const long long row = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+  const bool ok = row < rows;
+  const bf16* xr = x + (ok ? row : 0) * in_ld;
+  float v[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = 8 * sub + 128 * i;
+    if (c < C) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + c), v[i]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[i][e];
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (8 * sub + 128 * i < C) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { v[i][e] -= mean; q += v[i][e] * v[i][e]; }
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  if (!ok) return;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = 8 * sub + 128 * i;
+    if (c >= out_cols) continue;
+    float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = v[i][e] * rstd * gg[e] + bb[e];
+    }
+    *reinterpret_cast<uint4*>(out + row * out_ld + c) = pack8(y);
+  }
+}
+
 __device__ __forceinline__ void dw_accum(const DwArgs& a, int b, int y, int x, int c0, float (&acc)[8]) {
   const int ph = a.kh >> 1, pw = a.kw >> 1;
 #pragma unroll
@@ -980,6 +1036,18 @@ extern "C" int ff_layernorm(const void* x, int x_is_bf16, int in_ld, long long r
       (!out_f32 || (out_f32_ld % 4 == 0 && a16(out_f32)))) {
     layernorm_w192_kernel<<<ff_cdiv(rows, 16), 256, 0, st>>>(reinterpret_cast<const float*>(x), in_ld, rows, C, gamma, beta, eps,
                                                               reinterpret_cast<bf16*>(out_bf16), out_ld, out_f32, out_f32_ld);
+    ++g_ff_launches;
+    FF_CHECK_LAUNCH("ff_layernorm");
+    return FF_OK;
+  }
+  if (x_is_bf16 && out_bf16 && !out_f32 && C % 8 == 0 && out_cols % 8 == 0 && out_cols > 128 && out_cols <= 512 && in_ld % 8 == 0 && out_ld % 8 == 0 &&
+      a16(x) && a16(out_bf16) && a16(gamma) && a16(beta)) {
+    const bf16* xb = reinterpret_cast<const bf16*>(x);
+    bf16* ob = reinterpret_cast<bf16*>(out_bf16);
+    const int nv = ff_cdiv(out_cols, 128), nb = ff_cdiv(rows, 16);
+    if (nv == 2) layernorm_bf16_wide_kernel<2><<<nb, 256, 0, st>>>(xb, in_ld, rows, C, gamma, beta, eps, ob, out_ld, out_cols);
+    else if (nv == 3) layernorm_bf16_wide_kernel<3><<<nb, 256, 0, st>>>(xb, in_ld, rows, C, gamma, beta, eps, ob, out_ld, out_cols);
+    else layernorm_bf16_wide_kernel<4><<<nb, 256, 0, st>>>(xb, in_ld, rows, C, gamma, beta, eps, ob, out_ld, out_cols);
     ++g_ff_launches;
     FF_CHECK_LAUNCH("ff_layernorm");
     return FF_OK;

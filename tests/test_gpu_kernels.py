@@ -677,3 +677,21 @@ def test_pack_taps_and_split_bf16_convs():
     assert (out.cpu() - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
     ref32 = _nhwc(F.conv2d(img, w, bias, padding=1))
     assert (out.cpu() - ref32).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("rows,C_,cols,off", [(1000, 360, 384, 384), (37, 256, 256, 0), (515, 480, 512, 8)])
+def test_layernorm_bf16_wide_rows(rows, C_, cols, off):
+    """bf16-input LayerNorm over 129..512 columns (DAT SGFN norm on the gated half of the hidden tensor, dat_arch.py:118):
+    the 16-lanes-per-row octet kernel against F.layer_norm, padding columns zero, ragged row count."""
+    from isr2_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    d = _dev()
+    x = (torch.randn(rows, off + cols + 8, generator=g) * 2 + 0.5).to(BF16)
+    gam, bet = torch.randn(C_, generator=g), torch.randn(C_, generator=g)
+    ref = F.layer_norm(x[:, off:off + C_].float(), (C_,), gam, bet, 1e-5)
+    out = torch.full((rows, cols), 9.0, dtype=BF16, device=d)
+    ops.layernorm(x.to(d), rows, C_, gam.to(d), bet.to(d), 1e-5, out_bf16=out, out_cols=cols, x_off=off)
+    torch.cuda.synchronize()
+    got = out.cpu().float()
+    assert ((got[:, :C_] - ref).abs() <= 4e-3 * ref.abs() + 1e-3).all()
+    assert torch.all(got[:, C_:] == 0)
