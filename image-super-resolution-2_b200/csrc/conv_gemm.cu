@@ -874,6 +874,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       if (lane == 0) tma_prefetch_desc(&tmO);
+      const bool plain_store = p.act == FF_ACT_NONE && p.col_sums == nullptr;
+      (void)plain_store;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
         const int b = m_tile / a.tiles_per_img;
@@ -889,22 +891,37 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t raw[32];
           tmem_ld16(taddr + cb * 32, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
           tmem_ld16(taddr + cb * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
+          // the block's bias is requested while the TMEM load is in flight (tc_wait_ld is a compiler barrier for loads)
+          float4 bq[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bq[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n_blk) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           // the staging buffer about to be overwritten must have been read by the TMA store issued two blocks ago
-          if (lane == 0) tma_store_wait_read<1>();
+          if (elect_one()) tma_store_wait_read<1>();      // elect.sync picks the same (lowest) lane every time: it owns the bulk groups
           __syncwarp();
           tc_wait_ld();
           uint8_t* dst = stg_base + buf * 2048 + lane * 64;
           const int sw = (lane >> 1) & 3;
+          if (EPI == EPI_STORE && plain_store) {
+            // lean path (bias only): 16 packed adds, 16 packs, four 16-byte stores
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t w[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 bv = bq[2 * c + (i >> 1)];
+                const float2 b2 = (i & 1) ? make_float2(bv.z, bv.w) : make_float2(bv.x, bv.y);
+                const float2 x2 = __fadd2_rn(make_float2(__uint_as_float(raw[c * 8 + 2 * i]), __uint_as_float(raw[c * 8 + 2 * i + 1])), b2);
+                __nv_bfloat162 h = __floats2bfloat162_rn(x2.x, x2.y);
+                w[i] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          } else {
           float cs_v[EPI == EPI_STORE ? 32 : 1];      // this lane's row of the block, kept for the column sums (EPI_STORE only)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t w[4];
-            float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (p.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk + c * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n_blk + c * 8) + 1);
-              bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
-            }
+            const float bb[8] = {bq[2 * c].x, bq[2 * c].y, bq[2 * c].z, bq[2 * c].w, bq[2 * c + 1].x, bq[2 * c + 1].y, bq[2 * c + 1].z, bq[2 * c + 1].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float x0 = __uint_as_float(raw[c * 8 + 2 * i]) + bb[2 * i], x1 = __uint_as_float(raw[c * 8 + 2 * i + 1]) + bb[2 * i + 1];
@@ -932,9 +949,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (n_blk + lane < p.n_store) p.col_sums[((long long)m_tile * 4 + quad) * p.n_store + n_blk + lane] = cs_v[0];
             }
           }
+          }  // !plain_store
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_blk(&tmO, stg_base + buf * 2048, a, n_blk, tx * TW, ty * TH + quad * QR, b);
             tma_store_commit();
           }
@@ -945,7 +963,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (lane == 0) tma_store_wait_all();
+      if (elect_one()) tma_store_wait_all();
     } else {
     // 8 warps: TMEM lane quadrant = warp % 4; the two warps of a quadrant alternate over CB-wide column blocks.
     // Per column block: TMEM -> registers (one accumulator row per thread) -> per-warp smem staging (transpose) ->

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libffb200.so")
+LIB_PATH = os.environ.get("FFB200_LIB") or os.path.join(_HERE, "csrc", "libffb200.so")      # FFB200_LIB: development override
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_CLAMP01 = range(6)
 CONV_1X1, CONV_3X3, CONV_2X2S2 = range(3)
