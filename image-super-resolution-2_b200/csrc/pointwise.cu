@@ -589,6 +589,8 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3x3_tma_kernel(const __g
   const int toff = half * DWT_HALF_BYTES + px * PP + sub * 8;
   int stage = 0;
   uint32_t phase = 0;
+  float2 w[9][2], bv[2];
+  int w_ct = -1;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int ct = tile % ctiles;
     int r = tile / ctiles;
@@ -597,17 +599,20 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3x3_tma_kernel(const __g
     const int ty = r % tiles_y, b = r / tiles_y;
     const int cin0 = MODE == 1 ? half * cout + ct * 32 + sub * 4 : ct * 64 + sub * 4;     // input channel of this thread
     const int co0 = MODE == 1 ? ct * 32 + sub * 4 : cin0;                                   // output channel
-    float2 w[9][2], bv[2];
+    // the grid is a multiple of the channel-tile count whenever possible, so a CTA keeps one channel tile and its weights
+    if (ct != w_ct) {
+      w_ct = ct;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(a.w + (long long)t * a.C + cin0));
-      w[t][0] = make_float2(q.x, q.y); w[t][1] = make_float2(q.z, q.w);
-    }
-    if (a.bias) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(a.bias + cin0));
-      bv[0] = make_float2(q.x, q.y); bv[1] = make_float2(q.z, q.w);
-    } else {
-      bv[0] = bv[1] = make_float2(0.f, 0.f);
+      for (int t = 0; t < 9; ++t) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(a.w + (long long)t * a.C + cin0));
+        w[t][0] = make_float2(q.x, q.y); w[t][1] = make_float2(q.z, q.w);
+      }
+      if (a.bias) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(a.bias + cin0));
+        bv[0] = make_float2(q.x, q.y); bv[1] = make_float2(q.z, q.w);
+      } else {
+        bv[0] = bv[1] = make_float2(0.f, 0.f);
+      }
     }
     // refill the stage consumed in the previous iteration (every thread passed the barrier at its end)
     if (tid == 0) {
@@ -753,6 +758,8 @@ __global__ void __launch_bounds__(DWL_THREADS, 1) dwconv_large_tma_kernel(const 
   if (tid == 0 && (int)blockIdx.x < num_tiles) issue(blockIdx.x, 0);
   int stage = 0;
   uint32_t phase = 0;
+  float2 w[KC][K], bv = make_float2(0.f, 0.f);
+  int w_ct = -1;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int ct = tile % ctiles;
     int r = tile / ctiles;
@@ -765,15 +772,17 @@ __global__ void __launch_bounds__(DWL_THREADS, 1) dwconv_large_tma_kernel(const 
       const int t2 = tile + gridDim.x;
       if (t2 < num_tiles) issue(t2, stage ^ 1);
     }
-    float2 w[KC][K];
+    if (ct != w_ct) {       // the grid is a multiple of the channel-tile count whenever possible: one load per CTA
+      w_ct = ct;
 #pragma unroll
-    for (int c = 0; c < KC; ++c)
+      for (int c = 0; c < KC; ++c)
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const int tap = Cf::ALONG_X ? c * KW + k : k * KW + c;
-        w[c][k] = __ldg(reinterpret_cast<const float2*>(a.w + (long long)tap * a.C + c0));
-      }
-    const float2 bv = a.bias ? __ldg(reinterpret_cast<const float2*>(a.bias + c0)) : make_float2(0.f, 0.f);
+        for (int k = 0; k < K; ++k) {
+          const int tap = Cf::ALONG_X ? c * KW + k : k * KW + c;
+          w[c][k] = __ldg(reinterpret_cast<const float2*>(a.w + (long long)tap * a.C + c0));
+        }
+      bv = a.bias ? __ldg(reinterpret_cast<const float2*>(a.bias + c0)) : make_float2(0.f, 0.f);
+    }
     mbar_wait(&full[stage], phase);
     const uint32_t base = smem_u32(smem) + stage * Cf::TILE_BYTES + lane * 4;
 #pragma unroll 1
@@ -847,7 +856,8 @@ static int launch_dw_large(const DwArgs& a, cudaStream_t st) {
   }
   const int tiles_x = a.W / TX, tiles_y = a.H / TY, ctiles = a.C / 64;
   const long long ntiles = (long long)a.B * tiles_x * tiles_y * ctiles;
-  const int grid = (int)(ntiles < ff_num_sms() ? ntiles : ff_num_sms());
+  int grid = (int)(ntiles < ff_num_sms() ? ntiles : ff_num_sms());
+  if (grid >= 8 * ctiles) grid -= grid % ctiles;      // constant channel tile per CTA: weights are loaded once
   dwconv_large_tma_kernel<KH, KW, TY, TX><<<grid, DWL_THREADS, Cf::SMEM, st>>>(tm, a, tiles_x, tiles_y, ctiles);
   return FF_OK;
 }
@@ -1167,7 +1177,8 @@ static int dwconv_impl(const void* x, int x_ld, int B, int H, int W, int C, int 
       }
       const int tiles_x = W / DWT_TX, tiles_y = H / DWT_TY, ctiles = cout_ / (mode == 1 ? 32 : 64);
       const long long ntiles = (long long)B * tiles_x * tiles_y * ctiles;
-      const int grid = (int)(ntiles < ff_num_sms() ? ntiles : ff_num_sms());
+      int grid = (int)(ntiles < ff_num_sms() ? ntiles : ff_num_sms());
+      if (grid >= 8 * ctiles) grid -= grid % ctiles;      // constant channel tile per CTA: weights are loaded once
       int rc;
       if (mode == 1) rc = launch_dw_tma<1, 0, false>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_);
       else if (mul) rc = act == FF_ACT_NONE ? launch_dw_tma<0, 0, true>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_)
