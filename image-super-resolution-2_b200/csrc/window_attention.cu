@@ -73,7 +73,7 @@ __device__ __forceinline__ void tile_pos(int kc, int n, int& ki, int& kj0) {
 
 // SGN = rel_sign (compile time so key offsets become LDS immediates); SGN < 0 (HAT OCAB) also enables the negative-index wrap
 template <int KW, int SGN>
-__global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_kernel(const __grid_constant__ FFWinAttn p) {
+__global__ void __launch_bounds__(NTHREADS, 2) window_attention_kernel(const __grid_constant__ FFWinAttn p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int NK = p.kh * KW;
   bf16* sQ = reinterpret_cast<bf16*>(smem);
@@ -139,131 +139,147 @@ __global__ void __launch_bounds__(NTHREADS, SGN > 0 ? 3 : 2) window_attention_ke
   const int tq = 2 * (lane & 3);
   bf16* outp = reinterpret_cast<bf16*>(p.out);
 
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const int q0 = warp * 32 + pass * 16;
-    uint32_t qa[2][4];
-    {
-      const int row = q0 + (lane & 15);
+  // Each warp owns 32 query rows as two m16 groups that share every K / V fragment load (half the ldmatrix traffic of a
+  // 16-row pass: the kernel is shared-memory-pipe bound); keys are consumed 32 at a time to keep the two groups' logits,
+  // outputs and Q fragments under 128 registers (2 CTAs / SM).
+  {
+    const int q0 = warp * 32;
+    uint32_t qa[2][2][4];
+    int A[2][2], qr[2][2] = {{0, 0}, {0, 0}}, qi[2][2], qj[2][2];
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[ks], smem_u32(sQ + swz(row, ks * 2 + (lane >> 4))));
+    for (int g = 0; g < 2; ++g) {
+      const int row = q0 + g * 16 + (lane & 15);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[g][ks], smem_u32(sQ + swz(row, ks * 2 + (lane >> 4))));
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = q0 + g * 16 + h * 8 + (lane >> 2);
+        qi[g][h] = r / p.ww;
+        qj[g][h] = r - qi[g][h] * p.ww;
+        // bias index of (row, key (ki,kj)) = (sgn*(qi-ki)+offy)*stride + sgn*(qj-kj)+offx = A_row - rowmul*ki - sgn*kj
+        A[g][h] = (sgn * qi[g][h] + p.rel_off_y) * p.rel_stride + sgn * (qj[g][h] - tq) + p.rel_off_x;
+        if (need_mask)
+          qr[g][h] = region3(wy * p.wh + qi[g][h], p.H, p.wh, p.shift_y) * 3 + region3(wx * p.ww + qj[g][h], p.W, p.ww, p.shift_x);
+      }
     }
-    const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
-    const int qi0 = r0 / p.ww, qj0 = r0 - qi0 * p.ww, qi1 = r1 / p.ww, qj1 = r1 - qi1 * p.ww;
-    // bias index of (row, key (ki,kj)) = (sgn*(qi-ki)+offy)*stride + sgn*(qj-kj)+offx = A_row - rowmul*ki - sgn*kj
-    const int A0 = (sgn * qi0 + p.rel_off_y) * p.rel_stride + sgn * (qj0 - tq) + p.rel_off_x;
-    const int A1 = (sgn * qi1 + p.rel_off_y) * p.rel_stride + sgn * (qj1 - tq) + p.rel_off_x;
-    int qr0 = 0, qr1 = 0;
-    if (need_mask) {
-      qr0 = region3(wy * p.wh + qi0, p.H, p.wh, p.shift_y) * 3 + region3(wx * p.ww + qj0, p.W, p.ww, p.shift_x);
-      qr1 = region3(wy * p.wh + qi1, p.H, p.wh, p.shift_y) * 3 + region3(wx * p.ww + qj1, p.W, p.ww, p.shift_x);
-    }
-
-    float m0 = -1e30f, m1 = -1e30f;
-    float o[4][4];
+    float m[2][2] = {{-1e30f, -1e30f}, {-1e30f, -1e30f}};
+    float o[2][4][4];
 #pragma unroll
-    for (int n = 0; n < 4; ++n)
+    for (int g = 0; g < 2; ++g)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[g][n][i] = 0.f;
 
 #pragma unroll 1
-    for (int kc = 0; kc < NK; kc += KCHUNK) {
+    for (int kc = 0; kc < NK; kc += 32) {
       // accumulators start from the relative-position bias (x log2 e): S = bias + Q K^T comes out of the MMA directly
-      float s[8][4];
+      float s[2][4][4];
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
+      for (int n = 0; n < 4; ++n) {
         int ki, kj0;
         tile_pos<KW>(kc, n, ki, kj0);
         const int off = rowmul * ki + sgn * kj0;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          int i0 = A0 - off - sgn * e, i1 = A1 - off - sgn * e;
-          if constexpr (WRAP) {
-            i0 += (i0 >> 31) & p.T;
-            i1 += (i1 >> 31) & p.T;
-          }
-          s[n][e] = sT[i0];
-          s[n][2 + e] = sT[i1];
-        }
-      }
-      // S += Q K^T : B fragments (k16 x n8) come from K rows [key][dim] (non-transposed ldmatrix)
+        for (int g = 0; g < 2; ++g)
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
+          for (int e = 0; e < 2; ++e) {
+            int i0 = A[g][0] - off - sgn * e, i1 = A[g][1] - off - sgn * e;
+            if constexpr (WRAP) {
+              i0 += (i0 >> 31) & p.T;
+              i1 += (i1 >> 31) & p.T;
+            }
+            s[g][n][e] = sT[i0];
+            s[g][n][2 + e] = sT[i1];
+          }
+      }
+      // S += Q K^T : B fragments (k16 x n8) come from K rows [key][dim] (non-transposed ldmatrix), shared by both row groups
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           uint32_t kb[4];
           const int key = kc + np * 16 + (lane & 7) + ((lane >> 4) << 3);
           ldsm_x4(kb, smem_u32(sK + swz(key, ks * 2 + ((lane >> 3) & 1))));
-          mma16816(s[2 * np], qa[ks], kb[0], kb[1]);
-          mma16816(s[2 * np + 1], qa[ks], kb[2], kb[3]);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            mma16816(s[g][2 * np], qa[g][ks], kb[0], kb[1]);
+            mma16816(s[g][2 * np + 1], qa[g][ks], kb[2], kb[3]);
+          }
         }
       }
-      float cm0 = -1e30f, cm1 = -1e30f;
       if (need_mask) {
 #pragma unroll
-        for (int n = 0; n < 8; ++n)
+        for (int n = 0; n < 4; ++n)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int kr = sKr[kc + n * 8 + tq + e];
-            if (kr != qr0) s[n][e] -= MASKV;
-            if (kr != qr1) s[n][2 + e] -= MASKV;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              if (kr != qr[g][0]) s[g][n][e] -= MASKV;
+              if (kr != qr[g][1]) s[g][n][2 + e] -= MASKV;
+            }
           }
       }
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        cm0 = fmaxf(cm0, fmaxf(s[n][0], s[n][1]));
-        cm1 = fmaxf(cm1, fmaxf(s[n][2], s[n][3]));
+      for (int g = 0; g < 2; ++g) {
+        float cm0 = -1e30f, cm1 = -1e30f;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          cm0 = fmaxf(cm0, fmaxf(s[g][n][0], s[g][n][1]));
+          cm1 = fmaxf(cm1, fmaxf(s[g][n][2], s[g][n][3]));
+        }
+        cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
+        cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+        cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
+        cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+        const float nm0 = fmaxf(m[g][0], cm0), nm1 = fmaxf(m[g][1], cm1);
+        const float sc0 = ex2(m[g][0] - nm0), sc1 = ex2(m[g][1] - nm1);
+        m[g][0] = nm0; m[g][1] = nm1;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { o[g][n][0] *= sc0; o[g][n][1] *= sc0; o[g][n][2] *= sc1; o[g][n][3] *= sc1; }
       }
-      cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
-      cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
-      cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
-      cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
-      const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);
-      const float sc0 = ex2(m0 - nm0), sc1 = ex2(m1 - nm1);
-      m0 = nm0; m1 = nm1;
+      // P = exp2(S - m), O += P V (the V fragments are shared by both row groups)
 #pragma unroll
-      for (int n = 0; n < 4; ++n) { o[n][0] *= sc0; o[n][1] *= sc0; o[n][2] *= sc1; o[n][3] *= sc1; }
-      // P = exp2(S - m), row sums, O += P V
+      for (int kk = 0; kk < 2; ++kk) {
+        uint32_t pa[2][4];
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t pa[4];
-        const float e00 = ex2(s[2 * kk][0] - m0), e01 = ex2(s[2 * kk][1] - m0);
-        const float e02 = ex2(s[2 * kk][2] - m1), e03 = ex2(s[2 * kk][3] - m1);
-        const float e10 = ex2(s[2 * kk + 1][0] - m0), e11 = ex2(s[2 * kk + 1][1] - m0);
-        const float e12 = ex2(s[2 * kk + 1][2] - m1), e13 = ex2(s[2 * kk + 1][3] - m1);
-        pa[0] = pack_bf16(e00, e01);
-        pa[1] = pack_bf16(e02, e03);
-        pa[2] = pack_bf16(e10, e11);
-        pa[3] = pack_bf16(e12, e13);
+        for (int g = 0; g < 2; ++g) {
+          const float m0 = m[g][0], m1 = m[g][1];
+          pa[g][0] = pack_bf16(ex2(s[g][2 * kk][0] - m0), ex2(s[g][2 * kk][1] - m0));
+          pa[g][1] = pack_bf16(ex2(s[g][2 * kk][2] - m1), ex2(s[g][2 * kk][3] - m1));
+          pa[g][2] = pack_bf16(ex2(s[g][2 * kk + 1][0] - m0), ex2(s[g][2 * kk + 1][1] - m0));
+          pa[g][3] = pack_bf16(ex2(s[g][2 * kk + 1][2] - m1), ex2(s[g][2 * kk + 1][3] - m1));
+        }
 #pragma unroll
         for (int dp = 0; dp < 2; ++dp) {
           uint32_t vb[4];
           const int key = kc + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
           ldsm_x4_t(vb, smem_u32(sV + swz(key, dp * 2 + (lane >> 4))));
-          mma16816(o[2 * dp], pa, vb[0], vb[1]);
-          mma16816(o[2 * dp + 1], pa, vb[2], vb[3]);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            mma16816(o[g][2 * dp], pa[g], vb[0], vb[1]);
+            mma16816(o[g][2 * dp + 1], pa[g], vb[2], vb[3]);
+          }
         }
       }
     }
     // softmax denominators: V carries an all-ones column at dim 31 (bias of the packed v projection), so sum_k P[k]
     // accumulates in O[:, 31] (lane quad member 3, second element of the last n8 tile) with the same bf16-rounded P
-    const float inv0 = 1.f / __shfl_sync(0xffffffffu, o[3][1], (lane & ~3) | 3);
-    const float inv1 = 1.f / __shfl_sync(0xffffffffu, o[3][3], (lane & ~3) | 3);
-
-    // ---- store at the un-shifted token position ----
-    {
-      int y = wy * p.wh + qi0 + p.shift_y; if (y >= p.H) y -= p.H;
-      int x = wx * p.ww + qj0 + p.shift_x; if (x >= p.W) x -= p.W;
-      bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + head * HD + tq;
 #pragma unroll
-      for (int n = 0; n < 4; ++n) *reinterpret_cast<uint32_t*>(dst + n * 8) = pack_bf16(o[n][0] * inv0, o[n][1] * inv0);
-    }
-    {
-      int y = wy * p.wh + qi1 + p.shift_y; if (y >= p.H) y -= p.H;
-      int x = wx * p.ww + qj1 + p.shift_x; if (x >= p.W) x -= p.W;
-      bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + head * HD + tq;
+    for (int g = 0; g < 2; ++g) {
+      const float inv0 = 1.f / __shfl_sync(0xffffffffu, o[g][3][1], (lane & ~3) | 3);
+      const float inv1 = 1.f / __shfl_sync(0xffffffffu, o[g][3][3], (lane & ~3) | 3);
+      // ---- store at the un-shifted token position ----
 #pragma unroll
-      for (int n = 0; n < 4; ++n) *reinterpret_cast<uint32_t*>(dst + n * 8) = pack_bf16(o[n][2] * inv1, o[n][3] * inv1);
+      for (int h = 0; h < 2; ++h) {
+        int y = wy * p.wh + qi[g][h] + p.shift_y; if (y >= p.H) y -= p.H;
+        int x = wx * p.ww + qj[g][h] + p.shift_x; if (x >= p.W) x -= p.W;
+        bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + head * HD + tq;
+        const float inv = h ? inv1 : inv0;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) *reinterpret_cast<uint32_t*>(dst + n * 8) = pack_bf16(o[g][n][2 * h] * inv, o[g][n][2 * h + 1] * inv);
+      }
     }
   }
 }
