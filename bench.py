@@ -57,7 +57,27 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
 
+    def _run_nvml(self):
+        """Fast path: NVML in-process (a few hundred samples per second of timed region instead of one nvidia-smi spawn each)."""
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+        while not self.stop_flag:
+            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            r = int(get_reasons(h))
+            flags = {n: ("Active" if r & b else "Not Active") for b, n in bits}
+            self.samples.append([str(sm), str(mx), flags["hw_slowdown"], flags["hw_thermal_slowdown"], flags["sw_thermal_slowdown"], flags["sw_power_cap"]])
+            time.sleep(0.02)
+
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -225,8 +245,10 @@ def main():
     os.environ.pop("FFB200_EXPERT_STREAMS", None)
     achieved = prof["algo_flops"] / (prof["ms"] / 1e3) / 1e12
     traffic, traffic_note = None, "no ncu capture found under profiles/"
-    tpath = os.path.join(ROOT, "profiles", "r01_conv_gemm_traffic.json")
-    if os.path.exists(tpath) and B == 16 and S == 128:
+    import glob
+    tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_gemm_traffic.json")))      # newest capture last
+    tpath = tpaths[-1] if tpaths else ""
+    if tpath and B == 16 and S == 128:
         tj = json.load(open(tpath))
         traffic, traffic_note = tj["mean_dram_bytes_per_launch"], tj["source"]
     step_ms = ms_total / K

@@ -204,29 +204,30 @@ __global__ void __launch_bounds__(256) gap_partial_kernel(const TIn* __restrict_
     if (c < C) partial[((long long)b * nsplit + split) * C + c] = t;
   }
 }
-// one block per (32 channels, sample): lane = channel, the 8 warps split the partial rows (4 independent loads in flight each)
-__global__ void __launch_bounds__(256) gap_final_kernel(const float* __restrict__ partial, int C, int nsplit, float inv,
-                                                       float* __restrict__ out, int out_ld) {
-  __shared__ float red[8][33];
+// one block per (32 channels, sample): lane = channel, the 32 warps split the partial rows (4 independent loads in flight each)
+constexpr int GAPF_WARPS = 32;
+__global__ void __launch_bounds__(GAPF_WARPS * 32) gap_final_kernel(const float* __restrict__ partial, int C, int nsplit, float inv,
+                                                                   float* __restrict__ out, int out_ld) {
+  __shared__ float red[GAPF_WARPS][33];
   const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5, c = blockIdx.x * 32 + lane;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
   if (c < C) {
     const float* pb = partial + (long long)b * nsplit * C + c;
     int s = w;
-    for (; s + 24 < nsplit; s += 32) {
+    for (; s + 3 * GAPF_WARPS < nsplit; s += 4 * GAPF_WARPS) {
       t0 += pb[(long long)s * C];
-      t1 += pb[(long long)(s + 8) * C];
-      t2 += pb[(long long)(s + 16) * C];
-      t3 += pb[(long long)(s + 24) * C];
+      t1 += pb[(long long)(s + GAPF_WARPS) * C];
+      t2 += pb[(long long)(s + 2 * GAPF_WARPS) * C];
+      t3 += pb[(long long)(s + 3 * GAPF_WARPS) * C];
     }
-    for (; s < nsplit; s += 8) t0 += pb[(long long)s * C];
+    for (; s < nsplit; s += GAPF_WARPS) t0 += pb[(long long)s * C];
   }
   red[w][lane] = (t0 + t1) + (t2 + t3);
   __syncthreads();
   if (w == 0 && c < out_ld) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][lane];
+    for (int i = 0; i < GAPF_WARPS; ++i) t += red[i][lane];
     out[(long long)b * out_ld + c] = c < C ? t * inv : 0.f;
   }
 }
@@ -1088,7 +1089,7 @@ extern "C" int ff_gap(const void* x, int x_is_bf16, int ld, int B, int P, int C,
   dim3 grid(ff_cdiv(C, 32), nsplit, B);
   if (x_is_bf16) gap_partial_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ld, P, C, nsplit, scratch);
   else gap_partial_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), ld, P, C, nsplit, scratch);
-  gap_final_kernel<<<dim3(ff_cdiv(out_ld, 32), B), 256, 0, st>>>(scratch, C, nsplit, 1.0f / P, out, out_ld);
+  gap_final_kernel<<<dim3(ff_cdiv(out_ld, 32), B), GAPF_WARPS * 32, 0, st>>>(scratch, C, nsplit, 1.0f / P, out, out_ld);
   g_ff_launches += 2;
   FF_CHECK_LAUNCH("ff_gap");
   return FF_OK;
@@ -1096,7 +1097,7 @@ extern "C" int ff_gap(const void* x, int x_is_bf16, int ld, int B, int P, int C,
 
 extern "C" int ff_gap_finalize(const float* partial, int B, int nsplit, int C, float inv, float* out, int out_ld, void* stream) {
   FF_CHECK_ARG(partial && out && B > 0 && nsplit > 0 && out_ld >= C, "ff_gap_finalize: bad args");
-  gap_final_kernel<<<dim3(ff_cdiv(out_ld, 32), B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, C, nsplit, inv, out, out_ld);
+  gap_final_kernel<<<dim3(ff_cdiv(out_ld, 32), B), GAPF_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partial, C, nsplit, inv, out, out_ld);
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_gap_finalize");
   return FF_OK;

@@ -53,7 +53,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.ff_last_error.restype = C.c_char_p
     lib.ff_launch_count.restype = C.c_longlong
-    if lib.ff_abi_version() != 2:
+    if lib.ff_abi_version() != 3:
         raise FFError("libffb200.so ABI version mismatch")
     _lib = lib
     return lib

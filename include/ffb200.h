@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FFB200_ABI_VERSION 2
+#define FFB200_ABI_VERSION 3
 
 int ff_abi_version(void);
 const char* ff_last_error(void);

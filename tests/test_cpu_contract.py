@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     exported = set(re.findall(r" T (ff_[a-z0-9_]+)", subprocess.run(["nm", "-D", lib.LIB_PATH], capture_output=True, text=True).stdout))
     extra = sorted(exported - declared - {"ff_set_error", "ff_num_sms"})
     assert not [e for e in extra if not e.startswith("_Z")], f"exported but undeclared: {extra}"
-    assert so.ff_abi_version() == 2
+    assert so.ff_abi_version() == 3
 
 
 def test_ctypes_structs_match_header_field_order():
