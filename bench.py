@@ -280,7 +280,7 @@ def main():
         "config": {"workload": f"full FreqFusion (HAT-L+DAT+NAFNet-64+fusion head), batch {B} of {S}x{S} LR tiles -> {4*S}x{4*S} per GPU, random-init weights",
                    "tiles_per_gpu": B, "lr_tile": S, "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no explicit flush",
                    "sharding": f"tiles sharded over {world} rank(s), no data-path collective"},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / K},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": world * host_in.numel() * 4, "d2h_bytes_per_step": world * host_out.numel() * 4, "ms_per_step": ms_e2e / K},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": roofline,
