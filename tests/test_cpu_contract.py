@@ -167,3 +167,37 @@ def test_two_rank_gloo_sharding_and_final_gather():
     assert sorted(merged) == [0, 1, 2, 3, 4]
     assert {v[0] for v in merged.values()} == {0, 1}          # both ranks did work
     assert all(v[2] < 1e-6 for v in merged.values())          # every stitched image is exact
+
+
+def test_split_bf16_weight_packing_reproduces_fp32_convs():
+    """Host side of the split-bf16 tensor-core path (packing.pack_conv_split3 / pack_conv_im2col2 + the operand layout that
+    ff_pack_taps writes): a bf16 x bf16 -> fp32 contraction over the packed K axis must reproduce the fp32 conv to ~1e-5
+    (three-term split) / to the weight rounding only (two-term activation split)."""
+    import torch.nn.functional as F
+    from isr2_b200 import packing
+    g = torch.Generator().manual_seed(3)
+    bf = torch.bfloat16
+    # (a) 64 -> 32 3x3, terms = 3: activations [hi | lo | hi] per pixel, conv_gemm taps over the 192-channel rows
+    x = torch.randn(1, 64, 12, 16, generator=g)
+    w = torch.randn(32, 64, 3, 3, generator=g) / 24
+    hi = x.to(bf).float()
+    lo = (x - hi).to(bf).float()
+    xs = torch.cat([hi, lo, hi], 1)                                   # what ff_pack_taps(k=1, terms=3) emits (as channels)
+    wp = packing.pack_conv_split3(w, 32, device="cpu").float()        # [32][9 * 192], K index = tap * 192 + c
+    assert wp.shape == (32, 9 * 192)
+    cols = F.unfold(xs, 3, padding=1).view(1, 192, 9, -1).permute(0, 3, 2, 1).reshape(-1, 9 * 192)   # [p][tap][c]
+    got = (cols.double() @ wp.double().t()).float()
+    ref = F.conv2d(x.double(), w.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, 32).float()
+    assert (got - ref).abs().max().item() < 5e-5 * max(1.0, ref.abs().max().item())
+    # (b) 3 -> 64 3x3, im2col with terms = 2: K index = (t * 9 + tap) * 3 + c inside one 64-wide block
+    img = torch.rand(1, 3, 10, 16, generator=g)
+    w = torch.randn(64, 3, 3, 3, generator=g) / 5
+    c27 = F.unfold(img, 3, padding=1).view(1, 3, 9, -1).permute(0, 3, 2, 1).reshape(-1, 27)
+    chi = c27.to(bf).float()
+    clo = (c27 - chi).to(bf).float()
+    rows = torch.cat([chi, clo, torch.zeros(c27.shape[0], 10)], 1)
+    wp = packing.pack_conv_im2col2(w, 64, device="cpu").float()
+    assert wp.shape == (64, 64) and torch.all(wp[:, 54:] == 0)
+    got = (rows.double() @ wp.double().t()).float()
+    ref = F.conv2d(img, w.to(bf).float(), padding=1).permute(0, 2, 3, 1).reshape(-1, 64)
+    assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
