@@ -49,6 +49,9 @@ def _filtered_update(base, incoming, prefixes=("module.",), replace_anywhere=Fal
     return n
 
 
+GRAPH_MAX_LR_PIXELS = 4 * 128 * 128      # forwards up to this many LR pixels run as replayed CUDA graphs (launch bound otherwise)
+
+
 class FreqFusionB200:
     """Inference-only model object.  `state` holds four fp32 CPU state dicts (reference key names)."""
 
@@ -111,6 +114,7 @@ class FreqFusionB200:
             self._runners = dict(hat=HATRunner(self.state["hat"], dev), dat=DATRunner(self.state["dat"], dev),
                                  nafnet=NAFNetRunner(self.state["nafnet"], dev), head=HeadRunner(self.state["fusion"], dev))
             self._stacks = {}
+            self._graphs = {}
         return self._runners
 
     def _stack(self, B, S0, S1):
@@ -156,10 +160,44 @@ class FreqFusionB200:
         if not lr.is_cuda:
             raise L.FFError("FreqFusionB200.forward needs a CUDA tensor (no CPU fallback)")
         lr = lr.contiguous().float()
+        B, _, h, w = lr.shape
+        if intermediates is None and B * h * w <= GRAPH_MAX_LR_PIXELS and os.environ.get("FFB200_GRAPHS", "1") != "0":
+            return self._forward_graphed(lr, out)
         stack = self.forward_experts(lr)
         return self.runners()["head"].forward(lr, stack, out=out, intermediates=intermediates)
 
     __call__ = forward
+
+    def _forward_graphed(self, lr, out):
+        """Small batches are bound by the ~2 000 host-side launches of a forward (~10 us each), not by the GPU: the forward
+        of each (B, h, w) shape is captured once into a CUDA graph (static input / output buffers, the cached workspaces keep
+        every address stable, the three expert streams fork and join inside the capture) and replayed."""
+        self.runners()
+        key = tuple(lr.shape)
+        ent = self._graphs.get(key)
+        if ent is None:
+            B, _, h, w = lr.shape
+            x_s = lr.clone()
+            o_s = torch.empty(B, 3, 4 * h, 4 * w, dtype=torch.float32, device=self.device)
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):      # allocates the workspaces and configures the kernels outside the capture
+                    self.runners()["head"].forward(x_s, self.forward_experts(x_s), out=o_s)
+                side.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    self.runners()["head"].forward(x_s, self.forward_experts(x_s), out=o_s)
+            cur.wait_stream(side)
+            ent = self._graphs[key] = (graph, x_s, o_s)
+        graph, x_s, o_s = ent
+        x_s.copy_(lr)
+        graph.replay()
+        if out is None:
+            return o_s.clone()
+        out.copy_(o_s)
+        return out
 
     @torch.no_grad()
     def forward_with_precomputed(self, lr, expert_outputs, out=None, intermediates=None):

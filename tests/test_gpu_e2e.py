@@ -55,6 +55,29 @@ def test_batch_independence():
     assert (a - b).abs().max().item() < 1e-3
 
 
+def test_cuda_graph_replay_matches_eager(monkeypatch):
+    """Small forwards run as replayed CUDA graphs (model.GRAPH_MAX_LR_PIXELS): identical bits to the eager launch sequence,
+    fresh inputs are honoured on every replay, `out=` and returned tensors do not alias the graph's static buffers."""
+    from isr2_b200 import model as M
+    m = M.FreqFusionB200("cuda:0", init_seed=0, verbose=False)
+    xs = [_lr(2, 64, 64, 30 + i).cuda() for i in range(3)]
+    monkeypatch.setenv("FFB200_GRAPHS", "0")
+    eager = [m.forward(x).clone() for x in xs]
+    monkeypatch.setenv("FFB200_GRAPHS", "1")
+    got = [m.forward(x) for x in xs]                  # first call captures, the next two replay
+    assert tuple(xs[0].shape) in m._graphs
+    for e, g in zip(eager, got):
+        assert torch.equal(e, g)
+    out = torch.empty_like(eager[0])
+    r = m.forward(xs[1], out=out)
+    assert r is out and torch.equal(out, eager[1]) and torch.equal(got[0], eager[0])
+    # shapes above the threshold stay on the eager path
+    big = _lr(1, 128, 128 * 5, 40).cuda()
+    assert big.shape[0] * big.shape[2] * big.shape[3] > M.GRAPH_MAX_LR_PIXELS
+    m.forward(big)
+    assert tuple(big.shape) not in m._graphs
+
+
 @pytest.mark.parametrize("h,w,tile,ov", [(339, 510, 128, 32), (150, 170, 64, 8), (128, 128, 128, 32), (256, 300, 128, 32)])
 def test_stitch_bit_exact(h, w, tile, ov):
     """Stitch kernel == the reference's sequential accumulation, bit for bit, incl. the uint8 quantisation."""
