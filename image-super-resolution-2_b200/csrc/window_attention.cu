@@ -304,6 +304,7 @@ int launch(const FFWinAttn& p, size_t smem, cudaStream_t st) {
 }  // namespace
 
 extern long long g_ff_launches;
+int ff_window_attention_tc_try(const FFWinAttn& p, cudaStream_t st);   // window_attention_tc.cu (tcgen05 path)
 
 extern "C" int ff_window_attention(const FFWinAttn* pp, void* stream) {
   FF_CHECK_ARG(pp != nullptr, "ff_window_attention: null params");
@@ -324,6 +325,11 @@ extern "C" int ff_window_attention(const FFWinAttn* pp, void* stream) {
   const size_t smem = (size_t)(NQ + 2 * NK) * ROWP * 2 + (size_t)p.T * 4 + (size_t)NK + 16;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ++g_ff_launches;
+  {
+    // 16x16 (shifted-)window MSA runs on tcgen05/TMEM; other window shapes stay on the mma.sync kernel below
+    const int r = ff_window_attention_tc_try(p, st);
+    if (r <= 0) return r;
+  }
   const bool wrap = p.rel_sign < 0;      // HAT's overlapping-window table is indexed with negative offsets
   switch (p.kw) {
     case 8: return wrap ? launch<8, -1>(p, smem, st) : launch<8, 1>(p, smem, st);
