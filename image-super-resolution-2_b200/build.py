@@ -14,6 +14,7 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libffb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+FLAGS += os.environ.get("FFB200_NVCC_EXTRA", "").split()      # development builds, e.g. -DFF_ATTN_PROF (phase timers)
 
 
 def _sources():

@@ -72,6 +72,10 @@ extern "C" int ff_stitch(const float* tiles, const int* ty, const int* tx, const
 // crop_border=4, MSE on [0,1] data).  Two-phase deterministic reduction: per-block partial sums of squared Y differences.
 // ----------------------------------------------------------------------------------------------
 namespace {
+// metrics.py:30-52 after the clamp(0, 1) of calculate_psnr / calculate_ssim (:104-105, :208-209)
+__device__ __forceinline__ float luma601(const float* __restrict__ p, long long o, long long hw) {
+  return (65.481f * __saturatef(p[o]) + 128.553f * __saturatef(p[hw + o]) + 24.966f * __saturatef(p[2 * hw + o]) + 16.0f) / 255.0f;
+}
 __global__ void __launch_bounds__(256) sqdiff_y_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int crop,
                                                       double* __restrict__ partial) {
   __shared__ double red[256];
@@ -84,8 +88,7 @@ __global__ void __launch_bounds__(256) sqdiff_y_kernel(const float* __restrict__
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const int y = (int)(i / Wc) + crop, x = (int)(i % Wc) + crop;
     const long long o = (long long)y * W + x;
-    const float ya = (65.481f * pa[o] + 128.553f * pa[hw + o] + 24.966f * pa[2 * hw + o] + 16.0f) / 255.0f;
-    const float yb = (65.481f * pb[o] + 128.553f * pb[hw + o] + 24.966f * pb[2 * hw + o] + 16.0f) / 255.0f;
+    const float ya = luma601(pa, o, hw), yb = luma601(pb, o, hw);
     const double d = (double)ya - (double)yb;
     s += d * d;
   }
@@ -116,5 +119,121 @@ extern "C" int ff_psnr_y(const float* a, const float* b, int B, int H, int W, in
   psnr_final_kernel<<<B, 1, 0, st>>>(scratch, nblk, (double)(H - 2 * crop) * (W - 2 * crop), out);
   g_ff_launches += 2;
   FF_CHECK_LAUNCH("ff_psnr_y");
+  return FF_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// SSIM on the BT.601 luma channel with a border crop (reference src/utils/metrics.py:189-246 -> :129-186, the PyTorch branch
+// calculate_ssim takes without scikit-image): 11x11 Gaussian window (sigma 1.5, outer product of the normalised 1-D
+// window), zero padding of the cropped image, C1 = 0.01^2, C2 = 0.03^2, mean of the full map.  One CTA per 32x32 tile of
+// the map: both luma tiles with a 5-pixel halo in smem, separable filter of the five moments (rows, then columns), two-phase
+// deterministic fp64 reduction.
+// ----------------------------------------------------------------------------------------------
+namespace {
+constexpr int SS_T = 32, SS_R = 5, SS_H = SS_T + 2 * SS_R;   // tile, window radius, tile + halo
+__constant__ float c_ssim_win[11];
+
+__global__ void __launch_bounds__(256) ssim_y_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int crop,
+                                                    int tiles_x, double* __restrict__ partial) {
+  __shared__ float ya[SS_H][SS_H + 1], yb[SS_H][SS_H + 1];
+  __shared__ float hq[5][SS_H][SS_T];
+  __shared__ double red[256];
+  const int Hc = H - 2 * crop, Wc = W - 2 * crop;
+  const long long hw = (long long)H * W;
+  const float* pa = a + (long long)blockIdx.y * 3 * hw;
+  const float* pb = b + (long long)blockIdx.y * 3 * hw;
+  const int ty0 = (blockIdx.x / tiles_x) * SS_T, tx0 = (blockIdx.x % tiles_x) * SS_T;
+  for (int i = threadIdx.x; i < SS_H * SS_H; i += 256) {
+    const int r = i / SS_H, c = i - r * SS_H;
+    const int y = ty0 + r - SS_R, x = tx0 + c - SS_R;      // coordinates in the cropped image
+    float va = 0.f, vb = 0.f;                               // conv2d zero padding
+    if (y >= 0 && y < Hc && x >= 0 && x < Wc) {
+      const long long o = (long long)(y + crop) * W + (x + crop);
+      va = luma601(pa, o, hw);
+      vb = luma601(pb, o, hw);
+    }
+    ya[r][c] = va;
+    yb[r][c] = vb;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SS_H * SS_T; i += 256) {
+    const int r = i / SS_T, c = i - r * SS_T;
+    float s1 = 0.f, s2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const float w = c_ssim_win[k], u = ya[r][c + k], v = yb[r][c + k];
+      s1 += w * u; s2 += w * v; s11 += w * (u * u); s22 += w * (v * v); s12 += w * (u * v);
+    }
+    hq[0][r][c] = s1; hq[1][r][c] = s2; hq[2][r][c] = s11; hq[3][r][c] = s22; hq[4][r][c] = s12;
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < SS_T * SS_T; i += 256) {
+    const int r = i / SS_T, c = i - r * SS_T;
+    if (ty0 + r >= Hc || tx0 + c >= Wc) continue;
+    float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const float w = c_ssim_win[k];
+      m1 += w * hq[0][r + k][c]; m2 += w * hq[1][r + k][c]; e11 += w * hq[2][r + k][c]; e22 += w * hq[3][r + k][c];
+      e12 += w * hq[4][r + k][c];
+    }
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+    const float v1 = e11 - m11, v2 = e22 - m22, cov = e12 - m12;
+    acc += (double)(((2.f * m12 + C1) * (2.f * cov + C2)) / ((m11 + m22 + C1) * (v1 + v2 + C2)));
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(long long)blockIdx.y * gridDim.x + blockIdx.x] = red[0];
+}
+__global__ void ssim_final_kernel(const double* __restrict__ partial, int nblk, double n, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += 256) s += partial[(long long)blockIdx.x * nblk + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)(red[0] / n);
+}
+}  // namespace
+
+extern "C" size_t ff_ssim_y_scratch_bytes(int B, int H, int W, int crop) {
+  if (B <= 0 || H <= 2 * crop || W <= 2 * crop || crop < 0) return 0;
+  const size_t tiles = (size_t)((H - 2 * crop + SS_T - 1) / SS_T) * (size_t)((W - 2 * crop + SS_T - 1) / SS_T);
+  return (size_t)B * tiles * sizeof(double);
+}
+
+extern "C" int ff_ssim_y(const float* a, const float* b, int B, int H, int W, int crop, float* out, double* scratch, size_t scratch_bytes,
+                         void* stream) {
+  FF_CHECK_ARG(a && b && out && scratch && B > 0 && H > 2 * crop && W > 2 * crop && crop >= 0, "ff_ssim_y: bad args");
+  FF_CHECK_ARG(B <= 65535, "ff_ssim_y: batch too large");
+  FF_CHECK_ARG(scratch_bytes >= ff_ssim_y_scratch_bytes(B, H, W, crop), "ff_ssim_y: scratch too small");
+  static bool have_window = false;
+  if (!have_window) {
+    // metrics.py:150-154: exp(-(x-5)^2 / (2 sigma^2)) normalised to sum 1 (float32 tensor arithmetic in the reference)
+    float g[11], sum = 0.f;
+    for (int x = 0; x < 11; ++x) { g[x] = (float)exp(-(double)((x - 5) * (x - 5)) / (2.0 * 1.5 * 1.5)); sum += g[x]; }
+    for (int x = 0; x < 11; ++x) g[x] /= sum;
+    cudaError_t e = cudaMemcpyToSymbol(c_ssim_win, g, sizeof(g));
+    if (e != cudaSuccess) {
+      ff_set_error("ff_ssim_y: window upload: %s", cudaGetErrorString(e));
+      return FF_ERR_CUDA;
+    }
+    have_window = true;
+  }
+  const int tiles_x = (W - 2 * crop + SS_T - 1) / SS_T, tiles_y = (H - 2 * crop + SS_T - 1) / SS_T;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ssim_y_kernel<<<dim3(tiles_x * tiles_y, B), 256, 0, st>>>(a, b, H, W, crop, tiles_x, scratch);
+  ssim_final_kernel<<<B, 256, 0, st>>>(scratch, tiles_x * tiles_y, (double)(H - 2 * crop) * (W - 2 * crop), out);
+  g_ff_launches += 2;
+  FF_CHECK_LAUNCH("ff_ssim_y");
   return FF_OK;
 }

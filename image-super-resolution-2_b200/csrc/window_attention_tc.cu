@@ -121,6 +121,18 @@ __device__ __forceinline__ void softmax_pass2(uint32_t t_s, uint32_t (&raw)[2][3
   }
 }
 
+#ifdef FF_ATTN_PROF
+// development build: per-phase cycle counters of thread 0 of every CTA (gather, S wait, pass 1, pass 2, PV wait, read-out)
+__device__ unsigned long long g_attn_prof[8];
+#define PROF_DECL long long prof_t = clock64(); unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF(i) { const long long t_ = clock64(); prof_acc[i] += (unsigned long long)(t_ - prof_t); prof_t = t_; }
+#define PROF_FLUSH if (tid == 0) { for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_attn_prof[i_], prof_acc[i_]); atomicAdd(&g_attn_prof[7], 1ull); }
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_FLUSH
+#endif
+
 __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const __grid_constant__ FFWinAttn p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar;
@@ -146,6 +158,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
   const bool shifted = (p.shift_y | p.shift_x) != 0;
   const bool need_mask = shifted && (wy == nwy - 1 || wx == nwx - 1);
 
+  PROF_DECL
   if (tid == 0) {
     mbar_init(&mma_bar, 1);
     fence_mbar_init();
@@ -157,16 +170,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
 
   // ---- gather: 3 operands x 256 tokens x 8 chunks of 16 B ----
   {
+    // two cp.async groups: Q and K (needed by the first S = Q K^T) and V (first needed by the first P V, so it travels under
+    // the first tile's logits and softmax)
     const bf16* base = reinterpret_cast<const bf16*>(p.qkv);
-    for (int idx = tid; idx < NT * 8; idx += NTHREADS) {
-      const int t = idx >> 3, c = idx & 7;
-      int y = wy * 16 + (t >> 4) + p.shift_y; if (y >= p.H) y -= p.H;
-      int x = wx * 16 + (t & 15) + p.shift_x; if (x >= p.W) x -= p.W;
-      const bf16* src = base + (img0 + (long long)y * p.W + x) * p.ld + head0 * 32 + c * 8;
-      const uint32_t dst = sbase + t * ROWB + ((c ^ (t & 7)) << 4);
-      cp_async16(dst + SMEM_Q, src + p.q_off);
-      cp_async16(dst + SMEM_K, src + p.k_off);
-      cp_async16(dst + SMEM_V, src + p.v_off);
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+      for (int idx = tid; idx < NT * 8; idx += NTHREADS) {
+        const int t = idx >> 3, c = idx & 7;
+        int y = wy * 16 + (t >> 4) + p.shift_y; if (y >= p.H) y -= p.H;
+        int x = wx * 16 + (t & 15) + p.shift_x; if (x >= p.W) x -= p.W;
+        const bf16* src = base + (img0 + (long long)y * p.W + x) * p.ld + head0 * 32 + c * 8;
+        const uint32_t dst = sbase + t * ROWB + ((c ^ (t & 7)) << 4);
+        if (part == 0) {
+          cp_async16(dst + SMEM_Q, src + p.q_off);
+          cp_async16(dst + SMEM_K, src + p.k_off);
+        } else {
+          cp_async16(dst + SMEM_V, src + p.v_off);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
     // bias tables of the two heads, x log2(e), re-laid with row stride 48
     const float* tb = p.bias_table + (long long)(p.bias_head_off + head0_l) * p.T;
@@ -182,13 +204,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
     tm[0] = warp_max(tm[0]);
     tm[1] = warp_max(tm[1]);
     if (lane == 0) { sRed[0][warp] = tm[0]; sRed[1][warp] = tm[1]; }
-    cp_async_wait_all();
+    asm volatile("cp.async.wait_group 1;" ::: "memory");      // Q and K have landed
     fence_proxy_async_smem();      // generic/cp.async writes -> visible to the tensor core's async-proxy reads
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  PROF(0)
   if (tid < 2) {
     float m = sRed[tid][0];
 #pragma unroll
@@ -238,6 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
     mbar_wait(&mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
+    PROF(1)
 
     // ---- pass 1: row max of the raw logits (the next chunk's TMEM load is in flight while a chunk is reduced) ----
     uint32_t raw[2][32];
@@ -256,6 +280,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
     tmem_ld32(t_s, raw[0]);            // first chunk of pass 2 travels under the exchange
     sMax[ch * 128 + rih] = fmaxf(mx0, mx1);
     __syncthreads();
+    PROF(2)
     // softmax shift = max_k(q.k) + max(bias table): an upper bound of the true row max that exceeds it by at most the
     // spread of the table (softmax is shift invariant; exp2 has 126 binades of headroom), which spares a bias pass
     const float mshift = fmaxf(fmaxf(mx0, mx1), sMax[(ch ^ 1) * 128 + rih]) + sTabMax[h];
@@ -264,8 +289,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
     if (need_mask) softmax_pass2<true>(t_s, raw, mshift, tabp, bad_y, bad_x);     // CTA-uniform branch
     else softmax_pass2<false>(t_s, raw, mshift, tabp, 0u, 0u);
     tc_wait_st();
+    PROF(3)
+    if (unit == 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");    // V has landed (this thread's part; the barrier covers the rest)
+      fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
+    PROF(4)
 
     // ---- O = P V ----
     if (warp == 0) {
@@ -283,6 +314,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
     mbar_wait(&mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
+    PROF(5)
 
     // ---- normalise and store: warps 0-3 dims 0-15, warps 4-7 dims 16-31 of head h ----
     {
@@ -309,7 +341,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
     tc_fence_before();
     __syncthreads();      // O read out before the next unit's S overwrites the columns
     if (warp == 0) tc_fence_after();
+    PROF(6)
   }
+  PROF_FLUSH
 
   tc_fence_before();
   __syncthreads();
@@ -322,6 +356,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
 int g_mode = -1;   // -1 unread, 0 off, 1 on
 
 }  // namespace
+
+#ifdef FF_ATTN_PROF
+extern "C" int ff_debug_attn_prof(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_attn_prof, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_attn_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 // Returns FF_OK when the tensor-core kernel was launched, 1 when the shape is not covered (caller falls back to the
 // mma.sync kernel of window_attention.cu), < 0 on error.

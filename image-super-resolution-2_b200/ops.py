@@ -229,3 +229,19 @@ def psnr_y(a, b, crop=4):
     L.check(L.load().ff_psnr_y(_ptr(a.contiguous()), _ptr(b.contiguous()), B, H, W, crop, _ptr(out), _ptr(scratch), C.c_size_t(scratch.numel() * 8), _stream()),
             "ff_psnr_y")
     return out
+
+
+def ssim_y(a, b, crop=4):
+    """SSIM on BT.601 Y, border crop (reference src/utils/metrics.py:189-246 -> :129-186, 11x11 Gaussian window, zero padding);
+    a, b: fp32 NCHW [B,3,H,W] on the GPU -> fp32 [B]."""
+    _req_cuda(a, b)
+    B, _, H, W = a.shape
+    lib = L.load()
+    nbytes = int(lib.ff_ssim_y_scratch_bytes(B, H, W, crop))
+    if nbytes == 0:
+        raise ValueError(f"ssim_y: image {H}x{W} does not survive a crop of {crop}")
+    out = torch.empty(B, dtype=torch.float32, device=a.device)
+    scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=a.device)
+    L.check(lib.ff_ssim_y(_ptr(a.contiguous()), _ptr(b.contiguous()), B, H, W, crop, _ptr(out), _ptr(scratch), C.c_size_t(nbytes), _stream()),
+            "ff_ssim_y")
+    return out

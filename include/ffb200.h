@@ -274,6 +274,13 @@ int ff_stitch(const float* tiles, const int* ty, const int* tx, const float* wy,
  * (reference src/utils/metrics.py:30-52, 76-126).  out: fp32 [B]; scratch >= B*64 doubles.  Identical inputs give 100 dB. */
 int ff_psnr_y(const float* a, const float* b, int B, int H, int W, int crop, float* out, double* scratch, size_t scratch_bytes, void* stream);
 
+/* SSIM on the BT.601 Y channel with a `crop`-pixel border removed, per sample, same operands as ff_psnr_y (inputs are clamped
+ * to [0,1] first, as the reference does).  Reference src/utils/metrics.py:189-246 in its PyTorch branch :129-186 (taken when
+ * scikit-image is absent): 11x11 Gaussian window sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2, mean over the cropped
+ * map.  out: fp32 [B]; scratch >= ff_ssim_y_scratch_bytes(B, H, W, crop) bytes (one double per 32x32 map tile and sample). */
+int ff_ssim_y(const float* a, const float* b, int B, int H, int W, int crop, float* out, double* scratch, size_t scratch_bytes, void* stream);
+size_t ff_ssim_y_scratch_bytes(int B, int H, int W, int crop);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,3 +135,26 @@ def test_psnr_y_kernel():
     for i in range(2):
         assert abs(got[i].item() - _psnr_y(a[i:i + 1], b[i:i + 1])) < 1e-3
     assert ops.psnr_y(a.cuda(), a.cuda()).cpu()[0].item() == 100.0
+
+
+def test_metrics_kernels_vs_golden_and_oracle():
+    """ff_psnr_y / ff_ssim_y against the reference's own values (tests/golden/metrics.pt: inputs overshoot [0,1], so the
+    clamp is exercised; odd sizes exercise partial 32x32 map tiles) and against the oracle on a batch at an HR tile size."""
+    import os
+    from isr2_b200 import ops
+    from oracle import metrics
+    cases = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics.pt"))
+    for c in cases:
+        a, b = c["a"].cuda(), c["b"].cuda()
+        assert abs(ops.psnr_y(a, b).item() - c["psnr"]) < 1e-3
+        assert abs(ops.ssim_y(a, b).item() - c["ssim"]) < 2e-6
+        assert abs(ops.ssim_y(a, a).item() - 1.0) < 1e-6
+    g = torch.Generator().manual_seed(12)
+    a = torch.rand(3, 3, 256, 200, generator=g)
+    b = (a + 0.05 * torch.randn(3, 3, 256, 200, generator=g))
+    got = ops.ssim_y(a.cuda(), b.cuda()).cpu()
+    ref = metrics.ssim_y(a, b)
+    for i in range(3):
+        assert abs(got[i].item() - ref[i]) < 2e-6
+    with pytest.raises(ValueError):
+        ops.ssim_y(a[:, :, :8, :8].cuda(), b[:, :, :8, :8].cuda())

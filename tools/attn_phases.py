@@ -1,0 +1,26 @@
+"""Phase timers of window_attention_tc_kernel (development helper; needs a library built with
+FFB200_NVCC_EXTRA=-DFF_ATTN_PROF).  Prints average cycles per CTA for each phase of thread 0."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from isr2_b200 import ops, lib
+L = lib.load()
+dev = torch.device("cuda:0")
+B, S = int(sys.argv[1]), int(sys.argv[2])
+M = B * S * S
+qkv = (torch.randn(M, 576, device=dev) * 0.3).to(torch.bfloat16)
+out = torch.empty(M, 192, device=dev, dtype=torch.bfloat16)
+buf = (C.c_ulonglong * 8)()
+names = ["gather+table", "S issue+wait", "pass 1 + sync", "pass 2", "sync", "PV issue+wait", "read-out + sync"]
+for shift in ((0, 0), (8, 8)):
+    kw = dict(bias_table=torch.randn(6, 961, device=dev), wh=16, ww=16, shift=shift)
+    ops.window_attention(qkv, B, S, S, out, **kw)
+    L.ff_debug_attn_prof(buf, 1)
+    ops.window_attention(qkv, B, S, S, out, **kw)
+    L.ff_debug_attn_prof(buf, 1)
+    n = buf[7]
+    tot = sum(buf[i] for i in range(7))
+    print(f"shift {shift}: {n} CTAs, {tot / n:.0f} cycles per CTA")
+    for i, nm in enumerate(names):
+        per = buf[i] / n / (1 if i == 0 else 4)
+        print(f"  {nm:18s} {per:8.0f} cycles per {'CTA' if i == 0 else 'tile'}  ({100 * buf[i] / tot:.1f} %)")
