@@ -138,7 +138,9 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"full FreqFusion (HAT-L+DAT+NAFNet-64+fusion head), LR tile {S}x{S} -> {4*S}x{4*S}, CPU"},
+        "config": {"workload": f"full FreqFusion (HAT-L+DAT+NAFNet-64+fusion head), batch {args.batch} of {S}x{S} LR tiles -> {4*S}x{4*S} per GPU, random-init weights",
+                   "tiles_per_gpu": args.batch, "lr_tile": S,
+                   "sample": f"each step = 1 of the {args.batch} tiles on the host CPU (the path is batch independent, so Mpix/s is the same)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

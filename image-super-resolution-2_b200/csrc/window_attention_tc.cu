@@ -105,15 +105,20 @@ __device__ __forceinline__ void softmax_pass2(uint32_t t_s, uint32_t (&raw)[2][3
     uint32_t pk[16];
     tc_wait_ld();
     if (cb < 3) tmem_ld32(t_s + (cb + 1) * 32, raw[(cb + 1) & 1]);
+    const float2 nshift = make_float2(-mshift, -mshift);
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int kil = cb * 2 + (c >> 4), kj = c & 15;     // key row within this half, key column
-      float s = (__uint_as_float(raw[cb & 1][c]) - mshift) + lds_f32(tabp - 4u * (uint32_t)(kil * TSTRIDE + kj));
+    for (int c = 0; c < 32; c += 2) {
+      const int kil = cb * 2 + (c >> 4), kj = c & 15;     // key row within this half, key column (pairs: packed FADD2)
+      const float2 r2 = make_float2(__uint_as_float(raw[cb & 1][c]), __uint_as_float(raw[cb & 1][c + 1]));
+      const float2 b2 = make_float2(lds_f32(tabp - 4u * (uint32_t)(kil * TSTRIDE + kj)), lds_f32(tabp - 4u * (uint32_t)(kil * TSTRIDE + kj + 1)));
+      float2 s2 = __fadd2_rn(__fadd2_rn(r2, nshift), b2);
       if (MASK) {
         const uint32_t eff = ((bad_y >> kil) & 1u) ? 0xFFFFu : bad_x;
-        if ((eff >> kj) & 1u) s -= MASKV;
+        if ((eff >> kj) & 1u) s2.x -= MASKV;
+        if ((eff >> (kj + 1)) & 1u) s2.y -= MASKV;
       }
-      raw[cb & 1][c] = __float_as_uint(ex2(s));
+      raw[cb & 1][c] = __float_as_uint(ex2(s2.x));
+      raw[cb & 1][c + 1] = __float_as_uint(ex2(s2.y));
     }
 #pragma unroll
     for (int c = 0; c < 16; ++c) pk[c] = pack_bf16(__uint_as_float(raw[cb & 1][2 * c]), __uint_as_float(raw[cb & 1][2 * c + 1]));
