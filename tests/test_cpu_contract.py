@@ -201,3 +201,55 @@ def test_split_bf16_weight_packing_reproduces_fp32_convs():
     got = (rows.double() @ wp.double().t()).float()
     ref = F.conv2d(img, w.to(bf).float(), padding=1).permute(0, 2, 3, 1).reshape(-1, 64)
     assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def _write_cache(d, stems, primary="hat", squeeze=False, seed=0):
+    """Synthetic cached-expert files in the reference's layout (src/data/cached_dataset.py:9-23)."""
+    g = torch.Generator().manual_seed(seed)
+    for s in stems:
+        lr, hr = torch.rand(3, 16, 16, generator=g), torch.rand(3, 64, 64, generator=g)
+        def img():
+            t = torch.rand(1, 3, 64, 64, generator=g)
+            return t.squeeze(0) if squeeze else t
+        second = "grl" if primary == "drct" else "dat"
+        torch.save({"outputs": {primary: img()}, "features": {primary: torch.rand(1, 8, 16, 16, generator=g)}, "lr": lr, "hr": hr, "filename": s},
+                   os.path.join(d, f"{s}_{primary}_part.pt"))
+        torch.save({"outputs": {second: img(), "nafnet": img()}, "features": {second: torch.rand(1, 8, 16, 16, generator=g)}, "filename": s},
+                   os.path.join(d, f"{s}_rest_part.pt"))
+
+
+@pytest.mark.parametrize("primary", ["hat", "drct"])
+def test_cached_expert_store_reads_the_reference_format(tmp_path, primary):
+    """isr2_b200.cached against the reference's own CachedSRDataset (augment=False) when /root/reference is present, and
+    against the documented format otherwise: discovery order, key aliases, batch-dim squeeze, dropped incomplete pairs."""
+    from isr2_b200 import cached
+    d = str(tmp_path)
+    stems = ["img_002_p1", "img_001_p0", "img_003"]
+    _write_cache(d, stems, primary=primary)
+    os.remove(os.path.join(d, "img_003_rest_part.pt"))          # incomplete pair: dropped with a warning
+    st = cached.CachedExpertStore(d, load_features=True)
+    assert st.file_stems == ["img_001_p0", "img_002_p1"]
+    rec = st[0]
+    assert set(rec["expert_imgs"]) == {"hat", "dat", "nafnet"} and rec["filename"] == "img_001_p0"
+    assert all(v.shape == (3, 64, 64) for v in rec["expert_imgs"].values()) and rec["lr"].shape == (3, 16, 16)
+    assert set(rec["expert_feats"]) == {"hat", "dat"} and rec["expert_feats"]["hat"].shape == (8, 16, 16)
+    assert [len(b) for b in st.batches(8)] == [2] and [len(b) for b in st.batches(1)] == [1, 1]
+    with pytest.raises(RuntimeError):
+        cached.CachedExpertStore(os.path.join(d, "nope"))
+    ref_file = "/root/reference/src/data/cached_dataset.py"
+    if os.path.exists(ref_file):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_cached_dataset", ref_file)
+        m = importlib.util.module_from_spec(spec)
+        sys.dont_write_bytecode = True
+        spec.loader.exec_module(m)
+        ds = m.CachedSRDataset(d, augment=False, repeat_factor=1, load_features=True)
+        assert ds.file_stems == st.file_stems
+        for i in range(len(ds)):
+            a, b = ds[i], st[i]
+            assert a["filename"] == b["filename"] and torch.equal(a["lr"], b["lr"]) and torch.equal(a["hr"], b["hr"])
+            assert set(a["expert_imgs"]) == set(b["expert_imgs"]) and set(a["expert_feats"]) == set(b["expert_feats"])
+            for k in a["expert_imgs"]:
+                assert torch.equal(a["expert_imgs"][k], b["expert_imgs"][k])
+            for k in a["expert_feats"]:
+                assert torch.equal(a["expert_feats"][k], b["expert_feats"][k])

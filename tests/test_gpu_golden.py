@@ -50,3 +50,33 @@ def test_forward_with_precomputed_vs_reference_golden_64():
     assert (out - g["out"]).abs().max() < 2e-2
     with pytest.raises(KeyError):
         m.forward_with_precomputed(lr.cuda(), {"hat": ex["hat"]})
+
+
+def test_cached_expert_files_through_the_head(tmp_path):
+    """The reference's cached-expert workflow (src/data/cached_dataset.py + forward_with_precomputed): the golden head input
+    written in the on-disk format ({stem}_drct_part.pt with keys drct / grl + {stem}_rest_part.pt), read back by
+    isr2_b200.cached and run through the fusion head; SR must match the reference's golden output, and the on-GPU PSNR / SSIM
+    against the cached HR patch must match the oracle metrics of the same SR."""
+    from isr2_b200 import cached, model as M
+    from oracle import metrics
+    g = torch.load(os.path.join(GOLD, "head_64.pt"))
+    lr = g["lr"]
+    gen = torch.Generator().manual_seed(g["expert_seed"])
+    up = F.interpolate(lr, scale_factor=4, mode="bicubic", align_corners=False)
+    ex = {k: (up + s * torch.randn(1, 3, 256, 256, generator=gen)).clamp(0, 1) for k, s in (("hat", 0.01), ("grl", 0.02), ("nafnet", 0.03))}
+    hr = up.clamp(0, 1)[0]
+    for stem in ("a_p0", "a_p1"):
+        torch.save({"outputs": {"drct": ex["hat"]}, "lr": lr[0], "hr": hr, "filename": stem}, tmp_path / f"{stem}_drct_part.pt")
+        torch.save({"outputs": {"grl": ex["grl"], "nafnet": ex["nafnet"]}, "filename": stem}, tmp_path / f"{stem}_rest_part.pt")
+    store = cached.CachedExpertStore(str(tmp_path))
+    assert len(store) == 2
+    m = M.FreqFusionB200("cuda:0", init_seed=0, verbose=False)
+    recs = cached.run_cached(m, store, batch_size=2)
+    assert [r["filename"] for r in recs] == ["a_p0", "a_p1"]
+    for r in recs:
+        sr = r["sr"].cpu()[None]
+        assert (sr - g["out"]).abs().max() < 2e-2
+        assert abs(r["psnr_y"] - metrics.psnr_y(sr, hr[None])[0]) < 1e-3
+        ref_ssim = metrics.ssim_y(sr, hr[None])[0]
+        print(f"cached: psnr_y {r['psnr_y']:.4f} dB, ssim_y {r['ssim_y']:.7f} (oracle {ref_ssim:.7f})")
+        assert abs(r["ssim_y"] - ref_ssim) < 2e-5      # smooth image: small variances in the denominator amplify fp32 summation-order noise
