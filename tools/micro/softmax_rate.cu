@@ -7,7 +7,19 @@
 #include <cuda_bf16.h>
 __device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-template <int MODE>   // 0: ex2 only; 1: sub+ex2; 2: sub+lds+add+ex2; 3: mode 2 + bf16 pack; 4: mode 3 without ex2 (FADD instead)
+// exp2 on the FMA/ALU pipes (Cody-Waite split + cubic, rel. error ~1e-4: below the bf16 rounding of P): 8-9 issue slots
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;          // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float n = t - 12582912.f;
+  const float f = x - n;                   // [-0.5, 0.5]
+  float p = fmaf(f, 0.0555041087f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+template <int MODE>   // 0: ex2 only; 1: sub+ex2; 2: sub+lds+add+ex2; 3: mode 2 + bf16 pack; 4: mode 3 without ex2 (FADD instead);
+                      // 5 / 6 / 7: mode 3 with every 8th / 4th / 2nd exponential on the FMA pipe (ex2_poly)
 __global__ void k(float* out, long long* cyc, int iters) {
   __shared__ float tab[2048];
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) tab[i] = 0.001f * i;
@@ -26,9 +38,10 @@ __global__ void k(float* out, long long* cyc, int iters) {
       float s = v[i];
       if (MODE >= 1) s = s - sh;
       if (MODE >= 2) s = s + lds_f32(tp + 4u * 48u * (i >> 4) + 4u * (i & 15));
-      v[i] = (MODE == 4) ? s + 1.0f : ex2(s);
+      const bool poly = (MODE == 5 && (i & 7) == 7) || (MODE == 6 && (i & 3) == 3) || (MODE == 7 && (i & 1) == 1);
+      v[i] = (MODE == 4) ? s + 1.0f : (poly ? ex2_poly(s) : ex2(s));
     }
-    if (MODE >= 3) {
+    if (MODE >= 3 && MODE != 4 || MODE == 4) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
@@ -71,6 +84,9 @@ int main() {
   run<2>("sub, lds, add, ex2", out, cyc);
   run<3>("sub, lds, add, ex2, pack", out, cyc);
   run<4>("sub, lds, add, add, pack (no ex2)", out, cyc);
+  run<5>("mode 3, 1/8 of ex2 on FMA pipe", out, cyc);
+  run<6>("mode 3, 1/4 of ex2 on FMA pipe", out, cyc);
+  run<7>("mode 3, 1/2 of ex2 on FMA pipe", out, cyc);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
