@@ -7,17 +7,22 @@
 //   gather   Q, K, V rows of the window (256 tokens x 2 heads x 32 dims = 128 B per token and operand) with 16-byte
 //            cp.async into the canonical 128-byte-swizzled K-major layout (1024-byte atoms of 8 rows) -- the cyclic shift
 //            is index arithmetic.  The 128-byte row holds both heads; a head is a 64-byte K offset of the descriptor.
+//            Q and K form one cp.async group, V a second one that is only waited for before the first P V.
 //   per unit (head h, query half r):
 //     S  = Q[r] K^T        tcgen05.mma M=128 N=256 K=16 x2  (A, B from smem)          -> TMEM cols [0,256)
-//     pass 1 (thread = query row, warps 0-3 keys 0-127, warps 4-7 keys 128-255):
-//            s += bias[qi-ki, qj-kj]  (table in smem, row stride 48 -> conflict-free LDS with immediate offsets),
-//            {0,-100} shift mask in border windows, row max, s written back to TMEM (tcgen05.st)
-//     pass 2 p = exp2(s - max) -> bf16 pairs -> tcgen05.st over the first half of the thread's own S columns
+//     pass 1 (thread = query row = TMEM lane, warps 0-3 keys 0-127, warps 4-7 keys 128-255): tcgen05.ld of the raw logits,
+//            row max, exchanged between the two key halves through smem
+//     pass 2 p = exp2(s + bias[qi-ki, qj-kj] (+ {0,-100} shift mask, border windows only: separate instantiation) - shift)
+//            with the bias table in smem (row stride 48 -> conflict-free LDS with immediate offsets), packed FADD2, and
+//            shift = max_k(q.k) + max(table) >= the true row max (softmax is shift invariant; exp2 has 126 binades of
+//            headroom) -> bf16 pairs -> tcgen05.st over the first half of the thread's own S columns
 //     O  = P V             tcgen05.mma M=128 N=64 K=16 x16 (A = P from TMEM, B = V from smem, MN-major) -> cols [64,128)
 //            N = 64 covers both heads' dims; the 32 columns of the other head are ignored (the tensor pipe is idle anyway)
 //     out    O[:, h*32 .. +32] / O[:, h*32+31]   (v carries 1.0 in padding dim 31 -> softmax row sums), bf16 store at the
 //            un-shifted token position
 // q is pre-scaled by head_dim^-0.5 * log2(e) in the packed qkv weights, so the softmax is exp2.
+// Measured alternatives (persistent CTAs, operand prefetch, two softmax groups, 16-warp single-pass team) and the phase
+// timers / ablations behind this shape: tools/micro/attn_variants/README.md, DESIGN.md section 6.
 #include "ff_common.cuh"
 #include "../../include/ffb200.h"
 #include <stdlib.h>
