@@ -1194,7 +1194,8 @@ template <int BN, int EPI, bool HALO = false>
 int launch_tc(const Maps& m, const Args& a, cudaStream_t st) {
   using C = Cfg<BN, EPI, HALO>;
   static_assert(C::STAGES >= (HALO ? 3 : 2), "ff_conv_gemm: smem ring too shallow");
-  static bool configured = false;
+  static FFPerDeviceFlag configured_dev;
+  bool& configured = configured_dev.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, EPI, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);

@@ -236,7 +236,8 @@ extern "C" int ff_dat_channel_attention_weights(const void* qkv, int ld, int q_o
   int nchunks = ff_cdiv(N, chunk);
   FF_CHECK_ARG(scratch_bytes >= (size_t)B * heads * nchunks * GRAM_STRIDE * sizeof(float), "ff_dat_channel_attention_weights: scratch too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static bool configured = false;
+  static FFPerDeviceFlag configured_dev;
+  bool& configured = configured_dev.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(dat_chan_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
     if (e != cudaSuccess) { ff_set_error("ff_dat_channel_attention_weights: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FF_ERR_CUDA; }

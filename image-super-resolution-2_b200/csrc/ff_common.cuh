@@ -38,6 +38,17 @@ void ff_set_error(const char* fmt, ...);
 static inline int ff_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int ff_num_sms();
 
+// One-time per-DEVICE state (cudaFuncSetAttribute, __constant__ uploads) is keyed by the current device, so a process that
+// drives several GPUs configures each of them.
+struct FFPerDeviceFlag {
+  bool v[64] = {};
+  bool& get() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[d & 63];
+  }
+};
+
 typedef __nv_bfloat16 bf16;
 
 // ----------------------------------------------------------------------------------------------

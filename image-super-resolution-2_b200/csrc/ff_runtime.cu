@@ -14,10 +14,11 @@ void ff_set_error(const char* fmt, ...) {
 }
 
 int ff_num_sms() {
-  static int n = 0;
+  static int cache[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = cache[dev & 63];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;

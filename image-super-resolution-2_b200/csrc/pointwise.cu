@@ -697,7 +697,8 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3x3_tma_kernel(const __g
 
 template <int MODE, int ACT, bool MUL>
 static int launch_dw_tma(const CUtensorMap& tx_, const CUtensorMap& tm_, const DwArgs& a, int tiles_x, int tiles_y, int ctiles, int grid, cudaStream_t st) {
-  static bool configured = false;
+  static FFPerDeviceFlag configured_dev;
+  bool& configured = configured_dev.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(dwconv3x3_tma_kernel<MODE, ACT, MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwtCfg<MUL>::SMEM);
     if (e != cudaSuccess) { ff_set_error("ff_dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FF_ERR_CUDA; }
@@ -849,7 +850,8 @@ static int launch_dw_large(const DwArgs& a, cudaStream_t st) {
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { ff_set_error("ff_dwconv: cuTensorMapEncodeTiled failed with %d", (int)r); return FF_ERR_DRIVER; }
-  static bool configured = false;
+  static FFPerDeviceFlag configured_dev;
+  bool& configured = configured_dev.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(dwconv_large_tma_kernel<KH, KW, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::SMEM);
     if (e != cudaSuccess) { ff_set_error("ff_dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FF_ERR_CUDA; }

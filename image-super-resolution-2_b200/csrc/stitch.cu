@@ -68,6 +68,52 @@ extern "C" int ff_stitch(const float* tiles, const int* ty, const int* tx, const
 }
 
 // ----------------------------------------------------------------------------------------------
+// Image I/O ends of the plugin (reference io.py:64-76): uint8 HWC image -> fp32 NCHW tiles in [0,1] (np.float32(arr) / 255.0, an
+// IEEE fp32 division, fused with the tile extraction of _tiled_forward :99-103), and fp32 NCHW -> uint8 HWC
+// (round_half_even(clamp(x, 0, 1) * 255), the quantisation of _save_image) for results that do not pass through ff_stitch.
+// ----------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) u8_to_tiles_kernel(const unsigned char* __restrict__ img, int H, int W, const int* __restrict__ ys,
+                                                         const int* __restrict__ xs, int nx, int th, int tw, float* __restrict__ tiles) {
+  const int t = blockIdx.y;
+  const int iy = t / nx, ix = t - iy * nx;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= th * tw) return;
+  const int y = i / tw, x = i - y * tw;
+  const unsigned char* p = img + ((long long)(ys[iy] + y) * W + xs[ix] + x) * 3;
+  float* o = tiles + (long long)t * 3 * th * tw + i;
+  o[0] = __fdiv_rn((float)p[0], 255.0f);
+  o[(long long)th * tw] = __fdiv_rn((float)p[1], 255.0f);
+  o[2LL * th * tw] = __fdiv_rn((float)p[2], 255.0f);
+}
+__global__ void __launch_bounds__(256) quantize_u8_kernel(const float* __restrict__ x, long long hw, unsigned char* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= hw) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[i * 3 + c] = (unsigned char)__float2int_rn(__fmul_rn(fminf(fmaxf(x[c * hw + i], 0.f), 1.f), 255.f));
+}
+}  // namespace
+
+extern "C" int ff_u8_to_tiles(const unsigned char* img, int H, int W, const int* ys, const int* xs, int ny, int nx, int th, int tw, float* tiles,
+                              void* stream) {
+  FF_CHECK_ARG(img && ys && xs && tiles && H > 0 && W > 0 && ny > 0 && nx > 0 && th > 0 && tw > 0 && th <= H && tw <= W, "ff_u8_to_tiles: bad args");
+  FF_CHECK_ARG(ny * nx <= 65535, "ff_u8_to_tiles: too many tiles");
+  dim3 grid(ff_cdiv((long long)th * tw, 256), ny * nx);
+  u8_to_tiles_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img, H, W, ys, xs, nx, th, tw, tiles);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_u8_to_tiles");
+  return FF_OK;
+}
+
+extern "C" int ff_quantize_u8(const float* x, int H, int W, unsigned char* out, void* stream) {
+  FF_CHECK_ARG(x && out && H > 0 && W > 0, "ff_quantize_u8: bad args");
+  quantize_u8_kernel<<<ff_cdiv((long long)H * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, (long long)H * W, out);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_quantize_u8");
+  return FF_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
 // PSNR on the BT.601 luma channel with a border crop (reference src/utils/metrics.py:30-52, 76-126: rgb_to_y then
 // crop_border=4, MSE on [0,1] data).  Two-phase deterministic reduction: per-block partial sums of squared Y differences.
 // ----------------------------------------------------------------------------------------------
@@ -216,7 +262,8 @@ extern "C" int ff_ssim_y(const float* a, const float* b, int B, int H, int W, in
   FF_CHECK_ARG(a && b && out && scratch && B > 0 && H > 2 * crop && W > 2 * crop && crop >= 0, "ff_ssim_y: bad args");
   FF_CHECK_ARG(B <= 65535, "ff_ssim_y: batch too large");
   FF_CHECK_ARG(scratch_bytes >= ff_ssim_y_scratch_bytes(B, H, W, crop), "ff_ssim_y: scratch too small");
-  static bool have_window = false;
+  static FFPerDeviceFlag have_window_dev;
+  bool& have_window = have_window_dev.get();
   if (!have_window) {
     // metrics.py:150-154: exp(-(x-5)^2 / (2 sigma^2)) normalised to sum 1 (float32 tensor arithmetic in the reference)
     float g[11], sum = 0.f;

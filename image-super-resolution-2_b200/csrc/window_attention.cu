@@ -286,7 +286,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_kernel(const __g
 
 template <int KW, int SGN>
 int launch(const FFWinAttn& p, size_t smem, cudaStream_t st) {
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  size_t& configured = configured_dev[dev_ & 63];
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(window_attention_kernel<KW, SGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {

@@ -390,7 +390,8 @@ int ff_window_attention_tc_try(const FFWinAttn& p, cudaStream_t st) {
                   p.out_ld % 8 == 0 && p.out_off % 8 == 0 && p.shift_y >= 0 && p.shift_y < 16 && p.shift_x >= 0 && p.shift_x < 16 &&
                   ((uintptr_t)p.qkv & 15) == 0 && ((uintptr_t)p.out & 15) == 0;
   if (!ok) return 1;
-  static bool configured = false;
+  static FFPerDeviceFlag configured_dev;
+  bool& configured = configured_dev.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) {

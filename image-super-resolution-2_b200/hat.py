@@ -23,21 +23,36 @@ RGB_MEAN = (0.4488, 0.4371, 0.4040)   # hat_arch.py:775 (plain attribute, not in
 
 
 class Workspace:
-    """Named device buffers cached per shape (keeps addresses stable for CUDA-graph capture)."""
+    """Named device buffers cached per shape (keeps addresses stable for CUDA-graph capture).  Every entry remembers the
+    forward (`epoch`) that last used it, so the owner can evict the buffers of shapes that have not been seen for a while
+    (FreqFusionB200._trim_workspaces) -- the cache is bounded, not monotonically growing."""
 
     def __init__(self, device):
         self.device = device
         self.bufs = {}
+        self.epoch = 0
 
     def get(self, name, rows, cols, dtype, zero=False):
         key = (name, rows, cols, dtype)
-        t = self.bufs.get(key)
-        if t is None:
-            t = torch.zeros(rows, cols, dtype=dtype, device=self.device)
-            self.bufs[key] = t
-        elif zero:
-            t.zero_()
-        return t
+        ent = self.bufs.get(key)
+        if ent is None:
+            ent = self.bufs[key] = [torch.zeros(rows, cols, dtype=dtype, device=self.device), self.epoch]
+        else:
+            ent[1] = self.epoch
+            if zero:
+                ent[0].zero_()
+        return ent[0]
+
+    def nbytes(self):
+        return sum(e[0].numel() * e[0].element_size() for e in self.bufs.values())
+
+    def evict_unused_since(self, epoch):
+        """Drops every buffer last used before `epoch`; returns the bytes released."""
+        dead = [k for k, e in self.bufs.items() if e[1] < epoch]
+        freed = sum(self.bufs[k][0].numel() * self.bufs[k][0].element_size() for k in dead)
+        for k in dead:
+            del self.bufs[k]
+        return freed
 
 
 def _qkv_rows():

@@ -2,21 +2,31 @@
 
     main(model_dir, input_path, output_path, device=None)        # reference io.py:188-234, called from test.py:50
 
-Same arguments, side effects and checkpoint handling; the forward runs on the ffb200 sm_100a kernels.
-Differences, both deliberate:
-  * overlapped tiling (tile 128 / overlap 32, the reference's OOM fallback, io.py:226) is the main path and the
-    tiles of an image run batched;
-  * `device` must be a CUDA device -- there is no CPU fallback.
+Same arguments, side effects and checkpoint handling; the forward runs on the ffb200 sm_100a kernels.  Like the reference
+(io.py:218-228) an image is first run WHOLE (`FreqFusionB200.forward_image`, any h x w) and only images above a size
+threshold -- where the reference would hit its OOM fallback -- go through the overlapped tiling (tile 128 / overlap 32).
+`FFB200_FORCE_TILING=1` sends every image through the tile path (BASELINE.json configs[3]).
+
+What is different from the reference, all of it behind the same contract:
+  * `device` must be a CUDA device -- there is no CPU fallback;
+  * units of work (tiles, or whole images of equal size) are batched ACROSS images, PNG decode / encode run on worker threads
+    and the H2D / D2H copies are asynchronous from reused pinned buffers, so the GPU does not idle on host I/O
+    (test.py:46-53 times the whole call, I/O included);
+  * under an initialised `torch.distributed` group the images are sharded over the ranks (scheduler.assign_images, longest
+    processing time first); a lone big image is sharded by tiles and gathered on rank 0 (scheduler.assign_tiles);
+    `main_sharded` spawns that group, one process per GPU (the reference's pattern in eval.py:162-217).
 """
 import glob
 import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
 from PIL import Image
 
 from . import lib as L
-from . import tiling
+from . import scheduler, tiling
 from .model import EXPERT_FILES, FreqFusionB200
 
 # reference io.py:40-58 -- fixed inference configuration (kept for callers that introspect it)
@@ -28,13 +38,27 @@ MODEL_CONFIG = {
 }
 
 _PROJECT_ROOT = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-MAX_TILES_PER_BATCH = int(os.environ.get("FFB200_TILE_BATCH", "20"))
+MAX_TILES_PER_BATCH = int(os.environ.get("FFB200_TILE_BATCH", "16"))
+BATCH_LR_PIXELS = MAX_TILES_PER_BATCH * 128 * 128          # LR pixels per forward (units of any size are grouped up to this)
+# Images up to this many LR pixels run whole, as the reference does until it runs out of memory (io.py:218-221); the
+# workspaces of the whole-image path take ~35 KB per LR pixel, so 2 Mpix stays far inside the 180 GB of a B200.
+WHOLE_MAX_LR_PIXELS = int(os.environ.get("FFB200_WHOLE_MAX_LR_PIXELS", str(2 * 1024 * 1024)))
+PNG_COMPRESS_LEVEL = int(os.environ.get("FFB200_PNG_LEVEL", "1"))      # pixel-identical output; zlib level only trades CPU for bytes
 
 
 def _load_image(path):
     """PNG -> [1,3,H,W] float32 in [0,1]  (reference io.py:64-68)."""
     arr = np.array(Image.open(path).convert("RGB"), dtype=np.float32) / 255.0
     return torch.from_numpy(arr).permute(2, 0, 1).unsqueeze(0)
+
+
+def _decode_u8(path):
+    """PNG -> uint8 HWC array; the /255 of io._load_image happens on the GPU (ff_u8_to_tiles, bit-identical)."""
+    return np.ascontiguousarray(np.array(Image.open(path).convert("RGB"), dtype=np.uint8))
+
+
+_MODEL_CACHE = {}
+_MODEL_LOCK = threading.Lock()
 
 
 def _build_and_load(model_dir, device, pretrained_root=None, verbose=True):
@@ -44,6 +68,20 @@ def _build_and_load(model_dir, device, pretrained_root=None, verbose=True):
         model.load_expert_checkpoint(name, os.path.join(root, rel))
     model.load_fusion_checkpoint(model_dir)
     return model
+
+
+def _get_model(model_dir, device, verbose=True):
+    """test.py calls main() once per split (valid, test) with the same checkpoint: the packed model is kept per
+    (checkpoint files + mtimes, device) so the second call does not repack ~170 M parameters."""
+    root = os.environ.get("FFB200_PRETRAINED_ROOT", _PROJECT_ROOT)
+    files = [model_dir] + [os.path.join(root, rel) for rel in EXPERT_FILES.values()]
+    key = (str(torch.device(device)),) + tuple((f, os.path.getmtime(f) if os.path.exists(f) else None) for f in files)
+    with _MODEL_LOCK:
+        m = _MODEL_CACHE.get(key)
+        if m is None:
+            _MODEL_CACHE.clear()
+            m = _MODEL_CACHE[key] = _build_and_load(model_dir, device, verbose=verbose)
+    return m
 
 
 @torch.no_grad()
@@ -70,42 +108,312 @@ def tiled_forward(model, lr_img, tile_size=128, overlap=32, scale=4, return_u8=F
     return out.unsqueeze(0)
 
 
+# ------------------------------------------------------------------------------------------------
+# Streaming pipeline: decode threads -> pinned H2D -> units batched across images -> forward -> stitch / quantise ->
+# async D2H -> encode threads
+# ------------------------------------------------------------------------------------------------
+class _PinnedPool:
+    """Reused page-locked host buffers (allocating pinned memory per image costs a synchronising cudaHostAlloc each time)."""
+
+    def __init__(self):
+        self.free = {}
+        self.lock = threading.Lock()
+
+    def get(self, shape, dtype=torch.uint8):
+        key = (tuple(shape), dtype)
+        with self.lock:
+            lst = self.free.get(key)
+            if lst:
+                return lst.pop()
+        return torch.empty(shape, dtype=dtype).pin_memory()
+
+    def put(self, t):
+        with self.lock:
+            self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+
+def unit_plan(h, w, force_tiling=None):
+    """How one image is cut into forward units.  Returns dict(mode='whole'|'tiles', th, tw, ys, xs, plan).
+    whole: one unit = the image (reference io.py:219-221); tiles: the OOM fallback geometry (io.py:226), 128/32, or 64/8 for
+    images with a side below 128."""
+    if force_tiling is None:
+        force_tiling = os.environ.get("FFB200_FORCE_TILING", "0") == "1"
+    whole_ok = h * w <= WHOLE_MAX_LR_PIXELS and FreqFusionB200.supports_whole_image(h, w)
+    if whole_ok and not (force_tiling and min(h, w) >= 64):
+        return dict(mode="whole", th=h, tw=w, ys=[0], xs=[0], plan=None)
+    tile, ov = tiling.choose_tile(h, w)
+    pl = tiling.plan(h, w, tile, ov, 4)
+    return dict(mode="tiles", th=tile, tw=tile, ys=pl["ys"], xs=pl["xs"], plan=pl)
+
+
+def unit_count(h, w, force_tiling=None):
+    up = unit_plan(h, w, force_tiling)
+    return len(up["ys"]) * len(up["xs"])
+
+
+def unit_cost(h, w):
+    """LR pixels pushed through the model for one image (tile overlap included): the LPT sharding weight."""
+    up = unit_plan(h, w)
+    return len(up["ys"]) * len(up["xs"]) * up["th"] * up["tw"]
+
+
+class _Job:
+    __slots__ = ("index", "path", "h", "w", "up", "tiles", "sr", "remaining", "lo", "hi")
+
+
+class ImagePipeline:
+    """Runs a list of image files through the model with cross-image batching and overlapped host I/O."""
+
+    def __init__(self, model, output_path, io_threads=None, unit_range=None):
+        self.model, self.dev, self.output_path = model, model.device, output_path
+        n = io_threads or int(os.environ.get("FFB200_IO_THREADS", str(min(16, max(4, (os.cpu_count() or 8) // 2)))))
+        self.pool = ThreadPoolExecutor(max_workers=n)
+        self.pinned = _PinnedPool()
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.queues = {}            # (th, tw) -> list of (job, unit index)
+        self.stitchers = {}
+        self.saves = []
+        self.records = {}
+        self.unit_range = unit_range    # tile-sharded single image: this rank's [lo, hi) of the unit list; results returned, not saved
+        self.partial = {}
+
+    # -- host -> device
+    def _stage(self, job, arr):
+        h, w = arr.shape[:2]
+        job.h, job.w = h, w
+        job.up = up = unit_plan(h, w)
+        host = self.pinned.get((h, w, 3))
+        host.numpy()[...] = arr
+        dev_u8 = host.to(self.dev, non_blocking=True)
+        ys = torch.tensor(up["ys"], dtype=torch.int32).to(self.dev, non_blocking=True)
+        xs = torch.tensor(up["xs"], dtype=torch.int32).to(self.dev, non_blocking=True)
+        T = len(up["ys"]) * len(up["xs"])
+        th, tw = up["th"], up["tw"]
+        job.tiles = torch.empty(T, 3, th, tw, dtype=torch.float32, device=self.dev)
+        import ctypes as C
+        L.check(L.load().ff_u8_to_tiles(C.c_void_p(dev_u8.data_ptr()), h, w, C.c_void_p(ys.data_ptr()), C.c_void_p(xs.data_ptr()), len(up["ys"]), len(up["xs"]),
+                                        th, tw, C.c_void_p(job.tiles.data_ptr()), C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)), "ff_u8_to_tiles")
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pool.submit(self._release_after, ev, host)      # the pinned buffer returns to the pool once the copy has run
+        job.lo, job.hi = (0, T) if self.unit_range is None else self.unit_range(T)
+        job.sr = torch.empty(job.hi - job.lo, 3, 4 * th, 4 * tw, dtype=torch.float32, device=self.dev)
+        job.remaining = job.hi - job.lo
+        q = self.queues.setdefault((th, tw), [])
+        q.extend((job, u) for u in range(job.lo, job.hi))
+        if job.remaining == 0:
+            self._finish(job)
+
+    def _release_after(self, ev, host):
+        ev.synchronize()
+        self.pinned.put(host)
+
+    # -- compute
+    def _batch_size(self, th, tw):
+        return max(1, BATCH_LR_PIXELS // (th * tw))
+
+    def _drain(self, final=False):
+        for (th, tw), q in self.queues.items():
+            nb = self._batch_size(th, tw)
+            while len(q) >= nb or (final and q):
+                items, q[:] = q[:nb], q[nb:]
+                x = torch.stack([j.tiles[u] for j, u in items])
+                y = self.model.forward_any(x)
+                for k, (j, u) in enumerate(items):
+                    j.sr[u - j.lo].copy_(y[k])
+                    j.remaining -= 1
+                    if j.remaining == 0:
+                        self._finish(j)
+
+    # -- device -> host -> file
+    def _finish(self, job):
+        up = job.up
+        if self.unit_range is not None:
+            self.partial[job.index] = job.sr
+            job.tiles = None
+            return
+        H, W = 4 * job.h, 4 * job.w
+        u8 = torch.empty(H, W, 3, dtype=torch.uint8, device=self.dev)
+        if up["mode"] == "whole":
+            import ctypes as C
+            L.check(L.load().ff_quantize_u8(C.c_void_p(job.sr.data_ptr()), H, W, C.c_void_p(u8.data_ptr()),
+                                            C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)), "ff_quantize_u8")
+        else:
+            key = (job.h, job.w, up["th"])
+            st = self.stitchers.get(key)
+            if st is None:
+                st = self.stitchers[key] = tiling.Stitcher(up["plan"], self.dev)
+            st(job.sr, out_u8=u8)
+        self._save_async(u8, os.path.join(self.output_path, os.path.basename(job.path)))
+        self.records[job.index] = (os.path.basename(job.path), H, W, len(up["ys"]) * len(up["xs"]), up["mode"])
+        job.tiles = job.sr = None
+
+    def _save_async(self, u8, path):
+        ready = torch.cuda.Event()
+        ready.record()
+        host = self.pinned.get(tuple(u8.shape))
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ready)
+            host.copy_(u8, non_blocking=True)
+            u8.record_stream(self.copy_stream)
+            done = torch.cuda.Event()
+            done.record()
+        self.saves.append(self.pool.submit(self._encode, done, host, path))
+
+    def _encode(self, done, host, path):
+        done.synchronize()
+        Image.fromarray(host.numpy()).save(path, format="PNG", compress_level=PNG_COMPRESS_LEVEL)
+        self.pinned.put(host)
+
+    def run(self, paths, indices=None, prefetch=4):
+        indices = list(range(len(paths))) if indices is None else indices
+        with torch.cuda.device(self.dev):
+            futs = {}
+            order = list(indices)
+            for i in order[:prefetch]:
+                futs[i] = self.pool.submit(_decode_u8, paths[i])
+            for n, i in enumerate(order):
+                arr = futs.pop(i).result()
+                if n + prefetch < len(order):
+                    k = order[n + prefetch]
+                    futs[k] = self.pool.submit(_decode_u8, paths[k])
+                job = _Job()
+                job.index, job.path = i, paths[i]
+                try:
+                    self._stage(job, arr)
+                except ValueError as e:       # a size the scheduler cannot cut: skip this file, keep the folder going
+                    print(f"[team29_FreqFusion/b200] WARNING skipping {os.path.basename(paths[i])}: {e}")
+                    self.records[i] = (os.path.basename(paths[i]), 0, 0, 0, "skipped")
+                    continue
+                self._drain()
+            self._drain(final=True)
+            for f in self.saves:
+                f.result()                  # every file is on disk before run() returns
+            self.saves = []
+        return self.records
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+
+
+def _image_sizes(paths):
+    out = []
+    for p in paths:
+        with Image.open(p) as im:      # header only
+            out.append((im.size[1], im.size[0]))
+    return out
+
+
+def gather_tiles(local, counts, rank, world, group=None):
+    """Final gather of a tile-sharded image (the only data-path collective): every rank contributes its
+    contiguous range of SR units `local` [n_r, ...]; rank 0 returns them concatenated in unit order (so the stitch keeps the
+    reference's accumulation order bit for bit), the other ranks return None.  Works on NCCL (device tensors) and gloo."""
+    import torch.distributed as dist
+    dev = local.device
+    if dist.get_backend(group) != "nccl":
+        local = local.cpu()                # gloo gathers host tensors
+    mx = max(counts)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, parts, dst=0, group=group)
+    if rank != 0:
+        return None
+    return torch.cat([p[:c] for p, c in zip(parts, counts)]).to(dev)
+
+
 @torch.no_grad()
 def main(model_dir, input_path, output_path, device=None):
-    """NTIRE2026 plugin interface (same contract as the reference's main)."""
+    """NTIRE2026 plugin interface (same contract as the reference's main, io.py:188-234)."""
+    import torch.distributed as dist
+    sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    rank, world = (dist.get_rank(), dist.get_world_size()) if sharded else (0, 1)
     if device is None:
-        device = torch.device("cuda")
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     device = torch.device(device)
     if device.type != "cuda" or not torch.cuda.is_available():
         raise L.FFError("team29_FreqFusion (b200 build) needs a CUDA device: there is no CPU fallback")
-    print(f"[team29_FreqFusion/b200] Device: {device}")
-    model = _build_and_load(model_dir, device)
+    say = print if rank == 0 else (lambda *a, **k: None)
+    say(f"[team29_FreqFusion/b200] Device: {device}" + (f"  ({world} ranks)" if sharded else ""))
+    model = _get_model(model_dir, device, verbose=(rank == 0))
     input_imgs = sorted(glob.glob(os.path.join(input_path, "*.[pP][nN][gG]")))
     if not input_imgs:
         input_imgs = sorted(glob.glob(os.path.join(input_path, "*.[jJ][pP]*[gG]")))
-    print(f"[team29_FreqFusion/b200] Found {len(input_imgs)} images in {input_path}")
+    say(f"[team29_FreqFusion/b200] Found {len(input_imgs)} images in {input_path}")
     os.makedirs(output_path, exist_ok=True)
-    # Host I/O is overlapped with the GPU: the next image is decoded and the previous result is PNG-encoded on worker
-    # threads while the current image runs (test.py times the whole call, I/O included: reference test.py:46-53).
-    from concurrent.futures import ThreadPoolExecutor
-    workers = max(1, int(os.environ.get("FFB200_IO_THREADS", "4")))
-    pending = []
 
-    def _save(u8_host, path):
-        Image.fromarray(u8_host.numpy()).save(path, format="PNG")
+    if sharded and 0 < len(input_imgs) < world:
+        records = _run_tile_sharded(model, input_imgs, output_path, rank, world)
+    else:
+        mine = None
+        if sharded:
+            costs = [unit_cost(h, w) for h, w in _image_sizes(input_imgs)]
+            mine = scheduler.assign_images(costs, world)[rank]
+        pipe = ImagePipeline(model, output_path)
+        try:
+            records = pipe.run(input_imgs, mine)
+        finally:
+            pipe.close()
+        if sharded:
+            records = scheduler.gather_records(records)      # the only exchange: small per-image records to every rank
+            if len(records) != len(input_imgs):
+                raise RuntimeError(f"sharded run covered {len(records)} of {len(input_imgs)} images")
+    say(f"[team29_FreqFusion/b200] Done. {len(input_imgs)} images saved to {output_path}")
+    return None
 
-    with ThreadPoolExecutor(max_workers=workers) as pool:
-        nxt = pool.submit(_load_image, input_imgs[0]) if input_imgs else None
-        for i, img_path in enumerate(input_imgs):
-            lr_host = nxt.result()
-            nxt = pool.submit(_load_image, input_imgs[i + 1]) if i + 1 < len(input_imgs) else None
-            lr_img = lr_host.pin_memory().to(device, non_blocking=True)
-            _, _, h, w = lr_img.shape
-            tile, ov = tiling.choose_tile(h, w)
-            u8 = tiled_forward(model, lr_img, tile_size=tile, overlap=ov, scale=4, return_u8=True)
-            host = torch.empty(u8.shape, dtype=torch.uint8).pin_memory()
-            host.copy_(u8)                      # synchronous D2H: the result is complete before the encoder sees it
-            pending.append(pool.submit(_save, host, os.path.join(output_path, os.path.basename(img_path))))
-        for f in pending:
-            f.result()                          # every file is on disk before main() returns
-    print(f"[team29_FreqFusion/b200] Done. {len(input_imgs)} images saved to {output_path}")
+
+def _run_tile_sharded(model, paths, output_path, rank, world):
+    """Fewer images than ranks: every image is cut into units, rank r runs the contiguous range scheduler.assign_tiles gives it
+    and rank 0 gathers, stitches (in the reference's order) and writes."""
+    records = {}
+    for i, p in enumerate(paths):
+        ranges = {}
+
+        def my_range(T, _r=ranges):
+            _r["all"] = scheduler.assign_tiles(T, world)
+            return _r["all"][rank]
+        pipe = ImagePipeline(model, output_path, unit_range=my_range)
+        try:
+            pipe.run([p], [0])
+            local = pipe.partial[0]
+        finally:
+            pipe.close()
+        counts = [hi - lo for lo, hi in ranges["all"]]
+        full = gather_tiles(local, counts, rank, world)
+        if rank == 0:
+            with Image.open(p) as im:
+                w, h = im.size
+            up = unit_plan(h, w)
+            u8 = torch.empty(4 * h, 4 * w, 3, dtype=torch.uint8, device=model.device)
+            with torch.cuda.device(model.device):
+                if up["mode"] == "whole":
+                    import ctypes as C
+                    L.check(L.load().ff_quantize_u8(C.c_void_p(full.data_ptr()), 4 * h, 4 * w, C.c_void_p(u8.data_ptr()),
+                                                    C.c_void_p(torch.cuda.current_stream(model.device).cuda_stream)), "ff_quantize_u8")
+                else:
+                    tiling.Stitcher(up["plan"], model.device)(full.contiguous(), out_u8=u8)
+            Image.fromarray(u8.cpu().numpy()).save(os.path.join(output_path, os.path.basename(p)), format="PNG", compress_level=PNG_COMPRESS_LEVEL)
+            records[i] = (os.path.basename(p), 4 * h, 4 * w, sum(counts), up["mode"] + "/tile-sharded")
+    return records
+
+
+def _sharded_worker(rank, world, model_dir, input_path, output_path, port, backend):
+    import torch.distributed as dist
+    idx = rank % torch.cuda.device_count()      # (ranks may share a GPU under gloo: single-GPU test of the sharded path)
+    torch.cuda.set_device(idx)
+    dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        main(model_dir, input_path, output_path, torch.device("cuda", idx))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main_sharded(model_dir, input_path, output_path, world_size=None, port=29541, backend="nccl"):
+    """One process per GPU over a partition of the input folder (the reference's multi-GPU pattern, eval.py:162-217:
+    mp.spawn over ranks, one model replica each, results written by the rank that computed them)."""
+    import torch.multiprocessing as mp
+    world = world_size or torch.cuda.device_count()
+    if world <= 1:
+        return main(model_dir, input_path, output_path)
+    mp.spawn(_sharded_worker, args=(world, model_dir, input_path, output_path, port, backend), nprocs=world, join=True)

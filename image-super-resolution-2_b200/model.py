@@ -14,7 +14,7 @@ import torch
 from . import lib as L
 from . import ops, weights
 from .dat import DATRunner
-from .hat import HATRunner
+from .hat import HATRunner, Workspace
 from .head import HeadRunner
 from .nafnet import NAFNetRunner
 
@@ -50,6 +50,8 @@ def _filtered_update(base, incoming, prefixes=("module.",), replace_anywhere=Fal
 
 
 GRAPH_MAX_LR_PIXELS = 4 * 128 * 128      # forwards up to this many LR pixels run as replayed CUDA graphs (launch bound otherwise)
+GRAPH_CACHE_MAX = 8                      # captured shapes kept (least recently used dropped first)
+WORKSPACE_LIMIT_BYTES = int(float(os.environ.get("FFB200_WS_LIMIT_GB", "64")) * 2 ** 30)      # cached workspaces over all shapes
 
 
 class FreqFusionB200:
@@ -60,6 +62,8 @@ class FreqFusionB200:
         if device.type != "cuda":
             raise L.FFError("FreqFusionB200 runs on CUDA devices only: there is no CPU fallback")
         L.load()
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         self.device = device
         self.verbose = verbose
         # random-init stand-ins (the reference keeps its random init when a checkpoint is missing)
@@ -68,12 +72,14 @@ class FreqFusionB200:
 
     # ---- checkpoint contract ------------------------------------------------------------------
     def load_fusion_checkpoint(self, path):
+        """io._build_and_load, reference io.py:164-176: the checkpoint is applied to the WHOLE module tree with the name+shape
+        filter, so a checkpoint written with live experts (checkpoint_manager saves model.state_dict(), which then holds
+        `expert_ensemble.{hat,dat,nafnet.nafnet}.*`) also overrides the expert weights -- not only the fusion head."""
         ckpt = torch.load(path, map_location="cpu", weights_only=False)
         sd = ckpt.get("model_state_dict", ckpt) if isinstance(ckpt, dict) else ckpt
-        n = _filtered_update(self.state["fusion"], sd, prefixes=("module.", "model."))
+        n = self.load_state_dict(sd)
         if self.verbose:
-            print(f"[team29_FreqFusion/b200] Loaded {n} fusion weight tensors from checkpoint")
-        self._runners = None
+            print(f"[team29_FreqFusion/b200] Loaded {n} weight tensors from the fusion checkpoint")
         return n
 
     def load_expert_checkpoint(self, name, path):
@@ -101,9 +107,25 @@ class FreqFusionB200:
         return out
 
     def load_state_dict(self, sd, strict=False):
-        n = _filtered_update(self.state["fusion"], sd, prefixes=("module.", "model."))
-        for name, pre in (("hat", "expert_ensemble.hat."), ("dat", "expert_ensemble.dat."), ("nafnet", "expert_ensemble.nafnet.nafnet.")):
-            n += _filtered_update(self.state[name], {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        """name + shape filtered update of all four state dicts from one flat dict in the reference's module-tree naming
+        (fusion keys bare, experts under `expert_ensemble.`; `module.` / `model.` prefixes stripped first, io.py:166-170).
+        NAFNet tensors are registered twice by the reference (nafnet/__init__.py:76-82: `expert_ensemble.nafnet.nafnet.X`
+        and the alias `expert_ensemble.nafnet.X`); both spellings are accepted and counted like the reference counts them."""
+        clean = {}
+        for k, v in sd.items():
+            ck = k
+            for p in ("module.", "model."):
+                if ck.startswith(p):
+                    ck = ck[len(p):]
+            clean[ck] = v
+        n = _filtered_update(self.state["fusion"], clean, prefixes=())
+        for name, pres in (("hat", ("expert_ensemble.hat.",)), ("dat", ("expert_ensemble.dat.",)),
+                           ("nafnet", ("expert_ensemble.nafnet.", "expert_ensemble.nafnet.nafnet."))):
+            for pre in pres:      # the canonical spelling last, so it wins when both are present
+                sub = {k[len(pre):]: v for k, v in clean.items() if k.startswith(pre)}
+                if name == "nafnet":      # `body` is a second alias of `middle_blks` (nafnet/__init__.py:82)
+                    sub = {("middle_blks." + k[5:] if k.startswith("body.") else k): v for k, v in sub.items()}
+                n += _filtered_update(self.state[name], sub, prefixes=())
         self._runners = None
         return n
 
@@ -111,17 +133,51 @@ class FreqFusionB200:
     def runners(self):
         if self._runners is None:
             dev = self.device
-            self._runners = dict(hat=HATRunner(self.state["hat"], dev), dat=DATRunner(self.state["dat"], dev),
-                                 nafnet=NAFNetRunner(self.state["nafnet"], dev), head=HeadRunner(self.state["fusion"], dev))
-            self._stacks = {}
-            self._graphs = {}
+            with torch.cuda.device(dev):
+                self._runners = dict(hat=HATRunner(self.state["hat"], dev), dat=DATRunner(self.state["dat"], dev),
+                                     nafnet=NAFNetRunner(self.state["nafnet"], dev), head=HeadRunner(self.state["fusion"], dev))
+            self._stacks = Workspace(dev)
+            self._graphs = OrderedDict()
+            self._epoch = 0
         return self._runners
 
+    def _workspaces(self):
+        return [r.ws for r in self._runners.values()] + [self._stacks]
+
+    def workspace_bytes(self):
+        return sum(w.nbytes() for w in self._workspaces()) if self._runners is not None else 0
+
+    def _begin_forward(self):
+        """Bounded buffer cache: every forward is an epoch; when the cached workspaces of all shapes seen so far exceed
+        WORKSPACE_LIMIT_BYTES, the buffers of the least recently used shapes are released (oldest first) and the CUDA graphs,
+        which hold raw pointers into them, are dropped and re-captured on demand."""
+        self.runners()
+        self._epoch += 1
+        for w in self._workspaces():
+            w.epoch = self._epoch
+        if self.workspace_bytes() <= WORKSPACE_LIMIT_BYTES:
+            return
+        torch.cuda.synchronize(self.device)
+        for age in (8, 4, 2, 1, 0):
+            freed = sum(w.evict_unused_since(self._epoch - age) for w in self._workspaces())
+            if freed:
+                self._graphs.clear()
+            if self.workspace_bytes() <= WORKSPACE_LIMIT_BYTES // 2:
+                break
+
     def _stack(self, B, S0, S1):
-        key = (B, S0, S1)
-        if key not in self._stacks:
-            self._stacks[key] = torch.zeros(B * 16 * S0 * S1, 12, dtype=torch.float32, device=self.device)
-        return self._stacks[key]
+        return self._stacks.get("expert_stack", B * 16 * S0 * S1, 12, torch.float32)
+
+    def _check_input(self, lr, what):
+        if not torch.is_tensor(lr) or not lr.is_cuda:
+            raise L.FFError(f"{what} needs a CUDA tensor (no CPU fallback)")
+        if lr.dim() != 4 or lr.shape[1] != 3:
+            raise L.FFError(f"{what}: expected an NCHW batch with 3 channels, got {tuple(lr.shape)}")
+        if lr.device != self.device:
+            raise L.FFError(f"{what}: input lives on {lr.device}, the model on {self.device}")
+        _, _, h, w = lr.shape
+        if h % 64 or w % 64:
+            raise L.FFError(f"{what}: tile sides must be multiples of 64 (got {h}x{w}); arbitrary sizes go through forward_image")
 
     @torch.no_grad()
     def forward_experts(self, lr):
@@ -135,7 +191,10 @@ class FreqFusionB200:
             r["nafnet"].forward(lr, stack, 6)
             return stack
         # the experts are independent (disjoint workspaces, disjoint channels of `stack`): run them on three streams so the
-        # small / low-occupancy kernels of one expert fill the gaps of the others
+        # small / low-occupancy kernels of one expert fill the gaps of the others.  Invariant: the side streams start after
+        # an event on the caller's stream (so `lr` and `stack` are ready) and the caller's stream waits for both before this
+        # function returns -- `lr` / `stack` are therefore never used by a side stream outside this call, which is why no
+        # record_stream() is needed on them.
         if not hasattr(self, "_streams"):
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
         cur = torch.cuda.current_stream(self.device)
@@ -156,23 +215,34 @@ class FreqFusionB200:
 
     @torch.no_grad()
     def forward(self, lr, out=None, intermediates=None):
-        """lr: fp32 NCHW [B,3,S,S] in [0,1], S a multiple of 64 -> fp32 NCHW [B,3,4S,4S]."""
-        if not lr.is_cuda:
-            raise L.FFError("FreqFusionB200.forward needs a CUDA tensor (no CPU fallback)")
+        """lr: fp32 NCHW [B,3,h,w] in [0,1] on the model's device, h and w multiples of 64 -> fp32 NCHW [B,3,4h,4w].
+        `intermediates` (a dict to fill) forces the eager path: the CUDA-graph replay keeps no per-stage tensors."""
+        self._check_input(lr, "FreqFusionB200.forward")
         lr = lr.contiguous().float()
         B, _, h, w = lr.shape
-        if intermediates is None and B * h * w <= GRAPH_MAX_LR_PIXELS and os.environ.get("FFB200_GRAPHS", "1") != "0":
-            return self._forward_graphed(lr, out)
-        stack = self.forward_experts(lr)
-        return self.runners()["head"].forward(lr, stack, out=out, intermediates=intermediates)
+        with torch.cuda.device(self.device):
+            self._begin_forward()
+            if intermediates is None and B * h * w <= GRAPH_MAX_LR_PIXELS and os.environ.get("FFB200_GRAPHS", "1") != "0":
+                return self._forward_graphed(lr, out)
+            stack = self.forward_experts(lr)
+            return self._runners["head"].forward(lr, stack, out=out, intermediates=intermediates)
 
     __call__ = forward
+
+    @staticmethod
+    def supports_whole_image(h, w):
+        """Sizes the un-tiled path accepts (forward_image)."""
+        return h % 64 == 0 and w % 64 == 0
+
+    def forward_any(self, lr, out=None):
+        """Batch of equal-size LR images / tiles of any supported size."""
+        return self.forward(lr, out=out)
 
     def _forward_graphed(self, lr, out):
         """Small batches are bound by the ~2 000 host-side launches of a forward (~10 us each), not by the GPU: the forward
         of each (B, h, w) shape is captured once into a CUDA graph (static input / output buffers, the cached workspaces keep
-        every address stable, the three expert streams fork and join inside the capture) and replayed."""
-        self.runners()
+        every address stable, the three expert streams fork and join inside the capture) and replayed.  At most
+        GRAPH_CACHE_MAX shapes stay captured (least recently used first out)."""
         key = tuple(lr.shape)
         ent = self._graphs.get(key)
         if ent is None:
@@ -184,13 +254,17 @@ class FreqFusionB200:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 for _ in range(2):      # allocates the workspaces and configures the kernels outside the capture
-                    self.runners()["head"].forward(x_s, self.forward_experts(x_s), out=o_s)
+                    self._runners["head"].forward(x_s, self.forward_experts(x_s), out=o_s)
                 side.synchronize()
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=side):
-                    self.runners()["head"].forward(x_s, self.forward_experts(x_s), out=o_s)
+                    self._runners["head"].forward(x_s, self.forward_experts(x_s), out=o_s)
             cur.wait_stream(side)
             ent = self._graphs[key] = (graph, x_s, o_s)
+            while len(self._graphs) > GRAPH_CACHE_MAX:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)      # (an eviction of its workspaces drops the graph too: _begin_forward)
         graph, x_s, o_s = ent
         x_s.copy_(lr)
         graph.replay()
@@ -210,25 +284,30 @@ class FreqFusionB200:
         missing = [k for k in ("hat", "dat", "nafnet") if k not in ex]
         if missing:
             raise KeyError(f"forward_with_precomputed: missing expert outputs {missing}")
+        self._check_input(lr, "forward_with_precomputed")
         lr = lr.contiguous().float()
         B, _, h, w = lr.shape
-        self.runners()
-        stack = self._stack(B, h, w)
-        for i, k in enumerate(("hat", "dat", "nafnet")):
-            t = ex[k]
-            if not t.is_cuda or tuple(t.shape) != (B, 3, 4 * h, 4 * w):
-                raise L.FFError(f"forward_with_precomputed: expert output '{k}' must be a CUDA tensor of shape {(B, 3, 4 * h, 4 * w)}")
-            # NCHW -> channels 3i..3i+2 of the NHWC expert stack (layout plumbing; no arithmetic)
-            stack.view(B, 4 * h, 4 * w, 12)[..., 3 * i:3 * i + 3].copy_(t.float().permute(0, 2, 3, 1))
-        return self.runners()["head"].forward(lr, stack, out=out, intermediates=intermediates)
+        with torch.cuda.device(self.device):
+            self._begin_forward()
+            stack = self._stack(B, h, w)
+            for i, k in enumerate(("hat", "dat", "nafnet")):
+                t = ex[k]
+                if not t.is_cuda or tuple(t.shape) != (B, 3, 4 * h, 4 * w):
+                    raise L.FFError(f"forward_with_precomputed: expert output '{k}' must be a CUDA tensor of shape {(B, 3, 4 * h, 4 * w)}")
+                # NCHW -> channels 3i..3i+2 of the NHWC expert stack (layout plumbing; no arithmetic)
+                stack.view(B, 4 * h, 4 * w, 12)[..., 3 * i:3 * i + 3].copy_(t.float().permute(0, 2, 3, 1))
+            return self._runners["head"].forward(lr, stack, out=out, intermediates=intermediates)
 
     def expert_outputs_nchw(self, lr):
         """Testing helper: dict of NCHW expert outputs like ExpertEnsemble.forward_all(return_dict=True)."""
+        self._check_input(lr, "expert_outputs_nchw")
         B, _, h, w = lr.shape
-        stack = self.forward_experts(lr.contiguous().float())
         out = {}
-        for i, name in enumerate(("hat", "dat", "nafnet")):
-            t = torch.empty(B, 3, 4 * h, 4 * w, dtype=torch.float32, device=self.device)
-            ops.nhwc_to_nchw(stack, 3 * i, 3, t)
-            out[name] = t
+        with torch.cuda.device(self.device):
+            self._begin_forward()
+            stack = self.forward_experts(lr.contiguous().float())
+            for i, name in enumerate(("hat", "dat", "nafnet")):
+                t = torch.empty(B, 3, 4 * h, 4 * w, dtype=torch.float32, device=self.device)
+                ops.nhwc_to_nchw(stack, 3 * i, 3, t)
+                out[name] = t
         return out

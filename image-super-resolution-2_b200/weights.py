@@ -104,6 +104,25 @@ def make_state_dict(model, seed=0):
     return sd
 
 
+def heat(sd, model, logit_gain=2.5, table_gain=3.0):
+    """'Hot' variant of a synthetic state dict: attention logits and relative-position biases in the range pretrained
+    transformers reach (peaky softmax rows, |logit| of several units) instead of the near-uniform attention the benign factory
+    gives -- stresses the exp2-softmax, the bias / mask path and the bf16 operand rounding.
+    q and k rows of every qkv projection are scaled by `logit_gain` (logits by its square), bias tables / DAT's dynamic
+    position-bias output layer / channel-attention temperatures by `table_gain`.  Returns a new dict."""
+    out = {k: v.clone() for k, v in sd.items()}
+    if model not in ("hat", "dat"):
+        return out
+    for k, v in out.items():
+        if k.endswith("qkv.weight") or k.endswith("qkv.bias"):
+            v[: 2 * 180] *= logit_gain
+        elif k.endswith("relative_position_bias_table") or k.endswith("attn.temperature"):
+            v *= table_gain
+        elif ".pos.pos3.2." in k:
+            v *= table_gain
+    return out
+
+
 def save_checkpoints(root, seed=0):
     """Write the four checkpoint files in the formats the reference ingests (io.py:131-137,164-165;
     expert_loader.py:99-169; nafnet/__init__.py:84-115).  Returns the fusion checkpoint path."""

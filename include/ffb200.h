@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FFB200_ABI_VERSION 3
+#define FFB200_ABI_VERSION 4
 
 int ff_abi_version(void);
 const char* ff_last_error(void);
@@ -269,6 +269,15 @@ int ff_edge_final(const float* se, const float* gate, int gate_ld, int B, int H,
  * 1-D blend weights; out: fp32 [3][H][W] or NULL; out_u8: uint8 [H][W][3] or NULL. */
 int ff_stitch(const float* tiles, const int* ty, const int* tx, const float* wy, const float* wx, int ny, int nx, int ts, int H, int W,
               float* out, unsigned char* out_u8, void* stream);
+
+/* io._load_image (io.py:64-68) fused with the tile extraction of _tiled_forward (:99-103): HWC uint8 image on the device ->
+ * fp32 NCHW tiles [ny*nx][3][th][tw], value = (float)u8 / 255.0f (IEEE division, bit-identical to the reference's numpy
+ * expression).  ys/xs: LR origins of the tile rows / columns (device int32).  ny = nx = 1 with origin 0 converts a whole image. */
+int ff_u8_to_tiles(const unsigned char* img, int H, int W, const int* ys, const int* xs, int ny, int nx, int th, int tw, float* tiles,
+                   void* stream);
+
+/* io._save_image (io.py:71-76) for un-tiled results: fp32 NCHW [3][H][W] -> uint8 HWC, round_half_even(clamp(x,0,1) * 255). */
+int ff_quantize_u8(const float* x, int H, int W, unsigned char* out, void* stream);
 
 /* PSNR (dB) on the BT.601 Y channel with a `crop`-pixel border removed, per sample: a, b fp32 NCHW [B,3,H,W] in [0,1]
  * (reference src/utils/metrics.py:30-52, 76-126).  out: fp32 [B]; scratch >= B*64 doubles.  Identical inputs give 100 dB. */

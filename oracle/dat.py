@@ -50,7 +50,7 @@ def _ln(x, w, b, eps=1e-5):
 
 def dyn_pos_bias(sd, p, hs, ws):
     """DynamicPosBias MLP on the fixed offset grid -> [(2hs-1)(2ws-1), heads] (input independent)."""
-    x = F.linear(rpe_offsets(hs, ws), sd[p + "pos_proj.weight"], sd[p + "pos_proj.bias"])
+    x = F.linear(rpe_offsets(hs, ws).to(sd[p + "pos_proj.weight"].device), sd[p + "pos_proj.weight"], sd[p + "pos_proj.bias"])
     for name in ("pos1", "pos2", "pos3"):
         x = F.linear(F.relu(_ln(x, sd[p + name + ".0.weight"], sd[p + name + ".0.bias"])), sd[p + name + ".2.weight"], sd[p + name + ".2.bias"])
     return x
@@ -111,7 +111,7 @@ def spatial_attention(x, H, W, sd, p, rg, bi):
         sl = slice(0, C // 2) if br == 0 else slice(C // 2, C)
         sy, sx = hs // 2, ws // 2
         table = dyn_pos_bias(sd, p + f"attns.{br}.pos.", hs, ws)
-        bias = table[rel_index(hs, ws).reshape(-1)].view(hs * ws, hs * ws, 3).permute(2, 0, 1)
+        bias = table[rel_index(hs, ws).reshape(-1).to(x.device)].view(hs * ws, hs * ws, 3).permute(2, 0, 1)
         qq, kk, vv = qp[..., sl], kp[..., sl], vp[..., sl]
         mask = None
         if shift:

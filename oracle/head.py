@@ -67,10 +67,10 @@ def dct_bands(sd, x):
     ph, pw = (N - H % N) % N, (N - W % N) % N
     xp = F.pad(x, (0, pw, 0, ph), mode="reflect") if (ph or pw) else x
     Hp, Wp = xp.shape[-2:]
-    D = dct_matrix(N)
+    D = dct_matrix(N).to(x.device)
     blk = xp.reshape(B, C, Hp // N, N, Wp // N, N).permute(0, 1, 2, 4, 3, 5)
     Y = D @ blk @ D.t()
-    band = zigzag_band(N)
+    band = zigzag_band(N).to(x.device)
     out = []
     for k in range(3):
         sp = D.t() @ (Y * (band == k).float()) @ D
@@ -81,7 +81,7 @@ def dct_bands(sd, x):
 
 def dwt_bands(sd, x):
     B, C, H, W = x.shape
-    lo, hi = torch.tensor(DB4_LO), torch.tensor(DB4_HI)
+    lo, hi = torch.tensor(DB4_LO, device=x.device), torch.tensor(DB4_HI, device=x.device)
     row = lambda f: f.view(1, 1, 1, 8).repeat(C, 1, 1, 1)
     col = lambda f: f.view(1, 1, 8, 1).repeat(C, 1, 1, 1)
     xr = F.pad(x, (7, 7, 0, 0), mode="reflect")
@@ -216,7 +216,7 @@ def fuse(sd, lr, experts, band_feats):
 def edge_refine(sd, sr):
     p = "edge_refine."
     B, C, H, W = sr.shape
-    k1 = gaussian_1d()
+    k1 = gaussian_1d().to(sr.device)
     k2 = (k1[:, None] * k1[None, :]).expand(3, 1, 5, 5).contiguous()
     pyr, cur = [], sr
     for lvl in range(3):

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     exported = set(re.findall(r" T (ff_[a-z0-9_]+)", subprocess.run(["nm", "-D", lib.LIB_PATH], capture_output=True, text=True).stdout))
     extra = sorted(exported - declared - {"ff_set_error", "ff_num_sms"})
     assert not [e for e in extra if not e.startswith("_Z")], f"exported but undeclared: {extra}"
-    assert so.ff_abi_version() == 3
+    assert so.ff_abi_version() == 4
 
 
 def test_ctypes_structs_match_header_field_order():
@@ -253,3 +253,100 @@ def test_cached_expert_store_reads_the_reference_format(tmp_path, primary):
                 assert torch.equal(a["expert_imgs"][k], b["expert_imgs"][k])
             for k in a["expert_feats"]:
                 assert torch.equal(a["expert_feats"][k], b["expert_feats"][k])
+
+
+def _bare_model():
+    """FreqFusionB200 without a device (its constructor needs CUDA): enough for the checkpoint contract."""
+    from isr2_b200 import model, weights
+    m = object.__new__(model.FreqFusionB200)
+    m.verbose, m._runners = False, None
+    m.state = {k: weights.make_state_dict(k, 0) for k in ("hat", "dat", "nafnet", "fusion")}
+    return m
+
+
+def test_fusion_checkpoint_with_live_expert_keys_overrides_the_experts(tmp_path):
+    """reference io.py:164-176 applies the fusion checkpoint to the whole module tree: a checkpoint saved with live experts
+    carries `expert_ensemble.*` keys (checkpoint_manager.py:109-126 saves model.state_dict()) and they must land in the expert
+    weights -- with `module.` / `model.` prefixes, the NAFNet aliases and the name+shape filter of the reference."""
+    from isr2_b200 import weights
+    m = _bare_model()
+    other = {k: weights.make_state_dict(k, 5) for k in ("hat", "dat", "nafnet", "fusion")}
+    ck = {"module." + k: v for k, v in other["fusion"].items()}
+    ck["model.expert_ensemble.hat.conv_first.weight"] = other["hat"]["conv_first.weight"]
+    ck["expert_ensemble.dat.layers.0.blocks.1.attn.temperature"] = other["dat"]["layers.0.blocks.1.attn.temperature"]
+    ck["expert_ensemble.nafnet.nafnet.intro.weight"] = other["nafnet"]["intro.weight"]
+    ck["expert_ensemble.nafnet.body.3.beta"] = other["nafnet"]["middle_blks.3.beta"]          # alias of middle_blks
+    ck["expert_ensemble.hat.conv_last.weight"] = torch.zeros(1, 2, 3)                          # wrong shape: filtered out
+    ck["expert_ensemble.hat.not_a_key"] = torch.zeros(3)                                       # unknown name: filtered out
+    path = tmp_path / "live.pth"
+    torch.save({"epoch": 1, "model_state_dict": ck}, path)
+    before_last = m.state["hat"]["conv_last.weight"].clone()
+    n = m.load_fusion_checkpoint(str(path))
+    assert n == len(other["fusion"]) + 4
+    assert torch.equal(m.state["fusion"]["refine_net.0.weight"], other["fusion"]["refine_net.0.weight"])
+    assert torch.equal(m.state["hat"]["conv_first.weight"], other["hat"]["conv_first.weight"])
+    assert torch.equal(m.state["dat"]["layers.0.blocks.1.attn.temperature"], other["dat"]["layers.0.blocks.1.attn.temperature"])
+    assert torch.equal(m.state["nafnet"]["intro.weight"], other["nafnet"]["intro.weight"])
+    assert torch.equal(m.state["nafnet"]["middle_blks.3.beta"], other["nafnet"]["middle_blks.3.beta"])
+    assert torch.equal(m.state["hat"]["conv_last.weight"], before_last)
+    # round trip of the flat view
+    sd = m.state_dict()
+    m2 = _bare_model()
+    assert m2.load_state_dict(sd) == len(sd)
+    assert all(torch.equal(m2.state[k][n_], v) for k in m.state for n_, v in m.state[k].items())
+
+
+def test_workspace_cache_is_bounded_by_lru_eviction():
+    from isr2_b200.hat import Workspace
+    ws = Workspace("cpu")
+    ws.epoch = 1
+    a = ws.get("x", 4, 8, torch.float32)
+    ws.epoch = 2
+    b = ws.get("x", 8, 8, torch.float32)
+    assert ws.get("x", 8, 8, torch.float32) is b and ws.nbytes() == (32 + 64) * 4
+    assert ws.evict_unused_since(2) == 32 * 4 and ws.nbytes() == 64 * 4
+    assert ws.get("x", 4, 8, torch.float32) is not a
+
+
+def test_unit_plan_whole_image_first_then_tiles(monkeypatch):
+    """io.main order of the reference (io.py:218-228): whole image first, 128/32 tiles above the size threshold."""
+    from isr2_b200 import io as ffio
+    up = ffio.unit_plan(128, 192)
+    assert up["mode"] == "whole" and (up["th"], up["tw"]) == (128, 192) and ffio.unit_count(128, 192) == 1
+    monkeypatch.setattr(ffio, "WHOLE_MAX_LR_PIXELS", 128 * 128)
+    up = ffio.unit_plan(339, 510)
+    assert up["mode"] == "tiles" and ffio.unit_count(339, 510) == 20 and ffio.unit_cost(339, 510) == 20 * 128 * 128
+    monkeypatch.setenv("FFB200_FORCE_TILING", "1")
+    assert ffio.unit_plan(128, 192)["mode"] == "tiles"
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from isr2_b200 import io as ffio, scheduler
+    T = 5
+    ranges = scheduler.assign_tiles(T, world)
+    lo, hi = ranges[rank]
+    units = torch.arange(T * 6, dtype=torch.float32).view(T, 2, 3)
+    full = ffio.gather_tiles(units[lo:hi].clone(), [b - a for a, b in ranges], rank, world)
+    if rank == 0:
+        q.put(bool(torch.equal(full, units)))
+    else:
+        assert full is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tile_sharded_final_gather_keeps_unit_order():
+    """Tile-sharded single image: ranks own contiguous unit ranges, rank 0 gets them back in order."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    ok = q.get(timeout=180)
+    [p.join(60) for p in procs]
+    assert ok and all(p.exitcode == 0 for p in procs)

@@ -158,3 +158,40 @@ def test_metrics_kernels_vs_golden_and_oracle():
         assert abs(got[i].item() - ref[i]) < 2e-6
     with pytest.raises(ValueError):
         ops.ssim_y(a[:, :, :8, :8].cuda(), b[:, :, :8, :8].cuda())
+
+
+def _save_png(path, lr):
+    from PIL import Image
+    Image.fromarray((lr[0].permute(1, 2, 0).numpy() * 255).round().astype("uint8")).save(path)
+
+
+def test_io_main_pipeline_mixed_folder_and_sharded(tmp_path):
+    """The plugin on a folder of mixed sizes: equal-size images are batched across files, 64-aligned images run whole (the
+    reference's primary path, io.py:218-221), the rest through the tile path; every PNG is held to the oracle pipeline.  Then
+    the same folder through `main_sharded` with two ranks (gloo, both on this GPU): same pixels as the single-process run."""
+    from PIL import Image
+    from isr2_b200 import io as ffio, weights
+    from oracle import full, tiling as otil
+    root = str(tmp_path)
+    fusion = weights.save_checkpoints(root, seed=4)
+    os.environ["FFB200_PRETRAINED_ROOT"] = root
+    inp, outp, outp2 = os.path.join(root, "in"), os.path.join(root, "out"), os.path.join(root, "out2")
+    os.makedirs(inp)
+    imgs = {"a.png": _lr(1, 128, 128, 60), "b.png": _lr(1, 128, 128, 61), "c.png": _lr(1, 64, 96, 62), "d.PNG": _lr(1, 64, 64, 63)}
+    for n, t in imgs.items():
+        _save_png(os.path.join(inp, n), t)
+    ffio.main(model_dir=fusion, input_path=inp, output_path=outp, device=torch.device("cuda:0"))
+    state = {m: {k: v.cuda() for k, v in weights.make_state_dict(m, 4).items()} for m in ("hat", "dat", "nafnet", "fusion")}
+    fwd = lambda t: full.forward(state, t.cuda()).cpu()
+    for n, t in imgs.items():
+        got = np.array(Image.open(os.path.join(outp, n)))
+        h, w = t.shape[-2:]
+        assert got.shape == (4 * h, 4 * w, 3)
+        ref = fwd(t) if (h % 64 == 0 and w % 64 == 0) else otil.tiled_forward(fwd, t, 64, 8)[0]
+        diff = np.abs(got.astype(int) - otil.to_uint8(ref).astype(int))
+        print(f"pipeline {n}: max |diff| {diff.max()} gray levels, mean {diff.mean():.4f}")
+        assert diff.max() <= 5
+    ffio.main_sharded(fusion, inp, outp2, world_size=2, port=29700 + os.getpid() % 200, backend="gloo")
+    for n in imgs:
+        a, b = np.array(Image.open(os.path.join(outp, n))).astype(int), np.array(Image.open(os.path.join(outp2, n))).astype(int)
+        assert np.abs(a - b).max() <= 1, n
