@@ -28,6 +28,7 @@ constexpr int HALO_A_STAGES = 2;
 struct Args {
   FFConvGemm p;
   int Ho, Wo;
+  int Hc, Wc;   // geometry of the direct-store outputs (== Ho, Wo unless out_crop_h / out_crop_w crop the bottom / right edge)
   int tiles_x, tiles_per_img, m_tiles, n_tiles;
   int ntaps, cchunks;
   int vec_ok;   // every epilogue operand allows 16-byte fp32 / 8-byte bf16 vector access
@@ -326,6 +327,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(8) uint64_t res_bar[NUM_EPI_WARPS][2];
+  __shared__ float2 ln_part[TILE_M];            // fused LayerNorm: per-row exchange slot between the two warps of a lane quadrant (1 KB:
+                                                // the largest RES configuration leaves 2 KB of static shared memory)
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5;
@@ -513,7 +516,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t ph[2] = {0, 0};
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (lane == 0) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO32); if (AUX || p.out_bf16) tma_prefetch_desc(&tmO); }
+      if (lane == 0) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO32); if (AUX || p.out_bf16) tma_prefetch_desc(&tmO); if (p.ln_out) tma_prefetch_desc(&tmX); }
       // items of this warp: (tile, cb) with cb = half, half+2, ... while the block starts below n_store.  The residual
       // block of the NEXT item (possibly in the next tile) is prefetched while the current one is processed.
       auto valid = [&](int tl, int c) { return c < ncb && (tl % a.n_tiles) * BN + c * 32 < p.n_store; };
@@ -539,6 +542,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+        float ln_s1 = 0.f, ln_s2 = 0.f;      // fused LayerNorm: this thread's row, over this warp's column blocks
 #pragma unroll 1
         for (int cb = half; valid(tile, cb); cb += 2) {
           const int n_blk = n_tile * BN + cb * 32;
@@ -595,6 +599,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               uint2* op = reinterpret_cast<uint2*>(orow + (((c >> 1) ^ sw3) << 4) + ((c & 1) << 3));
               *op = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
             }
+            if (p.ln_out) {      // keep the updated row for the normalisation pass (written back over the accumulator below)
+              ln_s1 += (r.x + r.y) + (r.z + r.w);
+              ln_s2 += (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
+              raw[4 * c] = __float_as_uint(r.x); raw[4 * c + 1] = __float_as_uint(r.y);
+              raw[4 * c + 2] = __float_as_uint(r.z); raw[4 * c + 3] = __float_as_uint(r.w);
+            }
+          }
+          if (p.ln_out) {
+            tmem_st16(taddr + cb * 32, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+            tmem_st16(taddr + cb * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -604,6 +618,63 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_store_commit();
           }
           buf ^= 1;
+        }
+        if (p.ln_out) {
+          // ---------- fused LayerNorm of the updated rows: the n tile spans the whole row (host check), the two warps of a lane
+          // quadrant hold its two halves.  Row statistics = both warps' partial sums: the second warp publishes its partial, the
+          // first one combines and publishes (rstd, -mean*rstd) in the same smem slot (two 64-thread named barriers per tile);
+          // the fp32 row is re-read from TMEM, normalised, and leaves as bf16 through a TMA store.
+          float rstd, nmr;
+          {
+            float2* slot = &ln_part[quad * 32 + lane];
+            if (half == 1) *slot = make_float2(ln_s1, ln_s2);
+            named_bar_sync(1 + quad, 64);
+            if (half == 0) {
+              const float2 other = *slot;
+              const float inv_c = 1.0f / (float)p.ln_cols;
+              const float mean = (ln_s1 + other.x) * inv_c;
+              const float var = fmaxf((ln_s2 + other.y) * inv_c - mean * mean, 0.f);
+              rstd = rsqrtf(var + p.ln_eps);
+              nmr = -mean * rstd;
+              *slot = make_float2(rstd, nmr);
+            }
+            named_bar_sync(1 + quad, 64);
+            if (half == 1) { const float2 st2 = *slot; rstd = st2.x; nmr = st2.y; }
+          }
+          if (lane == 0) tma_store_wait_read<0>();      // R[buf^1] / the bf16 staging of the last item have been read
+          __syncwarp();
+          tc_wait_st();
+          const int sw3n = (lane >> 1) & 3;
+          int sb = 0;
+#pragma unroll 1
+          for (int cb = half; valid(tile, cb); cb += 2) {
+            const int n_blk = n_tile * BN + cb * 32;
+            uint32_t xr[32];
+            tmem_ld16(taddr + cb * 32, *reinterpret_cast<uint32_t(*)[16]>(&xr[0]));
+            tmem_ld16(taddr + cb * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&xr[16]));
+            uint8_t* stg = sb == 0 ? (wbase + (buf ^ 1) * 4096) : (AUX ? (wbase + 8192 + (buf ^ 1) * 2048) : (wbase + 8192));
+            if (lane == 0) tma_store_wait_read<1>();     // the store that read this staging buffer two blocks ago
+            __syncwarp();
+            tc_wait_ld();
+            uint8_t* srow = stg + lane * 64;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + n_blk + c * 4));
+              const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + n_blk + c * 4));
+              const float y0 = fmaf(fmaf(__uint_as_float(xr[4 * c]), rstd, nmr), g.x, be.x);
+              const float y1 = fmaf(fmaf(__uint_as_float(xr[4 * c + 1]), rstd, nmr), g.y, be.y);
+              const float y2 = fmaf(fmaf(__uint_as_float(xr[4 * c + 2]), rstd, nmr), g.z, be.z);
+              const float y3 = fmaf(fmaf(__uint_as_float(xr[4 * c + 3]), rstd, nmr), g.w, be.w);
+              *reinterpret_cast<uint2*>(srow + (((c >> 1) ^ sw3n) << 4) + ((c & 1) << 3)) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmX, stg, n_blk, tx * TW, ty * TH + quad * QR, b);
+              tma_store_commit();
+            }
+            sb ^= 1;
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -632,9 +703,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int t = m_tile - b * a.tiles_per_img;
         const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
         const int r = quad * 32 + lane;
-        const long long px = ((long long)(b * a.Ho + ty * TH + r / TW)) * a.Wo + tx * TW + r % TW;
+        const int oy = ty * TH + r / TW, ox = tx * TW + r % TW;
+        const bool inb = oy < a.Hc && ox < a.Wc;                  // partial edge tiles / cropped outputs
+        const long long px = ((long long)(b * a.Ho + oy)) * a.Wo + ox;      // operand (full) geometry
+        const long long pxo = ((long long)(b * a.Hc + oy)) * a.Wc + ox;     // output geometry
         float resv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (worker && p.res) {      // requested before the accumulator wait: the round trip hides behind the main loop
+        if (worker && inb && p.res) {      // requested before the accumulator wait: the round trip hides behind the main loop
 #pragma unroll
           for (int n = 0; n < 4; ++n)
             if (n < p.n_store)
@@ -654,8 +728,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (p.act) x = apply_act(x, p.act);
               x = fmaf(x, cs_r[n], resv[n]);
               if (p.post_act) x = apply_act(x, p.post_act);
-              if (p.out_f32) p.out_f32[px * p.out_f32_ld + n] = x;
-              if (p.out_bf16) reinterpret_cast<bf16*>(p.out_bf16)[px * p.out_ld + n] = __float2bfloat16_rn(x);
+              if (inb) {
+                if (p.out_f32) p.out_f32[pxo * p.out_f32_ld + n] = x;
+                if (p.out_bf16) reinterpret_cast<bf16*>(p.out_bf16)[pxo * p.out_ld + n] = __float2bfloat16_rn(x);
+              }
             }
           }
         }
@@ -935,6 +1011,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if constexpr (EPI == EPI_STORE) {
             if (p.col_sums) {
+              {   // rows of a partial edge tile that lie outside the image do not belong to the pool
+                const int r_ = quad * 32 + lane;
+                if (ty * TH + r_ / TW >= a.Ho || tx * TW + r_ % TW >= a.Wo) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) cs_v[j] = 0.f;
+                }
+              }
               // transpose-reduce: after the five halving steps lane c holds the sum of column c over the warp's 32 rows
 #pragma unroll
               for (int off = 16; off >= 1; off >>= 1) {
@@ -1061,20 +1144,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             long long opx[4];
             float4 accv[4];
 #pragma unroll
+            bool inb[4];
+#pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int row = (it0 + u) * rpi + rsub;           // row within the quadrant
               const int r = quad * 32 + row;
               const int oy = ty * TH + r / TW, ox = tx * TW + r % TW;
+              inb[u] = oy < a.Hc && ox < a.Wc;                  // partial edge tiles / cropped outputs
               int dummy;
               long long px;
               if (p.pixel_shuffle == 2) out_location(a, b, oy, ox, ncol, px, dummy);
-              else px = ((long long)(b * a.Ho + oy)) * a.Wo + ox;
+              else px = ((long long)(b * a.Hc + oy)) * a.Wc + ox;
               opx[u] = px;
-              vec4_load(p, px, oc, ops[u]);
+              if (inb[u]) vec4_load(p, px, oc, ops[u]);
               accv[u] = *reinterpret_cast<const float4*>(stg + row * C::STG_PITCH + c4);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
+              if (!inb[u]) continue;
               if (p.gate_pairs) {
                 // only the bf16 store applies
                 __nv_bfloat162 lo = __floats2bfloat162_rn(accv[u].x, accv[u].y), hi = __floats2bfloat162_rn(accv[u].z, accv[u].w);
@@ -1092,7 +1179,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row = it * rpi + rsub;
             const int r = quad * 32 + row;
             const int oy = ty * TH + r / TW, ox = tx * TW + r % TW;
-            const long long px = ((long long)(b * a.Ho + oy)) * a.Wo + ox;
+            if (oy >= a.Hc || ox >= a.Wc) continue;
+            const long long px = ((long long)(b * a.Hc + oy)) * a.Wc + ox;
             for (int i = 0; i < 4; ++i) {
               const int n = ncol + i;
               if (n >= width) break;
@@ -1145,6 +1233,7 @@ __global__ void __launch_bounds__(128) conv_gemm_simt_kernel(const __grid_consta
   const int t = m_tile - b * a.tiles_per_img;
   const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
   const int oy = ty * TILE_H + (r >> 4), ox = tx * TILE_W + (r & 15);
+  if (oy >= a.Ho || ox >= a.Wo) return;
   const bf16* x = reinterpret_cast<const bf16*>(p.x);
   const bf16* w = reinterpret_cast<const bf16*>(p.w);
   const int K = a.ntaps * p.cin;
@@ -1267,7 +1356,12 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   FF_CHECK_ARG(p.out_bf16 || p.out_f32, "ff_conv_gemm: no output buffer");
   a.Ho = (p.kind == FF_CONV_2X2S2) ? p.H / 2 : p.H;
   a.Wo = (p.kind == FF_CONV_2X2S2) ? p.W / 2 : p.W;
-  FF_CHECK_ARG(a.Ho % TILE_H == 0 && a.Wo % TILE_W == 0 && a.Ho > 0, "ff_conv_gemm: output %dx%d must be a multiple of %dx%d", a.Ho, a.Wo, TILE_H, TILE_W);
+  // Any output size: edge tiles are partial -- TMA zero-fills loads and clips stores outside the tensor, the direct-store
+  // epilogues mask by coordinates.
+  FF_CHECK_ARG(a.Ho > 0 && a.Wo > 0 && (p.kind != FF_CONV_2X2S2 || (p.H % 2 == 0 && p.W % 2 == 0)), "ff_conv_gemm: bad spatial size %dx%d", p.H, p.W);
+  a.Hc = p.out_crop_h > 0 ? p.out_crop_h : a.Ho;
+  a.Wc = p.out_crop_w > 0 ? p.out_crop_w : a.Wo;
+  FF_CHECK_ARG(a.Hc <= a.Ho && a.Wc <= a.Wo, "ff_conv_gemm: out_crop %dx%d exceeds the output %dx%d", a.Hc, a.Wc, a.Ho, a.Wo);
   static const bool halo_enabled = []() { const char* e = getenv("FFB200_CONV_HALO"); return !(e && e[0] == '0'); }();
   // bf16-operand TMA epilogue (EPI_OPS*): N tile 64, bf16 output, 1..3 bf16 operand tensors among res / mul / aux
   auto al16p = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -1277,7 +1371,7 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
       (!p.mul || (p.mul_ld % 8 == 0 && al16p(p.mul))) && (!p.aux || (p.aux_ld % 8 == 0 && al16p(p.aux))))
     n_ops = (p.res ? 1 : 0) + (p.mul ? 1 : 0) + (p.aux ? 1 : 0);
   const bool halo = halo_enabled && !p.debug_simt && p.kind == FF_CONV_3X3 && p.n_pad % 128 != 0 && p.n_pad % 192 != 0 && p.n_pad <= 4 * HALO_MAX_BN &&
-                    a.Ho % HALO_TH == 0 && a.Wo % HALO_TW == 0 && n_ops == 0;   // the operand rings and the halo slabs do not fit together (and measured slower at one ring)
+                    n_ops == 0;   // the operand rings and the halo slabs do not fit together (and measured slower at one ring)
   const int TW = halo ? HALO_TW : TILE_W, TH = halo ? HALO_TH : TILE_H;
   if (p.gate_pairs) {
     FF_CHECK_ARG(p.out_bf16 && !p.out_f32 && !p.act && !p.mul && !p.aux && !p.res && !p.pixel_shuffle && !p.col_scale && p.n_store % 16 == 0,
@@ -1286,6 +1380,24 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
     FF_CHECK_ARG(p.bias != nullptr && p.n_store >= 32, "ff_conv_gemm: gate_pairs needs a bias vector and n_store >= 32");
   }
   if (p.w_batch_rows) FF_CHECK_ARG(p.w_batch_rows >= p.n_pad, "ff_conv_gemm: w_batch_rows < n_pad");
+  if (p.pixel_shuffle && p.B > 1 && (a.Ho % TILE_H != 0 || a.Ho % HALO_TH != 0)) {
+    // The 5-D PixelShuffle maps merge (batch, output row) into one dimension, so the out-of-range rows of a partial edge tile
+    // would land in the next sample instead of being clipped: such shapes (deep UNet levels of un-aligned images) run one
+    // sample per launch.
+    FF_CHECK_ARG(!p.w_batch_rows && !p.aux_chan && !p.col_sums, "ff_conv_gemm: per-sample operands are not supported with an un-aligned PixelShuffle layer");
+    for (int b = 0; b < p.B; ++b) {
+      FFConvGemm q = p;
+      q.B = 1;
+      const long long in_px = (long long)b * p.H * p.W, out_px = (long long)b * 4 * a.Ho * a.Wo;
+      q.x = reinterpret_cast<const bf16*>(p.x) + in_px * p.x_ld;
+      if (p.res) q.res = p.res_is_f32 ? (const void*)(reinterpret_cast<const float*>(p.res) + out_px * p.res_ld) : (const void*)(reinterpret_cast<const bf16*>(p.res) + out_px * p.res_ld);
+      if (p.out_bf16) q.out_bf16 = reinterpret_cast<bf16*>(p.out_bf16) + out_px * p.out_ld;
+      if (p.out_f32) q.out_f32 = p.out_f32 + out_px * p.out_f32_ld;
+      const int rc = ff_conv_gemm(&q, stream);
+      if (rc != FF_OK) return rc;
+    }
+    return FF_OK;
+  }
   if (p.pixel_shuffle) {
     FF_CHECK_ARG(p.pixel_shuffle == 2 && p.n_store % 64 == 0, "ff_conv_gemm: pixel_shuffle needs r=2 and n_store%%64==0");
     FF_CHECK_ARG(!p.mul && !p.aux, "ff_conv_gemm: pixel_shuffle supports bias/act/res only");
@@ -1299,8 +1411,8 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   if (p.aux) FF_CHECK_ARG(p.aux_ld >= width_ok && (!vec || (p.aux_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)), "ff_conv_gemm: bad aux_ld");
   if (p.res) FF_CHECK_ARG(p.res_ld >= width_ok && (!vec || (p.res_ld % (p.res_is_f32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0)), "ff_conv_gemm: bad res_ld");
 
-  a.tiles_x = a.Wo / TW;
-  a.tiles_per_img = a.tiles_x * (a.Ho / TH);
+  a.tiles_x = ff_cdiv(a.Wo, TW);
+  a.tiles_per_img = a.tiles_x * ff_cdiv(a.Ho, TH);
   a.m_tiles = a.tiles_per_img * p.B;
   a.ntaps = (p.kind == FF_CONV_3X3) ? 9 : (p.kind == FF_CONV_2X2S2) ? 4 : 1;
   a.cchunks = p.cin / BLOCK_K;
@@ -1420,6 +1532,17 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
     if (ok) epi = EPI_RES_AUX;
   }
   if (BN == 16 && p.n_store <= 4 && !p.mul && !p.aux && !p.pixel_shuffle && !p.gate_pairs) epi = EPI_NARROW;
+  if (a.Hc != a.Ho || a.Wc != a.Wo)
+    FF_CHECK_ARG(epi == EPI_NARROW || (epi == EPI_GENERIC && !p.res && !p.mul && !p.aux && !p.pixel_shuffle),
+                 "ff_conv_gemm: out_crop needs a direct-store epilogue (narrow outputs, or no per-pixel operands)");
+  if (p.ln_out) {
+    FF_CHECK_ARG((epi == EPI_RES || epi == EPI_RES_AUX) && !halo && a.n_tiles == 1 && !p.pixel_shuffle && p.n_store == p.n_pad,
+                 "ff_conv_gemm: ln_out needs the fp32-residual epilogue with one n tile spanning the row (n_pad=%d n_store=%d epi=%d)", p.n_pad, p.n_store, epi);
+    FF_CHECK_ARG(p.ln_gamma && p.ln_beta && al16p(p.ln_gamma) && al16p(p.ln_beta) && p.ln_cols > 0 && p.ln_cols <= p.n_store && p.ln_eps > 0.f,
+                 "ff_conv_gemm: ln_gamma / ln_beta must be 16-byte aligned [n_store] vectors, 0 < ln_cols <= n_store");
+    FF_CHECK_ARG(p.ln_out_ld >= p.n_store && p.ln_out_ld % 8 == 0 && al16p(p.ln_out), "ff_conv_gemm: bad ln_out_ld=%d", p.ln_out_ld);
+    FF_CHECK_ARG(out_map(&m.X, p.ln_out, p.ln_out_ld, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B), "ff_conv_gemm: tensor map of ln_out failed");
+  }
   FF_CHECK_ARG(!p.col_sums || (epi == EPI_STORE && !p.pixel_shuffle), "ff_conv_gemm: col_sums needs the plain bf16-store epilogue (bias, optional non-GELU act)");
   ++g_ff_launches;
   switch (BN) {

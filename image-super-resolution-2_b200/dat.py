@@ -53,7 +53,7 @@ class DATRunner:
         self.mean = torch.tensor(RGB_MEAN, dtype=F32, device=dev)
         self.conv_first_w = pack_conv_direct(g("conv_first.weight"), CP, dev)
         self.conv_first_b = pack_vector(g("conv_first.bias"), CP, device=dev)
-        ln = lambda p: (g(p + "weight").to(dev), g(p + "bias").to(dev))
+        ln = lambda p: (pack_vector(g(p + "weight"), CP, device=dev), pack_vector(g(p + "bias"), CP, device=dev))   # zero-padded to the 192-wide row
         self.before = ln("before_RG.1.")
         half = torch.arange(HID // 2)
         fc1_rows = torch.cat([half, HP + half])
@@ -101,7 +101,7 @@ class DATRunner:
                 f = p + "ffn."
                 d["fc1_w"] = pack_matrix(g(f + "fc1.weight"), 2 * HP, CP, row_index=fc1_rows, device=dev)
                 d["fc1_b"] = pack_vector(g(f + "fc1.bias"), 2 * HP, index=fc1_rows, device=dev)
-                d["sg_norm"] = ln(f + "sg.norm.")
+                d["sg_norm"] = (g(f + "sg.norm.weight").to(dev), g(f + "sg.norm.bias").to(dev))
                 d["sg_w"] = pack_dw(g(f + "sg.conv.weight"), HP, device=dev)
                 d["sg_b"] = pack_vector(g(f + "sg.conv.bias"), HP, device=dev)
                 d["fc2_w"] = pack_matrix(g(f + "fc2.weight"), CP, HP, device=dev)
@@ -156,11 +156,14 @@ class DATRunner:
         ops.conv_direct(img, B, H, W, 3, 3, self.conv_first_w, self.conv_first_b, n_store=CP, out_f32=x0)
         ops.layernorm(x0, M, C, self.before[0], self.before[1], 1e-5, out_f32=G, out_cols=CP)
 
-        for layer in self.layers:
+        fused = ops.fused_ln_enabled()      # every LayerNorm after a residual add leaves the producing GEMM's epilogue
+        t_ready = False
+        for li, layer in enumerate(self.layers):
             src = G
             nb = len(layer["blocks"])
             for bi, d in enumerate(layer["blocks"]):
-                ops.layernorm(src, M, C, d["norm1"][0], d["norm1"][1], 1e-5, out_bf16=t, out_cols=CP)
+                if not t_ready:
+                    ops.layernorm(src, M, C, d["norm1"][0], d["norm1"][1], 1e-5, out_bf16=t, out_cols=CP)
                 ops.conv_gemm(t, B, H, W, CP, d["qkv_w"], n_store=3 * CP, bias=d["qkv_b"], out_bf16=qkv)
                 # conv branch on v (image form of v: channels 384..575 of qkv)
                 pool_rows = ops.dwconv_pool_rows(H, W, CP, 0) if d["spatial"] else 0
@@ -199,18 +202,28 @@ class DATRunner:
                                        C_.c_void_p(sih.data_ptr()), 32, C_.c_void_p(d["si2_w"].data_ptr()),
                                        C_.c_float(d["si2_b"]), d["si_hid"], mode, C_.c_longlong(M), N, C_.c_void_p(mix.data_ptr()), CP, st()),
                         "ff_dat_aim")
-                ops.conv_gemm(mix, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], res=src, out_f32=X)
+                ops.conv_gemm(mix, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], res=src, out_f32=X,
+                              ln=(d["norm2"][0], d["norm2"][1], 1e-5, C, t) if fused else None)
                 # SGFN
-                ops.layernorm(X, M, C, d["norm2"][0], d["norm2"][1], 1e-5, out_bf16=t, out_cols=CP)
+                if not fused:
+                    ops.layernorm(X, M, C, d["norm2"][0], d["norm2"][1], 1e-5, out_bf16=t, out_cols=CP)
                 ops.conv_gemm(t, B, H, W, CP, d["fc1_w"], n_store=2 * HP, bias=d["fc1_b"], act=ACT_GELU, out_bf16=h)
                 ops.layernorm(h, M, HID // 2, d["sg_norm"][0], d["sg_norm"][1], 1e-5, out_bf16=t2, out_cols=HP, x_off=HP)
                 ops.dwconv(t2, B, H, W, HP, 3, 3, d["sg_w"], d["sg_b"], gt, mul=h)
                 last = (bi == nb - 1)
-                ops.conv_gemm(gt, B, H, W, HP, d["fc2_w"], n_store=CP, bias=d["fc2_b"], res=X, out_f32=X, out_bf16=Xb if last else None)
+                nxt = None if last else layer["blocks"][bi + 1]["norm1"]
+                ops.conv_gemm(gt, B, H, W, HP, d["fc2_w"], n_store=CP, bias=d["fc2_b"], res=X, out_f32=X, out_bf16=Xb if last else None,
+                              ln=(nxt[0], nxt[1], 1e-5, C, t) if (fused and nxt is not None) else None)
+                t_ready = fused and nxt is not None
                 src = X
-            ops.conv_gemm(Xb, B, H, W, CP, layer["conv_w"], kind=CONV_3X3, n_store=CP, bias=layer["conv_b"], res=G, out_f32=G)
+            # group tail conv + residual; its epilogue emits the LayerNorm of the next consumer of G
+            nxt = self.layers[li + 1]["blocks"][0]["norm1"] if li + 1 < len(self.layers) else self.norm
+            ops.conv_gemm(Xb, B, H, W, CP, layer["conv_w"], kind=CONV_3X3, n_store=CP, bias=layer["conv_b"], res=G, out_f32=G,
+                          ln=(nxt[0], nxt[1], 1e-5, C, t) if fused else None)
+            t_ready = fused
 
-        ops.layernorm(G, M, C, self.norm[0], self.norm[1], 1e-5, out_bf16=t, out_cols=CP)
+        if not t_ready:
+            ops.layernorm(G, M, C, self.norm[0], self.norm[1], 1e-5, out_bf16=t, out_cols=CP)
         y = Xb
         ops.conv_gemm(t, B, H, W, CP, self.cab_w, kind=CONV_3X3, n_store=CP, bias=self.cab_b, res=x0, out_bf16=y)
         f64 = ws.get("f64", M, 64, BF16)

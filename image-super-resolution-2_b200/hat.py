@@ -105,7 +105,8 @@ class HATRunner:
             )
 
         def ln(prefix):
-            return (g(prefix + "weight").to(dev), g(prefix + "bias").to(dev))
+            # [gamma, beta] padded to the 192-wide row with zeros (the fused epilogue normalises whole rows; padding stays 0)
+            return (pack_vector(g(prefix + "weight"), CP, device=dev), pack_vector(g(prefix + "bias"), CP, device=dev))
 
         self.layers = []
         for i in range(depths):
@@ -147,10 +148,14 @@ class HATRunner:
         self.last_b = pack_vector(g("conv_last.bias") + torch.tensor(RGB_MEAN), 16, device=dev)
 
     # ------------------------------------------------------------------------------------------
-    def _mlp(self, d, X, t, h, B, H, W, M, extra_bf16=None):
-        ops.layernorm(X, M, C, d["norm2"][0], d["norm2"][1], 1e-5, out_bf16=t, out_cols=CP)
+    def _mlp(self, d, X, t, h, B, H, W, M, extra_bf16=None, t_ready=False, next_norm=None):
+        """x += fc2(GELU(fc1(LN2 x))) (hat_arch.py:308).  t_ready: LN2(x) was already emitted into `t` by the producer of X;
+        next_norm: (gamma, beta) of the LayerNorm that consumes the new X -- emitted into `t` by the fc2 epilogue."""
+        if not t_ready:
+            ops.layernorm(X, M, C, d["norm2"][0], d["norm2"][1], 1e-5, out_bf16=t, out_cols=CP)
         ops.conv_gemm(t, B, H, W, CP, d["fc1_w"], n_store=2 * CP, bias=d["fc1_b"], act=ACT_GELU, out_bf16=h)
-        ops.conv_gemm(h, B, H, W, 2 * CP, d["fc2_w"], n_store=CP, bias=d["fc2_b"], res=X, out_f32=X, out_bf16=extra_bf16)
+        ops.conv_gemm(h, B, H, W, 2 * CP, d["fc2_w"], n_store=CP, bias=d["fc2_b"], res=X, out_f32=X, out_bf16=extra_bf16,
+                      ln=(next_norm[0], next_norm[1], 1e-5, C, t) if next_norm is not None else None)
 
     def forward(self, x, out, out_off=0):
         """x: fp32 NCHW [B,3,H,W] (H, W multiples of 16) on the GPU.
@@ -177,16 +182,20 @@ class HATRunner:
         se_h = ws.get("se_h", B, 8, F32)
         se = ws.get("se", B, CP, F32)
         scratch = ws.get("gap_scratch", 1, B * 64 * CP, F32)
+        fused = ops.fused_ln_enabled()      # every LayerNorm after a residual add leaves the producing GEMM's epilogue
 
         ops.nchw_to_nhwc(x, img, sub=self.mean)
         ops.conv_direct(img, B, H, W, 3, 3, self.conv_first_w, self.conv_first_b, n_store=CP, out_f32=x0)
         ops.layernorm(x0, M, C, self.pe_norm[0], self.pe_norm[1], 1e-5, out_f32=G, out_cols=CP)
 
-        for layer in self.layers:
+        t_ready = False      # `t` already holds the LayerNorm the next consumer needs
+        for li, layer in enumerate(self.layers):
             src = G
+            nhab = len(layer["habs"])
             for j, d in enumerate(layer["habs"]):
                 shift = WS // 2 if (j % 2 == 1) else 0
-                ops.layernorm(src, M, C, d["norm1"][0], d["norm1"][1], 1e-5, out_bf16=t, out_cols=CP)
+                if not t_ready:
+                    ops.layernorm(src, M, C, d["norm1"][0], d["norm1"][1], 1e-5, out_bf16=t, out_cols=CP)
                 # CAB on the LN1 output (hat_arch.py:272-277)
                 ops.conv_gemm(t, B, H, W, CP, d["cab1_w"], kind=CONV_3X3, n_store=64, bias=d["cab1_b"], act=ACT_GELU, out_bf16=cab1)
                 # the conv's store epilogue also emits the per-tile column sums of the squeeze-excite average pool
@@ -197,22 +206,31 @@ class HATRunner:
                 # (S)W-MSA
                 ops.conv_gemm(t, B, H, W, CP, d["qkv_w"], n_store=3 * CP, bias=d["qkv_b"], out_bf16=qkv)
                 ops.window_attention(qkv, B, H, W, att, bias_table=d["table"], wh=WS, ww=WS, shift=(shift, shift))
-                # x = shortcut + attn + 0.01 * cab   (hat_arch.py:306)
+                # x = shortcut + attn + 0.01 * cab   (hat_arch.py:306); the epilogue also emits LN2(x) into t
                 ops.conv_gemm(att, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], aux=cab2, aux_chan=se,
-                              aux_alpha=0.01, res=src, out_f32=X)
-                self._mlp(d, X, t, h, B, H, W, M)
+                              aux_alpha=0.01, res=src, out_f32=X, ln=(d["norm2"][0], d["norm2"][1], 1e-5, C, t) if fused else None)
+                nxt = layer["habs"][j + 1]["norm1"] if j + 1 < nhab else layer["ocab"]["norm1"]
+                self._mlp(d, X, t, h, B, H, W, M, t_ready=fused, next_norm=nxt if fused else None)
+                t_ready = fused
                 src = X
             d = layer["ocab"]
-            ops.layernorm(X, M, C, d["norm1"][0], d["norm1"][1], 1e-5, out_bf16=t, out_cols=CP)
+            if not t_ready:
+                ops.layernorm(X, M, C, d["norm1"][0], d["norm1"][1], 1e-5, out_bf16=t, out_cols=CP)
             ops.conv_gemm(t, B, H, W, CP, d["qkv_w"], n_store=3 * CP, bias=d["qkv_b"], out_bf16=qkv)
             ops.window_attention(qkv, B, H, W, att, bias_table=d["table"], wh=WS, ww=WS, kh=24, kw=24, kpad=(4, 4),
                                  rel_sign=-1, rel_off=(-7, -7), rel_stride=39)
-            ops.conv_gemm(att, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], res=X, out_f32=X)
-            self._mlp(d, X, t, h, B, H, W, M, extra_bf16=Xb)
-            # RHAG tail: conv3x3 + group residual (hat_arch.py:618-619)
-            ops.conv_gemm(Xb, B, H, W, CP, layer["conv_w"], kind=CONV_3X3, n_store=CP, bias=layer["conv_b"], res=G, out_f32=G)
+            ops.conv_gemm(att, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], res=X, out_f32=X,
+                          ln=(d["norm2"][0], d["norm2"][1], 1e-5, C, t) if fused else None)
+            self._mlp(d, X, t, h, B, H, W, M, extra_bf16=Xb, t_ready=fused)
+            # RHAG tail: conv3x3 + group residual (hat_arch.py:618-619); its epilogue emits the LayerNorm of the next consumer
+            # of G: norm1 of the next group's first block, or the final `norm`
+            nxt = self.layers[li + 1]["habs"][0]["norm1"] if li + 1 < len(self.layers) else self.norm
+            ops.conv_gemm(Xb, B, H, W, CP, layer["conv_w"], kind=CONV_3X3, n_store=CP, bias=layer["conv_b"], res=G, out_f32=G,
+                          ln=(nxt[0], nxt[1], 1e-5, C, t) if fused else None)
+            t_ready = fused
 
-        ops.layernorm(G, M, C, self.norm[0], self.norm[1], 1e-5, out_bf16=t, out_cols=CP)
+        if not t_ready:
+            ops.layernorm(G, M, C, self.norm[0], self.norm[1], 1e-5, out_bf16=t, out_cols=CP)
         y = Xb
         ops.conv_gemm(t, B, H, W, CP, self.cab_w, kind=CONV_3X3, n_store=CP, bias=self.cab_b, res=x0, out_bf16=y)
         f64 = ws.get("f64", M, 64, BF16)

@@ -57,6 +57,34 @@ def _decode_u8(path):
     return np.ascontiguousarray(np.array(Image.open(path).convert("RGB"), dtype=np.uint8))
 
 
+def encode_png(arr, level=None):
+    """uint8 HWC RGB array -> PNG file bytes: 8-bit truecolour, every scanline Sub-filtered (PNG filter type 1), one zlib
+    stream.  Pixel-identical to what PIL writes; numpy and zlib release the GIL, so the encoder threads really run in parallel
+    (PIL's PNG writer holds it for most of an image, which serialised the 16 tiles of a bench step)."""
+    import struct
+    import zlib
+    h, w, c = arr.shape
+    assert c == 3 and arr.dtype == np.uint8
+    rows = np.empty((h, 1 + 3 * w), dtype=np.uint8)
+    rows[:, 0] = 1
+    flat = arr.reshape(h, 3 * w)
+    rows[:, 1:4] = flat[:, :3]
+    np.subtract(flat[:, 3:], flat[:, :-3], out=rows[:, 4:])          # uint8 arithmetic wraps mod 256, as the filter specifies
+    comp = zlib.compress(rows, PNG_COMPRESS_LEVEL if level is None else level)
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(data, zlib.crc32(tag)) & 0xFFFFFFFF)
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + chunk(b"IDAT", comp) + chunk(b"IEND", b"")
+
+
+def _write_png(arr, path):
+    if os.environ.get("FFB200_PNG_WRITER", "native") == "pil":
+        Image.fromarray(arr).save(path, format="PNG", compress_level=PNG_COMPRESS_LEVEL)
+        return
+    with open(path, "wb") as f:
+        f.write(encode_png(arr))
+
+
 _MODEL_CACHE = {}
 _MODEL_LOCK = threading.Lock()
 
@@ -262,7 +290,7 @@ class ImagePipeline:
 
     def _encode(self, done, host, path):
         done.synchronize()
-        Image.fromarray(host.numpy()).save(path, format="PNG", compress_level=PNG_COMPRESS_LEVEL)
+        _write_png(host.numpy(), path)
         self.pinned.put(host)
 
     def run(self, paths, indices=None, prefetch=4):
@@ -392,7 +420,7 @@ def _run_tile_sharded(model, paths, output_path, rank, world):
                                                     C.c_void_p(torch.cuda.current_stream(model.device).cuda_stream)), "ff_quantize_u8")
                 else:
                     tiling.Stitcher(up["plan"], model.device)(full.contiguous(), out_u8=u8)
-            Image.fromarray(u8.cpu().numpy()).save(os.path.join(output_path, os.path.basename(p)), format="PNG", compress_level=PNG_COMPRESS_LEVEL)
+            _write_png(u8.cpu().numpy(), os.path.join(output_path, os.path.basename(p)))
             records[i] = (os.path.basename(p), 4 * h, 4 * w, sum(counts), up["mode"] + "/tile-sharded")
     return records
 

@@ -71,12 +71,16 @@ class NAFNetRunner:
             c //= 2
             self.decoders.append([block(f"decoders.{s}.{k}.", c) for k in range(n)])
 
-    def _block(self, d, S, Sb, B, H, W, bufs, want_bf16):
-        """One NAFBlock in place on the fp32 stream S [P, c]; Sb receives a bf16 copy when want_bf16."""
+    def _block(self, d, S, Sb, B, H, W, bufs, want_bf16, t_ready=False, next_norm=None):
+        """One NAFBlock in place on the fp32 stream S [P, c]; Sb receives a bf16 copy when want_bf16.
+        t_ready: LayerNorm2d(norm1)(S) already sits in `t` (emitted by the previous block's conv5 epilogue); next_norm: norm1 of the
+        following block at this level, emitted the same way.  Rows up to 256 channels fit one n tile and take the fused path."""
         c = d["c"]
         P = B * H * W
         t, a, gt, gapv, sca, scratch = bufs
-        ops.layernorm(S, P, c, d["n1"][0], d["n1"][1], 1e-6, out_bf16=t, out_cols=c)
+        fused = ops.fused_ln_enabled() and c <= 256
+        if not t_ready:
+            ops.layernorm(S, P, c, d["n1"][0], d["n1"][1], 1e-6, out_bf16=t, out_cols=c)
         ops.conv_gemm(t, B, H, W, c, d["w1"], n_store=2 * c, bias=d["b1"], out_bf16=a)
         rows = ops.dwconv_pool_rows(H, W, c, 1)
         if rows:
@@ -88,18 +92,29 @@ class NAFNetRunner:
             ops.dwconv(a, B, H, W, 2 * c, 3, 3, d["dw"], d["dwb"], gt, mode=1)
             ops.gap(gt, B, H * W, c, gapv, scratch)
         ops.vec_linear(gapv, B, c, d["sca_w"], d["sca_b"], c, ACT_NONE, sca)
+        ln2 = (d["n2"][0], d["n2"][1], 1e-6, c, t) if fused else None
         if c < H * W:
             # x * sca folded into per-sample conv3 weights (c*c per sample instead of a pass over H*W*c activations)
             w3b = self.ws.get(f"w3b{c}", B * c, c, BF16)
             ops.scale_weight_cols(d["w3_f32"], sca, w3b.view(B, c, c))
-            ops.conv_gemm(gt, B, H, W, c, w3b, n_store=c, w_batch_rows=c, bias=d["b3"], col_scale=d["beta"], res=S, out_f32=S)
+            ops.conv_gemm(gt, B, H, W, c, w3b, n_store=c, w_batch_rows=c, bias=d["b3"], col_scale=d["beta"], res=S, out_f32=S, ln=ln2)
         else:
             ops.scale_channels(gt, B, H * W, c, sca)
-            ops.conv_gemm(gt, B, H, W, c, d["w3"], n_store=c, bias=d["b3"], col_scale=d["beta"], res=S, out_f32=S)
-        ops.layernorm(S, P, c, d["n2"][0], d["n2"][1], 1e-6, out_bf16=t, out_cols=c)
+            ops.conv_gemm(gt, B, H, W, c, d["w3"], n_store=c, bias=d["b3"], col_scale=d["beta"], res=S, out_f32=S, ln=ln2)
+        if not fused:
+            ops.layernorm(S, P, c, d["n2"][0], d["n2"][1], 1e-6, out_bf16=t, out_cols=c)
         ops.conv_gemm(t, B, H, W, c, d["w4"], n_store=2 * c, bias=d["b4"], gate_pairs=1, out_bf16=gt)
+        ln1 = (next_norm[0], next_norm[1], 1e-6, c, t) if (fused and next_norm is not None) else None
         ops.conv_gemm(gt, B, H, W, c, d["w5"], n_store=c, bias=d["b5"], col_scale=d["gamma"], res=S, out_f32=S,
-                      out_bf16=Sb if want_bf16 else None)
+                      out_bf16=Sb if want_bf16 else None, ln=ln1)
+        return ln1 is not None
+
+    def _run_blocks(self, blks, l, B):
+        """A run of NAFBlocks at one UNet level; each block's conv5 epilogue emits the next block's norm1."""
+        ready = False
+        for k, d in enumerate(blks):
+            nxt = blks[k + 1]["n1"] if k + 1 < len(blks) else None
+            ready = self._block(d, l["S"], l["Sb"], B, l["H"], l["W"], l["bufs"], want_bf16=(k == len(blks) - 1), t_ready=ready, next_norm=nxt)
 
     def forward(self, x, out, out_off=6):
         """x: fp32 NCHW [B,3,h,w] with 4h, 4w multiples of 256 / 16-aligned at every UNet level (h, w multiples of 64).
@@ -128,20 +143,16 @@ class NAFNetRunner:
         for s in range(nlev):
             l = lv[s]
             blks = self.encoders[s]
-            for k, d in enumerate(blks):
-                self._block(d, l["S"], l["Sb"], B, l["H"], l["W"], l["bufs"], want_bf16=(k == len(blks) - 1))
+            self._run_blocks(blks, l, B)
             dw_, db_ = self.downs[s]
             ops.conv_gemm(l["Sb"], B, l["H"], l["W"], l["c"], dw_, kind=CONV_2X2S2, n_store=2 * l["c"], bias=db_, out_f32=lv[s + 1]["S"])
         l = lv[nlev]
-        for k, d in enumerate(self.middle):
-            self._block(d, l["S"], l["Sb"], B, l["H"], l["W"], l["bufs"], want_bf16=(k == len(self.middle) - 1))
+        self._run_blocks(self.middle, l, B)
         for s in range(len(self.dec)):
             src, dst = lv[nlev - s], lv[nlev - s - 1]
             # 1x1 conv c -> 2c (no bias) + PixelShuffle(2) + encoder skip, written in place over the skip buffer
             ops.conv_gemm(src["Sb"], B, src["H"], src["W"], src["c"], self.ups[s], n_store=2 * src["c"], pixel_shuffle=2, res=dst["S"], out_f32=dst["S"])
-            blks = self.decoders[s]
-            for k, d in enumerate(blks):
-                self._block(d, dst["S"], dst["Sb"], B, dst["H"], dst["W"], dst["bufs"], want_bf16=(k == len(blks) - 1))
+            self._run_blocks(self.decoders[s], dst, B)
         ops.conv_gemm(l0["Sb"], B, H, W, WIDTH, self.end_w, kind=CONV_3X3, n_store=3, bias=self.end_b, res=up, post_act=ACT_CLAMP01,
                       out_f32=out[:, out_off:])
         return out

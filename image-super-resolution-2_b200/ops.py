@@ -14,6 +14,13 @@ _BF16 = torch.bfloat16
 _F32 = torch.float32
 
 
+def fused_ln_enabled():
+    """The LayerNorm that follows a residual add is emitted by the producing GEMM's epilogue (FFConvGemm.ln_*);
+    FFB200_FUSED_LN=0 restores the separate ff_layernorm passes (A/B measurements)."""
+    import os
+    return os.environ.get("FFB200_FUSED_LN", "1") != "0"
+
+
 class KernelProfile:
     """Optional per-launch CUDA-event timing of ff_conv_gemm (bench.py's roofline leg; off on the hot path)."""
 
@@ -46,7 +53,7 @@ def _req_cuda(*ts):
 
 def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_NONE, alpha=1.0, col_scale=None,
               mul=None, aux=None, aux_chan=None, aux_alpha=1.0, res=None, post_act=ACT_NONE, out_bf16=None,
-              out_f32=None, pixel_shuffle=0, gate_pairs=0, w_batch_rows=0, x_ld=None, debug_simt=0, col_sums=None):
+              out_f32=None, pixel_shuffle=0, gate_pairs=0, w_batch_rows=0, x_ld=None, debug_simt=0, col_sums=None, ln=None, out_crop=None):
     """Implicit-GEMM conv / linear on tcgen05 (see ff_conv_gemm in include/ffb200.h).
 
     x: bf16 tensor whose last dim is the channel pitch (or pass x_ld); w: packed bf16 [n_pad, taps*cin].
@@ -80,6 +87,14 @@ def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_
     if col_sums is not None:
         _req_cuda(col_sums)
         p.col_sums = col_sums.data_ptr()
+    if out_crop is not None:
+        p.out_crop_h, p.out_crop_w = out_crop
+    if ln is not None:
+        # fused LayerNorm of the updated residual row: ln = (gamma [n_store], beta [n_store], eps, real channel count, bf16 out)
+        g_, b_, eps_, cols_, lo_ = ln
+        _req_cuda(g_, b_, lo_)
+        p.ln_gamma = g_.data_ptr(); p.ln_beta = b_.data_ptr(); p.ln_eps = eps_; p.ln_cols = cols_
+        p.ln_out = lo_.data_ptr(); p.ln_out_ld = lo_.stride(-2)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -93,6 +108,7 @@ def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_
         width = n_real // (2 if gate_pairs else 1)
         byts = B * H * W * cin_real * 2 + n_real * k_real * 2 + Mo * width * ((2 if out_bf16 is not None else 0) + (4 if out_f32 is not None else 0))
         byts += Mo * width * ((4 if res.dtype == _F32 else 2) if res is not None else 0) + Mo * width * (2 if mul is not None else 0) + Mo * width * (2 if aux is not None else 0)
+        byts += Mo * ln[3] * 2 if ln is not None else 0
         PROFILE.records.append((e0, e1, 2.0 * Mo * n_real * k_real, 2.0 * Mo * p.n_pad * taps * cin, float(byts),
                                 (kind, cin, p.n_pad, B, H, W, act, res is not None, aux is not None, mul is not None, gate_pairs, pixel_shuffle, out_f32 is not None)))
         return

@@ -39,7 +39,8 @@ enum { FF_CONV_1X1 = 0, FF_CONV_3X3 = 1, FF_CONV_2X2S2 = 2 };
  * ff_conv_gemm -- implicit-GEMM convolution / linear layer on tcgen05 tensor cores.
  *   out[p, n] = epilogue( sum_{tap, c} x[pixel(p)+tap, c] * w[n, tap*cin + c] )
  * A tiles (128 output pixels = 8 rows x 16 cols) are fetched by 4-D TMA boxes shifted per tap with
- * hardware zero fill at the image border (= Conv2d zero padding); B tiles by 2-D TMA; fp32
+ * hardware zero fill at the image border (= Conv2d zero padding); any H x W is accepted (edge tiles are partial: TMA clips the
+ * stores, the direct-store epilogues mask by coordinates); B tiles by 2-D TMA; fp32
  * accumulators live in TMEM (double-buffered so the epilogue of tile i overlaps the MMAs of i+1).
  * Replaces: nn.Linear / nn.Conv2d call sites of hat_arch.py:156-158,83-85,65-69,596,874-893;
  * dat_arch.py:149-152,379-381,589-591,782; nafnet_arch.py:70-86,163-185; hierarchical_fusion.py:86-120;
@@ -85,6 +86,21 @@ typedef struct FFConvGemm {
   float* col_sums;     /* optional (plain bf16-store layers only): per-(128-pixel tile, 32-row quadrant) column sums of the stored
                         * values before bf16 rounding, [B][Ho*Wo/32][n_store] fp32 -- the global-average-pool partials of a
                         * squeeze-excite block, finished by ff_gap_finalize (deterministic two-phase sum) */
+  /* Fused LayerNorm of the NEW residual-stream row (fp32-residual layers whose n tile spans the whole row, n_pad <= 256):
+   * ln_out[p, n] = bf16((v[p, n] - mean_p) * rstd_p * ln_gamma[n] + ln_beta[n]) with the statistics over the first ln_cols
+   * columns (columns ln_cols..n_store must be structurally zero: zero weights / bias / residual; their gamma / beta zero).
+   * Replaces the separate nn.LayerNorm / LayerNorm2d pass that follows a residual add (hat_arch.py:268,308; dat_arch.py:727-733;
+   * nafnet_arch.py:112,124): the row is still in TMEM when its statistics are known. */
+  const float* ln_gamma; /* [n_store] or NULL */
+  const float* ln_beta;  /* [n_store] */
+  float ln_eps;
+  int ln_cols;
+  void* ln_out;          /* bf16 [pixels][ln_out_ld] or NULL */
+  int ln_out_ld;
+  /* Cropped output (0 = none): the layer computes H x W outputs but out_bf16 / out_f32 are [B][out_crop_h][out_crop_w] images
+   * holding the top-left part -- the crop that follows an expert run on a padded image (expert_loader.py:612-615, 643-646,
+   * nafnet_arch.py:216).  Direct-store epilogues only (n_store <= 4, or layers without per-pixel operands); `res` stays H x W. */
+  int out_crop_h, out_crop_w;
 } FFConvGemm;
 int ff_conv_gemm(const FFConvGemm* p, void* stream);
 

@@ -695,3 +695,54 @@ def test_layernorm_bf16_wide_rows(rows, C_, cols, off):
     got = out.cpu().float()
     assert ((got[:, :C_] - ref).abs() <= 4e-3 * ref.abs() + 1e-3).all()
     assert torch.all(got[:, C_:] == 0)
+
+
+@pytest.mark.parametrize("cin,n,c_real,H,W,B,kind,aux,with_bf16", [
+    (384, 192, 180, 32, 32, 2, 0, False, False), (192, 192, 180, 32, 16, 1, 1, False, True), (192, 192, 180, 16, 32, 2, 0, True, False),
+    (64, 64, 64, 16, 32, 1, 0, False, False), (128, 128, 128, 24, 16, 3, 0, False, True), (256, 256, 256, 8, 16, 2, 0, False, False)])
+def test_conv_gemm_fused_layernorm(cin, n, c_real, H, W, B, kind, aux, with_bf16):
+    """FFConvGemm.ln_*: the residual epilogue (EPI_RES / EPI_RES_AUX) also emits LayerNorm(new residual row) as bf16 -- the row is
+    re-read from TMEM after both warps of a lane quadrant exchanged their partial sums.  Checked against F.layer_norm of the fp32
+    result; padding columns (c_real..n) carry zero weights / bias / residual / gamma / beta and must come out exactly 0."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(19)
+    k = 3 if kind == 1 else 1
+    P = B * H * W
+    x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
+    w = torch.zeros(n, cin, k, k)
+    w[:c_real] = (torch.randn(c_real, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(BF16).float()
+    bias, res = torch.zeros(n), torch.zeros(P, n)
+    bias[:c_real] = torch.randn(c_real, generator=g)
+    res[:, :c_real] = torch.randn(P, c_real, generator=g) * 2 + 0.7        # non-zero row mean
+    gamma, beta = torch.zeros(n), torch.zeros(n)
+    gamma[:c_real], beta[:c_real] = 1 + 0.2 * torch.randn(c_real, generator=g), 0.1 * torch.randn(c_real, generator=g)
+    ref = _nhwc(F.conv2d(x, w, bias, padding=k // 2)) + res
+    d = _dev()
+    kw = {}
+    if aux:
+        av = torch.zeros(P, n)
+        av[:, :c_real] = torch.randn(P, c_real, generator=g)
+        av = av.to(BF16)
+        chan = torch.rand(B, n, generator=g)
+        ref = ref + 0.3 * av.float() * chan.repeat_interleave(H * W, 0)
+        kw = dict(aux=av.to(d), aux_chan=chan.to(d), aux_alpha=0.3)
+    ln_ref = torch.zeros(P, n)
+    ln_ref[:, :c_real] = F.layer_norm(ref[:, :c_real], (c_real,), gamma[:c_real], beta[:c_real], 1e-5)
+    stream = res.clone().to(d)
+    lno = torch.full((P, n), 7.0, dtype=BF16, device=d)
+    o16 = torch.zeros(P, n, dtype=BF16, device=d) if with_bf16 else None
+    ops.conv_gemm(_nhwc(x).to(d, BF16), B, H, W, cin, packing.pack_conv(w, n, cin, device=d), kind=kind, n_store=n, bias=bias.to(d),
+                  res=stream, out_f32=stream, out_bf16=o16, ln=(gamma.to(d), beta.to(d), 1e-5, c_real, lno), **kw)
+    torch.cuda.synchronize()
+    assert (stream.cpu() - ref).abs().max().item() < 3e-3
+    e = (lno.cpu().float() - ln_ref).abs().max().item()
+    assert e < 3e-2, e                                      # bf16 rounding of values up to ~4
+    assert (lno.cpu().float()[:, c_real:] == 0).all()
+    if with_bf16:
+        assert (o16.cpu().float() - ref).abs().max().item() < 4e-2
+    # rows wider than one n tile are rejected loudly
+    from isr2_b200 import lib
+    with pytest.raises(lib.FFError):
+        wide = torch.zeros(P, 512, device=d)
+        ops.conv_gemm(_nhwc(x).to(d, BF16), B, H, W, cin, packing.pack_conv(torch.zeros(512, cin, k, k), 512, cin, device=d), kind=kind, n_store=512,
+                      res=wide, out_f32=wide, ln=(torch.zeros(512, device=d), torch.zeros(512, device=d), 1e-5, 512, torch.zeros(P, 512, dtype=BF16, device=d)))
