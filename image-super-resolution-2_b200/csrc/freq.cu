@@ -24,16 +24,25 @@ __global__ void __launch_bounds__(64) dct_bands_kernel(const float* __restrict__
   D[threadIdx.x] = dmat[threadIdx.x];
   bo[threadIdx.x] = band_of[threadIdx.x];
   __syncthreads();
-  const int nbx = W / 8, nby = H / 8;
+  // sizes that are not multiples of 8 are reflect-padded on the right / bottom (multi_domain_frequency.py:151-157) and the
+  // result is cropped back (:190-193): edge blocks read mirrored pixels and only write the part inside the image
+  const int nbx = (W + 7) / 8, nby = (H + 7) / 8;
   const long long idx = (long long)blockIdx.x * 64 + threadIdx.x;
   if (idx >= (long long)B * 3 * nbx * nby) return;
   const int bx = (int)(idx % nbx), by = (int)((idx / nbx) % nby), c = (int)((idx / (nbx * nby)) % 3), b = (int)(idx / (3LL * nbx * nby));
-  const float* src = x + ((long long)(b * 3 + c) * H + by * 8) * W + bx * 8;
+  const float* plane = x + (long long)(b * 3 + c) * H * W;
   float X[64], T[64], Y[64];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 8; ++i) {
+    int yy = by * 8 + i;
+    if (yy >= H) yy = 2 * (H - 1) - yy;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) X[i * 8 + j] = src[i * W + j];
+    for (int j = 0; j < 8; ++j) {
+      int xx = bx * 8 + j;
+      if (xx >= W) xx = 2 * (W - 1) - xx;
+      X[i * 8 + j] = plane[(long long)yy * W + xx];
+    }
+  }
   // T = X * D^T  (T[i][k] = sum_n X[i][n] D[k][n]);  Y = D * T
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -72,7 +81,7 @@ __global__ void __launch_bounds__(64) dct_bands_kernel(const float* __restrict__
         float s = 0.f;
 #pragma unroll
         for (int n = 0; n < 8; ++n) s += D[n * 8 + i] * T[n * 8 + j];
-        out[((long long)(b * H + by * 8 + i) * W + bx * 8 + j) * NB + band * 3 + c] = s * sc;
+        if (by * 8 + i < H && bx * 8 + j < W) out[((long long)(b * H + by * 8 + i) * W + bx * 8 + j) * NB + band * 3 + c] = s * sc;
       }
   }
 }
@@ -87,7 +96,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 __global__ void __launch_bounds__(128) dwt_subbands_kernel(const float* __restrict__ x, int B, int H, int W,
                                                           const float* __restrict__ lo, const float* __restrict__ hi,
                                                           float* __restrict__ sub) {
-  const int Sh = H / 2 + 4, Sw = W / 2 + 4;
+  const int Sh = (H + 6) / 2 + 1, Sw = (W + 6) / 2 + 1;      // conv of the 7+7 reflect-padded axis with 8 taps, stride 2
   const long long idx = (long long)blockIdx.x * 128 + threadIdx.x;
   if (idx >= (long long)B * 3 * Sh * Sw) return;
   const int xo = (int)(idx % Sw), yo = (int)((idx / Sw) % Sh);
@@ -112,7 +121,7 @@ __global__ void __launch_bounds__(128) dwt_subbands_kernel(const float* __restri
 }
 __global__ void __launch_bounds__(256) dwt_upsample_kernel(const float* __restrict__ sub, int B, int H, int W,
                                                           const float* __restrict__ subband_scale, float* __restrict__ out) {
-  const int Sh = H / 2 + 4, Sw = W / 2 + 4;
+  const int Sh = (H + 6) / 2 + 1, Sw = (W + 6) / 2 + 1;      // conv of the 7+7 reflect-padded axis with 8 taps, stride 2
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)B * H * W) return;
   const int xo = (int)(idx % W), yo = (int)((idx / W) % H), b = (int)(idx / ((long long)W * H));
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(128) fft_rows_inv_kernel(const float2* __restr
   const int y = blockIdx.x, p = blockIdx.y;   // p = b*3 + c
   for (int i = threadIdx.x; i < Wh; i += 128) {
     const float2 v = Y1[((long long)p * H + y) * Wh + i];
-    const float w = (i == 0 || i == W / 2) ? 1.f : 2.f;
+    const float w = (i == 0 || (2 * i == W)) ? 1.f : 2.f;       // DC and (even W only) Nyquist bins appear once in the full spectrum
     re[i] = v.x * w; im[i] = v.y * w;
   }
   for (int i = threadIdx.x; i < W; i += 128) {
@@ -230,15 +239,16 @@ extern "C" int ff_freq_decompose(const float* lr, int B, int H, int W, const flo
                                  size_t scratch_bytes, void* stream) {
   FF_CHECK_ARG(lr && dct_mat && dct_band_of && dct_scale && dwt_lo && dwt_hi && dwt_scale && fft_mask && fft_scale && bands && scratch,
                "ff_freq_decompose: null buffer");
-  FF_CHECK_ARG(H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16 && H <= 1024 && W <= 1024, "ff_freq_decompose: tile %dx%d must be a multiple of 8 in [16,1024]", H, W);
-  const int Wh = W / 2 + 1, Sh = H / 2 + 4, Sw = W / 2 + 4;
+  // any size the reference accepts: reflect padding needs 7 < H, W (DWT, :252) and W <= 4096 keeps the DFT twiddles in 48 KB of smem
+  FF_CHECK_ARG(H >= 8 && W >= 8 && H <= 4096 && W <= 4096, "ff_freq_decompose: image %dx%d outside [8, 4096]", H, W);
+  const int Wh = W / 2 + 1, Sh = (H + 6) / 2 + 1, Sw = (W + 6) / 2 + 1;
   const size_t need = ((size_t)B * 3 * H * Wh * 2 * 2 + (size_t)B * 3 * 4 * Sh * Sw) * sizeof(float);
   FF_CHECK_ARG(scratch_bytes >= need, "ff_freq_decompose: scratch %zu < %zu", scratch_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float2* bufA = reinterpret_cast<float2*>(scratch);
   float2* bufB = bufA + (size_t)B * 3 * H * Wh;
   float* sub = reinterpret_cast<float*>(bufB + (size_t)B * 3 * H * Wh);
-  dct_bands_kernel<<<ff_cdiv((long long)B * 3 * (H / 8) * (W / 8), 64), 64, 0, st>>>(lr, B, H, W, dct_mat, dct_band_of, dct_scale, bands);
+  dct_bands_kernel<<<ff_cdiv((long long)B * 3 * ((H + 7) / 8) * ((W + 7) / 8), 64), 64, 0, st>>>(lr, B, H, W, dct_mat, dct_band_of, dct_scale, bands);
   dwt_subbands_kernel<<<ff_cdiv((long long)B * 3 * Sh * Sw, 128), 128, 0, st>>>(lr, B, H, W, dwt_lo, dwt_hi, sub);
   dwt_upsample_kernel<<<ff_cdiv((long long)B * H * W, 256), 256, 0, st>>>(sub, B, H, W, dwt_scale, bands);
   fft_rows_fwd_kernel<<<dim3(H, B * 3), 128, 3 * W * sizeof(float), st>>>(lr, H, W, bufA);

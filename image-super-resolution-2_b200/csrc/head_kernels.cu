@@ -178,14 +178,14 @@ __global__ void __launch_bounds__(128) band_fuse_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bilinear_f32_kernel(const float* __restrict__ in, int B, int Hi, int Wi, int ld_in, int C,
                                                           float* __restrict__ out, int Ho, int Wo, int ld_out, int accumulate,
-                                                          const float* __restrict__ bias) {
+                                                          const float* __restrict__ bias, float ratio_y, float ratio_x) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const int cg = (C + 3) / 4;
   if (idx >= (long long)B * Ho * Wo * cg) return;
   const int g = (int)(idx % cg);
   const long long pix = idx / cg;
   const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
-  const Bilin by = bilin(yo, (float)Hi / Ho, Hi), bx = bilin(xo, (float)Wi / Wo, Wi);
+  const Bilin by = bilin(yo, ratio_y, Hi), bx = bilin(xo, ratio_x, Wi);
   const float* base = in + (long long)b * Hi * Wi * ld_in;
   for (int c = g * 4; c < min(C, g * 4 + 4); ++c) {
     const float v00 = base[((long long)by.i0 * Wi + bx.i0) * ld_in + c], v01 = base[((long long)by.i0 * Wi + bx.i1) * ld_in + c];
@@ -506,8 +506,15 @@ extern "C" int ff_band_fuse(const float* bands, const float* att, int att_ld, lo
 extern "C" int ff_bilinear_f32(const float* in, int B, int Hi, int Wi, int ld_in, int C, float* out, int Ho, int Wo, int ld_out,
                                int accumulate, const float* bias, void* stream) {
   FF_CHECK_ARG(in && out && C <= ld_in && C <= ld_out, "ff_bilinear_f32: bad args");
-  bilinear_f32_kernel<<<ff_cdiv((long long)B * Ho * Wo * ((C + 3) / 4), 256), 256, 0, ST(stream)>>>(in, B, Hi, Wi, ld_in, C, out, Ho, Wo, ld_out, accumulate, bias);
+  bilinear_f32_kernel<<<ff_cdiv((long long)B * Ho * Wo * ((C + 3) / 4), 256), 256, 0, ST(stream)>>>(in, B, Hi, Wi, ld_in, C, out, Ho, Wo, ld_out, accumulate, bias,
+                                                                                                    (float)Hi / Ho, (float)Wi / Wo);
   ++g_ff_launches; FF_CHECK_LAUNCH("ff_bilinear_f32"); return FF_OK;
+}
+extern "C" int ff_bilinear_f32_scaled(const float* in, int B, int Hi, int Wi, int ld_in, int C, float* out, int Ho, int Wo, int ld_out, float ratio_y,
+                                      float ratio_x, void* stream) {
+  FF_CHECK_ARG(in && out && C <= ld_in && C <= ld_out && ratio_y > 0.f && ratio_x > 0.f, "ff_bilinear_f32_scaled: bad args");
+  bilinear_f32_kernel<<<ff_cdiv((long long)B * Ho * Wo * ((C + 3) / 4), 256), 256, 0, ST(stream)>>>(in, B, Hi, Wi, ld_in, C, out, Ho, Wo, ld_out, 0, nullptr, ratio_y, ratio_x);
+  ++g_ff_launches; FF_CHECK_LAUNCH("ff_bilinear_f32_scaled"); return FF_OK;
 }
 extern "C" int ff_bilinear_up2_bf16(const void* in, int B, int Hi, int Wi, int ld_in, int C, void* out, int ld_out, void* stream) {
   FF_CHECK_ARG(in && out && C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0, "ff_bilinear_up2_bf16: bad args");

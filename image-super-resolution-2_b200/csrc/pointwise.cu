@@ -914,7 +914,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant_
   const bool all_w = gridDim.y == 1;          // small Cin: every output-channel group's weights are staged once
   float* sIn = sm;                       // [PH*PW][cs]
   float* sW = sm + PH * PW * cs;         // [groups][KK][8]
-  const int tiles_x = a.W / 16, tiles_y = a.H / (8 * R);
+  const int tiles_x = (a.W + 15) / 16, tiles_y = (a.H + 8 * R - 1) / (8 * R);      // partial edge tiles: loads zero-fill, stores are masked
   int t = blockIdx.x;
   const int b = t / (tiles_x * tiles_y);
   t -= b * tiles_x * tiles_y;
@@ -967,6 +967,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const __grid_constant_
 #pragma unroll
     for (int r = 0; r < R; ++r) {
     float (&acc)[8] = accr[r];
+    if (ty * 8 * R + r * 8 + py >= a.H || tx * 16 + px >= a.W) continue;
     const long long opix = (long long)(b * a.H + ty * 8 * R + r * 8 + py) * a.W + tx * 16 + px;
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = act_apply(acc[o], a.act);
@@ -1007,6 +1008,26 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int C, i
   for (int c = 0; c < ld; ++c) {
     float v = 0.f;
     if (c < C) v = x[((long long)b * C + c) * hw + p] - (sub ? sub[c] : 0.f);
+    out[idx * ld + c] = v;
+  }
+}
+// NCHW fp32 image [B][C][H][W] -> NHWC fp32 [B*Hp*Wp][ld] padded on the right / bottom: mode 1 = reflect (F.pad(mode='reflect') of
+// pad_to_window_size, expert_loader.py:83-91), mode 0 = zeros; (x - sub) as above
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, int B, int C, int H, int W, const float* __restrict__ sub,
+                                        float* __restrict__ out, int ld, int Hp, int Wp, int mode) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * Hp * Wp) return;
+  const int xo = (int)(idx % Wp), yo = (int)((idx / Wp) % Hp), b = (int)(idx / ((long long)Wp * Hp));
+  int ys = yo, xs = xo;
+  bool inside = yo < H && xo < W;
+  if (!inside && mode == 1) {
+    if (ys >= H) ys = 2 * (H - 1) - ys;
+    if (xs >= W) xs = 2 * (W - 1) - xs;
+    inside = true;
+  }
+  for (int c = 0; c < ld; ++c) {
+    float v = 0.f;
+    if (c < C && inside) v = x[(((long long)b * C + c) * H + ys) * W + xs] - (sub ? sub[c] : 0.f);
     out[idx * ld + c] = v;
   }
 }
@@ -1319,7 +1340,7 @@ extern "C" int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int
                               void* out_bf16, int out_ld, float* out_f32, int out_f32_ld, void* stream) {
   FF_CHECK_ARG(x && w && (out_bf16 || out_f32), "ff_conv_direct: null buffer");
   FF_CHECK_ARG((k == 1 || k == 3) && Cin > 0 && Cin <= 192, "ff_conv_direct: k=%d Cin=%d unsupported", k, Cin);
-  FF_CHECK_ARG(H % 8 == 0 && W % 16 == 0, "ff_conv_direct: %dx%d must be a multiple of 8x16", H, W);
+  FF_CHECK_ARG(B > 0 && H > 0 && W > 0, "ff_conv_direct: bad size %dx%dx%d", B, H, W);
   FF_CHECK_ARG(Cout_pad % 8 == 0 && n_store <= Cout_pad, "ff_conv_direct: Cout_pad must be a multiple of 8");
   const int vb = (out_bf16 && out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0) ? 1 : 0;
   const int vf = (out_f32 && out_f32_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) ? 1 : 0;
@@ -1331,14 +1352,18 @@ extern "C" int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int
   // four rows per thread when the whole problem is large and the weights are staged once per block
   const int R = (all_w && H % 32 == 0 && (long long)B * H * W >= (1 << 18)) ? 4 : 1;
   const size_t smem = ((size_t)(16 + 2 * pad) * (8 * R + 2 * pad) * (Cin | 1) + (size_t)k * k * Cin * 8 * wgroups) * sizeof(float);
-  static size_t configured[2] = {48 * 1024, 48 * 1024};
+  static size_t configured_dev[64][2];
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  size_t* configured = configured_dev[dev_ & 63];
+  if (configured[0] == 0) configured[0] = configured[1] = 48 * 1024;
   if (smem > configured[R == 4]) {
     cudaError_t e = R == 4 ? cudaFuncSetAttribute(conv_direct_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                            : cudaFuncSetAttribute(conv_direct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ff_set_error("ff_conv_direct: smem %zu: %s", smem, cudaGetErrorString(e)); return FF_ERR_CUDA; }
     configured[R == 4] = smem;
   }
-  dim3 grid(B * (H / (8 * R)) * (W / 16), all_w ? 1 : Cout_pad / 8);
+  dim3 grid(B * ff_cdiv(H, 8 * R) * ff_cdiv(W, 16), all_w ? 1 : Cout_pad / 8);
   if (R == 4) conv_direct_kernel<4><<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   else conv_direct_kernel<1><<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   ++g_ff_launches;
@@ -1351,6 +1376,15 @@ extern "C" int ff_nchw_to_nhwc(const float* x, int B, int C, int H, int W, const
   nchw_to_nhwc_kernel<<<ff_cdiv((long long)B * H * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, B, C, H, W, sub, out, ld);
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_nchw_to_nhwc");
+  return FF_OK;
+}
+extern "C" int ff_nchw_to_nhwc_pad(const float* x, int B, int C, int H, int W, const float* sub, float* out, int ld, int Hp, int Wp, int mode,
+                                   void* stream) {
+  FF_CHECK_ARG(x && out && ld >= C && Hp >= H && Wp >= W && (mode == 0 || mode == 1), "ff_nchw_to_nhwc_pad: bad args");
+  FF_CHECK_ARG(mode == 0 || (Hp - H < H && Wp - W < W), "ff_nchw_to_nhwc_pad: reflect padding %d/%d must be smaller than the image %dx%d", Hp - H, Wp - W, H, W);
+  nchw_to_nhwc_pad_kernel<<<ff_cdiv((long long)B * Hp * Wp, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, B, C, H, W, sub, out, ld, Hp, Wp, mode);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_nchw_to_nhwc_pad");
   return FF_OK;
 }
 extern "C" int ff_nhwc_to_nchw(const float* x, int ld, int coff, int B, int C, int H, int W, float* out, void* stream) {

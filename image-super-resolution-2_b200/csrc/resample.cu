@@ -19,11 +19,16 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
 }
 
 // NCHW fp32 [B,C,h,w] -> NHWC fp32 [B*(s*h)*(s*w)][ld], bicubic (a = -0.75, border-clamped taps, not clamped in value)
-__global__ void bicubic_up_kernel(const float* __restrict__ x, int B, int C, int h, int w, int s, float* __restrict__ out, int ld) {
-  const int H = h * s, W = w * s;
+// The output image may be zero-padded on the right / bottom to Hp x Wp (NAFNet.check_image_size, nafnet_arch.py:219-225).
+__global__ void bicubic_up_kernel(const float* __restrict__ x, int B, int C, int h, int w, int s, float* __restrict__ out, int ld, int Hp, int Wp) {
+  const int H = Hp, W = Wp;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W) return;
   const int ox = (int)(idx % W), oy = (int)((idx / W) % H), b = (int)(idx / ((long long)W * H));
+  if (oy >= h * s || ox >= w * s) {
+    for (int c = 0; c < ld; ++c) out[idx * ld + c] = 0.f;
+    return;
+  }
   const float sy = (oy + 0.5f) / s - 0.5f, sx = (ox + 0.5f) / s - 0.5f;
   const float fy = floorf(sy), fx = floorf(sx);
   float wy[4], wx[4];
@@ -52,11 +57,14 @@ __global__ void bicubic_up_kernel(const float* __restrict__ x, int B, int C, int
 
 }  // namespace
 
-extern "C" int ff_bicubic_up(const float* x, int B, int C, int h, int w, int scale, float* out, int ld, void* stream) {
-  FF_CHECK_ARG(x && out && ld >= C && scale >= 1, "ff_bicubic_up: bad args");
-  const long long total = (long long)B * h * scale * w * scale;
-  bicubic_up_kernel<<<ff_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, B, C, h, w, scale, out, ld);
+extern "C" int ff_bicubic_up_pad(const float* x, int B, int C, int h, int w, int scale, float* out, int ld, int Hp, int Wp, void* stream) {
+  FF_CHECK_ARG(x && out && ld >= C && scale >= 1 && Hp >= h * scale && Wp >= w * scale, "ff_bicubic_up: bad args");
+  const long long total = (long long)B * Hp * Wp;
+  bicubic_up_kernel<<<ff_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, B, C, h, w, scale, out, ld, Hp, Wp);
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_bicubic_up");
   return FF_OK;
+}
+extern "C" int ff_bicubic_up(const float* x, int B, int C, int h, int w, int scale, float* out, int ld, void* stream) {
+  return ff_bicubic_up_pad(x, B, C, h, w, scale, out, ld, h * scale, w * scale, stream);
 }

@@ -83,7 +83,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_kernel(const __g
   // (one 128-byte line holds two heads) are fetched from DRAM once instead of once per head pass
   const int head_l = blockIdx.x % p.heads;
   const int head = p.head_off + head_l;
-  const int nwx = p.W / p.ww, nwy = p.H / p.wh;
+  // Padded geometry (DAT on sizes that are not multiples of its 32-wide windows, dat_arch.py:505-528): windows, cyclic shift and
+  // mask regions live on the Hp x Wp grid; tokens with y >= H or x >= W are the zero rows F.pad appended to q, k and v AFTER the
+  // projection (so no bias) -- as keys they still take softmax mass, as queries they are never stored.
+  const int Hp = p.Hp > 0 ? p.Hp : p.H, Wp = p.Wp > 0 ? p.Wp : p.W;
+  const int nwx = Wp / p.ww, nwy = Hp / p.wh;
   int win = blockIdx.x / p.heads;
   const int b = win / (nwx * nwy);
   win -= b * nwx * nwy;
@@ -98,19 +102,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_kernel(const __g
   for (int idx = tid; idx < NQ * 4; idx += NTHREADS) {
     const int t = idx >> 2, part = idx & 3;
     const int i = t / p.ww, j = t - i * p.ww;
-    int y = wy * p.wh + i + p.shift_y; if (y >= p.H) y -= p.H;
-    int x = wx * p.ww + j + p.shift_x; if (x >= p.W) x -= p.W;
-    const bf16* src = base + (img0 + (long long)y * p.W + x) * p.ld + p.q_off + head * HD + part * 8;
-    cp_async16(sQ + swz(t, part), src, 16);
+    int y = wy * p.wh + i + p.shift_y; if (y >= Hp) y -= Hp;
+    int x = wx * p.ww + j + p.shift_x; if (x >= Wp) x -= Wp;
+    const bool real = y < p.H && x < p.W;
+    const bf16* src = real ? base + (img0 + (long long)y * p.W + x) * p.ld + p.q_off + head * HD + part * 8 : base;
+    cp_async16(sQ + swz(t, part), src, real ? 16 : 0);
   }
   // ---- gather K, V ----
   for (int idx = tid; idx < NK * 4; idx += NTHREADS) {
     const int t = idx >> 2, part = idx & 3;
     const int i = t / KW, j = t - i * KW;
     const int ys = wy * p.wh - p.kpad_y + i, xs = wx * p.ww - p.kpad_x + j;
-    const bool inside = ys >= 0 && ys < p.H && xs >= 0 && xs < p.W;
-    int y = ys + p.shift_y; if (y >= p.H) y -= p.H;
-    int x = xs + p.shift_x; if (x >= p.W) x -= p.W;
+    const bool in_grid = ys >= 0 && ys < Hp && xs >= 0 && xs < Wp;
+    int y = ys + p.shift_y; if (y >= Hp) y -= Hp;
+    int x = xs + p.shift_x; if (x >= Wp) x -= Wp;
+    const bool inside = in_grid && y < p.H && x < p.W;
     const bf16* src = inside ? base + (img0 + (long long)y * p.W + x) * p.ld + head * HD + part * 8 : base;
     cp_async16(sK + swz(t, part), src + (inside ? p.k_off : 0), inside ? 16 : 0);
     if (inside || part != 3) {
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_kernel(const __g
       *reinterpret_cast<uint4*>(sV + swz(t, part)) = make_uint4(0, 0, 0, 0x3F800000u);
     }
     if (part == 0 && need_mask)
-      sKr[t] = inside ? (uint8_t)(region3(ys, p.H, p.wh, p.shift_y) * 3 + region3(xs, p.W, p.ww, p.shift_x)) : 0;
+      sKr[t] = in_grid ? (uint8_t)(region3(ys, Hp, p.wh, p.shift_y) * 3 + region3(xs, Wp, p.ww, p.shift_x)) : 0;
   }
   {
     const float* tb = p.bias_table + (long long)(p.bias_head_off + head_l) * p.T;   // table is [heads][T]
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_kernel(const __g
         // bias index of (row, key (ki,kj)) = (sgn*(qi-ki)+offy)*stride + sgn*(qj-kj)+offx = A_row - rowmul*ki - sgn*kj
         A[g][h] = (sgn * qi[g][h] + p.rel_off_y) * p.rel_stride + sgn * (qj[g][h] - tq) + p.rel_off_x;
         if (need_mask)
-          qr[g][h] = region3(wy * p.wh + qi[g][h], p.H, p.wh, p.shift_y) * 3 + region3(wx * p.ww + qj[g][h], p.W, p.ww, p.shift_x);
+          qr[g][h] = region3(wy * p.wh + qi[g][h], Hp, p.wh, p.shift_y) * 3 + region3(wx * p.ww + qj[g][h], Wp, p.ww, p.shift_x);
       }
     }
     float m[2][2] = {{-1e30f, -1e30f}, {-1e30f, -1e30f}};
@@ -269,8 +275,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_kernel(const __g
       // ---- store at the un-shifted token position ----
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        int y = wy * p.wh + qi[g][h] + p.shift_y; if (y >= p.H) y -= p.H;
-        int x = wx * p.ww + qj[g][h] + p.shift_x; if (x >= p.W) x -= p.W;
+        int y = wy * p.wh + qi[g][h] + p.shift_y; if (y >= Hp) y -= Hp;
+        int x = wx * p.ww + qj[g][h] + p.shift_x; if (x >= Wp) x -= Wp;
+        if (y >= p.H || x >= p.W) continue;      // padded query position
         bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + head * HD + tq;
         const float inv = h ? inv1 : inv0;
 #pragma unroll
@@ -294,7 +301,8 @@ int launch(const FFWinAttn& p, size_t smem, cudaStream_t st) {
     }
     configured = smem;
   }
-  dim3 grid((unsigned)(p.B * (p.H / p.wh) * (p.W / p.ww) * p.heads));
+  const int Hp = p.Hp > 0 ? p.Hp : p.H, Wp = p.Wp > 0 ? p.Wp : p.W;
+  dim3 grid((unsigned)(p.B * (Hp / p.wh) * (Wp / p.ww) * p.heads));
   window_attention_kernel<KW, SGN><<<grid, NTHREADS, smem, st>>>(p);
   FF_CHECK_LAUNCH("ff_window_attention");
   return FF_OK;
@@ -314,7 +322,10 @@ extern "C" int ff_window_attention(const FFWinAttn* pp, void* stream) {
   const int NK = p.kh * p.kw;
   FF_CHECK_ARG(NK % KCHUNK == 0 && NK >= KCHUNK, "ff_window_attention: key window %dx%d not a multiple of 64 tokens", p.kh, p.kw);
   FF_CHECK_ARG(p.kw == 8 || p.kw == 16 || p.kw == 24 || p.kw == 32, "ff_window_attention: key window width %d not in {8,16,24,32}", p.kw);
-  FF_CHECK_ARG(p.H % p.wh == 0 && p.W % p.ww == 0, "ff_window_attention: image %dx%d not divisible by window %dx%d", p.H, p.W, p.wh, p.ww);
+  {
+    const int Hp = p.Hp > 0 ? p.Hp : p.H, Wp = p.Wp > 0 ? p.Wp : p.W;
+    FF_CHECK_ARG(Hp >= p.H && Wp >= p.W && Hp % p.wh == 0 && Wp % p.ww == 0, "ff_window_attention: (padded) image %dx%d not divisible by window %dx%d", Hp, Wp, p.wh, p.ww);
+  }
   FF_CHECK_ARG(p.ld % 8 == 0 && p.out_ld % 8 == 0 && p.q_off % 8 == 0 && p.k_off % 8 == 0 && p.v_off % 8 == 0 && p.out_off % 8 == 0, "ff_window_attention: offsets/pitches must be multiples of 8");
   FF_CHECK_ARG(p.heads > 0 && p.T > 0 && p.rel_stride > 0 && (p.rel_sign == 1 || p.rel_sign == -1), "ff_window_attention: bad heads/T/rel_sign");
   FF_CHECK_ARG(p.shift_y >= 0 && p.shift_y < p.wh && p.shift_x >= 0 && p.shift_x < p.ww, "ff_window_attention: bad shift");

@@ -372,7 +372,7 @@ int ff_window_attention_tc_try(const FFWinAttn& p, cudaStream_t st) {
     g_mode = (e && e[0] == '0') ? 0 : 1;
   }
   if (!g_mode) return 1;
-  const bool ok = p.wh == 16 && p.ww == 16 && p.kh == 16 && p.kw == 16 && p.kpad_y == 0 && p.kpad_x == 0 && p.rel_sign == 1 &&
+  const bool ok = (p.Hp == 0 || p.Hp == p.H) && (p.Wp == 0 || p.Wp == p.W) && p.H % 16 == 0 && p.W % 16 == 0 && p.wh == 16 && p.ww == 16 && p.kh == 16 && p.kw == 16 && p.kpad_y == 0 && p.kpad_x == 0 && p.rel_sign == 1 &&
                   p.rel_stride == 31 && p.rel_off_y == 15 && p.rel_off_x == 15 && p.T == 961 && (p.heads & 1) == 0 &&
                   (p.head_off & 1) == 0 && p.q_off % 8 == 0 && p.k_off % 8 == 0 && p.v_off % 8 == 0 && p.ld % 8 == 0 &&
                   p.out_ld % 8 == 0 && p.out_off % 8 == 0 && p.shift_y >= 0 && p.shift_y < 16 && p.shift_x >= 0 && p.shift_x < 16 &&

@@ -4,7 +4,7 @@ Host-side mirror of `DAT.forward` (reference src/models/dat/dat_arch.py:1007-102
 expert_loader.py:412-420: embed 180, 6 residual groups x 6 DATB, 6 heads, split_size [8, 32], expansion 4.
 Even blocks: adaptive spatial attention (two 3-head branches with 8x32 / 32x8 windows, shifted in the
 blocks selected by `_should_shift`), odd blocks: adaptive channel attention; every block ends in SGFN.
-Consumes the reference state_dict unchanged.  Tile sides must be multiples of 32 (no internal padding).
+Consumes the reference state_dict unchanged.  Any image size the reference accepts (reflect padding to 16, window padding to 32).
 """
 import ctypes as C_
 
@@ -123,11 +123,17 @@ class DATRunner:
         self.last_b = pack_vector(g("conv_last.bias") + torch.tensor(RGB_MEAN), 16, device=dev)
 
     def forward(self, x, out, out_off=3):
-        """x: fp32 NCHW [B,3,H,W], H and W multiples of 32.  Writes clamp(DAT(x),0,1) into channels
+        """x: fp32 NCHW [B,3,h,w].  Writes clamp(DAT(x),0,1) into channels
         out_off..out_off+2 of the fp32 expert stack `out` ([B*4H*4W][ld])  (= forward_dat, expert_loader.py:623-652)."""
-        B, _, H, W = x.shape
-        if H % 32 or W % 32:
-            raise ValueError("DATRunner needs H, W multiples of 32")
+        B, _, h0, w0 = x.shape
+        # forward_dat (expert_loader.py:623-652): reflect-pad to a multiple of 16, run, crop.  Inside, the spatial attention
+        # zero-pads the projected q / k / v to multiples of 32 (dat_arch.py:505-512) -- done by the attention kernel's padded
+        # geometry, no copy.
+        H, W = -(-h0 // 16) * 16, -(-w0 // 16) * 16
+        if H - h0 >= h0 or W - w0 >= w0:
+            raise ValueError(f"DATRunner: image {h0}x{w0} is smaller than its reflect padding (the reference's F.pad fails here too)")
+        Hp, Wp = -(-H // 32) * 32, -(-W // 32) * 32
+        padded = (Hp, Wp) if (Hp, Wp) != (H, W) else None
         M, N = B * H * W, H * W
         ws = self.ws
         lib = L.load()
@@ -152,7 +158,10 @@ class DATRunner:
         scratch = ws.get("scratch", 1, max(B * 64 * CP, B * HEADS * ((N + 511) // 512) * 1088), F32)
         wb = ws.get("chan_w", B * CP, CP, BF16)   # block-diagonal channel-attention weights (off-diagonal stays zero)
 
-        ops.nchw_to_nhwc(x, img, sub=self.mean)
+        if (H, W) == (h0, w0):
+            ops.nchw_to_nhwc(x, img, sub=self.mean)
+        else:
+            ops.nchw_to_nhwc_pad(x, img, H, W, sub=self.mean, reflect=True)
         ops.conv_direct(img, B, H, W, 3, 3, self.conv_first_w, self.conv_first_b, n_store=CP, out_f32=x0)
         ops.layernorm(x0, M, C, self.before[0], self.before[1], 1e-5, out_f32=G, out_cols=CP)
 
@@ -177,7 +186,7 @@ class DATRunner:
                     for br in range(2):
                         wh, ww = (SPLIT[0], SPLIT[1]) if br == 0 else (SPLIT[1], SPLIT[0])
                         sh = (wh // 2, ww // 2) if d["shift"] else (0, 0)
-                        ops.window_attention(qkv, B, H, W, att, bias_table=d["tables"][br], wh=wh, ww=ww, shift=sh, heads=3, head_off=3 * br)
+                        ops.window_attention(qkv, B, H, W, att, bias_table=d["tables"][br], wh=wh, ww=ww, shift=sh, heads=3, head_off=3 * br, padded=padded)
                     gap_src, mode = convx, 0
                 else:
                     L.check(lib.ff_dat_channel_attention_weights(C_.c_void_p(qkv.data_ptr()), 3 * CP, 0, CP, B, N, HEADS, C // HEADS,
@@ -186,8 +195,8 @@ class DATRunner:
                             "ff_dat_channel_attention_weights")
                     # attn @ v with per-sample block-diagonal weights; A = v (channels 384.. of qkv)
                     # the store epilogue emits the pool partials of the attention branch
-                    gpart = ws.get("gpart_att", B * (N // 32), CP, F32)
-                    pool_rows = N // 32
+                    pool_rows = (H // 8) * (W // 16) * 4          # one row of partial sums per (8x16-pixel tile, 32-row quadrant)
+                    gpart = ws.get("gpart_att", B * pool_rows, CP, F32)
                     ops.conv_gemm(qkv[:, 2 * CP:], B, H, W, CP, wb, n_store=CP, w_batch_rows=CP, out_bf16=att, x_ld=3 * CP, col_sums=gpart)
                     gap_src, mode = att, 1
                 if pool_rows:
@@ -233,5 +242,5 @@ class DATRunner:
         u2 = ws.get("u2", M * 16, 64, BF16)
         ops.conv_gemm(u1, B, 2 * H, 2 * W, 64, self.up2_w, kind=CONV_3X3, n_store=256, bias=self.up2_b, pixel_shuffle=2, out_bf16=u2)
         ops.conv_gemm(u2, B, 4 * H, 4 * W, 64, self.last_w, kind=CONV_3X3, n_store=3, bias=self.last_b, post_act=ACT_CLAMP01,
-                      out_f32=out[:, out_off:])
+                      out_f32=out[:, out_off:], out_crop=(4 * h0, 4 * w0) if (H, W) != (h0, w0) else None)
         return out

@@ -158,12 +158,15 @@ class HATRunner:
                       ln=(next_norm[0], next_norm[1], 1e-5, C, t) if next_norm is not None else None)
 
     def forward(self, x, out, out_off=0):
-        """x: fp32 NCHW [B,3,H,W] (H, W multiples of 16) on the GPU.
-        out: fp32 [B*4H*4W][ld] expert stack; channels out_off..out_off+2 receive clamp(SR, 0, 1)
-        (= ExpertEnsemble.forward_hat, expert_loader.py:592-621, for window-aligned inputs)."""
-        B, _, H, W = x.shape
-        if H % WS or W % WS:
-            raise ValueError("HATRunner needs H, W multiples of 16 (pad in the caller)")
+        """x: fp32 NCHW [B,3,h,w] (any size the reference's reflect padding accepts) on the GPU.
+        out: fp32 [B*4h*4w][ld] expert stack; channels out_off..out_off+2 receive clamp(SR, 0, 1)
+        (= ExpertEnsemble.forward_hat, expert_loader.py:592-621)."""
+        B, _, h0, w0 = x.shape
+        # ExpertEnsemble.forward_hat (expert_loader.py:592-621): reflect-pad right / bottom to a multiple of the window size,
+        # run, crop to 4h x 4w.  The pad is fused into the NCHW -> NHWC conversion, the crop into the last conv's store.
+        H, W = -(-h0 // WS) * WS, -(-w0 // WS) * WS
+        if H - h0 >= h0 or W - w0 >= w0:
+            raise ValueError(f"HATRunner: image {h0}x{w0} is smaller than its reflect padding (the reference's F.pad fails here too)")
         M = B * H * W
         ws = self.ws
         img = ws.get("img", M, 4, F32)
@@ -184,7 +187,10 @@ class HATRunner:
         scratch = ws.get("gap_scratch", 1, B * 64 * CP, F32)
         fused = ops.fused_ln_enabled()      # every LayerNorm after a residual add leaves the producing GEMM's epilogue
 
-        ops.nchw_to_nhwc(x, img, sub=self.mean)
+        if (H, W) == (h0, w0):
+            ops.nchw_to_nhwc(x, img, sub=self.mean)
+        else:
+            ops.nchw_to_nhwc_pad(x, img, H, W, sub=self.mean, reflect=True)
         ops.conv_direct(img, B, H, W, 3, 3, self.conv_first_w, self.conv_first_b, n_store=CP, out_f32=x0)
         ops.layernorm(x0, M, C, self.pe_norm[0], self.pe_norm[1], 1e-5, out_f32=G, out_cols=CP)
 
@@ -240,5 +246,5 @@ class HATRunner:
         u2 = ws.get("u2", M * 16, 64, BF16)
         ops.conv_gemm(u1, B, 2 * H, 2 * W, 64, self.up2_w, kind=CONV_3X3, n_store=256, bias=self.up2_b, pixel_shuffle=2, out_bf16=u2)
         ops.conv_gemm(u2, B, 4 * H, 4 * W, 64, self.last_w, kind=CONV_3X3, n_store=3, bias=self.last_b, post_act=ACT_CLAMP01,
-                      out_f32=out[:, out_off:])
+                      out_f32=out[:, out_off:], out_crop=(4 * h0, 4 * w0) if (H, W) != (h0, w0) else None)
         return out

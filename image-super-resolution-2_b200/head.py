@@ -186,11 +186,11 @@ class HeadRunner:
 
     # ------------------------------------------------------------------------------------------
     def forward(self, lr, stack, out=None, intermediates=None):
-        """lr: fp32 NCHW [B,3,S,S] (S multiple of 64); stack: fp32 [B*16*S*S][12] expert outputs (hat 0-2, dat 3-5, nafnet 6-8).
-        Returns fp32 NCHW [B,3,4S,4S].  `intermediates` (dict) receives band_features [P][9] and fused_before_refine [P_hr][4]."""
+        """lr: fp32 NCHW [B,3,h,w] (any size); stack: fp32 [B*16*h*w][12] expert outputs (hat 0-2, dat 3-5, nafnet 6-8).
+        Returns fp32 NCHW [B,3,4h,4w].  `intermediates` (dict) receives band_features [P][9] and fused_before_refine [P_hr][4]."""
         B, _, h, w = lr.shape
-        if h % 64 or w % 64:
-            raise ValueError("HeadRunner needs tile sides that are multiples of 64")
+        if min(h, w) < 8:
+            raise ValueError(f"HeadRunner: image {h}x{w} is smaller than the DWT's reflect padding (the reference's F.pad fails here too)")
         H, W = 4 * h, 4 * w
         P, PH = B * h * w, B * H * W
         ws, lib, st = self.ws, L.load(), ops._stream
@@ -202,7 +202,7 @@ class HeadRunner:
         ops.nchw_to_nhwc(lr, lrn)
         # ---------------- phase 2: 9 frequency bands
         bands = ws.get("bands", P, 27, F32)
-        scratch = ws.get("fscratch", 1, B * 3 * (h * (w // 2 + 1) * 4 + 4 * (h // 2 + 4) * (w // 2 + 4)), F32)
+        scratch = ws.get("fscratch", 1, B * 3 * (h * (w // 2 + 1) * 4 + 4 * ((h + 6) // 2 + 1) * ((w + 6) // 2 + 1)), F32)
         ck(lib.ff_freq_decompose(_ptr(lr), B, h, w, _ptr(self.dct_mat), _ptr(self.dct_band), _ptr(self.dct_scale), _ptr(self.dwt_lo), _ptr(self.dwt_hi),
                                  _ptr(self.dwt_scale), _ptr(self._fft_mask(h, w)), _ptr(self.fft_scale), _ptr(bands), _ptr(scratch),
                                  C_.c_size_t(scratch.numel() * 4), st()), "ff_freq_decompose")
@@ -247,9 +247,11 @@ class HeadRunner:
         ops.conv_direct(lrn, B, h, w, 3, 3, self.ms_conv[0], None, n_store=64, act=ACT_RELU, out_f32=r)
         ops.conv_direct(r, B, h, w, 64, 1, self.ms_mix[0], self.ms_bias, n_store=64, out_f32=ms)
         for i, f in ((1, 2), (2, 4)):
+            # F.interpolate(scale_factor=1/f) (fusion_network.py:594,599): output floor(size / f), source coordinates scaled by
+            # exactly f -- not by the size ratio, which differs on sizes f does not divide
             hs, wsz = h // f, w // f
             lrs = ws.get(f"lr_d{f}", B * hs * wsz, 4, F32)
-            ck(lib.ff_bilinear_f32(_ptr(lrn), B, h, w, 4, 3, _ptr(lrs), hs, wsz, 4, 0, None, st()), "ff_bilinear_f32")
+            ck(lib.ff_bilinear_f32_scaled(_ptr(lrn), B, h, w, 4, 3, _ptr(lrs), hs, wsz, 4, C_.c_float(float(f)), C_.c_float(float(f)), st()), "ff_bilinear_f32_scaled")
             rs = ws.get(f"ms_r{f}", B * hs * wsz, 64, F32)
             mx = ws.get(f"ms_m{f}", B * hs * wsz, 64, F32)
             ops.conv_direct(lrs, B, hs, wsz, 3, 3, self.ms_conv[i], None, n_store=64, act=ACT_RELU, out_f32=rs)

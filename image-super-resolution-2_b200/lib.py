@@ -33,7 +33,7 @@ class FFWinAttn(C.Structure):
         ("heads", C.c_int), ("head_off", C.c_int), ("bias_table", C.c_void_p), ("T", C.c_int),
         ("bias_heads", C.c_int), ("bias_head_off", C.c_int), ("rel_sign", C.c_int), ("rel_off_y", C.c_int),
         ("rel_off_x", C.c_int), ("rel_stride", C.c_int), ("out", C.c_void_p), ("out_ld", C.c_int),
-        ("out_off", C.c_int),
+        ("out_off", C.c_int), ("Hp", C.c_int), ("Wp", C.c_int),
     ]
 
 

@@ -50,6 +50,7 @@ def _filtered_update(base, incoming, prefixes=("module.",), replace_anywhere=Fal
 
 
 GRAPH_MAX_LR_PIXELS = 4 * 128 * 128      # forwards up to this many LR pixels run as replayed CUDA graphs (launch bound otherwise)
+MIN_SIDE = 9                             # smallest LR side the reference's padding paths accept
 GRAPH_CACHE_MAX = 8                      # captured shapes kept (least recently used dropped first)
 WORKSPACE_LIMIT_BYTES = int(float(os.environ.get("FFB200_WS_LIMIT_GB", "64")) * 2 ** 30)      # cached workspaces over all shapes
 
@@ -176,8 +177,9 @@ class FreqFusionB200:
         if lr.device != self.device:
             raise L.FFError(f"{what}: input lives on {lr.device}, the model on {self.device}")
         _, _, h, w = lr.shape
-        if h % 64 or w % 64:
-            raise L.FFError(f"{what}: tile sides must be multiples of 64 (got {h}x{w}); arbitrary sizes go through forward_image")
+        if not self.supports_whole_image(h, w):
+            raise L.FFError(f"{what}: sides must be at least {MIN_SIDE} px (got {h}x{w}): below that the reference's own reflect padding "
+                            "(pad_to_window_size, expert_loader.py:83-91) fails")
 
     @torch.no_grad()
     def forward_experts(self, lr):
@@ -215,7 +217,11 @@ class FreqFusionB200:
 
     @torch.no_grad()
     def forward(self, lr, out=None, intermediates=None):
-        """lr: fp32 NCHW [B,3,h,w] in [0,1] on the model's device, h and w multiples of 64 -> fp32 NCHW [B,3,4h,4w].
+        """lr: fp32 NCHW [B,3,h,w] in [0,1] on the model's device, ANY h x w >= 9 -> fp32 NCHW [B,3,4h,4w]: the reference's
+        whole-image forward (CompleteEnhancedFusionSR.forward, enhanced_fusion.py:694-754) with its padding paths -- reflect
+        padding to the HAT / DAT window (expert_loader.py:63-91), DAT's zero padding to 32 with run-time masks
+        (dat_arch.py:505-528), NAFNet's zero padding to 16 (nafnet_arch.py:219-225), the DCT's reflect padding to 8, DFTs of any
+        length, floor-sized pyramids.
         `intermediates` (a dict to fill) forces the eager path: the CUDA-graph replay keeps no per-stage tensors."""
         self._check_input(lr, "FreqFusionB200.forward")
         lr = lr.contiguous().float()
@@ -231,11 +237,12 @@ class FreqFusionB200:
 
     @staticmethod
     def supports_whole_image(h, w):
-        """Sizes the un-tiled path accepts (forward_image)."""
-        return h % 64 == 0 and w % 64 == 0
+        """Sizes the forward accepts: everything the reference's forward accepts.  Its first reflect padding (right / bottom, up
+        to the next multiple of 16) needs pad < size, i.e. sides of at least 9 px."""
+        return min(h, w) >= MIN_SIDE
 
     def forward_any(self, lr, out=None):
-        """Batch of equal-size LR images / tiles of any supported size."""
+        """Batch of equal-size LR images / tiles (kept for the plugin pipeline; forward() takes any supported size)."""
         return self.forward(lr, out=out)
 
     def _forward_graphed(self, lr, out):

@@ -117,16 +117,18 @@ class NAFNetRunner:
             ready = self._block(d, l["S"], l["Sb"], B, l["H"], l["W"], l["bufs"], want_bf16=(k == len(blks) - 1), t_ready=ready, next_norm=nxt)
 
     def forward(self, x, out, out_off=6):
-        """x: fp32 NCHW [B,3,h,w] with 4h, 4w multiples of 256 / 16-aligned at every UNet level (h, w multiples of 64).
-        Writes clamp(NAFNetSR(x), 0, 1) into channels out_off..out_off+2 of the fp32 expert stack."""
+        """x: fp32 NCHW [B,3,h,w], any size.  Writes clamp(NAFNetSR(x), 0, 1) into channels out_off..out_off+2 of the fp32 expert
+        stack [B*4h*4w][ld]."""
         B, _, h, w = x.shape
-        H, W = 4 * h, 4 * w
         nlev = len(self.enc)
-        if (H >> nlev) % 8 or (W >> nlev) % 16:
-            raise ValueError("NAFNetRunner: tile too small / unaligned for the 4-level UNet (need h, w multiples of 32/64)")
+        ps = 1 << nlev
+        # NAFNet.check_image_size (nafnet_arch.py:219-225): the bicubic image is zero-padded on the right / bottom to a multiple
+        # of 2^levels, the network runs on the padded image (its pooled statistics include the padding) and the result is
+        # cropped (:216).  The padding is written by the bicubic kernel, the crop is fused into the last conv's store.
+        H, W = -(-4 * h // ps) * ps, -(-4 * w // ps) * ps
         ws = self.ws
         up = ws.get("up", B * H * W, 4, F32)
-        L.check(L.load().ff_bicubic_up(C_.c_void_p(x.data_ptr()), B, 3, h, w, 4, C_.c_void_p(up.data_ptr()), 4, ops._stream()), "ff_bicubic_up")
+        L.check(L.load().ff_bicubic_up_pad(C_.c_void_p(x.data_ptr()), B, 3, h, w, 4, C_.c_void_p(up.data_ptr()), 4, H, W, ops._stream()), "ff_bicubic_up")
         # per-level buffers
         lv = []
         c, Hc, Wc = WIDTH, H, W
@@ -154,5 +156,5 @@ class NAFNetRunner:
             ops.conv_gemm(src["Sb"], B, src["H"], src["W"], src["c"], self.ups[s], n_store=2 * src["c"], pixel_shuffle=2, res=dst["S"], out_f32=dst["S"])
             self._run_blocks(self.decoders[s], dst, B)
         ops.conv_gemm(l0["Sb"], B, H, W, WIDTH, self.end_w, kind=CONV_3X3, n_store=3, bias=self.end_b, res=up, post_act=ACT_CLAMP01,
-                      out_f32=out[:, out_off:])
+                      out_f32=out[:, out_off:], out_crop=(4 * h, 4 * w) if (H, W) != (4 * h, 4 * w) else None)
         return out

@@ -117,7 +117,7 @@ def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_
 
 def window_attention(qkv, B, H, W, out, *, bias_table, wh, ww, kh=None, kw=None, kpad=(0, 0), shift=(0, 0), heads=6,
                      head_off=0, bias_head_off=0, rel_sign=1, rel_off=None, rel_stride=None, q_off=0, k_off=192,
-                     v_off=384, out_off=0):
+                     v_off=384, out_off=0, padded=None):
     _req_cuda(qkv, out, bias_table)
     kh = wh if kh is None else kh
     kw = ww if kw is None else kw
@@ -135,6 +135,8 @@ def window_attention(qkv, B, H, W, out, *, bias_table, wh, ww, kh=None, kw=None,
     p.rel_off_y, p.rel_off_x = rel_off if rel_off is not None else (wh - 1, ww - 1)
     p.rel_stride = rel_stride if rel_stride is not None else (2 * ww - 1)
     p.out = out.data_ptr(); p.out_ld = out.stride(-2); p.out_off = out_off
+    if padded is not None:
+        p.Hp, p.Wp = padded
     L.check(L.load().ff_window_attention(C.byref(p), _stream()), "ff_window_attention")
 
 
@@ -228,6 +230,13 @@ def nchw_to_nhwc(x, out, sub=None):
     _req_cuda(x, out, sub)
     B, C_, H, W = x.shape
     L.check(L.load().ff_nchw_to_nhwc(_ptr(x), B, C_, H, W, _ptr(sub), _ptr(out), out.stride(-2), _stream()), "ff_nchw_to_nhwc")
+
+
+def nchw_to_nhwc_pad(x, out, Hp, Wp, sub=None, reflect=True):
+    """NCHW image -> NHWC rows of the right / bottom padded Hp x Wp image (reflect = pad_to_window_size, else zeros)."""
+    _req_cuda(x, out, sub)
+    B, C_, H, W = x.shape
+    L.check(L.load().ff_nchw_to_nhwc_pad(_ptr(x), B, C_, H, W, _ptr(sub), _ptr(out), out.stride(-2), Hp, Wp, 1 if reflect else 0, _stream()), "ff_nchw_to_nhwc_pad")
 
 
 def nhwc_to_nchw(x, coff, C_, out):

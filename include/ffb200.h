@@ -130,6 +130,9 @@ typedef struct FFWinAttn {
   const float* bias_table; int T, bias_heads, bias_head_off;
   int rel_sign, rel_off_y, rel_off_x, rel_stride;
   void* out; int out_ld, out_off;
+  int Hp, Wp;   /* 0, or the padded extent (multiples of wh / ww, >= H / W): windows, shift and mask regions are laid on the
+                 * Hp x Wp grid and tokens beyond H x W are all-zero q / k / v rows (DAT's F.pad of the projected qkv,
+                 * dat_arch.py:505-512); their outputs are dropped (the crop of :556-557) */
 } FFWinAttn;
 int ff_window_attention(const FFWinAttn* p, void* stream);
 
@@ -196,6 +199,10 @@ int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int H, int W, 
                    const float* bias, int Cout_pad, int n_store, int act, const float* mul_f32, int mul_ld,
                    void* out_bf16, int out_ld, float* out_f32, int out_f32_ld, void* stream);
 
+/* Same as ff_nchw_to_nhwc into a right / bottom padded image [B*Hp*Wp][ld]: mode 1 = reflect padding (pad_to_window_size,
+ * expert_loader.py:63-91: F.pad(..., mode='reflect') up to the next multiple of the window size), mode 0 = zero padding. */
+int ff_nchw_to_nhwc_pad(const float* x, int B, int C, int H, int W, const float* sub, float* out, int ld, int Hp, int Wp, int mode, void* stream);
+
 /* Layout conversion at the boundary: NCHW fp32 image <-> NHWC fp32 rows (optional per-channel subtraction,
  * hat_arch.py:972-973 `(x - mean) * img_range`). */
 int ff_nchw_to_nhwc(const float* x, int B, int C, int H, int W, const float* sub, float* out, int ld, void* stream);
@@ -204,6 +211,8 @@ int ff_nhwc_to_nchw(const float* x, int ld, int coff, int B, int C, int H, int W
 /* Bicubic up-sampling (a = -0.75, align_corners=False, border-clamped taps), NCHW fp32 -> NHWC fp32:
  * F.interpolate(mode='bicubic') of nafnet/__init__.py:128-133. */
 int ff_bicubic_up(const float* x, int B, int C, int h, int w, int scale, float* out, int ld, void* stream);
+/* ... into an image zero-padded on the right / bottom to Hp x Wp (NAFNet.check_image_size, nafnet_arch.py:219-225). */
+int ff_bicubic_up_pad(const float* x, int B, int C, int h, int w, int scale, float* out, int ld, int Hp, int Wp, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DAT-specific (csrc/dat_kernels.cu)
@@ -253,6 +262,10 @@ int ff_band_fuse(const float* bands, const float* att, int att_ld, long long P, 
 /* fp32 NHWC bilinear resize, align_corners=False (F.interpolate call sites of fusion_network.py:594-603); accumulate!=0 adds into out. */
 int ff_bilinear_f32(const float* in, int B, int Hi, int Wi, int ld_in, int C, float* out, int Ho, int Wo, int ld_out, int accumulate,
                     const float* bias, void* stream);
+/* Same with the source-coordinate ratio given instead of derived from the sizes: F.interpolate(scale_factor=s) maps
+ * src = (dst + 0.5) / s - 0.5 while the output size is floor(in * s) -- the two differ on sizes s does not divide (fusion_network.py:594,599). */
+int ff_bilinear_f32_scaled(const float* in, int B, int Hi, int Wi, int ld_in, int C, float* out, int Ho, int Wo, int ld_out, float ratio_y,
+                           float ratio_x, void* stream);
 /* bf16 NHWC bilinear x2 (hierarchical_fusion.py:155-158,177-180) written into channels [0,C) of a wider row. */
 int ff_bilinear_up2_bf16(const void* in, int B, int Hi, int Wi, int ld_in, int C, void* out, int ld_out, void* stream);
 /* DynamicExpertSelector tail (fusion_network.py:221-234), in place on [P][4] = (gate0, gate1, gate2, difficulty). */

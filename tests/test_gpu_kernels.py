@@ -746,3 +746,98 @@ def test_conv_gemm_fused_layernorm(cin, n, c_real, H, W, B, kind, aux, with_bf16
         wide = torch.zeros(P, 512, device=d)
         ops.conv_gemm(_nhwc(x).to(d, BF16), B, H, W, cin, packing.pack_conv(torch.zeros(512, cin, k, k), 512, cin, device=d), kind=kind, n_store=512,
                       res=wide, out_f32=wide, ln=(torch.zeros(512, device=d), torch.zeros(512, device=d), 1e-5, 512, torch.zeros(P, 512, dtype=BF16, device=d)))
+
+
+@pytest.mark.parametrize("kind,cin,n,H,W,B", [(0, 64, 64, 13, 20, 2), (1, 64, 64, 21, 27, 1), (1, 192, 192, 9, 33, 2), (0, 128, 256, 5, 7, 3),
+                                               (1, 64, 16, 30, 44, 1), (2, 64, 128, 26, 38, 2), (0, 192, 576, 19, 50, 1)])
+@pytest.mark.parametrize("epi", ["store", "gelu", "res", "generic"])
+def test_conv_gemm_partial_edge_tiles(kind, cin, n, H, W, B, epi):
+    """Sizes that are not multiples of the 8x16 (16x8 halo) output tile: TMA zero-fills the loads and clips the stores of the
+    partial edge tiles, the direct-store epilogues mask by coordinates -- nothing may leak into neighbouring rows / samples."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(23)
+    k = {0: 1, 1: 3, 2: 2}[kind]
+    x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
+    w = (torch.randn(n, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(BF16).float()
+    bias = torch.randn(n, generator=g)
+    conv = F.conv2d(x, w, bias, stride=2) if kind == 2 else F.conv2d(x, w, bias, padding=k // 2)
+    Ho, Wo = conv.shape[-2:]
+    conv = _nhwc(conv)
+    P = B * Ho * Wo
+    d = _dev()
+    xd, wd, bd = _nhwc(x).to(d, BF16), packing.pack_conv(w, n, cin, device=d), bias.to(d)
+    guard = 64      # rows after the tensor that must stay untouched
+    if epi in ("store", "gelu"):
+        out = torch.full((P + guard, n), 9.0, dtype=BF16, device=d)
+        ops.conv_gemm(xd, B, H, W, cin, wd, kind=kind, n_store=n, bias=bd, act=ops.ACT_GELU if epi == "gelu" else ops.ACT_NONE, out_bf16=out[:P])
+        ref = F.gelu(conv) if epi == "gelu" else conv
+        torch.cuda.synchronize()
+        assert (out[:P].cpu().float() - ref).abs().max().item() < 4e-2
+        assert (out[P:] == 9.0).all()
+    elif epi == "res":
+        res = torch.randn(P, n, generator=g)
+        stream = torch.full((P + guard, n), 9.0, device=d)
+        stream[:P] = res.to(d)
+        ops.conv_gemm(xd, B, H, W, cin, wd, kind=kind, n_store=n, bias=bd, res=stream[:P], out_f32=stream[:P])
+        torch.cuda.synchronize()
+        assert (stream[:P].cpu() - (conv + res)).abs().max().item() < 4e-3
+        assert (stream[P:] == 9.0).all()
+    else:
+        mul = torch.randn(P, n, generator=g).to(BF16)
+        res = torch.randn(P, n, generator=g).to(BF16)
+        out = torch.full((P + guard, n), 9.0, device=d)
+        ops.conv_gemm(xd, B, H, W, cin, wd, kind=kind, n_store=n, bias=bd, act=ops.ACT_SIGMOID, mul=mul.to(d), res=res.to(d), post_act=ops.ACT_RELU, out_f32=out[:P])
+        torch.cuda.synchronize()
+        ref = F.relu(torch.sigmoid(conv) * mul.float() + res.float())
+        assert (out[:P].cpu() - ref).abs().max().item() < 4e-3
+        assert (out[P:] == 9.0).all()
+
+
+def test_conv_gemm_cropped_narrow_store_and_unaligned_pixel_shuffle():
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(24)
+    d = _dev()
+    # last conv of an expert run on a padded image: 3 output channels, top-left crop of the output, residual in the padded geometry
+    B, cin, H, W, Hc, Wc = 2, 64, 32, 48, 29, 41
+    x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
+    w = (torch.randn(3, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(BF16).float()
+    bias = torch.randn(3, generator=g)
+    res = torch.randn(B * H * W, 4, generator=g)
+    ref = (F.conv2d(x, w, bias, padding=1) + _nchw(res[:, :3], B, H, W)).clamp(0, 1)[:, :, :Hc, :Wc]
+    out = torch.full((B * Hc * Wc + 32, 12), 9.0, device=d)
+    ops.conv_gemm(_nhwc(x).to(d, BF16), B, H, W, cin, packing.pack_conv(w, 16, cin, device=d), kind=1, n_store=3, bias=packing.pack_vector(bias, 16, device=d),
+                  res=res.to(d), post_act=ops.ACT_CLAMP01, out_f32=out[:B * Hc * Wc, 3:], out_crop=(Hc, Wc))
+    torch.cuda.synchronize()
+    got = _nchw(out[:B * Hc * Wc, 3:6].cpu(), B, Hc, Wc)
+    assert (got - ref).abs().max().item() < 4e-3
+    assert (out[B * Hc * Wc:] == 9.0).all() and (out[:, :3] == 9.0).all() and (out[:, 6:] == 9.0).all()
+    # PixelShuffle(2) layer with a residual at a size whose rows do not fill the 8-row tiles, two samples (per-sample launches)
+    B, cin, n, H, W = 2, 128, 256, 5, 12
+    x = torch.randn(B, cin, H, W, generator=g).to(BF16).float()
+    w = (torch.randn(n, cin, 1, 1, generator=g) / math.sqrt(cin)).to(BF16).float()
+    skip = torch.randn(B * 4 * H * W, n // 4, generator=g)
+    ref = F.pixel_shuffle(F.conv2d(x, w), 2) + _nchw(skip, B, 2 * H, 2 * W)
+    rows = packing.pixel_shuffle_rows(n)
+    stream = skip.clone().to(d)
+    ops.conv_gemm(_nhwc(x).to(d, BF16), B, H, W, cin, packing.pack_matrix(w.reshape(n, cin), n, cin, row_index=rows, device=d), n_store=n, pixel_shuffle=2,
+                  res=stream, out_f32=stream)
+    torch.cuda.synchronize()
+    assert (_nchw(stream.cpu(), B, 2 * H, 2 * W) - ref).abs().max().item() < 4e-3
+
+
+@pytest.mark.parametrize("cin,cout,k,H,W,B", [(3, 64, 3, 37, 50, 2), (27, 16, 3, 19, 23, 1), (64, 64, 1, 9, 12, 1), (8, 1, 3, 148, 200, 1)])
+def test_conv_direct_any_size(cin, cout, k, H, W, B):
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(25)
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    bias = torch.randn(cout, generator=g)
+    ref = _nhwc(F.relu(F.conv2d(x, w, bias, padding=k // 2)))
+    d = _dev()
+    cp = (cout + 7) // 8 * 8
+    out = torch.full((B * H * W + 16, cp), 9.0, device=d)
+    ops.conv_direct(_nhwc(x).to(d), B, H, W, cin, k, packing.pack_conv_direct(w, cp, d), packing.pack_vector(bias, cp, device=d), n_store=cout, act=ops.ACT_RELU,
+                    out_f32=out[:B * H * W])
+    torch.cuda.synchronize()
+    assert (out[:B * H * W, :cout].cpu() - ref).abs().max().item() < 1e-4
+    assert (out[B * H * W:] == 9.0).all()
