@@ -389,6 +389,12 @@ def main():
               "computed_mpix_per_s": world * n4 * 20 * 512 * 512 / 1e6 / (ms_c4 / 1e3), "images_written": n_c4,
               "note": "unique output pixels / wall time of main() incl. PNG decode + encode (zlib level 1) on the host threads; overlap recompute is overhead, not credit"}
 
+        # the same images the way main() runs them by default: WHOLE (reference io.py:218-221), equal-size images batched
+        with contextlib.redirect_stdout(_io.StringIO()):
+            ms_c4w, n_c4w = run_plugin("c4w", lambda i: synth_image(339, 510, 7000 + i), n4, 1)
+        c4["whole_image"] = {"value": world * n4 * 1356 * 2040 / 1e6 / (ms_c4w / 1e3), "unit": "unique " + UNIT, "ms_per_image_per_gpu": ms_c4w / n4, "images_written": n_c4w,
+                             "note": "same PNGs through main() in its default order: whole-image forward (339x510 LR, HAT / DAT on 352x512, NAFNet on 1360x2048), no tile overlap to recompute"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -31,21 +31,35 @@ namespace {
 
 constexpr int NT = 256;            // tokens per window
 constexpr int ROWB = 128;          // bytes per token row in smem (2 heads x 32 dims bf16)
-constexpr int TSTRIDE = 48;        // bias table row stride in smem (31 used): lanes 0-15 / 16-31 of a warp hit disjoint banks
-constexpr int TROWS = 31;
 constexpr int NTHREADS = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float MASKV = 100.0f * 1.4426950408889634f;
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t O_COL = 64;     // O accumulator columns [64,128): S columns that are dead once P is written
 
-constexpr size_t SMEM_Q = 0, SMEM_K = NT * ROWB, SMEM_V = 2 * NT * ROWB;
-constexpr size_t SMEM_TAB = 3 * NT * ROWB;                       // 2 heads x 31 x 48 floats
-constexpr size_t SMEM_MAX = SMEM_TAB + 2 * TROWS * TSTRIDE * 4;  // [2][128] floats
-constexpr size_t SMEM_TMAX = SMEM_MAX + 2 * 128 * 4;             // [2] floats: max of each head's table (x log2 e)
-constexpr size_t SMEM_END = SMEM_TMAX + 16;
-constexpr size_t SMEM_BYTES = SMEM_END + 1024;                   // + slack for the 1024-byte alignment of the operand tiles
+// Window geometry (compile time so the key offsets of the bias reads become LDS immediates):
+//   16 x 16  HAT (S)W-MSA;  8 x 32 / 32 x 8  the two branches of DAT's spatial attention (dat_arch.py:250-253).
+// The relative-position table of one head is [2WH-1][2WW-1]; in smem its rows are TSTRIDE apart, chosen so that the 32 query
+// rows of a warp (consecutive window tokens) hit 32 different banks for a fixed key.
+template <int WH_, int WW_>
+struct Geo {
+  static constexpr int WH = WH_, WW = WW_;
+  static_assert(WH * WW == NT, "windows hold 256 tokens");
+  static constexpr int TROWS = 2 * WH - 1, TCOLS = 2 * WW - 1;
+  static constexpr int TSTRIDE = WW == 16 ? 48 : (WW == 32 ? 64 : 24);
+  static constexpr int LOG_WW = WW == 8 ? 3 : (WW == 16 ? 4 : 5);
+  static constexpr int HALF_ROWS = 128 / WW;          // key rows in one 128-key half
+  static constexpr size_t SMEM_Q = 0, SMEM_K = NT * ROWB, SMEM_V = 2 * NT * ROWB;
+  static constexpr size_t SMEM_TAB = 3 * NT * ROWB;                        // 2 heads x TROWS x TSTRIDE floats
+  static constexpr size_t SMEM_MAX = SMEM_TAB + 2 * TROWS * TSTRIDE * 4;   // [2][128] floats
+  static constexpr size_t SMEM_TMAX = SMEM_MAX + 2 * 128 * 4;              // [2] floats: max of each head's table (x log2 e)
+  static constexpr size_t SMEM_END = SMEM_TMAX + 16;
+  static constexpr size_t SMEM_BYTES = SMEM_END + 1024;                    // + slack for the 1024-byte alignment of the operand tiles
+};
 
+__device__ __forceinline__ void cp_async16z(uint32_t smem_dst, const void* gsrc, int src_bytes) {      // src_bytes = 0 zero-fills
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
@@ -90,7 +104,7 @@ __device__ __forceinline__ int region3(int p, int size, int win, int shift) {
 
 // Second softmax pass of one thread (= one query row, 128 of its keys): the first 32 raw logits are already in flight into
 // raw[0]; exponentials are packed to bf16 pairs and stored over the first half of the thread's own S columns.
-template <bool MASK>
+template <class G, bool MASK>
 __device__ __forceinline__ void softmax_pass2(uint32_t t_s, uint32_t (&raw)[2][32], float mshift, uint32_t tabp, uint32_t bad_y,
                                               uint32_t bad_x) {
 #pragma unroll
@@ -101,12 +115,13 @@ __device__ __forceinline__ void softmax_pass2(uint32_t t_s, uint32_t (&raw)[2][3
     const float2 nshift = make_float2(-mshift, -mshift);
 #pragma unroll
     for (int c = 0; c < 32; c += 2) {
-      const int kil = cb * 2 + (c >> 4), kj = c & 15;     // key row within this half, key column (pairs: packed FADD2)
+      const int kidx = cb * 32 + c;                                  // key within this 128-key half (pairs: packed FADD2)
+      const int kil = kidx >> G::LOG_WW, kj = kidx & (G::WW - 1);     // key row within the half, key column
       const float2 r2 = make_float2(__uint_as_float(raw[cb & 1][c]), __uint_as_float(raw[cb & 1][c + 1]));
-      const float2 b2 = make_float2(lds_f32(tabp - 4u * (uint32_t)(kil * TSTRIDE + kj)), lds_f32(tabp - 4u * (uint32_t)(kil * TSTRIDE + kj + 1)));
+      const float2 b2 = make_float2(lds_f32(tabp - 4u * (uint32_t)(kil * G::TSTRIDE + kj)), lds_f32(tabp - 4u * (uint32_t)(kil * G::TSTRIDE + kj + 1)));
       float2 s2 = __fadd2_rn(__fadd2_rn(r2, nshift), b2);
       if (MASK) {
-        const uint32_t eff = ((bad_y >> kil) & 1u) ? 0xFFFFu : bad_x;
+        const uint32_t eff = ((bad_y >> kil) & 1u) ? 0xFFFFFFFFu : bad_x;
         if ((eff >> kj) & 1u) s2.x -= MASKV;
         if ((eff >> (kj + 1)) & 1u) s2.y -= MASKV;
       }
@@ -131,24 +146,30 @@ __device__ unsigned long long g_attn_prof[8];
 #define PROF_FLUSH
 #endif
 
+template <class G>
 __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const __grid_constant__ FFWinAttn p) {
+  constexpr int WH = G::WH, WW = G::WW, TROWS = G::TROWS, TCOLS = G::TCOLS, TSTRIDE = G::TSTRIDE;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  float* sTab = reinterpret_cast<float*>(smem + SMEM_TAB);
-  float* sMax = reinterpret_cast<float*>(smem + SMEM_MAX);
-  float* sTabMax = reinterpret_cast<float*>(smem + SMEM_TMAX);
+  float* sTab = reinterpret_cast<float*>(smem + G::SMEM_TAB);
+  float* sMax = reinterpret_cast<float*>(smem + G::SMEM_MAX);
+  float* sTabMax = reinterpret_cast<float*>(smem + G::SMEM_TMAX);
   __shared__ float sRed[2][NTHREADS / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int npairs = p.heads >> 1;
+  const int npairs = (p.heads + 1) >> 1;
   const int pair = blockIdx.x % npairs;          // head pairs are the fast index: the CTAs sharing a window run together
   const int head0_l = pair * 2;                  // local head index (bias table row = bias_head_off + local)
   const int head0 = p.head_off + head0_l;        // absolute head (channel block)
+  const int nh = min(2, p.heads - head0_l);      // an odd head count (DAT: 3 per branch) leaves the last pair with one head
+  // Padded geometry (DAT, dat_arch.py:505-528): windows / shift / mask regions on the Hp x Wp grid, tokens beyond H x W are
+  // all-zero q / k / v rows (their V row keeps the all-ones column: as keys they still take softmax mass), never stored.
+  const int Hp = p.Hp > 0 ? p.Hp : p.H, Wp = p.Wp > 0 ? p.Wp : p.W;
   int win = blockIdx.x / npairs;
-  const int nwx = p.W >> 4, nwy = p.H >> 4;
+  const int nwx = Wp / WW, nwy = Hp / WH;
   const int b = win / (nwx * nwy);
   win -= b * nwx * nwy;
   const int wy = win / nwx, wx = win - wy * nwx;
@@ -175,30 +196,35 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
     for (int part = 0; part < 2; ++part) {
       for (int idx = tid; idx < NT * 8; idx += NTHREADS) {
         const int t = idx >> 3, c = idx & 7;
-        int y = wy * 16 + (t >> 4) + p.shift_y; if (y >= p.H) y -= p.H;
-        int x = wx * 16 + (t & 15) + p.shift_x; if (x >= p.W) x -= p.W;
-        const bf16* src = base + (img0 + (long long)y * p.W + x) * p.ld + head0 * 32 + c * 8;
+        int y = wy * WH + (t >> G::LOG_WW) + p.shift_y; if (y >= Hp) y -= Hp;
+        int x = wx * WW + (t & (WW - 1)) + p.shift_x; if (x >= Wp) x -= Wp;
+        const bool real = y < p.H && x < p.W && (c < 4 || nh == 2);      // padded token, or the absent second head of an odd pair
+        const bf16* src = real ? base + (img0 + (long long)y * p.W + x) * p.ld + head0 * 32 + c * 8 : base;
         const uint32_t dst = sbase + t * ROWB + ((c ^ (t & 7)) << 4);
         if (part == 0) {
-          cp_async16(dst + SMEM_Q, src + p.q_off);
-          cp_async16(dst + SMEM_K, src + p.k_off);
+          cp_async16z(dst + G::SMEM_Q, src + (real ? p.q_off : 0), real ? 16 : 0);
+          cp_async16z(dst + G::SMEM_K, src + (real ? p.k_off : 0), real ? 16 : 0);
+        } else if (real || (c & 3) != 3) {
+          cp_async16z(dst + G::SMEM_V, src + (real ? p.v_off : 0), real ? 16 : 0);
         } else {
-          cp_async16(dst + SMEM_V, src + p.v_off);
+          // zero V row of a padded token: dim 31 (the all-ones column that accumulates the softmax row sums) stays 1.0
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %2};" ::"r"(dst + (uint32_t)G::SMEM_V), "r"(0u), "r"(0x3F800000u) : "memory");
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    // bias tables of the two heads, x log2(e), re-laid with row stride 48
+    // bias tables of the two heads, x log2(e), re-laid with row stride TSTRIDE
     const float* tb = p.bias_table + (long long)(p.bias_head_off + head0_l) * p.T;
     float tm[2] = {-1e30f, -1e30f};
 #pragma unroll
     for (int h = 0; h < 2; ++h)
-      for (int r = tid; r < TROWS * TROWS; r += NTHREADS) {
-        const int di = r / TROWS, dj = r - di * TROWS;
-        const float v = LOG2E * __ldg(tb + h * TROWS * TROWS + r);
-        sTab[h * TROWS * TSTRIDE + di * TSTRIDE + dj] = v;
-        tm[h] = fmaxf(tm[h], v);
-      }
+      if (h < nh)
+        for (int r = tid; r < TROWS * TCOLS; r += NTHREADS) {
+          const int di = r / TCOLS, dj = r - di * TCOLS;
+          const float v = LOG2E * __ldg(tb + h * TROWS * TCOLS + r);
+          sTab[h * TROWS * TSTRIDE + di * TSTRIDE + dj] = v;
+          tm[h] = fmaxf(tm[h], v);
+        }
     tm[0] = warp_max(tm[0]);
     tm[1] = warp_max(tm[1]);
     if (lane == 0) { sRed[0][warp] = tm[0]; sRed[1][warp] = tm[1]; }
@@ -223,14 +249,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
   const uint32_t t_s = t_lane + ch * 128;        // this thread's S columns
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);    // B (= V) is MN-major
-  const uint64_t desc_q = umma_desc_k_sw128(sbase + SMEM_Q);
-  const uint64_t desc_k = umma_desc_k_sw128(sbase + SMEM_K);
-  const uint64_t desc_v = umma_desc_k_sw128(sbase + SMEM_V);   // same fields: SBO = 1024 B between 8-key groups, one 64-wide MN atom
+  const uint64_t desc_q = umma_desc_k_sw128(sbase + G::SMEM_Q);
+  const uint64_t desc_k = umma_desc_k_sw128(sbase + G::SMEM_K);
+  const uint64_t desc_v = umma_desc_k_sw128(sbase + G::SMEM_V);   // same fields: SBO = 1024 B between 8-key groups, one 64-wide MN atom
   bf16* outp = reinterpret_cast<bf16*>(p.out);
   uint32_t phase = 0;
+  const int nunits = 2 * nh;
 
 #pragma unroll 1
-  for (int unit = 0; unit < 4; ++unit) {
+  for (int unit = 0; unit < nunits; ++unit) {
     const int h = unit >> 1, r = unit & 1;
     // ---- S = Q[r] K^T ----
     if (warp == 0) {
@@ -244,17 +271,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
       __syncwarp();
     }
     const int R = r * 128 + rih;                 // query token within the window
-    const int qi = R >> 4, qj = R & 15;
-    const uint32_t tabp = sbase + (uint32_t)SMEM_TAB + 4u * (uint32_t)(h * TROWS * TSTRIDE + (qi + 15 - ch * 8) * TSTRIDE + (qj + 15));
+    const int qi = R >> G::LOG_WW, qj = R & (WW - 1);
+    const uint32_t tabp = sbase + (uint32_t)G::SMEM_TAB + 4u * (uint32_t)(h * TROWS * TSTRIDE + (qi + WH - 1 - ch * G::HALF_ROWS) * TSTRIDE + (qj + WW - 1));
     uint32_t bad_x = 0, bad_y = 0;
     if (need_mask) {
-      const int rqy = region3(wy * 16 + qi, p.H, 16, p.shift_y), rqx = region3(wx * 16 + qj, p.W, 16, p.shift_x);
+      const int rqy = region3(wy * WH + qi, Hp, WH, p.shift_y), rqx = region3(wx * WW + qj, Wp, WW, p.shift_x);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        bad_y |= (uint32_t)(region3(wy * 16 + k, p.H, 16, p.shift_y) != rqy) << k;
-        bad_x |= (uint32_t)(region3(wx * 16 + k, p.W, 16, p.shift_x) != rqx) << k;
-      }
-      bad_y >>= ch * 8;
+      for (int k = 0; k < WH; ++k) bad_y |= (uint32_t)(region3(wy * WH + k, Hp, WH, p.shift_y) != rqy) << k;
+#pragma unroll
+      for (int k = 0; k < WW; ++k) bad_x |= (uint32_t)(region3(wx * WW + k, Wp, WW, p.shift_x) != rqx) << k;
+      bad_y >>= ch * G::HALF_ROWS;
     }
     mbar_wait(&mma_bar, phase);
     phase ^= 1;
@@ -284,8 +310,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
     const float mshift = fmaxf(fmaxf(mx0, mx1), sMax[(ch ^ 1) * 128 + rih]) + sTabMax[h];
 
     // ---- pass 2: P = exp2(s + bias (+mask) - shift) as bf16 pairs over the first half of this thread's own S columns ----
-    if (need_mask) softmax_pass2<true>(t_s, raw, mshift, tabp, bad_y, bad_x);     // CTA-uniform branch
-    else softmax_pass2<false>(t_s, raw, mshift, tabp, 0u, 0u);
+    if (need_mask) softmax_pass2<G, true>(t_s, raw, mshift, tabp, bad_y, bad_x);     // CTA-uniform branch
+    else softmax_pass2<G, false>(t_s, raw, mshift, tabp, 0u, 0u);
     tc_wait_st();
     PROF(3)
     if (unit == 0) {
@@ -321,20 +347,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(os[0]) : "r"(t_lane + O_COL + h * 32 + 31) : "memory");
       tc_wait_ld();
       const float inv = 1.f / __uint_as_float(os[0]);
-      int y = wy * 16 + qi + p.shift_y; if (y >= p.H) y -= p.H;
-      int x = wx * 16 + qj + p.shift_x; if (x >= p.W) x -= p.W;
-      bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + (head0 + h) * 32 + ch * 16;
-      uint4 v0, v1;
-      v0.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-      v0.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-      v0.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-      v0.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-      v1.x = pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-      v1.y = pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-      v1.z = pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-      v1.w = pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
-      reinterpret_cast<uint4*>(dst)[0] = v0;
-      reinterpret_cast<uint4*>(dst)[1] = v1;
+      int y = wy * WH + qi + p.shift_y; if (y >= Hp) y -= Hp;
+      int x = wx * WW + qj + p.shift_x; if (x >= Wp) x -= Wp;
+      if (y < p.H && x < p.W) {      // (padded query positions are dropped)
+        bf16* dst = outp + (img0 + (long long)y * p.W + x) * p.out_ld + p.out_off + (head0 + h) * 32 + ch * 16;
+        uint4 v0, v1;
+        v0.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        v0.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        v0.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        v0.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        v1.x = pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+        v1.y = pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+        v1.z = pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+        v1.w = pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+        reinterpret_cast<uint4*>(dst)[0] = v0;
+        reinterpret_cast<uint4*>(dst)[1] = v1;
+      }
     }
     tc_fence_before();
     __syncthreads();      // O read out before the next unit's S overwrites the columns
@@ -353,16 +381,26 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
 
 int g_mode = -1;   // -1 unread, 0 off, 1 on
 
-}  // namespace
-
-#ifdef FF_ATTN_PROF
-extern "C" int ff_debug_attn_prof(unsigned long long* out, int reset) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, g_attn_prof, sizeof(unsigned long long) * 8);
-  if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_attn_prof, z, sizeof(z)); }
-  return 0;
+template <class G>
+int launch_tc_attn(const FFWinAttn& p, cudaStream_t st) {
+  static FFPerDeviceFlag configured_dev;
+  bool& configured = configured_dev.get();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      ff_set_error("ff_window_attention(tc): smem %zu: %s", (size_t)G::SMEM_BYTES, cudaGetErrorString(e));
+      return FF_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int Hp = p.Hp > 0 ? p.Hp : p.H, Wp = p.Wp > 0 ? p.Wp : p.W;
+  dim3 grid((unsigned)(p.B * (Hp / G::WH) * (Wp / G::WW) * ((p.heads + 1) / 2)));
+  window_attention_tc_kernel<G><<<grid, NTHREADS, G::SMEM_BYTES, st>>>(p);
+  FF_CHECK_LAUNCH("ff_window_attention(tc)");
+  return FF_OK;
 }
-#endif
+
+}  // namespace
 
 // Returns FF_OK when the tensor-core kernel was launched, 1 when the shape is not covered (caller falls back to the
 // mma.sync kernel of window_attention.cu), < 0 on error.
@@ -372,24 +410,25 @@ int ff_window_attention_tc_try(const FFWinAttn& p, cudaStream_t st) {
     g_mode = (e && e[0] == '0') ? 0 : 1;
   }
   if (!g_mode) return 1;
-  const bool ok = (p.Hp == 0 || p.Hp == p.H) && (p.Wp == 0 || p.Wp == p.W) && p.H % 16 == 0 && p.W % 16 == 0 && p.wh == 16 && p.ww == 16 && p.kh == 16 && p.kw == 16 && p.kpad_y == 0 && p.kpad_x == 0 && p.rel_sign == 1 &&
-                  p.rel_stride == 31 && p.rel_off_y == 15 && p.rel_off_x == 15 && p.T == 961 && (p.heads & 1) == 0 &&
-                  (p.head_off & 1) == 0 && p.q_off % 8 == 0 && p.k_off % 8 == 0 && p.v_off % 8 == 0 && p.ld % 8 == 0 &&
-                  p.out_ld % 8 == 0 && p.out_off % 8 == 0 && p.shift_y >= 0 && p.shift_y < 16 && p.shift_x >= 0 && p.shift_x < 16 &&
-                  ((uintptr_t)p.qkv & 15) == 0 && ((uintptr_t)p.out & 15) == 0;
+  const int Hp = p.Hp > 0 ? p.Hp : p.H, Wp = p.Wp > 0 ? p.Wp : p.W;
+  // self-attention windows of 256 tokens (keys = the query window) with the standard relative-position table
+  const bool shape_ok = (p.wh == 16 && p.ww == 16) || (p.wh == 8 && p.ww == 32) || (p.wh == 32 && p.ww == 8);
+  const bool ok = shape_ok && p.kh == p.wh && p.kw == p.ww && p.kpad_y == 0 && p.kpad_x == 0 && p.rel_sign == 1 && p.rel_stride == 2 * p.ww - 1 &&
+                  p.rel_off_y == p.wh - 1 && p.rel_off_x == p.ww - 1 && p.T == (2 * p.wh - 1) * (2 * p.ww - 1) && p.heads > 0 && Hp >= p.H && Wp >= p.W &&
+                  Hp % p.wh == 0 && Wp % p.ww == 0 && p.q_off % 8 == 0 && p.k_off % 8 == 0 && p.v_off % 8 == 0 && p.ld % 8 == 0 && p.out_ld % 8 == 0 &&
+                  p.out_off % 8 == 0 && p.shift_y >= 0 && p.shift_y < p.wh && p.shift_x >= 0 && p.shift_x < p.ww && ((uintptr_t)p.qkv & 15) == 0 &&
+                  ((uintptr_t)p.out & 15) == 0;
   if (!ok) return 1;
-  static FFPerDeviceFlag configured_dev;
-  bool& configured = configured_dev.get();
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e != cudaSuccess) {
-      ff_set_error("ff_window_attention(tc): smem %zu: %s", SMEM_BYTES, cudaGetErrorString(e));
-      return FF_ERR_CUDA;
-    }
-    configured = true;
-  }
-  dim3 grid((unsigned)(p.B * (p.H / 16) * (p.W / 16) * (p.heads / 2)));
-  window_attention_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
-  FF_CHECK_LAUNCH("ff_window_attention(tc)");
-  return FF_OK;
+  if (p.ww == 16) return launch_tc_attn<Geo<16, 16>>(p, st);
+  if (p.ww == 32) return launch_tc_attn<Geo<8, 32>>(p, st);
+  return launch_tc_attn<Geo<32, 8>>(p, st);
 }
+
+#ifdef FF_ATTN_PROF
+extern "C" int ff_debug_attn_prof(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_attn_prof, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_attn_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif
