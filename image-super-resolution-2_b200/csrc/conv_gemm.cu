@@ -1143,7 +1143,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             Vec4Operands ops[4];
             long long opx[4];
             float4 accv[4];
-#pragma unroll
             bool inb[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {

@@ -311,7 +311,8 @@ int launch(const FFWinAttn& p, size_t smem, cudaStream_t st) {
 }  // namespace
 
 extern long long g_ff_launches;
-int ff_window_attention_tc_try(const FFWinAttn& p, cudaStream_t st);   // window_attention_tc.cu (tcgen05 path)
+int ff_window_attention_tc_try(const FFWinAttn& p, cudaStream_t st);       // window_attention_tc.cu (tcgen05: 256-key self-attention windows)
+int ff_window_attention_oca_tc_try(const FFWinAttn& p, cudaStream_t st);   // window_attention_oca_tc.cu (tcgen05: HAT's overlapping cross-attention)
 
 extern "C" int ff_window_attention(const FFWinAttn* pp, void* stream) {
   FF_CHECK_ARG(pp != nullptr, "ff_window_attention: null params");
@@ -336,8 +337,11 @@ extern "C" int ff_window_attention(const FFWinAttn* pp, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ++g_ff_launches;
   {
-    // 16x16 (shifted-)window MSA runs on tcgen05/TMEM; other window shapes stay on the mma.sync kernel below
-    const int r = ff_window_attention_tc_try(p, st);
+    // HAT's (shifted-)window MSA and OCAB and DAT's 8x32 / 32x8 spatial attention run on tcgen05 / TMEM; the mma.sync kernel
+    // below is the fallback for any other geometry (and for FFB200_ATTN_TC=0)
+    int r = ff_window_attention_tc_try(p, st);
+    if (r <= 0) return r;
+    r = ff_window_attention_oca_tc_try(p, st);
     if (r <= 0) return r;
   }
   const bool wrap = p.rel_sign < 0;      // HAT's overlapping-window table is indexed with negative offsets
