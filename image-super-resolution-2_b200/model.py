@@ -49,7 +49,8 @@ def _filtered_update(base, incoming, prefixes=("module.",), replace_anywhere=Fal
     return n
 
 
-GRAPH_MAX_LR_PIXELS = 4 * 128 * 128      # forwards up to this many LR pixels run as replayed CUDA graphs (launch bound otherwise)
+# forwards up to this many LR pixels run as replayed CUDA graphs (launch bound otherwise)
+GRAPH_MAX_LR_PIXELS = int(os.environ.get("FFB200_GRAPH_MAX_LR_PIXELS", str(4 * 128 * 128)))
 MIN_SIDE = 9                             # smallest LR side the reference's padding paths accept
 GRAPH_CACHE_MAX = 8                      # captured shapes kept (least recently used dropped first)
 WORKSPACE_LIMIT_BYTES = int(float(os.environ.get("FFB200_WS_LIMIT_GB", "64")) * 2 ** 30)      # cached workspaces over all shapes
