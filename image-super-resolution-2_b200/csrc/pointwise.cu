@@ -210,19 +210,25 @@ __global__ void __launch_bounds__(GAPF_WARPS * 32) gap_final_kernel(const float*
                                                                    float* __restrict__ out, int out_ld) {
   __shared__ float red[GAPF_WARPS][33];
   const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5, c = blockIdx.x * 32 + lane;
-  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  // 16 independent loads in flight per warp: a whole image (one sample, thousands of partial rows) gives this kernel only
+  // C / 32 blocks, so its time is the number of dependent memory round trips per warp
+  float t[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) t[i] = 0.f;
   if (c < C) {
     const float* pb = partial + (long long)b * nsplit * C + c;
     int s = w;
-    for (; s + 3 * GAPF_WARPS < nsplit; s += 4 * GAPF_WARPS) {
-      t0 += pb[(long long)s * C];
-      t1 += pb[(long long)(s + GAPF_WARPS) * C];
-      t2 += pb[(long long)(s + 2 * GAPF_WARPS) * C];
-      t3 += pb[(long long)(s + 3 * GAPF_WARPS) * C];
+    for (; s + 15 * GAPF_WARPS < nsplit; s += 16 * GAPF_WARPS) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) t[i] += pb[(long long)(s + i * GAPF_WARPS) * C];
     }
-    for (; s < nsplit; s += GAPF_WARPS) t0 += pb[(long long)s * C];
+    for (; s < nsplit; s += GAPF_WARPS) t[0] += pb[(long long)s * C];
   }
-  red[w][lane] = (t0 + t1) + (t2 + t3);
+#pragma unroll
+  for (int st = 8; st > 0; st >>= 1)
+#pragma unroll
+    for (int i = 0; i < st; ++i) t[i] += t[i + st];
+  red[w][lane] = t[0];
   __syncthreads();
   if (w == 0 && c < out_ld) {
     float t = 0.f;
@@ -663,7 +669,7 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3x3_tma_kernel(const __g
         }
       }
       psum.x += o[0]; psum.y += o[1]; psum.z += o[2]; psum.w += o[3];
-      if (writer) {
+      if (writer && tx * DWT_TX + px < a.W && ty * DWT_TY + row < a.H) {      // (partial edge tiles: the TMA load zero-filled the rest)
         const __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
         *reinterpret_cast<uint2*>(op + (long long)row * a.W * a.out_ld) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
       }
@@ -810,12 +816,14 @@ __global__ void __launch_bounds__(DWL_THREADS, 1) dwconv_large_tma_kernel(const 
           }
         }
       }
-      bf16* op = a.out + ((long long)(b * a.H + ty * TY + oy) * a.W + tx * TX + ox) * a.out_ld + c0;
+      const int gy = ty * TY + oy, gx = tx * TX + ox;
+      bf16* op = a.out + ((long long)(b * a.H + gy) * a.W + gx) * a.out_ld + c0;
       const long long step = Cf::ALONG_X ? (long long)a.out_ld : (long long)a.W * a.out_ld;
+      const int room = Cf::ALONG_X ? (gy < a.H ? a.W - gx : 0) : (gx < a.W ? a.H - gy : 0);      // outputs of this run inside the image
 #pragma unroll
       for (int o = 0; o < R; ++o) {
         const __nv_bfloat162 h = __floats2bfloat162_rn(acc[o].x, acc[o].y);
-        *reinterpret_cast<uint32_t*>(op + o * step) = *reinterpret_cast<const uint32_t*>(&h);
+        if (o < room) *reinterpret_cast<uint32_t*>(op + o * step) = *reinterpret_cast<const uint32_t*>(&h);
       }
     }
     __syncthreads();      // everyone is done with this stage before it is refilled in the next iteration
@@ -857,7 +865,7 @@ static int launch_dw_large(const DwArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) { ff_set_error("ff_dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FF_ERR_CUDA; }
     configured = true;
   }
-  const int tiles_x = a.W / TX, tiles_y = a.H / TY, ctiles = a.C / 64;
+  const int tiles_x = ff_cdiv(a.W, TX), tiles_y = ff_cdiv(a.H, TY), ctiles = a.C / 64;      // partial edge tiles: zero-filled loads, masked stores
   const long long ntiles = (long long)a.B * tiles_x * tiles_y * ctiles;
   int grid = (int)(ntiles < ff_num_sms() ? ntiles : ff_num_sms());
   if (grid >= 8 * ctiles) grid -= grid % ctiles;      // constant channel tile per CTA: weights are loaded once
@@ -1167,11 +1175,15 @@ static int dwconv_impl(const void* x, int x_ld, int B, int H, int W, int C, int 
   FF_CHECK_ARG((kh & 1) && (kw & 1), "ff_dwconv: odd kernel sizes only");
   DwArgs a{reinterpret_cast<const bf16*>(x), x_ld, B, H, W, C, kh, kw, w, bias, act, mode, reinterpret_cast<const bf16*>(mul), mul_ld, reinterpret_cast<bf16*>(out), out_ld, col_sums};
   const long long total = (long long)B * H * W * ((mode == 1 ? C / 2 : C) / 8);
-  if (kh == 3 && kw == 3 && W % 4 == 0) {
+  static const bool tma_enabled_ = []() { const char* e = getenv("FFB200_DW_TMA"); return !(e && e[0] == '0'); }();
+  const bool tma3_ok = kh == 3 && kw == 3 && (tma_enabled_ || col_sums) && (mode == 1 ? C / 2 : C) % (mode == 1 ? 32 : 64) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!mul || (mode != 1 && (reinterpret_cast<uintptr_t>(mul) & 15) == 0 && mul_ld % 8 == 0));
+  if (kh == 3 && kw == 3 && (W % 4 == 0 || (tma3_ok && !col_sums))) {      // (the register-tiled fallback below needs W % 4 == 0; the TMA kernel takes any size)
     cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
     static const bool tma_enabled = []() { const char* e = getenv("FFB200_DW_TMA"); return !(e && e[0] == '0'); }();
     const int cout_ = mode == 1 ? C / 2 : C;
-    if ((tma_enabled || col_sums) && W % DWT_TX == 0 && H % DWT_TY == 0 && cout_ % (mode == 1 ? 32 : 64) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+    const bool tiles_ok = W % DWT_TX == 0 && H % DWT_TY == 0;      // the fused pool needs whole tiles; the plain kernel masks edge tiles
+    if ((tma_enabled || col_sums) && (tiles_ok || !col_sums) && cout_ % (mode == 1 ? 32 : 64) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!mul || (mode != 1 && (reinterpret_cast<uintptr_t>(mul) & 15) == 0 && mul_ld % 8 == 0))) {
       typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1199,7 +1211,7 @@ static int dwconv_impl(const void* x, int x_ld, int B, int H, int W, int C, int 
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { ff_set_error("ff_dwconv: cuTensorMapEncodeTiled(mul) failed with %d", (int)r); return FF_ERR_DRIVER; }
       }
-      const int tiles_x = W / DWT_TX, tiles_y = H / DWT_TY, ctiles = cout_ / (mode == 1 ? 32 : 64);
+      const int tiles_x = ff_cdiv(W, DWT_TX), tiles_y = ff_cdiv(H, DWT_TY), ctiles = cout_ / (mode == 1 ? 32 : 64);
       const long long ntiles = (long long)B * tiles_x * tiles_y * ctiles;
       int grid = (int)(ntiles < ff_num_sms() ? ntiles : ff_num_sms());
       if (grid >= 8 * ctiles) grid -= grid % ctiles;      // constant channel tile per CTA: weights are loaded once
@@ -1227,9 +1239,9 @@ static int dwconv_impl(const void* x, int x_ld, int B, int H, int W, int C, int 
     const bool plain = mode == 0 && act == FF_ACT_NONE && !mul && C % 64 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(out) & 3) == 0 && out_ld % 2 == 0;
     int rc = 1;            // > 0: no fast path for this shape
-    if (plain && kh == 5 && kw == 5 && H % 16 == 0 && W % 32 == 0) rc = launch_dw_large<5, 5, 16, 32>(a, st_);
-    else if (plain && kh == 1 && kw == 21 && H % 8 == 0 && W % 64 == 0) rc = launch_dw_large<1, 21, 8, 64>(a, st_);
-    else if (plain && kh == 21 && kw == 1 && H % 64 == 0 && W % 8 == 0) rc = launch_dw_large<21, 1, 64, 8>(a, st_);
+    if (plain && kh == 5 && kw == 5) rc = launch_dw_large<5, 5, 16, 32>(a, st_);
+    else if (plain && kh == 1 && kw == 21) rc = launch_dw_large<1, 21, 8, 64>(a, st_);
+    else if (plain && kh == 21 && kw == 1) rc = launch_dw_large<21, 1, 64, 8>(a, st_);
     if (rc < 0) return rc;
     if (rc > 0) dwconv_kernel<<<ff_cdiv(total, 256), 256, 0, st_>>>(a);
   }

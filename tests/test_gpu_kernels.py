@@ -414,7 +414,7 @@ def test_dwconv3x3_variants(B, H, W, C_):
     assert err < 2e-2 * max(1.0, ref.abs().max().item()), f"gate: {err}"
 
 
-@pytest.mark.parametrize("B,H,W,C_", [(2, 64, 64, 128), (1, 128, 64, 576), (3, 64, 128, 64)])
+@pytest.mark.parametrize("B,H,W,C_", [(2, 64, 64, 128), (1, 128, 64, 576), (3, 64, 128, 64), (1, 37, 50, 576), (2, 21, 70, 64), (1, 339, 510, 64)])
 @pytest.mark.parametrize("kh,kw", [(5, 5), (1, 21), (21, 1)])
 def test_dwconv_large_kernel(B, H, W, C_, kh, kw):
     """The fusion head's large-kernel-attention depthwise chain (5x5, 1x21, 21x1; reference
