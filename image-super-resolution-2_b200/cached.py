@@ -87,7 +87,11 @@ def run_cached(model, store, batch_size=8, crop=4):
         lr = torch.stack([r["lr"] for r in recs]).float().to(dev)
         hr = torch.stack([r["hr"] for r in recs]).float().to(dev)
         ex = {k: torch.stack([r["expert_imgs"][k] for r in recs]).float().to(dev) for k in ("hat", "dat", "nafnet")}
-        sr = model.forward_with_precomputed(lr, ex)
+        feats = None
+        if all("expert_feats" in r and all(k in r["expert_feats"] for k in ("hat", "dat", "nafnet")) for r in recs):
+            # cached features present (load_features=True): the collaborative branch runs, as in the reference's cached mode
+            feats = {k: torch.stack([r["expert_feats"][k] for r in recs]).float().to(dev) for k in ("hat", "dat", "nafnet")}
+        sr = model.forward_with_precomputed(lr, ex, feats)
         psnr, ssim = ops.psnr_y(sr, hr, crop).cpu(), ops.ssim_y(sr, hr, crop).cpu()
         for i, r in enumerate(recs):
             out.append({"filename": r["filename"], "sr": sr[i].clone(), "psnr_y": psnr[i].item(), "ssim_y": ssim[i].item()})

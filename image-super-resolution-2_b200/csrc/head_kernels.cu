@@ -51,15 +51,18 @@ __global__ void __launch_bounds__(256) cb_embed_ln_kernel(const float* __restric
 
 // 9-token multi-head attention per pixel (nn.MultiheadAttention core, 4 heads x 16; q pre-scaled by 1/4 in the packed in_proj).
 // qkv: bf16 [tokens][192] (q | k | v); one thread per (token, head).
+// DIM = embedding width (64: cross-band attention, 4 heads; 128: the collaborative branch's cross-expert attention, 8 heads).
+template <int DIM>
 __global__ void __launch_bounds__(256) cb_attn_kernel(const bf16* __restrict__ qkv, long long tokens, int nb, bf16* __restrict__ out) {
+  constexpr int NH = DIM / 16;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= tokens * 4) return;
-  const int h = (int)(idx & 3);
-  const long long tok = idx >> 2;
+  if (idx >= tokens * NH) return;
+  const int h = (int)(idx % NH);
+  const long long tok = idx / NH;
   const long long pix = tok / nb;
   float q[16];
   {
-    const uint4* p = reinterpret_cast<const uint4*>(qkv + tok * 192 + h * 16);
+    const uint4* p = reinterpret_cast<const uint4*>(qkv + tok * (3 * DIM) + h * 16);
     const uint4 a = p[0], b = p[1];
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(256) cb_attn_kernel(const bf16* __restrict__ q
   float s[9];
   float m = -1e30f;
   for (int j = 0; j < nb; ++j) {
-    const uint4* p = reinterpret_cast<const uint4*>(qkv + (pix * nb + j) * 192 + 64 + h * 16);
+    const uint4* p = reinterpret_cast<const uint4*>(qkv + (pix * nb + j) * (3 * DIM) + DIM + h * 16);
     const uint4 a = p[0], b = p[1];
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     float d = 0.f;
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(256) cb_attn_kernel(const bf16* __restrict__ q
 #pragma unroll
   for (int i = 0; i < 16; ++i) o[i] = 0.f;
   for (int j = 0; j < nb; ++j) {
-    const uint4* p = reinterpret_cast<const uint4*>(qkv + (pix * nb + j) * 192 + 128 + h * 16);
+    const uint4* p = reinterpret_cast<const uint4*>(qkv + (pix * nb + j) * (3 * DIM) + 2 * DIM + h * 16);
     const uint4 a = p[0], b = p[1];
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     const float pj = s[j] * inv;
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(256) cb_attn_kernel(const bf16* __restrict__ q
   uint32_t w[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { __nv_bfloat162 hh = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&hh); }
-  uint4* dst = reinterpret_cast<uint4*>(out + tok * 64 + h * 16);
+  uint4* dst = reinterpret_cast<uint4*>(out + tok * DIM + h * 16);
   dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
   dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
@@ -488,8 +491,92 @@ extern "C" int ff_cb_embed_ln(const float* bands, long long tokens, const float*
 }
 extern "C" int ff_cb_attention(const void* qkv, long long tokens, int num_bands, void* out, void* stream) {
   FF_CHECK_ARG(qkv && out && num_bands > 0 && num_bands <= 9 && tokens % num_bands == 0, "ff_cb_attention: bad args");
-  cb_attn_kernel<<<ff_cdiv(tokens * 4, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(qkv), tokens, num_bands, reinterpret_cast<bf16*>(out));
+  cb_attn_kernel<64><<<ff_cdiv(tokens * 4, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(qkv), tokens, num_bands, reinterpret_cast<bf16*>(out));
   ++g_ff_launches; FF_CHECK_LAUNCH("ff_cb_attention"); return FF_OK;
+}
+extern "C" int ff_token_attention(const void* qkv, long long tokens, int group, int dim, void* out, void* stream) {
+  FF_CHECK_ARG(qkv && out && group > 0 && group <= 9 && tokens % group == 0 && (dim == 64 || dim == 128), "ff_token_attention: bad args");
+  if (dim == 64) cb_attn_kernel<64><<<ff_cdiv(tokens * 4, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(qkv), tokens, group, reinterpret_cast<bf16*>(out));
+  else cb_attn_kernel<128><<<ff_cdiv(tokens * 8, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const bf16*>(qkv), tokens, group, reinterpret_cast<bf16*>(out));
+  ++g_ff_launches; FF_CHECK_LAUNCH("ff_token_attention"); return FF_OK;
+}
+
+// ---- collaborative branch helpers (large_kernel_attention.py:327-419) ----
+namespace {
+// NCHW fp32 features -> NHWC bf16 rows [B*H*W][ld], columns >= C zero (GEMM operand of the align convs, :341-356)
+__global__ void __launch_bounds__(256) nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, int B, int C, long long hw, bf16* __restrict__ out, int ld) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int groups = ld >> 3;
+  if (idx >= (long long)B * hw * groups) return;
+  const int g = (int)(idx % groups);
+  const long long pix = idx / groups;
+  const int b = (int)(pix / hw);
+  const long long p = pix - (long long)b * hw;
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = g * 8 + 2 * i;
+    const float v0 = c < C ? x[((long long)b * C + c) * hw + p] : 0.f, v1 = c + 1 < C ? x[((long long)b * C + c + 1) * hw + p] : 0.f;
+    w[i] = pack_bf16(v0, v1);
+  }
+  *reinterpret_cast<uint4*>(out + pix * ld + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+// partial[b][blk][c] = sum over the HR pixels of block blk of GELU(bilinear_up_s(g)[pixel][c]):  the AdaptiveAvgPool2d(1) of
+// GELU(conv1x1(upsample(feat))) in a modulation head (:407-411) -- the 1x1 conv commutes with the bilinear up-sampling, so g is
+// the conv output at LR resolution and the up-sampled tensor never exists.  lane = channel (C <= 32), warps stride over pixels.
+__global__ void __launch_bounds__(256) up_gelu_pool_kernel(const float* __restrict__ g, int ld, int h, int w, int C, int s, int nblk, float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  const int b = blockIdx.y, blk = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int H = h * s, W = w * s;
+  const long long total = (long long)H * W, per = (total + nblk - 1) / nblk;
+  const long long p0 = blk * per, p1 = min(total, p0 + per);
+  const float ratio = 1.0f / s;
+  const float* gb = g + (long long)b * h * w * ld;
+  float acc = 0.f;
+  if (lane < C)
+    for (long long p = p0 + warp; p < p1; p += 8) {
+      const int X = (int)(p % W), Y = (int)(p / W);
+      const Bilin by = bilin(Y, ratio, h), bx = bilin(X, ratio, w);
+      const float v00 = gb[((long long)by.i0 * w + bx.i0) * ld + lane], v01 = gb[((long long)by.i0 * w + bx.i1) * ld + lane];
+      const float v10 = gb[((long long)by.i1 * w + bx.i0) * ld + lane], v11 = gb[((long long)by.i1 * w + bx.i1) * ld + lane];
+      acc += gelu_erf((1.f - by.l) * ((1.f - bx.l) * v00 + bx.l * v01) + by.l * ((1.f - bx.l) * v10 + bx.l * v11));
+    }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && lane < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][lane];
+    partial[((long long)b * nblk + blk) * C + lane] = t;
+  }
+}
+// x[p][c_off + c] = clamp(x * f[b][c], 0, 1): the soft modulation of an expert's SR output (:414-415) on the fp32 expert stack
+__global__ void __launch_bounds__(256) scale_clamp_channels_kernel(float* __restrict__ x, int ld, long long per_b, int B, int c_off, int C, const float* __restrict__ m, int m_ld,
+                                                                  float f0, float f1) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= per_b * B) return;
+  const int b = (int)(idx / per_b);
+  for (int c = 0; c < C; ++c) {
+    float* q = x + idx * ld + c_off + c;
+    *q = fminf(fmaxf(*q * (f0 + f1 * m[(long long)b * m_ld + c]), 0.f), 1.f);
+  }
+}
+}  // namespace
+extern "C" int ff_nchw_to_nhwc_bf16(const float* x, int B, int C, int H, int W, void* out, int ld, void* stream) {
+  FF_CHECK_ARG(x && out && ld >= C && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "ff_nchw_to_nhwc_bf16: bad args");
+  nchw_to_nhwc_bf16_kernel<<<ff_cdiv((long long)B * H * W * (ld / 8), 256), 256, 0, ST(stream)>>>(x, B, C, (long long)H * W, reinterpret_cast<bf16*>(out), ld);
+  ++g_ff_launches; FF_CHECK_LAUNCH("ff_nchw_to_nhwc_bf16"); return FF_OK;
+}
+extern "C" int ff_up_gelu_pool(const float* g, int ld, int B, int h, int w, int C, int scale, int nblk, float* partial, void* stream) {
+  FF_CHECK_ARG(g && partial && C > 0 && C <= 32 && ld >= C && scale >= 1 && nblk > 0 && B > 0 && B <= 65535, "ff_up_gelu_pool: bad args");
+  up_gelu_pool_kernel<<<dim3(nblk, B), 256, 0, ST(stream)>>>(g, ld, h, w, C, scale, nblk, partial);
+  ++g_ff_launches; FF_CHECK_LAUNCH("ff_up_gelu_pool"); return FF_OK;
+}
+extern "C" int ff_scale_clamp_channels(float* x, int ld, int B, long long pixels_per_sample, int c_off, int C, const float* m, int m_ld, float f0, float f1,
+                                       void* stream) {
+  FF_CHECK_ARG(x && m && C > 0 && c_off >= 0 && ld >= c_off + C && m_ld >= C, "ff_scale_clamp_channels: bad args");
+  scale_clamp_channels_kernel<<<ff_cdiv(pixels_per_sample * B, 256), 256, 0, ST(stream)>>>(x, ld, pixels_per_sample, B, c_off, C, m, m_ld, f0, f1);
+  ++g_ff_launches; FF_CHECK_LAUNCH("ff_scale_clamp_channels"); return FF_OK;
 }
 extern "C" int ff_affine_rows(const void* x, long long rows, int C, const float* a, const float* b, void* y, void* stream) {
   FF_CHECK_ARG(x && a && b && y && C % 8 == 0, "ff_affine_rows: bad args");

@@ -176,6 +176,108 @@ class HeadRunner:
         self.egate2 = (pack_conv_direct(g(p + "edge_gate.2.weight"), 8, dev), pack_vector(g(p + "edge_gate.2.bias"), 8, device=dev))
         self.edge_strength = float(g(p + "edge_strength"))
 
+    # ------------------------------------------------------------------------------------------
+    def _pack_collaborative(self):
+        """Weights of `collaborative.*` (EnhancedCollaborativeWithLKA, large_kernel_attention.py:251-325); packed on first use --
+        the branch only runs when expert features are passed to forward_with_precomputed."""
+        if getattr(self, "_collab", None) is not None:
+            return self._collab
+        g, dev = self._g, self.device
+        d = lambda t: t.to(dev).contiguous()
+        p = "collaborative."
+        c = {}
+        c["align"] = [(pack_matrix(g(p + f"align_layers.{n}.weight").reshape(128, cin), 128, cp, device=dev), d(g(p + f"align_layers.{n}.bias")), cin, cp)
+                      for n, cin, cp in (("hat", 180, 192), ("dat", 180, 192), ("nafnet", 64, 64))]
+        c["ln1"] = (d(g(p + "norm1.weight")), d(g(p + "norm1.bias")))
+        c["ln2"] = (d(g(p + "norm2.weight")), d(g(p + "norm2.bias")))
+        wi, bi = g(p + "cross_attn.in_proj_weight").clone(), g(p + "cross_attn.in_proj_bias").clone()
+        wi[:128] *= 0.25      # head_dim 16 ** -0.5, applied to q by nn.MultiheadAttention
+        bi[:128] *= 0.25
+        c["in"] = (pack_matrix(wi, 384, 128, device=dev), d(bi))
+        c["out"] = (pack_matrix(g(p + "cross_attn.out_proj.weight"), 128, 128, device=dev), d(g(p + "cross_attn.out_proj.bias")))
+        c["f0"] = (pack_matrix(g(p + "ffn.0.weight"), 256, 128, device=dev), d(g(p + "ffn.0.bias")))
+        c["f2"] = (pack_matrix(g(p + "ffn.2.weight"), 128, 256, device=dev), d(g(p + "ffn.2.bias")))
+        q = p + "lka_global."
+        a1, b1 = _bn_affine(g, q + "norm1.")
+        c["n1"] = (d(a1), d(b1))
+        tile3 = lambda w: pack_dw(w.repeat(3, 1, 1, 1), 128 * 3, device=dev)
+        c["dw5"], c["dwh"], c["dwv"] = tile3(g(q + "lka.local_conv.weight")), tile3(g(q + "lka.h_conv.weight")), tile3(g(q + "lka.v_conv.weight"))
+        ab, bb = _bn_affine(g, q + "lka.bn.")
+        c["pw"] = (pack_matrix(g(q + "lka.pw_conv.weight").reshape(128, 128) * ab[:, None], 128, 128, device=dev), d(bb))
+        c["s1"], c["s2"] = float(g(q + "scale1")), float(g(q + "scale2"))
+        a2, b2 = _bn_affine(g, q + "norm2.")
+        w0 = g(q + "ffn.0.weight").reshape(256, 128)
+        c["lf0"] = (pack_matrix(w0 * a2[None, :], 256, 128, device=dev), d(g(q + "ffn.0.bias") + w0 @ b2))
+        c["lf2"] = (pack_matrix(g(q + "ffn.2.weight").reshape(128, 256), 128, 256, device=dev), d(g(q + "ffn.2.bias")))
+        c["mod"] = [(pack_matrix(g(p + f"modulation.{i}.0.weight").reshape(32, 128), 32, 128, device=dev), d(g(p + f"modulation.{i}.0.bias")),
+                     d(g(p + f"modulation.{i}.3.weight").reshape(3, 32)), d(g(p + f"modulation.{i}.3.bias"))) for i in range(3)]
+        self._collab = c
+        return c
+
+    def collaborative(self, feats, stack, B, h, w, intermediates=None):
+        """EnhancedCollaborativeWithLKA.forward (large_kernel_attention.py:327-419) on expert features of the LR size:
+        feats = {'hat': [B,180,h,w], 'dat': [B,180,h,w], 'nafnet': [B,64,h,w]} fp32 NCHW on the device.  Modulates channels 0-8 of the
+        expert stack in place: out_e <- clamp(out_e * (1 + 0.2 (mod_e - 0.5)), 0, 1) with mod_e [B,3] from the e-th modulation head."""
+        c = self._pack_collaborative()
+        ws, lib, st, ck = self.ws, L.load(), ops._stream, L.check
+        P = B * h * w
+        T = 3 * P
+        stk = ws.get("co_stk", P, 384, BF16)
+        for e, name in enumerate(("hat", "dat", "nafnet")):
+            wgt, bias, cin, cp = c["align"][e]
+            f = feats[name]
+            if tuple(f.shape) != (B, cin, h, w) or not f.is_cuda:
+                raise L.FFError(f"expert_features['{name}'] must be a CUDA tensor of shape {(B, cin, h, w)} (features at the LR size), got {tuple(f.shape)}")
+            fb = ws.get(f"co_f{e}", P, cp, BF16)
+            ck(lib.ff_nchw_to_nhwc_bf16(_ptr(f.contiguous().float()), B, cin, h, w, _ptr(fb), cp, st()), "ff_nchw_to_nhwc_bf16")
+            ops.conv_gemm(fb, B, h, w, cp, wgt, n_store=128, bias=bias, out_bf16=stk[:, 128 * e:])
+        Wt = 3 * w
+        stk_t = stk.view(T, 128)
+        nrm = ws.get("co_nrm", T, 128, BF16)
+        qkv = ws.get("co_qkv", T, 384, BF16)
+        att = ws.get("co_att", T, 128, BF16)
+        A = ws.get("co_A", T, 128, BF16)
+        A2 = ws.get("co_A2", T, 128, BF16)
+        hid = ws.get("co_hid", T, 256, BF16)
+        n1 = ws.get("co_n1", T, 128, BF16)
+        d1 = ws.get("co_d1", T, 128, BF16)
+        d2 = ws.get("co_d2", T, 128, BF16)
+        ops.layernorm(stk_t, T, 128, c["ln1"][0], c["ln1"][1], 1e-5, out_bf16=nrm, out_cols=128)
+        ops.conv_gemm(nrm, B, h, Wt, 128, c["in"][0], n_store=384, bias=c["in"][1], out_bf16=qkv)
+        ck(lib.ff_token_attention(_ptr(qkv), C_.c_longlong(T), 3, 128, _ptr(att), st()), "ff_token_attention")
+        ops.conv_gemm(att, B, h, Wt, 128, c["out"][0], n_store=128, bias=c["out"][1], res=stk_t, out_bf16=A)
+        ops.layernorm(A, T, 128, c["ln2"][0], c["ln2"][1], 1e-5, out_bf16=nrm, out_cols=128)
+        ops.conv_gemm(nrm, B, h, Wt, 128, c["f0"][0], n_store=256, bias=c["f0"][1], act=ACT_GELU, out_bf16=hid)
+        ops.conv_gemm(hid, B, h, Wt, 256, c["f2"][0], n_store=128, bias=c["f2"][1], res=A, out_bf16=A2)
+        # shared LKA block on the [B, h, w, 3*128] view (weights tiled over the three experts)
+        ck(lib.ff_affine_rows(_ptr(A2), C_.c_longlong(T), 128, _ptr(c["n1"][0]), _ptr(c["n1"][1]), _ptr(n1), st()), "ff_affine_rows")
+        CB = 384
+        ops.dwconv(n1, B, h, w, CB, 5, 5, c["dw5"], None, d1.view(P, CB), x_ld=CB)
+        ops.dwconv(d1, B, h, w, CB, 1, 21, c["dwh"], None, d2.view(P, CB), x_ld=CB)
+        ops.dwconv(d2, B, h, w, CB, 21, 1, c["dwv"], None, d1.view(P, CB), x_ld=CB)
+        ops.conv_gemm(d1, B, h, Wt, 128, c["pw"][0], n_store=128, bias=c["pw"][1], act=ACT_SIGMOID, alpha=c["s1"], mul=n1, res=A2, out_bf16=d2)
+        ops.conv_gemm(d2, B, h, Wt, 128, c["lf0"][0], n_store=256, bias=c["lf0"][1], act=ACT_GELU, out_bf16=hid)
+        ops.conv_gemm(hid, B, h, Wt, 128 * 2, c["lf2"][0], n_store=128, bias=c["lf2"][1], alpha=c["s2"], res=d2, out_bf16=A)
+        # per-expert modulation heads: 1x1 conv at LR (it commutes with the bilinear x4), GELU + global mean at HR, 1x1 + sigmoid
+        A3 = A.view(P, 384)
+        gbuf = ws.get("co_g", P, 32, F32)
+        NBLK = 64
+        part = ws.get("co_part", B * NBLK, 32, F32)
+        pooled = ws.get("co_pool", B, 32, F32)
+        mods = ws.get("co_mod", B, 12, F32)
+        for e in range(3):
+            w0, b0, w3, b3 = c["mod"][e]
+            ops.conv_gemm(A3[:, 128 * e:], B, h, w, 128, w0, n_store=32, bias=b0, out_f32=gbuf)
+            ck(lib.ff_up_gelu_pool(_ptr(gbuf), 32, B, h, w, 32, 4, NBLK, _ptr(part), st()), "ff_up_gelu_pool")
+            ops.gap_finalize(part, B, NBLK, 32, 1.0 / (16 * h * w), pooled)
+            me = mods[:, 4 * e:]
+            ops.vec_linear(pooled, B, 32, w3, b3, 3, ACT_SIGMOID, me, y_cols=3)
+            ck(lib.ff_scale_clamp_channels(_ptr(stack), stack.stride(0), B, C_.c_longlong(16 * h * w), 3 * e, 3, _ptr(me), mods.stride(0), C_.c_float(0.9), C_.c_float(0.2), st()),
+               "ff_scale_clamp_channels")
+        if intermediates is not None:
+            intermediates["modulation"] = mods.view(B, 3, 4)[:, :, :3].clone()
+        return stack
+
     def _fft_mask(self, H, W):
         key = (H, W)
         if key not in self._fft_masks:

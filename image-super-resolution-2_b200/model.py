@@ -282,11 +282,14 @@ class FreqFusionB200:
         return out
 
     @torch.no_grad()
-    def forward_with_precomputed(self, lr, expert_outputs, out=None, intermediates=None):
+    def forward_with_precomputed(self, lr, expert_outputs, expert_features=None, out=None, intermediates=None):
         """Fusion head only, on pre-computed expert SR outputs (reference CompleteEnhancedFusionSR.forward_with_precomputed,
         src/models/enhanced_fusion.py:756-812, eval path; BASELINE.json configs[0]).
         expert_outputs: dict with keys 'hat', 'dat', 'nafnet' (the cached-dataset aliases 'drct' -> hat and 'grl' / 'mambair' -> dat
-        of src/data/cached_dataset.py are accepted), each fp32 NCHW [B,3,4h,4w] on the device."""
+        of src/data/cached_dataset.py are accepted), each fp32 NCHW [B,3,4h,4w] on the device.
+        expert_features: optional dict of the experts' intermediate features at the LR size ({'hat': [B,180,h,w], 'dat': [B,180,h,w],
+        'nafnet': [B,64,h,w]}); when given, the collaborative branch (EnhancedCollaborativeWithLKA) modulates the expert outputs first,
+        exactly as the reference does in cached mode."""
         alias = {"drct": "hat", "grl": "dat", "mambair": "dat"}
         ex = {alias.get(k, k): v for k, v in expert_outputs.items()}
         missing = [k for k in ("hat", "dat", "nafnet") if k not in ex]
@@ -304,6 +307,14 @@ class FreqFusionB200:
                     raise L.FFError(f"forward_with_precomputed: expert output '{k}' must be a CUDA tensor of shape {(B, 3, 4 * h, 4 * w)}")
                 # NCHW -> channels 3i..3i+2 of the NHWC expert stack (layout plumbing; no arithmetic)
                 stack.view(B, 4 * h, 4 * w, 12)[..., 3 * i:3 * i + 3].copy_(t.float().permute(0, 2, 3, 1))
+            if expert_features is not None:
+                # phase 4 of the reference: collaborative feature learning runs whenever features are passed
+                # (apply_collaborative_learning, enhanced_fusion.py:466-496; MODEL_CONFIG enables it)
+                fe = {alias.get(k, k): v for k, v in expert_features.items()}
+                miss = [k for k in ("hat", "dat", "nafnet") if k not in fe]
+                if miss:
+                    raise KeyError(f"forward_with_precomputed: missing expert features {miss}")
+                self._runners["head"].collaborative(fe, stack, B, h, w, intermediates=intermediates)
             return self._runners["head"].forward(lr, stack, out=out, intermediates=intermediates)
 
     def expert_outputs_nchw(self, lr):

@@ -253,6 +253,19 @@ int ff_cb_embed_ln(const float* bands, long long tokens, const float* proj_w, co
                    void* stacked, void* normed, void* stream);
 /* Core of nn.MultiheadAttention over the num_bands tokens of each pixel (4 heads x 16, :228): qkv bf16 [tokens][192] -> bf16 [tokens][64]. */
 int ff_cb_attention(const void* qkv, long long tokens, int num_bands, void* out, void* stream);
+/* Same core for `group` tokens of width dim = 64 (4 heads) or 128 (8 heads): qkv bf16 [tokens][3*dim], out bf16 [tokens][dim].  dim 128 /
+ * group 3 is the cross-expert attention of the collaborative branch (large_kernel_attention.py:375-381). */
+int ff_token_attention(const void* qkv, long long tokens, int group, int dim, void* out, void* stream);
+/* Collaborative branch of forward_with_precomputed(..., expert_features) (large_kernel_attention.py:327-419):
+ *  - NCHW fp32 expert features -> NHWC bf16 GEMM operand rows [B*H*W][ld], columns >= C zero (:341-356);
+ *  - partial[b][blk][c] = sum over HR pixels of GELU(bilinear_up_scale(g)[.][c]), g fp32 [B*h*w][ld] = the modulation head's first 1x1
+ *    conv at LR resolution (it commutes with the up-sampling); ff_gap_finalize(partial, B, nblk, C, 1/(HR pixels)) ends the
+ *    AdaptiveAvgPool2d(1) of :407-411;
+ *  - x[p][c_off + c] = clamp(x * (f0 + f1 * m[b][c]), 0, 1) on fp32 rows: out * (1 + 0.2 (mod - 0.5)), clamped (:414-415). */
+int ff_nchw_to_nhwc_bf16(const float* x, int B, int C, int H, int W, void* out, int ld, void* stream);
+int ff_up_gelu_pool(const float* g, int ld, int B, int h, int w, int C, int scale, int nblk, float* partial, void* stream);
+int ff_scale_clamp_channels(float* x, int ld, int B, long long pixels_per_sample, int c_off, int C, const float* m, int m_ld, float f0, float f1,
+                            void* stream);
 /* y = x * a[c] + b[c] on bf16 rows (eval-mode BatchNorm that cannot be folded through a zero-padded depthwise conv, :145). */
 int ff_affine_rows(const void* x, long long rows, int C, const float* a, const float* b, void* y, void* stream);
 /* AdaptiveBandFusionModule 9->3 (multi_domain_frequency.py:478-526) fused with the frequency guidance of

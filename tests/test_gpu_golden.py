@@ -80,3 +80,59 @@ def test_cached_expert_files_through_the_head(tmp_path):
         ref_ssim = metrics.ssim_y(sr, hr[None])[0]
         print(f"cached: psnr_y {r['psnr_y']:.4f} dB, ssim_y {r['ssim_y']:.7f} (oracle {ref_ssim:.7f})")
         assert abs(r["ssim_y"] - ref_ssim) < 2e-5      # smooth image: small variances in the denominator amplify fp32 summation-order noise
+
+
+def _collab_inputs(g):
+    from oracle import collab
+    lr = g["lr"]
+    gen = torch.Generator().manual_seed(g["expert_seed"])
+    up = F.interpolate(lr, scale_factor=4, mode="bicubic", align_corners=False)
+    ex = {k: (up + s * torch.randn(1, 3, 256, 256, generator=gen)).clamp(0, 1) for k, s in (("hat", 0.01), ("dat", 0.02), ("nafnet", 0.03))}
+    return lr, ex, collab.synth_features(1, 64, 64, g["feature_seed"])
+
+
+def test_forward_with_precomputed_and_expert_features_vs_reference_golden():
+    """The reference's cached-mode path WITH expert features: forward_with_precomputed(lr, outputs, features) runs
+    EnhancedCollaborativeWithLKA (align 1x1 convs -> 3-token cross-expert attention -> FFN -> shared LKA block -> per-expert
+    modulation heads) before the fusion head (enhanced_fusion.py:466-496, large_kernel_attention.py:251-419).  Golden output of
+    the reference itself: tests/golden/head_collab_64.pt (oracle/make_golden_collab.py)."""
+    from isr2_b200 import model as M
+    g = torch.load(os.path.join(GOLD, "head_collab_64.pt"))
+    lr, ex, feats = _collab_inputs(g)
+    m = M.FreqFusionB200("cuda:0", init_seed=0, verbose=False)
+    out = m.forward_with_precomputed(lr.cuda(), {k: v.cuda() for k, v in ex.items()}, {k: v.cuda() for k, v in feats.items()}).cpu()
+    stack = m._stack(1, 64, 64).cpu().view(1, 256, 256, 12)[..., :9].permute(0, 3, 1, 2)
+    e_enh = (stack - g["enhanced"].float()).abs().max().item()
+    e_out = (out - g["out"]).abs().max().item()
+    print(f"collaborative: enhanced expert outputs {e_enh:.2e}, final output {e_out:.2e}")
+    assert e_enh < 2e-3 and e_out < 2e-2
+    with pytest.raises(KeyError):
+        m.forward_with_precomputed(lr.cuda(), {k: v.cuda() for k, v in ex.items()}, {"hat": feats["hat"].cuda()})
+
+
+def test_collaborative_modulation_vs_oracle_with_strong_heads():
+    """Same branch against the oracle with the modulation heads' last layer scaled up (the benign factory leaves every modulation
+    within 1 % of 1.0, too little to tell a wrong attention / LKA / pooling from a right one): the per-expert, per-channel
+    modulation values themselves must agree."""
+    from isr2_b200 import model as M
+    from oracle import collab
+    g = torch.load(os.path.join(GOLD, "head_collab_64.pt"))
+    lr, ex, feats = _collab_inputs(g)
+    m = M.FreqFusionB200("cuda:0", init_seed=0, verbose=False)
+    for i in range(3):
+        m.state["fusion"][f"collaborative.modulation.{i}.3.weight"] = m.state["fusion"][f"collaborative.modulation.{i}.3.weight"] * 6
+        m.state["fusion"][f"collaborative.modulation.{i}.0.weight"] = m.state["fusion"][f"collaborative.modulation.{i}.0.weight"] * 3
+    m._runners = None
+    sd = m.state["fusion"]
+    exl = [ex["hat"], ex["dat"], ex["nafnet"]]
+    with torch.no_grad():
+        _, ref_mod = collab.collaborative(sd, feats, exl, return_mod=True)      # [1, 3 experts, 3 channels]
+        ref = collab.head_forward_with_features(sd, lr, exl, feats)
+    inter = {}
+    out = m.forward_with_precomputed(lr.cuda(), {k: v.cuda() for k, v in ex.items()}, {k: v.cuda() for k, v in feats.items()}, intermediates=inter).cpu()
+    got_mod = inter["modulation"].cpu()
+    print("modulation (oracle):", [f"{v:.3f}" for v in ref_mod.flatten().tolist()])
+    print("modulation (ours):  ", [f"{v:.3f}" for v in got_mod.flatten().tolist()])
+    assert (ref_mod - 0.5).abs().max() > 0.05                      # the test has teeth
+    assert (got_mod - ref_mod).abs().max().item() < 1e-2
+    assert (out - ref).abs().max().item() < 2e-2
