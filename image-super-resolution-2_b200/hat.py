@@ -153,9 +153,14 @@ class HATRunner:
         next_norm: (gamma, beta) of the LayerNorm that consumes the new X -- emitted into `t` by the fc2 epilogue."""
         if not t_ready:
             ops.layernorm(X, M, C, d["norm2"][0], d["norm2"][1], 1e-5, out_bf16=t, out_cols=CP)
-        ops.conv_gemm(t, B, H, W, CP, d["fc1_w"], n_store=2 * CP, bias=d["fc1_b"], act=ACT_GELU, out_bf16=h)
-        ops.conv_gemm(h, B, H, W, 2 * CP, d["fc2_w"], n_store=CP, bias=d["fc2_b"], res=X, out_f32=X, out_bf16=extra_bf16,
-                      ln=(next_norm[0], next_norm[1], 1e-5, C, t) if next_norm is not None else None)
+        ln = (next_norm[0], next_norm[1], 1e-5, C, t) if next_norm is not None else None
+        if ops.mlp_fused_enabled():
+            # one kernel, hidden tile on chip.  The next LayerNorm may overwrite t in place: a CTA stores the rows of a tile only
+            # after that tile's A operand (the same rows of t) has been consumed, and no other CTA reads them
+            ops.mlp_fused(t, B, H, W, d["fc1_w"], d["fc1_b"], d["fc2_w"], d["fc2_b"], X, out_bf16=extra_bf16, ln=ln)
+        else:
+            ops.conv_gemm(t, B, H, W, CP, d["fc1_w"], n_store=2 * CP, bias=d["fc1_b"], act=ACT_GELU, out_bf16=h)
+            ops.conv_gemm(h, B, H, W, 2 * CP, d["fc2_w"], n_store=CP, bias=d["fc2_b"], res=X, out_f32=X, out_bf16=extra_bf16, ln=ln)
 
     def forward(self, x, out, out_off=0):
         """x: fp32 NCHW [B,3,h,w] (any size the reference's reflect padding accepts) on the GPU.

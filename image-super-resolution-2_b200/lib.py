@@ -37,6 +37,15 @@ class FFWinAttn(C.Structure):
     ]
 
 
+class FFMlpFused(C.Structure):
+    _fields_ = [
+        ("t", C.c_void_p), ("t_ld", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("w1", C.c_void_p), ("b1", C.c_void_p),
+        ("w2", C.c_void_p), ("b2", C.c_void_p), ("x", C.c_void_p), ("x_ld", C.c_int), ("out_bf16", C.c_void_p), ("out_ld", C.c_int),
+        ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float), ("ln_cols", C.c_int), ("ln_out", C.c_void_p),
+        ("ln_out_ld", C.c_int),
+    ]
+
+
 class FFError(RuntimeError):
     pass
 

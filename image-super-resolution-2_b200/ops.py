@@ -115,6 +115,43 @@ def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_
     L.check(L.load().ff_conv_gemm(C.byref(p), _stream()), "ff_conv_gemm")
 
 
+def mlp_fused_enabled():
+    """fc1 + GELU + fc2 (+ residual, + next LayerNorm) as one kernel with the hidden tile on chip (ff_mlp_fused);
+    FFB200_FUSED_MLP=0 restores the two conv_gemm launches."""
+    import os
+    return os.environ.get("FFB200_FUSED_MLP", "1") != "0"
+
+
+def mlp_fused(t, B, H, W, w1, b1, w2, b2, x, *, out_bf16=None, ln=None):
+    """x += fc2(GELU(fc1(t))) in place on the fp32 residual stream x; ln = (gamma, beta, eps, cols, bf16 out) as in conv_gemm."""
+    _req_cuda(t, w1, b1, w2, b2, x, out_bf16)
+    p = L.FFMlpFused()
+    p.t = t.data_ptr(); p.t_ld = t.stride(-2)
+    p.B, p.H, p.W = B, H, W
+    p.w1 = w1.data_ptr(); p.b1 = b1.data_ptr(); p.w2 = w2.data_ptr(); p.b2 = b2.data_ptr()
+    p.x = x.data_ptr(); p.x_ld = x.stride(-2)
+    if out_bf16 is not None:
+        p.out_bf16 = out_bf16.data_ptr(); p.out_ld = out_bf16.stride(-2)
+    if ln is not None:
+        g_, b_, eps_, cols_, lo_ = ln
+        _req_cuda(g_, b_, lo_)
+        p.ln_gamma = g_.data_ptr(); p.ln_beta = b_.data_ptr(); p.ln_eps = eps_; p.ln_cols = cols_
+        p.ln_out = lo_.data_ptr(); p.ln_out_ld = lo_.stride(-2)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.load().ff_mlp_fused(C.byref(p), _stream()), "ff_mlp_fused")
+        e1.record()
+        M = B * H * W
+        n1, k1 = getattr(w1, "ff_real", tuple(w1.shape))
+        n2, k2 = getattr(w2, "ff_real", tuple(w2.shape))
+        flops = 2.0 * M * (n1 * k1 + n2 * k2)
+        byts = M * k1 * 2 + (n1 * k1 + n2 * k2) * 2 + M * n2 * 8 + (M * n2 * 2 if out_bf16 is not None else 0) + (M * ln[3] * 2 if ln is not None else 0)
+        PROFILE.records.append((e0, e1, flops, 2.0 * M * (w1.shape[0] * w1.shape[1] + w2.shape[0] * w2.shape[1]), float(byts), ("mlp_fused", B, H, W)))
+        return
+    L.check(L.load().ff_mlp_fused(C.byref(p), _stream()), "ff_mlp_fused")
+
+
 def window_attention(qkv, B, H, W, out, *, bias_table, wh, ww, kh=None, kw=None, kpad=(0, 0), shift=(0, 0), heads=6,
                      head_off=0, bias_head_off=0, rel_sign=1, rel_off=None, rel_stride=None, q_off=0, k_off=192,
                      v_off=384, out_off=0, padded=None):

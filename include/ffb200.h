@@ -105,6 +105,27 @@ typedef struct FFConvGemm {
 int ff_conv_gemm(const FFConvGemm* p, void* stream);
 
 /*
+ * ff_mlp_fused -- the transformer MLP of HAT's HAB / OCAB blocks as one kernel (csrc/mlp_fused.cu):
+ *   x[p, :] += fc2(GELU(fc1(t[p, :])))          (Mlp.forward, hat_arch.py:77-94, called at :308 and :437)
+ * t = the LayerNorm output (bf16, 192-wide rows: 180 channels + zero padding), fc1 192 -> 384 (360 + zero padding), fc2 384 -> 192.
+ * The 128 x 384 hidden tile stays on the SM: fc1 accumulates 64 hidden columns at a time in TMEM, the GELU warps write them as a
+ * bf16 A-operand tile in shared memory, fc2 accumulates over the six chunks.  x is the fp32 residual stream, updated in place;
+ * out_bf16 (optional) receives a bf16 copy of the new x, ln_out (optional) LayerNorm(new x) for the next consumer (as in
+ * FFConvGemm.ln_*).  Weights: packed bf16 w1 [384][192], w2 [192][384] (packing.pack_matrix), biases fp32 [384] / [192].
+ */
+typedef struct FFMlpFused {
+  const void* t; int t_ld;       /* bf16 [B*H*W][t_ld] */
+  int B, H, W;                   /* the token matrix as an image (tiles are 8 x 16 pixels) */
+  const void* w1; const float* b1;
+  const void* w2; const float* b2;
+  float* x; int x_ld;            /* fp32 [B*H*W][x_ld], in place */
+  void* out_bf16; int out_ld;    /* optional */
+  const float* ln_gamma; const float* ln_beta; float ln_eps; int ln_cols;
+  void* ln_out; int ln_out_ld;   /* optional */
+} FFMlpFused;
+int ff_mlp_fused(const FFMlpFused* p, void* stream);
+
+/*
  * ff_window_attention -- fused window attention (QK^T + relative-position bias + shift mask + softmax + PV).
  * Replaces hat_arch.py:165-196 (WindowAttention.forward) with the roll / window_partition / window_reverse
  * copies of HAB.forward (hat_arch.py:279-303), OCAB's unfold + attention (hat_arch.py:398-435), and DAT's

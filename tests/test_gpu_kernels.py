@@ -841,3 +841,43 @@ def test_conv_direct_any_size(cin, cout, k, H, W, B):
     torch.cuda.synchronize()
     assert (out[:B * H * W, :cout].cpu() - ref).abs().max().item() < 1e-4
     assert (out[B * H * W:] == 9.0).all()
+
+
+@pytest.mark.parametrize("B,H,W,with_bf16,with_ln", [(2, 32, 32, False, True), (1, 16, 48, True, False), (3, 24, 16, True, True), (1, 128, 128, False, True)])
+def test_mlp_fused(B, H, W, with_bf16, with_ln):
+    """ff_mlp_fused: x += fc2(GELU(fc1(t))) with the hidden tile on chip (csrc/mlp_fused.cu), optional bf16 copy and fused LayerNorm
+    of the new row, against plain fp32 PyTorch on the bf16-rounded operands (180 / 360 real channels inside 192 / 384 padded)."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(31)
+    P, C, HD, CP = B * H * W, 180, 360, 192
+    t = torch.zeros(P, CP)
+    t[:, :C] = torch.randn(P, C, generator=g)
+    t = t.to(BF16)
+    w1 = (torch.randn(HD, C, generator=g) / math.sqrt(C)).to(BF16).float()
+    w2 = (torch.randn(C, HD, generator=g) / math.sqrt(HD)).to(BF16).float()
+    b1, b2 = torch.randn(HD, generator=g) * 0.3, torch.randn(C, generator=g) * 0.3
+    x = torch.zeros(P, CP)
+    x[:, :C] = torch.randn(P, C, generator=g) * 2 + 0.5
+    hid = F.gelu(t.float()[:, :C] @ w1.t() + b1)
+    ref = x.clone()
+    ref[:, :C] += hid.to(BF16).float() @ w2.t() + b2
+    gamma, beta = torch.zeros(CP), torch.zeros(CP)
+    gamma[:C], beta[:C] = 1 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    ln_ref = torch.zeros(P, CP)
+    ln_ref[:, :C] = F.layer_norm(ref[:, :C], (C,), gamma[:C], beta[:C], 1e-5)
+    d = _dev()
+    xd = x.clone().to(d)
+    o16 = torch.full((P, CP), 7.0, dtype=BF16, device=d) if with_bf16 else None
+    lno = torch.full((P, CP), 7.0, dtype=BF16, device=d) if with_ln else None
+    ops.mlp_fused(t.to(d), B, H, W, packing.pack_matrix(w1, 2 * CP, CP, device=d), packing.pack_vector(b1, 2 * CP, device=d),
+                  packing.pack_matrix(w2, CP, 2 * CP, device=d), packing.pack_vector(b2, CP, device=d), xd, out_bf16=o16,
+                  ln=(gamma.to(d), beta.to(d), 1e-5, C, lno) if with_ln else None)
+    torch.cuda.synchronize()
+    e = (xd.cpu() - ref).abs().max().item()
+    assert e < 2e-2, e                                  # bf16 hidden activations (values up to ~3) through a 360-long contraction
+    assert (xd.cpu()[:, C:] == 0).all()
+    if with_bf16:
+        assert (o16.cpu().float() - ref).abs().max().item() < 6e-2
+    if with_ln:
+        assert (lno.cpu().float() - ln_ref).abs().max().item() < 4e-2
+        assert (lno.cpu().float()[:, C:] == 0).all()
