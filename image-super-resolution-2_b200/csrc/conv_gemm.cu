@@ -56,7 +56,11 @@ struct Cfg {
   static constexpr int TH = HALO ? HALO_TH : TILE_H;
   static constexpr int QR = 32 / TW;                              // tile rows per TMEM lane quadrant
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = HALO ? B_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;
+  // HALO: one ring stage holds the weights of a whole kernel ROW (three taps) of a 64-channel chunk, so the MMA warp issues 12
+  // instructions per barrier wait instead of 4 (N <= 64 instructions are issue bound: the wait + fence + election between
+  // taps cost as much as the four MMAs)
+  static constexpr int HALO_TAPS = (EPI == 3 || EPI == 4) ? 1 : 3;      // (the residual epilogues' staging leaves room for single-tap stages only)
+  static constexpr int STAGE_BYTES = HALO ? HALO_TAPS * B_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int HALO_BYTES = HALO ? HALO_A_STAGES * HALO_A_BYTES : 0;
   static constexpr int CB = BN < 32 ? BN : 32;                    // epilogue column block
   static constexpr int STG_PITCH = CB + 4;                        // floats; +4 keeps float4 accesses conflict-free (generic path)
@@ -66,7 +70,7 @@ struct Cfg {
   static constexpr int EPI_WARPS = ((EPI == 1 || EPI == 2) && !HALO) ? 16 : NUM_EPI_WARPS;   // HALO tiles hold <= 2 column blocks; the smaller staging area leaves room for a 9-stage weight ring (417 vs 463 us on the HR 64->64 layers)
   static constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
   static constexpr int STAGES_RAW = (225 * 1024 - STG_BYTES - HALO_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES_MAX = HALO ? 9 : 6;
+  static constexpr int STAGES_MAX = HALO ? (HALO_TAPS == 3 ? 4 : 9) : 6;
   static constexpr int STAGES = STAGES_RAW > STAGES_MAX ? STAGES_MAX : STAGES_RAW;
   static constexpr int RING_BYTES = HALO_BYTES + STAGES * STAGE_BYTES;        // [halo A stages][ring]; staging follows
   static constexpr int SMEM_BYTES = RING_BYTES + STG_BYTES + 1024;            // + alignment slack
@@ -382,11 +386,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // weights only, chunk-major k order; the A slabs come from the last warp
         uint8_t* ring = smem + C::HALO_BYTES;
         for (int cc = 0; cc < a.cchunks; ++cc) {
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int g = 0; g < 9 / C::HALO_TAPS; ++g) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&full_bar[stage], C::B_STAGE_BYTES);
-              tma_load_2d(ring + stage * C::STAGE_BYTES, &tmB, &full_bar[stage], (tap * a.cchunks + cc) * BLOCK_K, brow);
+              mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+#pragma unroll
+              for (int j = 0; j < C::HALO_TAPS; ++j)
+                tma_load_2d(ring + stage * C::STAGE_BYTES + j * C::B_STAGE_BYTES, &tmB, &full_bar[stage], ((g * C::HALO_TAPS + j) * a.cchunks + cc) * BLOCK_K, brow);
             }
             __syncwarp();
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -465,16 +471,20 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&halo_full[hs], hphase);
           const uint64_t dslab = desc_halo + (uint64_t)(hs * (HALO_A_BYTES >> 4));
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int g = 0; g < 9 / C::HALO_TAPS; ++g) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t da = dslab + (uint64_t)((tap % 3) * (HALO_SLAB_BYTES >> 4) + (tap / 3) * (1024 >> 4));   // dx slab, dy row offset
-              const uint64_t db = desc_ring + (uint64_t)(stage * (C::STAGE_BYTES >> 4));
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / 16; ++k) tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
+              for (int j = 0; j < C::HALO_TAPS; ++j) {
+                const int tap = g * C::HALO_TAPS + j;
+                const uint64_t da = dslab + (uint64_t)((tap % 3) * (HALO_SLAB_BYTES >> 4) + (tap / 3) * (1024 >> 4));   // dx slab, dy row offset
+                const uint64_t db = desc_ring + (uint64_t)((stage * C::STAGE_BYTES + j * C::B_STAGE_BYTES) >> 4);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k) tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (cc | tap | k) != 0 ? 1u : 0u);
+              }
               tc_commit(&empty_bar[stage]);
-              if (tap == 8) tc_commit(&halo_empty[hs]);
+              if (g == 9 / C::HALO_TAPS - 1) tc_commit(&halo_empty[hs]);
             }
             __syncwarp();
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -1281,7 +1291,7 @@ struct Maps { CUtensorMap A, B, O, R, O32, X; };
 template <int BN, int EPI, bool HALO = false>
 int launch_tc(const Maps& m, const Args& a, cudaStream_t st) {
   using C = Cfg<BN, EPI, HALO>;
-  static_assert(C::STAGES >= (HALO ? 3 : 2), "ff_conv_gemm: smem ring too shallow");
+  static_assert(C::STAGES >= 2, "ff_conv_gemm: smem ring too shallow");
   static FFPerDeviceFlag configured_dev;
   bool& configured = configured_dev.get();
   if (!configured) {
