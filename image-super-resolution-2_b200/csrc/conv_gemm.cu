@@ -31,6 +31,7 @@ struct Args {
   int Hc, Wc;   // geometry of the direct-store outputs (== Ho, Wo unless out_crop_h / out_crop_w crop the bottom / right edge)
   int tiles_x, tiles_per_img, m_tiles, n_tiles;
   int ntaps, cchunks;
+  int cchunks1;   // k-blocks taken from x (the rest, up to cchunks, come from the second operand tensor x2: K-concatenated 1x1 layers)
   int vec_ok;   // every epilogue operand allows 16-byte fp32 / 8-byte bf16 vector access
 };
 
@@ -319,7 +320,8 @@ template <int BN, int EPI, bool HALO>
 __global__ void __launch_bounds__(Cfg<BN, EPI, HALO>::THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
-                    const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Args a) {
+                    const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ Args a) {
   using C = Cfg<BN, EPI, HALO>;
   constexpr int TW = C::TW, TH = C::TH, QR = C::QR;
   extern __shared__ uint8_t smem_raw[];
@@ -417,7 +419,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (elect_one()) {
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
             mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-            tma_load_4d(sa, &tmA, &full_bar[stage], cc * BLOCK_K, cx, cy, b);
+            if (cc < a.cchunks1) tma_load_4d(sa, &tmA, &full_bar[stage], cc * BLOCK_K, cx, cy, b);
+            else tma_load_4d(sa, &tmA2, &full_bar[stage], (cc - a.cchunks1) * BLOCK_K, cx, cy, b);      // second K segment (x2)
             tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, brow);
           }
           __syncwarp();
@@ -1286,7 +1289,7 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-struct Maps { CUtensorMap A, B, O, R, O32, X; };
+struct Maps { CUtensorMap A, B, O, R, O32, X, A2; };
 
 template <int BN, int EPI, bool HALO = false>
 int launch_tc(const Maps& m, const Args& a, cudaStream_t st) {
@@ -1305,7 +1308,7 @@ int launch_tc(const Maps& m, const Args& a, cudaStream_t st) {
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < ff_num_sms() ? tiles : ff_num_sms();
-  conv_gemm_tc_kernel<BN, EPI, HALO><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(m.A, m.B, m.O, m.R, m.O32, m.X, a);
+  conv_gemm_tc_kernel<BN, EPI, HALO><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(m.A, m.B, m.O, m.R, m.O32, m.X, m.A2, a);
   FF_CHECK_LAUNCH("ff_conv_gemm");
   return FF_OK;
 }
@@ -1425,6 +1428,15 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   a.m_tiles = a.tiles_per_img * p.B;
   a.ntaps = (p.kind == FF_CONV_3X3) ? 9 : (p.kind == FF_CONV_2X2S2) ? 4 : 1;
   a.cchunks = p.cin / BLOCK_K;
+  a.cchunks1 = a.cchunks;
+  if (p.x2) {
+    // K-concatenated 1x1 layer: out = [x | x2] . W^T with W [n_pad][cin + cin2]; x2 has the geometry of x.  Lets an epilogue add
+    // (HAT: x = shortcut + proj(attn) + 0.01 * cab * se, hat_arch.py:306) run on the tensor pipe: x2 = cab, its weight block =
+    // diag(0.01 * se_b) per sample (ff_build_concat_diag_weights), and the layer keeps the plain residual epilogue.
+    FF_CHECK_ARG(p.kind == FF_CONV_1X1 && p.cin2 > 0 && p.cin2 % BLOCK_K == 0 && p.cin2 <= p.x2_ld && p.x2_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(p.x2) & 15) == 0 && !p.debug_simt,
+                 "ff_conv_gemm: x2 needs a 1x1 layer, cin2 a multiple of 64 and 16-byte aligned rows");
+    a.cchunks = (p.cin + p.cin2) / BLOCK_K;
+  }
 
   if (p.debug_simt) {
     a.n_tiles = 1;
@@ -1466,7 +1478,7 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
     }
   }
   {
-    const cuuint64_t K = (cuuint64_t)a.ntaps * p.cin;
+    const cuuint64_t K = (cuuint64_t)a.ntaps * (p.cin + (p.x2 ? p.cin2 : 0));
     cuuint64_t dims[2] = {K, (cuuint64_t)(p.w_batch_rows ? (long long)p.w_batch_rows * p.B : p.n_pad)};
     cuuint64_t strides[1] = {K * 2};
     cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN};
@@ -1482,7 +1494,16 @@ extern "C" int ff_conv_gemm(const FFConvGemm* pp, void* stream) {
   // epilogue selection: plain "bias (+GELU) -> bf16" layers and fp32-residual layers take the TMA epilogues
   int epi = EPI_GENERIC;
   Maps m;
-  m.A = tmA; m.B = tmB; m.O = tmA; m.R = tmA; m.O32 = tmA; m.X = tmA;
+  m.A = tmA; m.B = tmB; m.O = tmA; m.R = tmA; m.O32 = tmA; m.X = tmA; m.A2 = tmA;
+  if (p.x2) {
+    cuuint64_t dims[4] = {(cuuint64_t)p.cin2, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    cuuint64_t strides[3] = {(cuuint64_t)p.x2_ld * 2, (cuuint64_t)p.x2_ld * 2 * p.W, (cuuint64_t)p.x2_ld * 2 * p.W * p.H};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)TILE_W, (cuuint32_t)TILE_H, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&m.A2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.x2), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ff_set_error("ff_conv_gemm: cuTensorMapEncodeTiled(x2) failed with %d", (int)r); return FF_ERR_DRIVER; }
+  }
   auto out_map = [&](CUtensorMap* tm, void* ptr, int ld, int esz, CUtensorMapDataType dt, CUtensorMapSwizzle sw) {
     if (p.pixel_shuffle) {
       const cuuint64_t e = (cuuint64_t)ld * esz;

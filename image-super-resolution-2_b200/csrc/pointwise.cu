@@ -1264,6 +1264,27 @@ __global__ void __launch_bounds__(256) scale_weight_cols_kernel(const float* __r
   out[idx] = __float2bfloat16_rn(v);
 }
 
+// out[b][n][k] = k < k1 ? w[n][k] : (k - k1 == n ? bf16(alpha * s[b][n]) : 0)   (FFConvGemm.x2: the aux term as a diagonal weight block)
+__global__ void __launch_bounds__(256) concat_diag_weights_kernel(const bf16* __restrict__ w, int n_pad, int k1, const float* __restrict__ s, int s_ld, float alpha,
+                                                                 int B, bf16* __restrict__ out) {
+  const int K = k1 + n_pad;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)B * n_pad * K) return;
+  const int k = (int)(idx % K);
+  const int n = (int)((idx / K) % n_pad);
+  const int b = (int)(idx / ((long long)K * n_pad));
+  out[idx] = k < k1 ? w[(long long)n * k1 + k] : (k - k1 == n ? __float2bfloat16_rn(alpha * __ldg(s + (long long)b * s_ld + n)) : __float2bfloat16_rn(0.f));
+}
+extern "C" int ff_build_concat_diag_weights(const void* w, int n_pad, int k1, const float* s, int s_ld, float alpha, int B, void* out, void* stream) {
+  FF_CHECK_ARG(w && s && out && n_pad > 0 && k1 > 0 && B > 0 && s_ld >= n_pad, "ff_build_concat_diag_weights: bad args");
+  const long long total = (long long)B * n_pad * (k1 + n_pad);
+  concat_diag_weights_kernel<<<ff_cdiv(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(w), n_pad, k1, s, s_ld, alpha, B,
+                                                                                                  reinterpret_cast<bf16*>(out));
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_build_concat_diag_weights");
+  return FF_OK;
+}
+
 extern "C" int ff_scale_weight_cols(const float* w, int N, int K, const float* s, int s_ld, int B, void* out, int n_pad, int k_pad, void* stream) {
   FF_CHECK_ARG(w && s && out && N > 0 && K > 0 && B > 0 && n_pad >= N && k_pad >= K, "ff_scale_weight_cols: bad args");
   const long long total = (long long)B * n_pad * k_pad;

@@ -190,6 +190,7 @@ class HATRunner:
         se_h = ws.get("se_h", B, 8, F32)
         se = ws.get("se", B, CP, F32)
         scratch = ws.get("gap_scratch", 1, B * 64 * CP, F32)
+        wcat = ws.get("proj_cat_w", B * CP, 2 * CP, BF16)      # per-sample [W_proj | diag(0.01 se)] of the current block
         fused = ops.fused_ln_enabled()      # every LayerNorm after a residual add leaves the producing GEMM's epilogue
 
         if (H, W) == (h0, w0):
@@ -218,8 +219,14 @@ class HATRunner:
                 ops.conv_gemm(t, B, H, W, CP, d["qkv_w"], n_store=3 * CP, bias=d["qkv_b"], out_bf16=qkv)
                 ops.window_attention(qkv, B, H, W, att, bias_table=d["table"], wh=WS, ww=WS, shift=(shift, shift))
                 # x = shortcut + attn + 0.01 * cab   (hat_arch.py:306); the epilogue also emits LN2(x) into t
-                ops.conv_gemm(att, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], aux=cab2, aux_chan=se,
-                              aux_alpha=0.01, res=src, out_f32=X, ln=(d["norm2"][0], d["norm2"][1], 1e-5, C, t) if fused else None)
+                ln2 = (d["norm2"][0], d["norm2"][1], 1e-5, C, t) if fused else None
+                if ops.concat_aux_enabled():
+                    # the + 0.01 * cab * se term rides on the tensor pipe: [att | cab] . [W_proj ; diag(0.01 * se_b)] per sample,
+                    # so the layer keeps the plain (faster) residual epilogue
+                    ops.build_concat_diag_weights(d["proj_w"], se, 0.01, wcat.view(B, CP, 2 * CP))
+                    ops.conv_gemm(att, B, H, W, CP, wcat, n_store=CP, w_batch_rows=CP, bias=d["proj_b"], x2=cab2, res=src, out_f32=X, ln=ln2)
+                else:
+                    ops.conv_gemm(att, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], aux=cab2, aux_chan=se, aux_alpha=0.01, res=src, out_f32=X, ln=ln2)
                 nxt = layer["habs"][j + 1]["norm1"] if j + 1 < nhab else layer["ocab"]["norm1"]
                 self._mlp(d, X, t, h, B, H, W, M, t_ready=fused, next_norm=nxt if fused else None)
                 t_ready = fused

@@ -21,7 +21,7 @@ class FFConvGemm(C.Structure):
         ("out_f32_ld", C.c_int), ("pixel_shuffle", C.c_int), ("gate_pairs", C.c_int), ("w_batch_rows", C.c_int),
         ("debug_simt", C.c_int), ("col_sums", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
         ("ln_eps", C.c_float), ("ln_cols", C.c_int), ("ln_out", C.c_void_p), ("ln_out_ld", C.c_int),
-        ("out_crop_h", C.c_int), ("out_crop_w", C.c_int),
+        ("out_crop_h", C.c_int), ("out_crop_w", C.c_int), ("x2", C.c_void_p), ("x2_ld", C.c_int), ("cin2", C.c_int),
     ]
 
 

@@ -53,7 +53,7 @@ def _req_cuda(*ts):
 
 def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_NONE, alpha=1.0, col_scale=None,
               mul=None, aux=None, aux_chan=None, aux_alpha=1.0, res=None, post_act=ACT_NONE, out_bf16=None,
-              out_f32=None, pixel_shuffle=0, gate_pairs=0, w_batch_rows=0, x_ld=None, debug_simt=0, col_sums=None, ln=None, out_crop=None):
+              out_f32=None, pixel_shuffle=0, gate_pairs=0, w_batch_rows=0, x_ld=None, debug_simt=0, col_sums=None, ln=None, out_crop=None, x2=None):
     """Implicit-GEMM conv / linear on tcgen05 (see ff_conv_gemm in include/ffb200.h).
 
     x: bf16 tensor whose last dim is the channel pitch (or pass x_ld); w: packed bf16 [n_pad, taps*cin].
@@ -89,6 +89,9 @@ def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_
         p.col_sums = col_sums.data_ptr()
     if out_crop is not None:
         p.out_crop_h, p.out_crop_w = out_crop
+    if x2 is not None:
+        _req_cuda(x2)
+        p.x2 = x2.data_ptr(); p.x2_ld = x2.stride(-2); p.cin2 = x2.shape[-1]
     if ln is not None:
         # fused LayerNorm of the updated residual row: ln = (gamma [n_store], beta [n_store], eps, real channel count, bf16 out)
         g_, b_, eps_, cols_, lo_ = ln
@@ -106,13 +109,21 @@ def conv_gemm(x, B, H, W, cin, w, *, kind=CONV_1X1, n_store, bias=None, act=ACT_
         # compulsory HBM bytes of this launch: A once (its real channels), weights, every epilogue operand / output at its dtype
         cin_real = k_real // taps
         width = n_real // (2 if gate_pairs else 1)
-        byts = B * H * W * cin_real * 2 + n_real * k_real * 2 + Mo * width * ((2 if out_bf16 is not None else 0) + (4 if out_f32 is not None else 0))
+        if x2 is not None:
+            byts_x2 = B * H * W * n_real * 2
+        byts = (byts_x2 if x2 is not None else 0) + B * H * W * cin_real * 2 + n_real * k_real * 2 + Mo * width * ((2 if out_bf16 is not None else 0) + (4 if out_f32 is not None else 0))
         byts += Mo * width * ((4 if res.dtype == _F32 else 2) if res is not None else 0) + Mo * width * (2 if mul is not None else 0) + Mo * width * (2 if aux is not None else 0)
         byts += Mo * ln[3] * 2 if ln is not None else 0
         PROFILE.records.append((e0, e1, 2.0 * Mo * n_real * k_real, 2.0 * Mo * p.n_pad * taps * cin, float(byts),
                                 (kind, cin, p.n_pad, B, H, W, act, res is not None, aux is not None, mul is not None, gate_pairs, pixel_shuffle, out_f32 is not None)))
         return
     L.check(L.load().ff_conv_gemm(C.byref(p), _stream()), "ff_conv_gemm")
+
+
+def concat_aux_enabled():
+    """HAT's proj + 0.01 * cab * se as one K-concatenated GEMM (FFConvGemm.x2); FFB200_CONCAT_AUX=0 restores the aux epilogue."""
+    import os
+    return os.environ.get("FFB200_CONCAT_AUX", "1") != "0"
 
 
 def mlp_fused_enabled():
@@ -233,6 +244,14 @@ def scale_channels(x, B, pixels_per_sample, C_, s):
     _req_cuda(x, s)
     L.check(L.load().ff_scale_channels(_ptr(x), x.stride(-2), B, C.c_longlong(pixels_per_sample), C_, _ptr(s), s.stride(0), _stream()),
             "ff_scale_channels")
+
+
+def build_concat_diag_weights(w, s, alpha, out):
+    """out[b] = [w | diag(alpha * s[b])] (bf16 [B][n_pad][k1 + n_pad]) -- the per-sample weights of a K-concatenated layer (conv_gemm x2=)."""
+    _req_cuda(w, s, out)
+    n_pad, k1 = w.shape
+    B = out.shape[0]
+    L.check(L.load().ff_build_concat_diag_weights(_ptr(w), n_pad, k1, _ptr(s), s.stride(0), C.c_float(alpha), B, _ptr(out), _stream()), "ff_build_concat_diag_weights")
 
 
 def scale_weight_cols(w_f32, s, out):

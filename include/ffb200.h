@@ -101,8 +101,15 @@ typedef struct FFConvGemm {
    * holding the top-left part -- the crop that follows an expert run on a padded image (expert_loader.py:612-615, 643-646,
    * nafnet_arch.py:216).  Direct-store epilogues only (n_store <= 4, or layers without per-pixel operands); `res` stays H x W. */
   int out_crop_h, out_crop_w;
+  /* K-concatenated second operand of a 1x1 layer (NULL = none): out = [x | x2] . W^T with W [n_pad][cin + cin2]; x2 is a bf16 NHWC
+   * tensor of the geometry of x.  With the weight block of x2 = diag(s_b) per sample (ff_build_concat_diag_weights,
+   * w_batch_rows) an epilogue term  s_b[n] * x2[p, n]  runs on the tensor pipe instead (HAT: + 0.01 * cab * se, hat_arch.py:306). */
+  const void* x2; int x2_ld; int cin2;
 } FFConvGemm;
 int ff_conv_gemm(const FFConvGemm* p, void* stream);
+/* Per-sample weights [B][n_pad][k1 + n_pad] (bf16) for a K-concatenated layer: block 1 = w [n_pad][k1] (bf16, copied), block 2 =
+ * diag(alpha * s[b][n]) -- see FFConvGemm.x2. */
+int ff_build_concat_diag_weights(const void* w, int n_pad, int k1, const float* s, int s_ld, float alpha, int B, void* out, void* stream);
 
 /*
  * ff_mlp_fused -- the transformer MLP of HAT's HAB / OCAB blocks as one kernel (csrc/mlp_fused.cu):

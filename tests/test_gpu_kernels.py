@@ -881,3 +881,30 @@ def test_mlp_fused(B, H, W, with_bf16, with_ln):
     if with_ln:
         assert (lno.cpu().float() - ln_ref).abs().max().item() < 4e-2
         assert (lno.cpu().float()[:, C:] == 0).all()
+
+
+def test_conv_gemm_k_concatenated_second_operand():
+    """FFConvGemm.x2: out = [x | x2] . W^T with per-sample weights [W | diag(alpha * s_b)] (ff_build_concat_diag_weights) reproduces the
+    aux epilogue  x.W^T + bias + alpha * s_b[n] * x2[p, n] + res  of HAT's proj layer (hat_arch.py:306) on the tensor pipe."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(41)
+    B, H, W, C = 3, 16, 32, 192
+    P = B * H * W
+    x = torch.randn(P, C, generator=g).to(BF16)
+    x2 = torch.randn(P, C, generator=g).to(BF16)
+    w = (torch.randn(C, C, generator=g) / math.sqrt(C)).to(BF16)
+    bias, res = torch.randn(C, generator=g), torch.randn(P, C, generator=g)
+    s = torch.rand(B, C, generator=g)
+    ref = x.float() @ w.float().t() + bias + (0.01 * s).to(BF16).float().repeat_interleave(H * W, 0) * x2.float() + res
+    d = _dev()
+    wcat = torch.empty(B, C, 2 * C, dtype=BF16, device=d)
+    ops.build_concat_diag_weights(w.to(d), s.to(d), 0.01, wcat)
+    assert torch.equal(wcat[:, :, :C].cpu(), w.expand(B, C, C)) and torch.equal(torch.diagonal(wcat[1, :, C:].cpu().float()), (0.01 * s[1]).to(BF16).float())
+    stream = res.clone().to(d)
+    lno = torch.zeros(P, C, dtype=BF16, device=d)
+    gam, bet = torch.ones(C, device=d), torch.zeros(C, device=d)
+    ops.conv_gemm(x.to(d), B, H, W, C, wcat.view(B * C, 2 * C), n_store=C, w_batch_rows=C, bias=bias.to(d), x2=x2.to(d), res=stream, out_f32=stream,
+                  ln=(gam, bet, 1e-5, C, lno))
+    torch.cuda.synchronize()
+    assert (stream.cpu() - ref).abs().max().item() < 4e-3
+    assert (lno.cpu().float() - F.layer_norm(ref, (C,))).abs().max().item() < 3e-2
