@@ -483,6 +483,7 @@ def _run_tile_sharded(model, paths, output_path, rank, world):
 
 def _sharded_worker(rank, world, model_dir, input_path, output_path, port, backend):
     import torch.distributed as dist
+    os.environ.setdefault("LOCAL_WORLD_SIZE", str(world))      # the ranks share this host's cores (sizes the encoder pools)
     idx = rank % torch.cuda.device_count()      # (ranks may share a GPU under gloo: single-GPU test of the sharded path)
     torch.cuda.set_device(idx)
     dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
