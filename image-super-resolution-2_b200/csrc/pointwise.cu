@@ -701,6 +701,146 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3x3_tma_kernel(const __g
   }
 }
 
+constexpr int DWG_TY = 16;      // taller tiles than the MODE 0 kernels: the per-tile index arithmetic and the 2-row halo amortise over twice the rows
+struct DwgCfg {
+  static constexpr int STAGES = 2;
+  static constexpr int HALF_BYTES = (DWG_TY + 2) * (DWT_TX + 2) * 32 * 2;      // one 32-channel box
+  static constexpr int STAGE_BYTES = 2 * HALF_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 128;
+};
+// SimpleGate depthwise 3x3 (NAFBlock conv2 + x1 * x2, nafnet_arch.py:116-118), TMA-staged like the kernel above but with BOTH halves
+// of a gate pair in one thread: thread = (pixel column, channel pair) reads the two bf16 of x1 and the two of x2 with one LDS.32
+// each, slides down the 16 rows of the tile with two 3x3 windows in registers (18 FFMA2 per output row), multiplies the halves and
+// stores one bf16 pair -- no cross-lane shuffles, no duplicated gate work.  (The MODE 1 path above spent 93 warp-instructions per
+// 4-channel item against 18 FFMA2 of real work: issue bound at 31 % of DRAM.)
+__global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3x3_gate_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ DwArgs a, int tiles_x,
+                                                                            int tiles_y, int ctiles) {
+  using Cf = DwgCfg;
+  extern __shared__ uint8_t dwg_smem_raw[];
+  __shared__ __align__(8) uint64_t full[Cf::STAGES];
+  __shared__ float2 pool_red[2][DWT_THREADS / 32][16];      // per-warp column sums of a tile (global-average-pool partials), by tile parity
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dwg_smem_raw) + 127) & ~(uintptr_t)127);
+  const int tid = threadIdx.x;
+  const int cout = a.C / 2;
+  const int num_tiles = a.B * tiles_y * tiles_x * ctiles;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < Cf::STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int s) {     // one thread: the two 32-channel halves (x1 chunk, its x2 partner chunk) of a halo tile
+    const int ct = tile % ctiles;
+    int r = tile / ctiles;
+    const int tx = r % tiles_x;
+    r /= tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    uint8_t* dst = smem + s * Cf::STAGE_BYTES;
+    mbar_arrive_expect_tx(&full[s], Cf::STAGE_BYTES);
+    tma_load_4d(dst, &tmX, &full[s], ct * 32, tx * DWT_TX - 1, ty * DWG_TY - 1, b);
+    tma_load_4d(dst + Cf::HALF_BYTES, &tmX, &full[s], cout + ct * 32, tx * DWT_TX - 1, ty * DWG_TY - 1, b);
+  };
+  if (tid == 0 && (int)blockIdx.x < num_tiles) issue(blockIdx.x, 0);
+  const int g = tid & 15, px = tid >> 4;      // channel pair of the 32-channel chunk, pixel column of the tile: a warp reads 2 x 64 contiguous bytes
+  const int toff = px * 64 + g * 4;
+  const long long row_step = (long long)a.W * a.out_ld;
+  int stage = 0;
+  uint32_t phase = 0;
+  float2 w1[9], w2[9], b1, b2;
+  int w_ct = -1;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int ct = tile % ctiles;
+    int r = tile / ctiles;
+    const int tx = r % tiles_x;
+    r /= tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    const int c1 = ct * 32 + g * 2;      // x1 input channel = output channel; the x2 partner is c1 + cout
+    if (ct != w_ct) {
+      w_ct = ct;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        w1[t] = __ldg(reinterpret_cast<const float2*>(a.w + (long long)t * a.C + c1));
+        w2[t] = __ldg(reinterpret_cast<const float2*>(a.w + (long long)t * a.C + cout + c1));
+      }
+      b1 = a.bias ? __ldg(reinterpret_cast<const float2*>(a.bias + c1)) : make_float2(0.f, 0.f);
+      b2 = a.bias ? __ldg(reinterpret_cast<const float2*>(a.bias + cout + c1)) : make_float2(0.f, 0.f);
+    }
+    if (tid == 0) {      // refill the other stage (every thread passed the barrier that ended its last use)
+      const int t2 = tile + gridDim.x;
+      if (t2 < num_tiles) issue(t2, stage ^ 1);
+    }
+    mbar_wait(&full[stage], phase);
+    const uint32_t base = smem_u32(smem) + stage * Cf::STAGE_BYTES + toff;
+    float2 wa[3][3], wb[3][3];      // [row slot][column] of x1 / x2, unpacked
+    auto load_row = [&](int slot, int hr) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t q1, q2;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q1) : "r"(base + (hr * (DWT_TX + 2) + c) * 64));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q2) : "r"(base + Cf::HALF_BYTES + (hr * (DWT_TX + 2) + c) * 64));
+        wa[slot][c] = make_float2(__uint_as_float(q1 << 16), __uint_as_float(q1 & 0xffff0000u));
+        wb[slot][c] = make_float2(__uint_as_float(q2 << 16), __uint_as_float(q2 & 0xffff0000u));
+      }
+    };
+    load_row(0, 0);
+    load_row(1, 1);
+    // rows of this tile inside the image (0 when the pixel column lies outside: partial edge tiles)
+    const int rows_in = (tx * DWT_TX + px < a.W) ? min(DWG_TY, a.H - ty * DWG_TY) : 0;
+    bf16* op = a.out + ((long long)(b * a.H + ty * DWG_TY) * a.W + tx * DWT_TX + px) * a.out_ld + c1;
+    float2 psum = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int row = 0; row < DWG_TY; ++row) {
+      load_row((row + 2) % 3, row + 2);
+      float2 acc1 = b1, acc2 = b2;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          acc1 = __ffma2_rn(wa[(row + dy) % 3][dx], w1[dy * 3 + dx], acc1);
+          acc2 = __ffma2_rn(wb[(row + dy) % 3][dx], w2[dy * 3 + dx], acc2);
+        }
+      const float2 o = __fmul2_rn(acc1, acc2);
+      if (row < rows_in) {      // rows / columns beyond the image hold bias products, not zeros: keep them out of the store and the pool
+        psum = __fadd2_rn(psum, o);
+        *reinterpret_cast<uint32_t*>(op) = pack_bf16(o.x, o.y);
+      }
+      op += row_step;
+    }
+    const int par = ((tile - (int)blockIdx.x) / (int)gridDim.x) & 1;
+    if (a.col_sums) {
+      // a warp holds two pixel columns of every channel pair: fold them, then one float2 per (warp, channel pair)
+      psum.x += __shfl_xor_sync(0xffffffffu, psum.x, 16);
+      psum.y += __shfl_xor_sync(0xffffffffu, psum.y, 16);
+      if ((tid & 31) < 16) pool_red[par][tid >> 5][tid & 15] = psum;
+    }
+    __syncthreads();      // everyone is done with this stage before it is refilled in the next iteration
+    if (a.col_sums && tid < 16) {
+      float2 t = pool_red[par][0][tid];
+#pragma unroll
+      for (int w2_ = 1; w2_ < DWT_THREADS / 32; ++w2_) {
+        const float2 q = pool_red[par][w2_][tid];
+        t.x += q.x; t.y += q.y;
+      }
+      const long long prow = ((long long)b * tiles_y + ty) * tiles_x + tx;
+      *reinterpret_cast<float2*>(a.col_sums + prow * cout + ct * 32 + tid * 2) = t;
+    }
+    stage ^= 1;
+    if (stage == 0) phase ^= 1;
+  }
+}
+
+static int launch_dw_gate_tma(const CUtensorMap& tx_, const DwArgs& a, int tiles_x, int tiles_y, int ctiles, int grid, cudaStream_t st) {
+  static FFPerDeviceFlag configured_dev;
+  bool& configured = configured_dev.get();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_gate_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DwgCfg::SMEM);
+    if (e != cudaSuccess) { ff_set_error("ff_dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return FF_ERR_CUDA; }
+    configured = true;
+  }
+  dwconv3x3_gate_tma_kernel<<<grid, DWT_THREADS, DwgCfg::SMEM, st>>>(tx_, a, tiles_x, tiles_y, ctiles);
+  return FF_OK;
+}
+
 template <int MODE, int ACT, bool MUL>
 static int launch_dw_tma(const CUtensorMap& tx_, const CUtensorMap& tm_, const DwArgs& a, int tiles_x, int tiles_y, int ctiles, int grid, cudaStream_t st) {
   static FFPerDeviceFlag configured_dev;
@@ -1162,9 +1302,17 @@ extern "C" int ff_dwconv_pool(const void* x, int x_ld, int B, int H, int W, int 
   return dwconv_impl(x, x_ld, B, H, W, C, 3, 3, w, bias, act, mode, mul, mul_ld, out, out_ld, col_sums, stream);
 }
 
+static bool dw_gate2_enabled() {
+  static const bool on = []() { const char* e = getenv("FFB200_DW_GATE2"); return !(e && e[0] == '0'); }();
+  return on;
+}
+static int dw_tile_rows(int mode) { return (mode == 1 && dw_gate2_enabled()) ? DWG_TY : DWT_TY; }
+
 extern "C" int ff_dwconv_pool_rows(int H, int W, int cout, int mode) {
-  if (H <= 0 || W <= 0 || W % DWT_TX || H % DWT_TY || cout % (mode == 1 ? 32 : 64)) return 0;
-  return (H / DWT_TY) * (W / DWT_TX);
+  const int ty = dw_tile_rows(mode);
+  const bool partial_rows_ok = mode == 1 && dw_gate2_enabled();      // the SimpleGate kernel masks its pool sums by row
+  if (H <= 0 || W <= 0 || W % DWT_TX || (H % ty && !partial_rows_ok) || cout % (mode == 1 ? 32 : 64)) return 0;
+  return ff_cdiv(H, ty) * (W / DWT_TX);
 }
 
 static int dwconv_impl(const void* x, int x_ld, int B, int H, int W, int C, int kh, int kw, const float* w,
@@ -1182,7 +1330,9 @@ static int dwconv_impl(const void* x, int x_ld, int B, int H, int W, int C, int 
     cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
     static const bool tma_enabled = []() { const char* e = getenv("FFB200_DW_TMA"); return !(e && e[0] == '0'); }();
     const int cout_ = mode == 1 ? C / 2 : C;
-    const bool tiles_ok = W % DWT_TX == 0 && H % DWT_TY == 0;      // the fused pool needs whole tiles; the plain kernel masks edge tiles
+    const int TYv = dw_tile_rows(mode);
+    // the fused pool needs whole tiles (the SimpleGate kernel: whole tile columns); the plain kernels mask edge tiles
+    const bool tiles_ok = W % DWT_TX == 0 && (H % TYv == 0 || (mode == 1 && dw_gate2_enabled()));
     if ((tma_enabled || col_sums) && (tiles_ok || !col_sums) && cout_ % (mode == 1 ? 32 : 64) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!mul || (mode != 1 && (reinterpret_cast<uintptr_t>(mul) & 15) == 0 && mul_ld % 8 == 0))) {
       typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -1198,7 +1348,7 @@ static int dwconv_impl(const void* x, int x_ld, int B, int H, int W, int C, int 
       CUtensorMap tm, tmm;
       cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
       cuuint64_t strides[3] = {(cuuint64_t)x_ld * 2, (cuuint64_t)x_ld * 2 * W, (cuuint64_t)x_ld * 2 * W * H};
-      cuuint32_t box[4] = {(cuuint32_t)(mode == 1 ? 32 : 64), DWT_TX + 2, DWT_TY + 2, 1};
+      cuuint32_t box[4] = {(cuuint32_t)(mode == 1 ? 32 : 64), DWT_TX + 2, (cuuint32_t)(TYv + 2), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1211,12 +1361,13 @@ static int dwconv_impl(const void* x, int x_ld, int B, int H, int W, int C, int 
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { ff_set_error("ff_dwconv: cuTensorMapEncodeTiled(mul) failed with %d", (int)r); return FF_ERR_DRIVER; }
       }
-      const int tiles_x = ff_cdiv(W, DWT_TX), tiles_y = ff_cdiv(H, DWT_TY), ctiles = cout_ / (mode == 1 ? 32 : 64);
+      const int tiles_x = ff_cdiv(W, DWT_TX), tiles_y = ff_cdiv(H, TYv), ctiles = cout_ / (mode == 1 ? 32 : 64);
       const long long ntiles = (long long)B * tiles_x * tiles_y * ctiles;
       int grid = (int)(ntiles < ff_num_sms() ? ntiles : ff_num_sms());
       if (grid >= 8 * ctiles) grid -= grid % ctiles;      // constant channel tile per CTA: weights are loaded once
       int rc;
-      if (mode == 1) rc = launch_dw_tma<1, 0, false>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_);
+      const bool gate2 = dw_gate2_enabled();
+      if (mode == 1) rc = gate2 ? launch_dw_gate_tma(tm, a, tiles_x, tiles_y, ctiles, grid, st_) : launch_dw_tma<1, 0, false>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_);
       else if (mul) rc = act == FF_ACT_NONE ? launch_dw_tma<0, 0, true>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_)
                                             : launch_dw_tma<0, 2, true>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_);
       else if (act == FF_ACT_NONE) rc = launch_dw_tma<0, 0, false>(tm, tmm, a, tiles_x, tiles_y, ctiles, grid, st_);
