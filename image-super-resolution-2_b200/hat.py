@@ -192,6 +192,7 @@ class HATRunner:
         scratch = ws.get("gap_scratch", 1, B * 64 * CP, F32)
         wcat = ws.get("proj_cat_w", B * CP, 2 * CP, BF16)      # per-sample [W_proj | diag(0.01 se)] of the current block
         fused = ops.fused_ln_enabled()      # every LayerNorm after a residual add leaves the producing GEMM's epilogue
+        tail = fused and ops.hab_tail_enabled()      # proj + shortcut + LN2 + MLP + residual + next LN as one kernel
 
         if (H, W) == (h0, w0):
             ops.nchw_to_nhwc(x, img, sub=self.mean)
@@ -219,6 +220,15 @@ class HATRunner:
                 ops.conv_gemm(t, B, H, W, CP, d["qkv_w"], n_store=3 * CP, bias=d["qkv_b"], out_bf16=qkv)
                 ops.window_attention(qkv, B, H, W, att, bias_table=d["table"], wh=WS, ww=WS, shift=(shift, shift))
                 # x = shortcut + attn + 0.01 * cab   (hat_arch.py:306); the epilogue also emits LN2(x) into t
+                nxt = layer["habs"][j + 1]["norm1"] if j + 1 < nhab else layer["ocab"]["norm1"]
+                if tail:
+                    # everything after the attention as one kernel: x1 stays in TMEM, LN2(x1) in shared memory (csrc/hab_tail.cu)
+                    ops.build_concat_diag_weights(d["proj_w"], se, 0.01, wcat.view(B, CP, 2 * CP))
+                    ops.hab_tail(att, B, H, W, wcat, d["proj_b"], src, d["norm2"], d["fc1_w"], d["fc1_b"], d["fc2_w"], d["fc2_b"], X,
+                                 a1=cab2, wp_batch_rows=CP, ln=(nxt[0], nxt[1], t))
+                    t_ready = True
+                    src = X
+                    continue
                 ln2 = (d["norm2"][0], d["norm2"][1], 1e-5, C, t) if fused else None
                 if ops.concat_aux_enabled():
                     # the + 0.01 * cab * se term rides on the tensor pipe: [att | cab] . [W_proj ; diag(0.01 * se_b)] per sample,
@@ -227,7 +237,6 @@ class HATRunner:
                     ops.conv_gemm(att, B, H, W, CP, wcat, n_store=CP, w_batch_rows=CP, bias=d["proj_b"], x2=cab2, res=src, out_f32=X, ln=ln2)
                 else:
                     ops.conv_gemm(att, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], aux=cab2, aux_chan=se, aux_alpha=0.01, res=src, out_f32=X, ln=ln2)
-                nxt = layer["habs"][j + 1]["norm1"] if j + 1 < nhab else layer["ocab"]["norm1"]
                 self._mlp(d, X, t, h, B, H, W, M, t_ready=fused, next_norm=nxt if fused else None)
                 t_ready = fused
                 src = X
@@ -237,9 +246,12 @@ class HATRunner:
             ops.conv_gemm(t, B, H, W, CP, d["qkv_w"], n_store=3 * CP, bias=d["qkv_b"], out_bf16=qkv)
             ops.window_attention(qkv, B, H, W, att, bias_table=d["table"], wh=WS, ww=WS, kh=24, kw=24, kpad=(4, 4),
                                  rel_sign=-1, rel_off=(-7, -7), rel_stride=39)
-            ops.conv_gemm(att, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], res=X, out_f32=X,
-                          ln=(d["norm2"][0], d["norm2"][1], 1e-5, C, t) if fused else None)
-            self._mlp(d, X, t, h, B, H, W, M, extra_bf16=Xb, t_ready=fused)
+            if tail:
+                ops.hab_tail(att, B, H, W, d["proj_w"], d["proj_b"], X, d["norm2"], d["fc1_w"], d["fc1_b"], d["fc2_w"], d["fc2_b"], X, out_bf16=Xb)
+            else:
+                ops.conv_gemm(att, B, H, W, CP, d["proj_w"], n_store=CP, bias=d["proj_b"], res=X, out_f32=X,
+                              ln=(d["norm2"][0], d["norm2"][1], 1e-5, C, t) if fused else None)
+                self._mlp(d, X, t, h, B, H, W, M, extra_bf16=Xb, t_ready=fused)
             # RHAG tail: conv3x3 + group residual (hat_arch.py:618-619); its epilogue emits the LayerNorm of the next consumer
             # of G: norm1 of the next group's first block, or the final `norm`
             nxt = self.layers[li + 1]["habs"][0]["norm1"] if li + 1 < len(self.layers) else self.norm

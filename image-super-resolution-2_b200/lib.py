@@ -46,6 +46,16 @@ class FFMlpFused(C.Structure):
     ]
 
 
+class FFHabTail(C.Structure):
+    _fields_ = [
+        ("a0", C.c_void_p), ("a0_ld", C.c_int), ("a1", C.c_void_p), ("a1_ld", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("wp", C.c_void_p), ("wp_batch_rows", C.c_int), ("bp", C.c_void_p), ("res", C.c_void_p), ("res_ld", C.c_int),
+        ("ln2_gamma", C.c_void_p), ("ln2_beta", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("x", C.c_void_p), ("x_ld", C.c_int), ("out_bf16", C.c_void_p), ("out_ld", C.c_int), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
+        ("ln_out", C.c_void_p), ("ln_out_ld", C.c_int), ("ln_eps", C.c_float), ("ln_cols", C.c_int),
+    ]
+
+
 class FFError(RuntimeError):
     pass
 
@@ -65,7 +75,7 @@ def load():
     lib.ff_last_error.restype = C.c_char_p
     lib.ff_launch_count.restype = C.c_longlong
     lib.ff_ssim_y_scratch_bytes.restype = C.c_size_t
-    if lib.ff_abi_version() != 4:
+    if lib.ff_abi_version() != 5:
         raise FFError("libffb200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -163,6 +163,50 @@ def mlp_fused(t, B, H, W, w1, b1, w2, b2, x, *, out_bf16=None, ln=None):
     L.check(L.load().ff_mlp_fused(C.byref(p), _stream()), "ff_mlp_fused")
 
 
+def hab_tail_enabled():
+    """proj + shortcut + LayerNorm2 + MLP + residual (+ next LayerNorm) of a HAT block as one kernel (ff_hab_tail);
+    FFB200_HAB_TAIL=0 restores the residual GEMM followed by ff_mlp_fused."""
+    import os
+    return os.environ.get("FFB200_HAB_TAIL", "1") != "0"
+
+
+def hab_tail(a0, B, H, W, wp, bp, res, ln2, w1, b1, w2, b2, x, *, a1=None, wp_batch_rows=0, out_bf16=None, ln=None, eps=1e-5, cols=180):
+    """x = x1 + fc2(GELU(fc1(LN2(x1)))) with x1 = res + [a0 | a1] . wp^T + bp; ln = (gamma, beta, bf16 out) of the next LayerNorm."""
+    _req_cuda(a0, a1, wp, bp, res, ln2[0], ln2[1], w1, b1, w2, b2, x, out_bf16)
+    p = L.FFHabTail()
+    p.a0 = a0.data_ptr(); p.a0_ld = a0.stride(-2)
+    if a1 is not None:
+        p.a1 = a1.data_ptr(); p.a1_ld = a1.stride(-2)
+    p.B, p.H, p.W = B, H, W
+    p.wp = wp.data_ptr(); p.wp_batch_rows = wp_batch_rows; p.bp = bp.data_ptr()
+    p.res = res.data_ptr(); p.res_ld = res.stride(-2)
+    p.ln2_gamma = ln2[0].data_ptr(); p.ln2_beta = ln2[1].data_ptr()
+    p.w1 = w1.data_ptr(); p.b1 = b1.data_ptr(); p.w2 = w2.data_ptr(); p.b2 = b2.data_ptr()
+    p.x = x.data_ptr(); p.x_ld = x.stride(-2)
+    if out_bf16 is not None:
+        p.out_bf16 = out_bf16.data_ptr(); p.out_ld = out_bf16.stride(-2)
+    if ln is not None:
+        g_, b_, lo_ = ln
+        _req_cuda(g_, b_, lo_)
+        p.ln_gamma = g_.data_ptr(); p.ln_beta = b_.data_ptr(); p.ln_out = lo_.data_ptr(); p.ln_out_ld = lo_.stride(-2)
+    p.ln_eps = eps; p.ln_cols = cols
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.load().ff_hab_tail(C.byref(p), _stream()), "ff_hab_tail")
+        e1.record()
+        M = B * H * W
+        n0, k0 = getattr(wp, "ff_real", (cols, cols))
+        n1, k1 = getattr(w1, "ff_real", tuple(w1.shape))
+        n2, k2 = getattr(w2, "ff_real", tuple(w2.shape))
+        flops = 2.0 * M * (n0 * k0 + n1 * k1 + n2 * k2 + (cols if a1 is not None else 0))
+        executed = 2.0 * M * (192 * 192 + (3 * 64 * 64 if a1 is not None else 0) + w1.shape[0] * w1.shape[1] + w2.shape[0] * w2.shape[1])
+        byts = M * k0 * 2 * (2 if a1 is not None else 1) + (n0 * k0 + n1 * k1 + n2 * k2) * 2 + M * n2 * 8 + (M * n2 * 2 if out_bf16 is not None else 0) + (M * cols * 2 if ln is not None else 0)
+        PROFILE.records.append((e0, e1, flops, executed, float(byts), ("hab_tail", B, H, W)))
+        return
+    L.check(L.load().ff_hab_tail(C.byref(p), _stream()), "ff_hab_tail")
+
+
 def window_attention(qkv, B, H, W, out, *, bias_table, wh, ww, kh=None, kw=None, kpad=(0, 0), shift=(0, 0), heads=6,
                      head_off=0, bias_head_off=0, rel_sign=1, rel_off=None, rel_stride=None, q_off=0, k_off=192,
                      v_off=384, out_off=0, padded=None):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FFB200_ABI_VERSION 4
+#define FFB200_ABI_VERSION 5
 
 int ff_abi_version(void);
 const char* ff_last_error(void);
@@ -131,6 +131,36 @@ typedef struct FFMlpFused {
   void* ln_out; int ln_out_ld;   /* optional */
 } FFMlpFused;
 int ff_mlp_fused(const FFMlpFused* p, void* stream);
+
+/*
+ * ff_hab_tail -- everything of a HAT block after the attention as one kernel (hat_arch.py:303-309 HAB.forward tail,
+ * :435-438 OCAB.forward tail):
+ *     x1 = res + [a0 | a1] . wp^T + bp                  (attn.proj + shortcut; a1 / the second K half of wp carry the
+ *                                                        0.01 * conv_block(x) * channel-attention term of :306 as a diagonal block)
+ *     x  = x1 + fc2(GELU(fc1(LayerNorm(x1; ln2))))     (norm2 + Mlp + residual, :308)
+ *     ln_out = LayerNorm(x; ln_gamma, ln_beta)          (optional: the norm1 of the next block)
+ * x1 and LayerNorm(x1) never reach HBM (x1 stays in TMEM as the initial value of the fc2 accumulator).
+ * a0, a1: bf16 [B*H*W][ld] with 192 columns (zero padded from 180); wp: bf16 [192 or B*192][K0] with K0 = 192 (a1 NULL) or 384,
+ * per-sample rows when wp_batch_rows = 192 (see ff_build_concat_diag_weights); only the three 64 x 64 diagonal slabs of the
+ * second K half are read.  res / x: fp32 [B*H*W][ld] (may alias).  w1 [384][192], w2 [192][384] bf16, biases fp32 padded.
+ */
+typedef struct FFHabTail {
+  const void* a0; int a0_ld;
+  const void* a1; int a1_ld;     /* optional */
+  int B, H, W;                   /* the token matrix as an image (tiles are 8 x 16 pixels) */
+  const void* wp; int wp_batch_rows;
+  const float* bp;
+  const float* res; int res_ld;
+  const float* ln2_gamma; const float* ln2_beta;   /* [192], zero padded */
+  const void* w1; const float* b1;
+  const void* w2; const float* b2;
+  float* x; int x_ld;
+  void* out_bf16; int out_ld;    /* optional bf16 copy of x */
+  const float* ln_gamma; const float* ln_beta;
+  void* ln_out; int ln_out_ld;   /* optional */
+  float ln_eps; int ln_cols;     /* shared by both LayerNorms (180, 1e-5 in HAT) */
+} FFHabTail;
+int ff_hab_tail(const FFHabTail* p, void* stream);
 
 /*
  * ff_window_attention -- fused window attention (QK^T + relative-position bias + shift mask + softmax + PV).

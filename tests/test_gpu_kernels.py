@@ -883,6 +883,71 @@ def test_mlp_fused(B, H, W, with_bf16, with_ln):
         assert (lno.cpu().float()[:, C:] == 0).all()
 
 
+@pytest.mark.parametrize("B,H,W,with_cab,with_bf16,with_ln,inplace", [(2, 16, 32, True, False, True, False), (1, 24, 40, True, False, True, True),
+                                                                  (3, 64, 64, True, False, True, True), (2, 13, 21, False, True, False, True),
+                                                                  (5, 48, 80, False, True, True, False)])
+def test_hab_tail(B, H, W, with_cab, with_bf16, with_ln, inplace):
+    """ff_hab_tail (csrc/hab_tail.cu): proj + shortcut (+ 0.01 * cab * se through the diagonal K block) -> LayerNorm2 -> MLP -> residual
+    (-> next LayerNorm) as one kernel with x1 in TMEM, against plain fp32 PyTorch on the bf16-rounded operands, on whole and partial tiles,
+    several tiles per CTA (B=3, 64x64 = 96 tiles... per-SM queues of one; B=5, 48x80 = 150 tiles > 148 SMs)."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(53 + B)
+    P, C, HD, CP = B * H * W, 180, 360, 192
+    def padded(v):
+        o = torch.zeros(P, CP)
+        o[:, :C] = v
+        return o
+    att = padded(torch.randn(P, C, generator=g)).to(BF16)
+    cab = padded(torch.randn(P, C, generator=g) * 3).to(BF16)
+    wp = (torch.randn(C, C, generator=g) / math.sqrt(C)).to(BF16).float()
+    bp = torch.randn(C, generator=g) * 0.3
+    se = torch.rand(B, C, generator=g)
+    res = padded(torch.randn(P, C, generator=g) * 2 + 0.5)
+    w1 = (torch.randn(HD, C, generator=g) / math.sqrt(C)).to(BF16).float()
+    w2 = (torch.randn(C, HD, generator=g) / math.sqrt(HD)).to(BF16).float()
+    b1, b2 = torch.randn(HD, generator=g) * 0.3, torch.randn(C, generator=g) * 0.3
+    def lnp():
+        ga, be = torch.zeros(CP), torch.zeros(CP)
+        ga[:C], be[:C] = 1 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+        return ga, be
+    g2, be2 = lnp()
+    gn, ben = lnp()
+    x1 = res[:, :C] + att.float()[:, :C] @ wp.t() + bp
+    if with_cab:
+        x1 = x1 + (0.01 * se).to(BF16).float().repeat_interleave(H * W, 0) * cab.float()[:, :C]
+    t = F.layer_norm(x1, (C,), g2[:C], be2[:C], 1e-5).to(BF16).float()
+    hid = F.gelu(t @ w1.t() + b1)
+    ref = padded(x1 + hid.to(BF16).float() @ w2.t() + b2)
+    ln_ref = padded(F.layer_norm(ref[:, :C], (C,), gn[:C], ben[:C], 1e-5))
+    d = _dev()
+    wpd = packing.pack_matrix(wp, CP, CP, device=d)
+    if with_cab:
+        wcat = torch.empty(B, CP, 2 * CP, dtype=BF16, device=d)
+        sed = torch.zeros(B, CP, device=d)
+        sed[:, :C] = se.to(d)
+        ops.build_concat_diag_weights(wpd, sed, 0.01, wcat)
+        wuse, wbr = wcat.view(B * CP, 2 * CP), CP
+    else:
+        wuse, wbr = wpd, 0
+    resd = res.clone().to(d)
+    xd = resd if inplace else torch.full((P, CP), 9.0, device=d)
+    o16 = torch.full((P, CP), 7.0, dtype=BF16, device=d) if with_bf16 else None
+    lno = torch.full((P, CP), 7.0, dtype=BF16, device=d) if with_ln else None
+    ops.hab_tail(att.to(d), B, H, W, wuse, packing.pack_vector(bp, CP, device=d), resd, (g2.to(d), be2.to(d)),
+                 packing.pack_matrix(w1, 2 * CP, CP, device=d), packing.pack_vector(b1, 2 * CP, device=d),
+                 packing.pack_matrix(w2, CP, 2 * CP, device=d), packing.pack_vector(b2, CP, device=d), xd,
+                 a1=cab.to(d) if with_cab else None, wp_batch_rows=wbr, out_bf16=o16, ln=(gn.to(d), ben.to(d), lno) if with_ln else None)
+    torch.cuda.synchronize()
+    e = (xd.cpu() - ref).abs().max().item()
+    assert e < 3e-2, e              # bf16 LayerNorm2 output and hidden activations through 180 / 360-long contractions
+    assert (xd.cpu()[:, C:] == 0).all()
+    if with_bf16:
+        assert (o16.cpu().float() - ref).abs().max().item() < 8e-2
+    if with_ln:
+        assert (lno.cpu().float() - ln_ref).abs().max().item() < 5e-2
+        assert (lno.cpu().float()[:, C:] == 0).all()
+
+
 def test_conv_gemm_k_concatenated_second_operand():
     """FFConvGemm.x2: out = [x | x2] . W^T with per-sample weights [W | diag(alpha * s_b)] (ff_build_concat_diag_weights) reproduces the
     aux epilogue  x.W^T + bias + alpha * s_b[n] * x2[p, n] + res  of HAT's proj layer (hat_arch.py:306) on the tensor pipe."""
