@@ -26,6 +26,7 @@
 #include "ff_common.cuh"
 #include "../../include/ffb200.h"
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -141,10 +142,11 @@ __device__ unsigned long long g_attn_prof[8];
 #endif
 
 template <class G>
-__global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const __grid_constant__ FFWinAttn p) {
+__global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const __grid_constant__ FFWinAttn p, const __grid_constant__ CUtensorMap tmQKV,
+                                                                          const int use_tma) {
   constexpr int WH = G::WH, WW = G::WW, TROWS = G::TROWS, TCOLS = G::TCOLS, TSTRIDE = G::TSTRIDE;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ __align__(8) uint64_t mma_bar, qk_bar, v_bar;
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -172,9 +174,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
   const bool need_mask = shifted && (wy == nwy - 1 || wx == nwx - 1);
 
   PROF_DECL
+  // A window that neither wraps around the (padded) image under the cyclic shift nor holds padded tokens is one dense
+  // [WH][WW][64 channels] box per operand: three TMA loads with the 128-byte swizzle land it in exactly the layout the cp.async
+  // gather below builds (token = y * WW + x -> 128-byte row, 1024-byte atoms of 8 rows).  Border windows of shifted blocks, the
+  // padded windows of DAT keep the gather.  (The single-head tail of an odd head count loads 64 channels as well: the second
+  // half of its rows holds whatever follows in the qkv row -- never read by Q K^T, and it only feeds ignored columns of P V.)
+  const int wy0 = wy * WH + p.shift_y, wx0 = wx * WW + p.shift_x;
+  const bool tma_win = use_tma && wy0 + WH <= p.H && wx0 + WW <= p.W;      // CTA-uniform
   if (tid == 0) {
     mbar_init(&mma_bar, 1);
+    mbar_init(&qk_bar, 1);
+    mbar_init(&v_bar, 1);
     fence_mbar_init();
+    if (tma_win) {
+      mbar_arrive_expect_tx(&qk_bar, 2 * NT * ROWB);
+      tma_load_4d(smem + G::SMEM_Q, &tmQKV, &qk_bar, p.q_off + head0 * 32, wx0, wy0, b);
+      tma_load_4d(smem + G::SMEM_K, &tmQKV, &qk_bar, p.k_off + head0 * 32, wx0, wy0, b);
+      mbar_arrive_expect_tx(&v_bar, NT * ROWB);
+      tma_load_4d(smem + G::SMEM_V, &tmQKV, &v_bar, p.v_off + head0 * 32, wx0, wy0, b);
+    }
   }
   if (warp == 1) {
     tmem_alloc(&tmem_slot, TMEM_COLS);
@@ -188,6 +206,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
     const bf16* base = reinterpret_cast<const bf16*>(p.qkv);
 #pragma unroll
     for (int part = 0; part < 2; ++part) {
+      if (!tma_win)
       for (int idx = tid; idx < NT * 8; idx += NTHREADS) {
         const int t = idx >> 3, c = idx & 7;
         int y = wy * WH + (t >> G::LOG_WW) + p.shift_y; if (y >= Hp) y -= Hp;
@@ -224,6 +243,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
     if (lane == 0) { sRed[0][warp] = tm[0]; sRed[1][warp] = tm[1]; }
     asm volatile("cp.async.wait_group 1;" ::: "memory");      // Q and K have landed
     fence_proxy_async_smem();      // generic/cp.async writes -> visible to the tensor core's async-proxy reads
+    if (tma_win && warp == 0) mbar_wait(&qk_bar, 0);      // the warp that issues the MMAs sees the TMA transaction complete
   }
   tc_fence_before();
   __syncthreads();
@@ -311,6 +331,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
     if (unit == 0) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");    // V has landed (this thread's part; the barrier covers the rest)
       fence_proxy_async_smem();
+      if (tma_win && warp == 0) mbar_wait(&v_bar, 0);
     }
     tc_fence_before();
     __syncthreads();
@@ -374,6 +395,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) window_attention_tc_kernel(const 
 }
 
 int g_mode = -1;   // -1 unread, 0 off, 1 on
+int g_tma = 1;     // FFB200_ATTN_TMA=0: every window through the cp.async gather
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  return nullptr;
+}
 
 template <class G>
 int launch_tc_attn(const FFWinAttn& p, cudaStream_t st) {
@@ -388,8 +420,23 @@ int launch_tc_attn(const FFWinAttn& p, cudaStream_t st) {
     configured = true;
   }
   const int Hp = p.Hp > 0 ? p.Hp : p.H, Wp = p.Wp > 0 ? p.Wp : p.W;
+  // one tensor map over the qkv rows: box = a whole window of one head pair of one operand ([WH][WW][64 channels])
+  CUtensorMap tm;
+  int use_tma = g_tma;
+  if (use_tma) {
+    static EncodeTiledFn enc = get_encode();
+    cuuint64_t dims[4] = {(cuuint64_t)p.ld, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    cuuint64_t strides[3] = {(cuuint64_t)p.ld * 2, (cuuint64_t)p.ld * 2 * p.W, (cuuint64_t)p.ld * 2 * p.W * p.H};
+    cuuint32_t box[4] = {64, (cuuint32_t)G::WW, (cuuint32_t)G::WH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!enc || p.H < G::WH || p.W < G::WW ||
+        enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.qkv), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      use_tma = 0;
+  }
+  if (!use_tma) memset(&tm, 0, sizeof(tm));
   dim3 grid((unsigned)(p.B * (Hp / G::WH) * (Wp / G::WW) * ((p.heads + 1) / 2)));
-  window_attention_tc_kernel<G><<<grid, NTHREADS, G::SMEM_BYTES, st>>>(p);
+  window_attention_tc_kernel<G><<<grid, NTHREADS, G::SMEM_BYTES, st>>>(p, tm, use_tma);
   FF_CHECK_LAUNCH("ff_window_attention(tc)");
   return FF_OK;
 }
@@ -402,6 +449,8 @@ int ff_window_attention_tc_try(const FFWinAttn& p, cudaStream_t st) {
   if (g_mode < 0) {
     const char* e = getenv("FFB200_ATTN_TC");
     g_mode = (e && e[0] == '0') ? 0 : 1;
+    const char* t = getenv("FFB200_ATTN_TMA");
+    g_tma = (t && t[0] == '0') ? 0 : 1;
   }
   if (!g_mode) return 1;
   const int Hp = p.Hp > 0 ? p.Hp : p.H, Wp = p.Wp > 0 ? p.Wp : p.W;
