@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) hab_tail_kernel(const __grid_cons
       float s1sum = 0.f, s2sum = 0.f;
       uint32_t raw[2][16];
       tmem_ld16(taddr + half * SUB, raw[0]);
-#pragma unroll
+#pragma unroll 2
       for (int j = 0; j < SUB_PER_WARP; ++j) {      // (the next sub-block's TMEM load is in flight while this one is updated)
         const int sb = half + 2 * j;
         const int buf = j & 1;
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) hab_tail_kernel(const __grid_cons
         p_ae ^= 1;
       }
       if (mw == 0) TPROF(11)
-#pragma unroll
+#pragma unroll 2
       for (int j = 0; j < SUB_PER_WARP; ++j) {
         const int sb = half + 2 * j;
         tc_wait_ld();
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) hab_tail_kernel(const __grid_cons
       float s1sum = 0.f, s2sum = 0.f;
       uint32_t raw[2][16];
       tmem_ld16(taddr + half * SUB, raw[0]);
-#pragma unroll
+#pragma unroll 2
       for (int j = 0; j < SUB_PER_WARP; ++j) {
         const int sb = half + 2 * j;
         tc_wait_ld();
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) hab_tail_kernel(const __grid_cons
         tmem_ld16(taddr + half * SUB, raw[0]);
         if (lane == 0) tma_store_wait_read<0>();      // F is reused as two bf16 stages
         __syncwarp();
-#pragma unroll
+#pragma unroll 2
         for (int j = 0; j < SUB_PER_WARP; ++j) {
           const int sb = half + 2 * j;
           tc_wait_ld();
