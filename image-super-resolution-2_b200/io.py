@@ -83,12 +83,33 @@ def encode_png(arr, level=None):
     return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + chunk(b"IDAT", comp) + chunk(b"IEND", b"")
 
 
+def encode_png_native(arr):
+    """uint8 HWC RGB array -> PNG file bytes through ff_png_encode_rgb8 (csrc/png_writer.cu): Sub filter + one literal-only
+    dynamic-Huffman deflate block, ~10x faster than zlib's fastest setting at the same size on super-resolved content; ctypes
+    releases the GIL for the call."""
+    import ctypes as C
+    from . import lib as L
+    h, w, c = arr.shape
+    assert c == 3 and arr.dtype == np.uint8
+    arr = np.ascontiguousarray(arr)
+    so = L.load()
+    so.ff_png_bound_rgb8.restype = C.c_longlong
+    so.ff_png_encode_rgb8.restype = C.c_longlong
+    cap = so.ff_png_bound_rgb8(h, w)
+    out = np.empty(cap, dtype=np.uint8)
+    n = so.ff_png_encode_rgb8(C.c_void_p(arr.ctypes.data), h, w, C.c_longlong(arr.strides[0]), C.c_void_p(out.ctypes.data), C.c_longlong(cap))
+    if n < 0:
+        L.check(int(n), "ff_png_encode_rgb8")
+    return out[:n]
+
+
 def _write_png(arr, path):
-    if os.environ.get("FFB200_PNG_WRITER", "native") == "pil":
+    writer = os.environ.get("FFB200_PNG_WRITER", "native")
+    if writer == "pil":
         Image.fromarray(arr).save(path, format="PNG", compress_level=PNG_COMPRESS_LEVEL)
         return
     with open(path, "wb") as f:
-        f.write(encode_png(arr))
+        f.write(encode_png(arr) if writer == "zlib" else encode_png_native(arr))
 
 
 _MODEL_CACHE = {}

@@ -133,6 +133,15 @@ typedef struct FFMlpFused {
 int ff_mlp_fused(const FFMlpFused* p, void* stream);
 
 /*
+ * ff_png_encode_rgb8 -- host-side PNG writer of the plugin's save path (models/team29_FreqFusion/io.py:71-76 _save_image).
+ * rgb: uint8 [h][w][3], row_stride bytes between rows; out: at least ff_png_bound_rgb8(h, w) bytes.  Returns the file size
+ * (8-bit truecolour, Sub-filtered scanlines, one literal-only dynamic-Huffman deflate block) or a negative error code.
+ * Pure CPU code, thread safe, no CUDA call: decoding the file gives back exactly the input pixels.
+ */
+long long ff_png_bound_rgb8(int h, int w);
+long long ff_png_encode_rgb8(const unsigned char* rgb, int h, int w, long long row_stride, unsigned char* out, long long cap);
+
+/*
  * ff_hab_tail -- everything of a HAT block after the attention as one kernel (hat_arch.py:303-309 HAB.forward tail,
  * :435-438 OCAB.forward tail):
  *     x1 = res + [a0 | a1] . wp^T + bp                  (attn.proj + shortcut; a1 / the second K half of wp carry the

@@ -350,3 +350,51 @@ def test_tile_sharded_final_gather_keeps_unit_order():
     ok = q.get(timeout=180)
     [p.join(60) for p in procs]
     assert ok and all(p.exitcode == 0 for p in procs)
+
+
+def test_native_png_writer_round_trips():
+    """ff_png_encode_rgb8 (csrc/png_writer.cu, the plugin's _save_image replacement, io.py:71-76 of the reference): the files decode
+    (PIL / libpng / zlib) to exactly the input pixels for ragged sizes, flat images and histograms skewed enough to need the 15-bit
+    length limit; the zlib writer (encode_png) gives the same pixels."""
+    import io as _io
+    import struct
+    import zlib
+    import numpy as np
+    from PIL import Image
+    from isr2_b200 import io as ffio
+    rng = np.random.default_rng(5)
+
+    def check(a):
+        b = bytes(ffio.encode_png_native(a))
+        assert b[:8] == b"\x89PNG\r\n\x1a\n"
+        Image.open(_io.BytesIO(b)).verify()                                  # chunk CRCs
+        d = np.array(Image.open(_io.BytesIO(b)).convert("RGB"))
+        assert d.shape == a.shape and (d == a).all()
+        n = struct.unpack(">I", b[33:37])[0]
+        raw = zlib.decompress(b[41:41 + n])                                  # Adler-32 checked by zlib
+        assert len(raw) == a.shape[0] * (1 + 3 * a.shape[1])
+        d2 = np.array(Image.open(_io.BytesIO(ffio.encode_png(a))).convert("RGB"))
+        assert (d2 == a).all()
+        return len(b)
+
+    for h, w in [(1, 1), (1, 7), (3, 2), (17, 31), (64, 64), (203, 155), (512, 512)]:
+        check((rng.random((h, w, 3)) * 255).astype(np.uint8))
+        check(np.zeros((h, w, 3), np.uint8))
+        check(np.full((h, w, 3), 255, np.uint8))
+    # geometric symbol frequencies after the Sub filter: an unconstrained Huffman tree would be ~40 levels deep
+    v = np.zeros(512 * 512 * 3, np.uint8)
+    pos = 0
+    for s in range(1, 40):
+        n = max(1, int(2 ** (s / 2)))
+        v[pos:pos + n] = s
+        pos += n
+    check(np.cumsum(v.reshape(512, 512, 3), axis=1).astype(np.uint8))
+    # smooth content compresses; noise costs at most a few bytes of header over the raw size
+    img = np.kron(rng.random((64, 64, 3)), np.ones((8, 8, 1)))
+    smooth = (np.clip(img + 0.01 * rng.standard_normal(img.shape), 0, 1) * 255).round().astype(np.uint8)
+    assert check(smooth) < 0.8 * smooth.size
+    from isr2_b200 import lib
+    so = lib.load()
+    so.ff_png_encode_rgb8.restype = ctypes.c_longlong
+    out = np.empty(16, np.uint8)
+    assert so.ff_png_encode_rgb8(ctypes.c_void_p(smooth.ctypes.data), 512, 512, ctypes.c_longlong(1536), ctypes.c_void_p(out.ctypes.data), ctypes.c_longlong(16)) < 0
