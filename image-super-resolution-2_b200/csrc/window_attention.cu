@@ -311,7 +311,8 @@ int launch(const FFWinAttn& p, size_t smem, cudaStream_t st) {
 }  // namespace
 
 extern long long g_ff_launches;
-int ff_window_attention_tc_try(const FFWinAttn& p, cudaStream_t st);       // window_attention_tc.cu (tcgen05: 256-key self-attention windows)
+int ff_window_attention_tc4_try(const FFWinAttn& p, cudaStream_t st);      // window_attention_tc4.cu (tcgen05: 256-key self-attention windows, 4 CTAs / SM)
+int ff_window_attention_tc_try(const FFWinAttn& p, cudaStream_t st);       // window_attention_tc.cu (the two-CTA variant, FFB200_ATTN_TC4=0)
 int ff_window_attention_oca_tc_try(const FFWinAttn& p, cudaStream_t st);   // window_attention_oca_tc.cu (tcgen05: HAT's overlapping cross-attention)
 
 extern "C" int ff_window_attention(const FFWinAttn* pp, void* stream) {
@@ -339,7 +340,9 @@ extern "C" int ff_window_attention(const FFWinAttn* pp, void* stream) {
   {
     // HAT's (shifted-)window MSA and OCAB and DAT's 8x32 / 32x8 spatial attention run on tcgen05 / TMEM; the mma.sync kernel
     // below is the fallback for any other geometry (and for FFB200_ATTN_TC=0)
-    int r = ff_window_attention_tc_try(p, st);
+    int r = ff_window_attention_tc4_try(p, st);
+    if (r <= 0) return r;
+    r = ff_window_attention_tc_try(p, st);
     if (r <= 0) return r;
     r = ff_window_attention_oca_tc_try(p, st);
     if (r <= 0) return r;
