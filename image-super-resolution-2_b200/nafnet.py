@@ -109,9 +109,9 @@ class NAFNetRunner:
                       out_bf16=Sb if want_bf16 else None, ln=ln1)
         return ln1 is not None
 
-    def _run_blocks(self, blks, l, B):
-        """A run of NAFBlocks at one UNet level; each block's conv5 epilogue emits the next block's norm1."""
-        ready = False
+    def _run_blocks(self, blks, l, B, ready=False):
+        """A run of NAFBlocks at one UNet level; each block's conv5 epilogue emits the next block's norm1 (ready: the first block's
+        norm1 was already emitted by the producer of the level's stream)."""
         for k, d in enumerate(blks):
             nxt = blks[k + 1]["n1"] if k + 1 < len(blks) else None
             ready = self._block(d, l["S"], l["Sb"], B, l["H"], l["W"], l["bufs"], want_bf16=(k == len(blks) - 1), t_ready=ready, next_norm=nxt)
@@ -139,17 +139,38 @@ class NAFNetRunner:
                                  ws.get(f"gap{c}", B, c, F32), ws.get(f"sca{c}", B, c, F32), ws.get("gscratch", 1, B * 64 * 1024, F32))))
             c, Hc, Wc = 2 * c, Hc // 2, Wc // 2
         l0 = lv[0]
-        im = l0["bufs"][0]        # [P, 64] bf16 scratch of level 0 (free until the first block's LayerNorm)
+        P0 = B * H * W
+        im = l0["bufs"][1].view(-1)[:P0 * 64].view(P0, 64)        # [P, 64] bf16 scratch of level 0 (the conv1 output buffer, free until the first block)
         ops.pack_taps(up, B, H, W, 3, 3, 2, im)
-        ops.conv_gemm(im, B, H, W, 64, self.intro_w, n_store=WIDTH, bias=self.intro_b, out_f32=l0["S"])
+        intro_fused = ops.fused_ln_enabled() and WIDTH <= 256
+        if intro_fused:
+            # intro conv through the fp32-residual epilogue (a never-written all-zero "residual"): one pass emits the fp32 stream AND
+            # the first block's LayerNorm2d, instead of the generic fp32-store epilogue followed by a LayerNorm pass
+            zero = ws.get("zero_stream", P0, WIDTH, F32)
+            n1 = self.encoders[0][0]["n1"]
+            ops.conv_gemm(im, B, H, W, 64, self.intro_w, n_store=WIDTH, bias=self.intro_b, res=zero, out_f32=l0["S"],
+                          ln=(n1[0], n1[1], 1e-6, WIDTH, l0["bufs"][0]))
+        else:
+            ops.conv_gemm(im, B, H, W, 64, self.intro_w, n_store=WIDTH, bias=self.intro_b, out_f32=l0["S"])
+        first_ready = {0: intro_fused}      # level -> the first block's norm1 already sits in the level's t buffer
         for s in range(nlev):
             l = lv[s]
             blks = self.encoders[s]
-            self._run_blocks(blks, l, B)
+            self._run_blocks(blks, l, B, ready=first_ready.get(s, False))
             dw_, db_ = self.downs[s]
-            ops.conv_gemm(l["Sb"], B, l["H"], l["W"], l["c"], dw_, kind=CONV_2X2S2, n_store=2 * l["c"], bias=db_, out_f32=lv[s + 1]["S"])
+            nl = lv[s + 1]
+            nblks = self.encoders[s + 1] if s + 1 < nlev else self.middle
+            down_fused = ops.fused_ln_enabled() and nl["c"] <= 256
+            if down_fused:      # as the intro conv: the level's fp32 stream and its first LayerNorm2d in one pass
+                zero = ws.get(f"zero_stream{nl['c']}", B * nl["H"] * nl["W"], nl["c"], F32)
+                n1 = nblks[0]["n1"]
+                ops.conv_gemm(l["Sb"], B, l["H"], l["W"], l["c"], dw_, kind=CONV_2X2S2, n_store=2 * l["c"], bias=db_, res=zero, out_f32=nl["S"],
+                              ln=(n1[0], n1[1], 1e-6, nl["c"], nl["bufs"][0]))
+            else:
+                ops.conv_gemm(l["Sb"], B, l["H"], l["W"], l["c"], dw_, kind=CONV_2X2S2, n_store=2 * l["c"], bias=db_, out_f32=nl["S"])
+            first_ready[s + 1] = down_fused
         l = lv[nlev]
-        self._run_blocks(self.middle, l, B)
+        self._run_blocks(self.middle, l, B, ready=first_ready.get(nlev, False))
         for s in range(len(self.dec)):
             src, dst = lv[nlev - s], lv[nlev - s - 1]
             # 1x1 conv c -> 2c (no bias) + PixelShuffle(2) + encoder skip, written in place over the skip buffer
