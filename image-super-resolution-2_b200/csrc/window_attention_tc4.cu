@@ -33,6 +33,9 @@ constexpr float MASKV = 100.0f * 1.4426950408889634f;
 constexpr uint32_t TMEM_COLS = 128;
 constexpr uint32_t O_COL = 96;
 constexpr int CHUNK = 96;
+#ifndef FF_ATTN_POLY16
+#define FF_ATTN_POLY16 0      // key pairs out of 16 whose exponentials run on the FMA pipe (0: all on the MUFU)
+#endif
 
 template <int WH_, int WW_>
 struct Geo {
@@ -93,8 +96,27 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   return d;
 }
 
+// exp2 of two arguments on the FMA / integer pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], 2^f by a cubic
+// (relative error < 1.1e-4, an order of magnitude below the bf16 rounding of P), the exponent added to the bit pattern.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);      // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 q = __ffma2_rn(f, make_float2(0.0555041087f, 0.0555041087f), make_float2(0.2402265070f, 0.2402265070f));
+  q = __ffma2_rn(q, f, make_float2(0.6931471806f, 0.6931471806f));
+  q = __ffma2_rn(q, f, make_float2(1.0f, 1.0f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)), __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
+
 // One 32-key piece of the second softmax pass: p = exp2(s + bias (+ mask) - shift) as 16 bf16 pairs.  `tabp` / `bad_y` are already
-// advanced to the piece's first key row, so every key offset below is a compile-time constant (LDS immediates).
+// advanced to the piece's first key row, so every key offset below is a compile-time constant (LDS immediates).  The MUFU does
+// 16 exponentials per clock and SM -- the floor of a softmax at head dim 30 -- so -DFF_ATTN_POLY16=n sends n of every 16 key pairs
+// through the polynomial on the FMA pipe instead.  Measured at the bench shape (W-MSA / SW-MSA / DAT 8x32 / 32x8, us):
+// n = 0: 182 / 191 / 97 / 110;  4: 179 / 195 / 96 / 111;  6: 179 / 201 / 97 / 114;  8: 186 / 209 / 99 / 118 -- no gain: the kernel is
+// bound by the serial latency chain of a chunk with 16 resident warps, not by the MUFU (54 % busy), so the default stays 0.
 template <class G, bool MASK>
 __device__ __forceinline__ void exp_piece(const uint32_t (&raw)[32], uint32_t (&pk)[16], float shift, uint32_t tabp, uint32_t bad_y, uint32_t bad_x) {
   const float2 nshift = make_float2(-shift, -shift);
@@ -109,7 +131,14 @@ __device__ __forceinline__ void exp_piece(const uint32_t (&raw)[32], uint32_t (&
       if ((eff >> kj) & 1u) s2.x -= MASKV;
       if ((eff >> (kj + 1)) & 1u) s2.y -= MASKV;
     }
-    pk[c >> 1] = pack_bf16(ex2(s2.x), ex2(s2.y));
+    const int pr = c >> 1;
+    const bool poly = FF_ATTN_POLY16 > 0 && ((pr * FF_ATTN_POLY16) / 16 != ((pr + 1) * FF_ATTN_POLY16) / 16);      // POLY16 of 16 pairs, evenly spread
+    if (poly) {
+      const float2 e = ex2_poly2(s2);
+      pk[pr] = pack_bf16(e.x, e.y);
+    } else {
+      pk[pr] = pack_bf16(ex2(s2.x), ex2(s2.y));
+    }
   }
 }
 
