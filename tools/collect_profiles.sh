@@ -2,8 +2,11 @@
 # Evidence run for profiles/ (one GPU).  Each ncu command runs only after the same program exited 0 without ncu.
 set -u
 O=gpurun_out
+T=${1:-r02n}
 python tools/full_forward.py 16 128 2 > $O/p_full.log 2>&1 || { echo "full_forward failed"; exit 1; }
-python tools/bench_attn.py 16 128 > $O/r02_bench_attn.txt 2>&1 || { echo "bench_attn failed"; exit 1; }
+python tools/bench_attn.py 16 128 > $O/${T}_bench_attn.txt 2>&1 || { echo "bench_attn failed"; exit 1; }
+python tools/bench_tail.py 16 128 > $O/${T}_bench_tail.txt 2>&1 || { echo "bench_tail failed"; exit 1; }
+python tools/bench_dw.py 16 128 > $O/${T}_bench_dw.txt 2>&1 || { echo "bench_dw failed"; exit 1; }
 # 1. launch list of one step at the bench shape (experts serialised for attribution); skip the first (warm-up) forward
 N=$(FFB200_EXPERT_STREAMS=0 FFB200_GRAPHS=0 python -c "
 import sys; sys.path.insert(0,'.')
@@ -12,12 +15,15 @@ from isr2_b200 import lib
 from isr2_b200.model import FreqFusionB200
 m = FreqFusionB200('cuda:0', verbose=False); x = torch.rand(16,3,128,128,device='cuda:0'); m.forward(x); n0 = lib.launch_count(); m.forward(x); torch.cuda.synchronize(); print(lib.launch_count()-n0)")
 echo "launches per step: $N"
-FFB200_EXPERT_STREAMS=0 FFB200_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:unnamed -s $N -c $N --csv --log-file $O/r02_launches_B16_S128.csv python tools/full_forward.py 16 128 2 > $O/p_ncu1.log 2>&1
-python tools/agg_launches.py $O/r02_launches_B16_S128.csv > $O/r02_full_model_B16_S128_launches.txt
+FFB200_EXPERT_STREAMS=0 FFB200_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:unnamed -s $N -c $N --csv --log-file $O/${T}_launches_B16_S128.csv python tools/full_forward.py 16 128 2 > $O/p_ncu1.log 2>&1
+python tools/agg_launches.py $O/${T}_launches_B16_S128.csv > $O/${T}_full_model_B16_S128_launches.txt
 # 2. --set full of 16 consecutive conv_gemm launches inside HAT blocks (DRAM traffic, tensor pipe, issue)
-FFB200_EXPERT_STREAMS=0 FFB200_GRAPHS=0 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:conv_gemm_tc -s 60 -c 16 -o $O/r02_conv_gemm -f python tools/full_forward.py 16 128 1 > $O/p_ncu2.log 2>&1
-# 3. --set full of the attention kernels (W-MSA, SW-MSA, OCAB, DAT 8x32, DAT 32x8): the 4th launch of each case
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:attention -s 3 -c 1 -o $O/r02_attn_wmsa -f python tools/bench_attn.py 16 128 > $O/p_ncu3.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:ocab_attention -s 3 -c 1 -o $O/r02_attn_ocab -f python tools/bench_attn.py 16 128 > $O/p_ncu4.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:Geo<8" -s 3 -c 1 -o $O/r02_attn_dat -f python tools/bench_attn.py 16 128 > $O/p_ncu5.log 2>&1
+FFB200_EXPERT_STREAMS=0 FFB200_GRAPHS=0 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:conv_gemm_tc -s 60 -c 16 -o $O/${T}_conv_gemm -f python tools/full_forward.py 16 128 1 > $O/p_ncu2.log 2>&1
+# 3. --set full of the attention kernels (W-MSA on the 4-CTA kernel, OCAB, DAT 8x32): the 4th launch of each case
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:window_attention_tc4 -s 3 -c 1 -o $O/${T}_attn_wmsa -f python tools/bench_attn.py 16 128 > $O/p_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:ocab_attention -s 3 -c 1 -o $O/${T}_attn_ocab -f python tools/bench_attn.py 16 128 > $O/p_ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:Geo<8" -s 3 -c 1 -o $O/${T}_attn_dat -f python tools/bench_attn.py 16 128 > $O/p_ncu5.log 2>&1
+# 4. the fused HAT-block tail and the SimpleGate depthwise kernel
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:hab_tail -s 30 -c 1 -o $O/${T}_hab_tail -f python tools/bench_tail.py 16 128 > $O/p_ncu6.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:dwconv3x3_gate -s 3 -c 1 -o $O/${T}_dwgate -f python tools/bench_dw.py 16 128 > $O/p_ncu7.log 2>&1
 ls -la $O/*.ncu-rep
