@@ -261,6 +261,88 @@ __global__ void __launch_bounds__(256) vec_linear_kernel(const float* __restrict
   if (lane == 0) y[(long long)r * y_ld + n] = (n < N) ? s : 0.f;
 }
 
+// Second phase of a global average pool FUSED with the one- or two-layer per-sample MLP that consumes it (squeeze-excite of HAT's
+// CAB, DAT's channel interaction, NAFNet's simplified channel attention): the blocks of a sample write their 32 channel means, take a
+// ticket, and the LAST one runs  hidden = act1(W1 . mean + b1),  out = act2(W2 . hidden + b2)  (h1 == 0: out = act1(W1 . mean + b1)).
+// Replaces three dependent micro-launches (pool finalise, two vec_linear: ~5 us of kernel + launch gap each) per block of the model.
+// Deterministic: fixed summation order, no floating-point atomics.
+__global__ void __launch_bounds__(GAPF_WARPS * 32) gap_final_mlp_kernel(const float* __restrict__ partial, int C, int nsplit, float inv, float* __restrict__ mean,
+                                                                       int mean_ld, unsigned int* __restrict__ counters, const float* __restrict__ w1,
+                                                                       const float* __restrict__ b1, int k1, int h1, int act1, const float* __restrict__ w2,
+                                                                       const float* __restrict__ b2, int n_out, int act2, float* __restrict__ out, int out_ld,
+                                                                       int out_cols) {
+  __shared__ float red[GAPF_WARPS][33];
+  __shared__ float s_in[1024];
+  __shared__ float s_hid[128];
+  __shared__ int s_last;
+  const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5, c = blockIdx.x * 32 + lane;
+  float t[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) t[i] = 0.f;
+  if (c < C) {
+    const float* pb = partial + (long long)b * nsplit * C + c;
+    int s = w;
+    for (; s + 15 * GAPF_WARPS < nsplit; s += 16 * GAPF_WARPS) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) t[i] += pb[(long long)(s + i * GAPF_WARPS) * C];
+    }
+    for (; s < nsplit; s += GAPF_WARPS) t[0] += pb[(long long)s * C];
+  }
+#pragma unroll
+  for (int st = 8; st > 0; st >>= 1)
+#pragma unroll
+    for (int i = 0; i < st; ++i) t[i] += t[i + st];
+  red[w][lane] = t[0];
+  __syncthreads();
+  if (w == 0 && c < mean_ld) {
+    float tt = 0.f;
+#pragma unroll
+    for (int i = 0; i < GAPF_WARPS; ++i) tt += red[i][lane];
+    mean[(long long)b * mean_ld + c] = c < C ? tt * inv : 0.f;
+  }
+  // ticket: the last block of this sample sees every block's means
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int tk = atomicAdd(&counters[b], 1u);
+    s_last = tk == gridDim.x - 1;
+    if (s_last) counters[b] = 0u;      // every block of the sample has taken its ticket: re-arm for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int k = threadIdx.x; k < k1; k += GAPF_WARPS * 32) s_in[k] = __ldcg(mean + (long long)b * mean_ld + k);
+  __syncthreads();
+  if (h1 > 0) {
+    for (int h = w; h < h1; h += GAPF_WARPS) {
+      float s = 0.f;
+      for (int k = lane; k < k1; k += 32) s += s_in[k] * __ldg(w1 + (long long)h * k1 + k);
+      s = warp_sum(s);
+      if (lane == 0) s_hid[h] = act_apply(s + (b1 ? __ldg(b1 + h) : 0.f), act1);
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < out_cols; n += GAPF_WARPS * 32) {
+      float s = 0.f;
+      if (n < n_out) {
+        s = b2 ? __ldg(b2 + n) : 0.f;
+        for (int h = 0; h < h1; ++h) s += s_hid[h] * __ldg(w2 + (long long)n * h1 + h);
+        s = act_apply(s, act2);
+      }
+      out[(long long)b * out_ld + n] = s;
+    }
+  } else {
+    for (int n = w; n < out_cols; n += GAPF_WARPS) {
+      float s = 0.f;
+      if (n < n_out) {
+        for (int k = lane; k < k1; k += 32) s += s_in[k] * __ldg(w1 + (long long)n * k1 + k);
+        s = warp_sum(s);
+        s = act_apply(s + (b1 ? __ldg(b1 + n) : 0.f), act1);
+      }
+      if (lane == 0) out[(long long)b * out_ld + n] = s;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Depthwise convolution, NHWC, 8 channels per thread (16-byte bf16 vectors).
 //   mode 0: out[c] = act(dw(x)[c] + bias[c]) (* mul[c])
@@ -1281,6 +1363,19 @@ extern "C" int ff_vec_linear(const float* x, int x_ld, int R, int K, const float
   vec_linear_kernel<<<ff_cdiv((long long)R * y_cols, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_ld, R, K, W, bias, N, act, y, y_ld, y_cols);
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_vec_linear");
+  return FF_OK;
+}
+
+extern "C" int ff_gap_finalize_mlp(const float* partial, int B, int nsplit, int C, float inv, float* mean, int mean_ld, unsigned int* counters,
+                                   const float* w1, const float* b1, int k1, int h1, int act1, const float* w2, const float* b2, int n_out, int act2,
+                                   float* out, int out_ld, int out_cols, void* stream) {
+  FF_CHECK_ARG(partial && mean && counters && w1 && out && B > 0 && nsplit > 0 && mean_ld >= C, "ff_gap_finalize_mlp: bad args");
+  FF_CHECK_ARG(k1 > 0 && k1 <= 1024 && k1 <= mean_ld && h1 >= 0 && h1 <= 128 && (h1 == 0 || w2) && n_out > 0 && out_cols >= n_out && out_ld >= out_cols,
+               "ff_gap_finalize_mlp: k1=%d (<= 1024, <= mean_ld), h1=%d (<= 128), n_out=%d, out_cols=%d, out_ld=%d", k1, h1, n_out, out_cols, out_ld);
+  gap_final_mlp_kernel<<<dim3(ff_cdiv(mean_ld, 32), B), GAPF_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial, C, nsplit, inv, mean, mean_ld, counters, w1, b1, k1, h1, act1, w2, b2, n_out, act2, out, out_ld, out_cols);
+  ++g_ff_launches;
+  FF_CHECK_LAUNCH("ff_gap_finalize_mlp");
   return FF_OK;
 }
 

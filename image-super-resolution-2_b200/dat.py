@@ -154,6 +154,8 @@ class DATRunner:
         gapv = ws.get("gap", B, CP, F32)
         ci_h = ws.get("ci_h", B, 24, F32)
         cmap = ws.get("cmap", B, CP, F32)
+        pool_mlp = ops.pool_mlp_enabled()
+        tickets = ws.get("pool_tickets", 1, max(B, 64), torch.int32)      # per-sample arrival counters of ff_gap_finalize_mlp (self-resetting)
         sih = ws.get("si_hid", M, 32, BF16)
         scratch = ws.get("scratch", 1, max(B * 64 * CP, B * HEADS * ((N + 511) // 512) * 1088), F32)
         wb = ws.get("chan_w", B * CP, CP, BF16)   # block-diagonal channel-attention weights (off-diagonal stays zero)
@@ -199,12 +201,16 @@ class DATRunner:
                     gpart = ws.get("gpart_att", B * pool_rows, CP, F32)
                     ops.conv_gemm(qkv[:, 2 * CP:], B, H, W, CP, wb, n_store=CP, w_batch_rows=CP, out_bf16=att, x_ld=3 * CP, col_sums=gpart)
                     gap_src, mode = att, 1
-                if pool_rows:
-                    ops.gap_finalize(gpart, B, pool_rows, CP, 1.0 / N, gapv)
+                if pool_rows and pool_mlp:      # pool finalise + both channel-interaction layers in one launch
+                    ops.gap_finalize_mlp(gpart, B, pool_rows, CP, 1.0 / N, gapv, tickets, d["ci1_w"], d["ci1_b"], CP, ACT_GELU, cmap, CP,
+                                         w2=d["ci2_w"], b2=d["ci2_b"], h1=24, act2=ACT_SIGMOID, out_cols=CP)
                 else:
-                    ops.gap(gap_src, B, N, CP, gapv, scratch)
-                ops.vec_linear(gapv, B, CP, d["ci1_w"], d["ci1_b"], 24, ACT_GELU, ci_h, y_cols=24)
-                ops.vec_linear(ci_h, B, 24, d["ci2_w"], d["ci2_b"], CP, ACT_SIGMOID, cmap, y_cols=CP)
+                    if pool_rows:
+                        ops.gap_finalize(gpart, B, pool_rows, CP, 1.0 / N, gapv)
+                    else:
+                        ops.gap(gap_src, B, N, CP, gapv, scratch)
+                    ops.vec_linear(gapv, B, CP, d["ci1_w"], d["ci1_b"], 24, ACT_GELU, ci_h, y_cols=24)
+                    ops.vec_linear(ci_h, B, 24, d["ci2_w"], d["ci2_b"], CP, ACT_SIGMOID, cmap, y_cols=CP)
                 # spatial interaction: first layer (C -> C/16, BN folded, GELU) on the tensor cores, second layer inside the gate kernel
                 ops.conv_gemm(convx if mode else att, B, H, W, CP, d["si1_w"], n_store=32, bias=d["si1_b"], act=ACT_GELU, out_bf16=sih)
                 L.check(lib.ff_dat_aim(C_.c_void_p(att.data_ptr()), CP, C_.c_void_p(convx.data_ptr()), CP, C_.c_void_p(cmap.data_ptr()), CP,

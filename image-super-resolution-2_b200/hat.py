@@ -193,6 +193,8 @@ class HATRunner:
         wcat = ws.get("proj_cat_w", B * CP, 2 * CP, BF16)      # per-sample [W_proj | diag(0.01 se)] of the current block
         fused = ops.fused_ln_enabled()      # every LayerNorm after a residual add leaves the producing GEMM's epilogue
         tail = fused and ops.hab_tail_enabled()      # proj + shortcut + LN2 + MLP + residual + next LN as one kernel
+        pool_mlp = ops.pool_mlp_enabled()
+        tickets = ws.get("pool_tickets", 1, max(B, 64), torch.int32)      # per-sample arrival counters of ff_gap_finalize_mlp (self-resetting)
 
         if (H, W) == (h0, w0):
             ops.nchw_to_nhwc(x, img, sub=self.mean)
@@ -213,9 +215,13 @@ class HATRunner:
                 ops.conv_gemm(t, B, H, W, CP, d["cab1_w"], kind=CONV_3X3, n_store=64, bias=d["cab1_b"], act=ACT_GELU, out_bf16=cab1)
                 # the conv's store epilogue also emits the per-tile column sums of the squeeze-excite average pool
                 ops.conv_gemm(cab1, B, H, W, 64, d["cab2_w"], kind=CONV_3X3, n_store=CP, bias=d["cab2_b"], out_bf16=cab2, col_sums=gpart)
-                ops.gap_finalize(gpart, B, H * W // 32, CP, 1.0 / (H * W), gapv)
-                ops.vec_linear(gapv, B, C, d["se1_w"], d["se1_b"], 6, ACT_RELU, se_h, y_cols=8)
-                ops.vec_linear(se_h, B, 6, d["se2_w"], d["se2_b"], C, ACT_SIGMOID, se, y_cols=CP)
+                if pool_mlp:      # pool finalise + the two squeeze-excite layers in one launch
+                    ops.gap_finalize_mlp(gpart, B, H * W // 32, CP, 1.0 / (H * W), gapv, tickets, d["se1_w"], d["se1_b"], C, ACT_RELU, se, C,
+                                         w2=d["se2_w"], b2=d["se2_b"], h1=6, act2=ACT_SIGMOID, out_cols=CP)
+                else:
+                    ops.gap_finalize(gpart, B, H * W // 32, CP, 1.0 / (H * W), gapv)
+                    ops.vec_linear(gapv, B, C, d["se1_w"], d["se1_b"], 6, ACT_RELU, se_h, y_cols=8)
+                    ops.vec_linear(se_h, B, 6, d["se2_w"], d["se2_b"], C, ACT_SIGMOID, se, y_cols=CP)
                 # (S)W-MSA
                 ops.conv_gemm(t, B, H, W, CP, d["qkv_w"], n_store=3 * CP, bias=d["qkv_b"], out_bf16=qkv)
                 ops.window_attention(qkv, B, H, W, att, bias_table=d["table"], wh=WS, ww=WS, shift=(shift, shift))

@@ -87,11 +87,16 @@ class NAFNetRunner:
             # the SimpleGate depthwise kernel also emits the per-tile sums of the SCA average pool
             gpart = self.ws.get(f"gpart{c}", B * rows, c, F32)
             ops.dwconv_pool(a, B, H, W, 2 * c, d["dw"], d["dwb"], gt, gpart, mode=1)
-            ops.gap_finalize(gpart, B, rows, c, 1.0 / (H * W), gapv)
+            if ops.pool_mlp_enabled():      # pool finalise + the SCA 1x1 conv in one launch
+                tickets = self.ws.get("pool_tickets", 1, max(B, 64), torch.int32)
+                ops.gap_finalize_mlp(gpart, B, rows, c, 1.0 / (H * W), gapv, tickets, d["sca_w"], d["sca_b"], c, ACT_NONE, sca, c)
+            else:
+                ops.gap_finalize(gpart, B, rows, c, 1.0 / (H * W), gapv)
+                ops.vec_linear(gapv, B, c, d["sca_w"], d["sca_b"], c, ACT_NONE, sca)
         else:
             ops.dwconv(a, B, H, W, 2 * c, 3, 3, d["dw"], d["dwb"], gt, mode=1)
             ops.gap(gt, B, H * W, c, gapv, scratch)
-        ops.vec_linear(gapv, B, c, d["sca_w"], d["sca_b"], c, ACT_NONE, sca)
+            ops.vec_linear(gapv, B, c, d["sca_w"], d["sca_b"], c, ACT_NONE, sca)
         ln2 = (d["n2"][0], d["n2"][1], 1e-6, c, t) if fused else None
         if c < H * W:
             # x * sca folded into per-sample conv3 weights (c*c per sample instead of a pass over H*W*c activations)

@@ -257,6 +257,20 @@ def gap_finalize(partial, B, nsplit, C_, inv, out):
     L.check(L.load().ff_gap_finalize(_ptr(partial), B, nsplit, C_, C.c_float(inv), _ptr(out), out.stride(0), _stream()), "ff_gap_finalize")
 
 
+def pool_mlp_enabled():
+    """Pool finalise + the per-sample MLP behind it as one launch (ff_gap_finalize_mlp); FFB200_POOL_MLP=0 restores the three launches."""
+    import os
+    return os.environ.get("FFB200_POOL_MLP", "1") != "0"
+
+
+def gap_finalize_mlp(partial, B, nsplit, C_, inv, mean, counters, w1, b1, k1, act1, out, n_out, *, w2=None, b2=None, h1=0, act2=ACT_NONE, out_cols=None):
+    """mean = pooled partials; out = act2(w2 . act1(w1 . mean + b1) + b2) (h1 > 0) or act1(w1 . mean + b1) (h1 == 0), see ff_gap_finalize_mlp."""
+    _req_cuda(partial, mean, counters, w1, b1, w2, b2, out)
+    L.check(L.load().ff_gap_finalize_mlp(_ptr(partial), B, nsplit, C_, C.c_float(inv), _ptr(mean), mean.stride(0), _ptr(counters), _ptr(w1), _ptr(b1), k1, h1, act1,
+                                         _ptr(w2), _ptr(b2), n_out, act2, _ptr(out), out.stride(0), out_cols if out_cols is not None else n_out, _stream()),
+            "ff_gap_finalize_mlp")
+
+
 def vec_linear(x, R, K, W, bias, N, act, y, y_cols=None):
     _req_cuda(x, W, bias, y)
     L.check(L.load().ff_vec_linear(_ptr(x), x.stride(0), R, K, _ptr(W), _ptr(bias), N, act, _ptr(y), y.stride(0),

@@ -227,6 +227,16 @@ int ff_gap_finalize(const float* partial, int B, int nsplit, int C, float inv, f
 int ff_vec_linear(const float* x, int x_ld, int R, int K, const float* W, const float* bias, int N, int act, float* y,
                   int y_ld, int y_cols, void* stream);
 
+/* ff_gap_finalize fused with the per-sample MLP that consumes the pooled vector (one launch instead of three):
+ *   mean[b][c]   = inv * sum_s partial[b][s][c]                       (also written out: [B][mean_ld], columns C.. zero)
+ *   h1 > 0:  hid = act1(w1 [h1][k1] . mean[:k1] + b1),  out[b][n] = act2(w2 [n_out][h1] . hid + b2)
+ *   h1 == 0: out[b][n] = act1(w1 [n_out][k1] . mean[:k1] + b1)
+ * columns n_out..out_cols-1 of out are written as zero.  counters: B zero-initialised uint32 (left zero by every launch).
+ * Squeeze-excite of HAT's CAB (hat_arch.py:45-58), DAT's channel interaction (dat_arch.py:411-416), NAFNet's SCA (nafnet_arch.py:86-89). */
+int ff_gap_finalize_mlp(const float* partial, int B, int nsplit, int C, float inv, float* mean, int mean_ld, unsigned int* counters,
+                        const float* w1, const float* b1, int k1, int h1, int act1, const float* w2, const float* b2, int n_out, int act2,
+                        float* out, int out_ld, int out_cols, void* stream);
+
 /* Depthwise kh x kw convolution (zero padding), bf16 NHWC in/out, fp32 weights [kh*kw][C] and accumulate.
  * mode 0: out = act(dw(x)+bias) * (mul ? mul : 1);  mode 1 (SimpleGate, nafnet_arch.py:47-52,112-114):
  * out[c] = (dw(x)+bias)[c] * (dw(x)+bias)[c + C/2].  Also dat_arch.py:115,403-407 and the LKA chain

@@ -973,3 +973,45 @@ def test_conv_gemm_k_concatenated_second_operand():
     torch.cuda.synchronize()
     assert (stream.cpu() - ref).abs().max().item() < 4e-3
     assert (lno.cpu().float() - F.layer_norm(ref, (C,))).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("B,nsplit,C_,k1,h1,n_out,out_cols,act1,act2", [(16, 512, 192, 180, 6, 180, 192, 2, 4), (3, 37, 192, 192, 24, 192, 192, 1, 4),
+                                                                        (2, 64, 64, 64, 0, 64, 64, 0, 0), (5, 16, 1024, 1024, 0, 1024, 1024, 0, 0)])
+def test_gap_finalize_mlp(B, nsplit, C_, k1, h1, n_out, out_cols, act1, act2):
+    """ff_gap_finalize_mlp (pool finalise + the squeeze-excite / channel-interaction / SCA layers in one launch, last-block ticket per
+    sample) against ff_gap_finalize + ff_vec_linear x 2 and plain PyTorch; repeated launches leave the ticket counters re-armed."""
+    from isr2_b200 import ops
+    g = torch.Generator().manual_seed(9 + B)
+    d = _dev()
+    part = torch.randn(B * nsplit, C_, generator=g).to(d)
+    w1 = (torch.randn(h1 if h1 else n_out, k1, generator=g) / math.sqrt(k1)).to(d)
+    b1 = torch.randn(h1 if h1 else n_out, generator=g).to(d)
+    w2 = (torch.randn(n_out, h1, generator=g) / math.sqrt(max(h1, 1))).to(d) if h1 else None
+    b2 = torch.randn(n_out, generator=g).to(d) if h1 else None
+    inv = 1.0 / (nsplit * 32)
+    mean_ref = torch.zeros(B, C_, device=d)
+    ops.gap_finalize(part, B, nsplit, C_, inv, mean_ref)
+    if h1:
+        hid = torch.zeros(B, h1, device=d)
+        ops.vec_linear(mean_ref, B, k1, w1, b1, h1, act1, hid)
+        ref = torch.full((B, out_cols), 5.0, device=d)
+        ops.vec_linear(hid, B, h1, w2, b2, n_out, act2, ref, y_cols=out_cols)
+    else:
+        ref = torch.full((B, out_cols), 5.0, device=d)
+        ops.vec_linear(mean_ref, B, k1, w1, b1, n_out, act1, ref, y_cols=out_cols)
+    tickets = torch.zeros(1, 64, dtype=torch.int32, device=d)
+    for _ in range(3):
+        mean = torch.full((B, C_), 7.0, device=d)
+        out = torch.full((B, out_cols), 7.0, device=d)
+        ops.gap_finalize_mlp(part, B, nsplit, C_, inv, mean, tickets, w1, b1, k1, act1, out, n_out, w2=w2, b2=b2, h1=h1, act2=act2, out_cols=out_cols)
+        torch.cuda.synchronize()
+        assert torch.equal(mean, mean_ref)
+        assert (out - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+        assert (tickets == 0).all()
+    acts = {0: lambda v: v, 1: F.gelu, 2: F.relu, 4: torch.sigmoid}
+    m = part.view(B, nsplit, C_).sum(1).cpu() * inv
+    y = acts[act1](m[:, :k1] @ w1.cpu().t() + b1.cpu())
+    if h1:
+        y = acts[act2](y @ w2.cpu().t() + b2.cpu())
+    assert (out.cpu()[:, :n_out] - y).abs().max().item() < 2e-4
+    assert (out.cpu()[:, n_out:] == 0).all()
