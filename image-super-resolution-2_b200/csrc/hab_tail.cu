@@ -61,6 +61,9 @@ struct Args {
   int B, H, W;
   int tiles_x, tiles_per_img, m_tiles;
   int has_cab, wp_batch_rows;
+  const float* diag;      // [B][diag_ld] per-sample channel scale of the a1 term (the diagonal K block is generated on chip), or null
+  int diag_ld;
+  float diag_alpha;
   const float* bp;        // [192] proj bias
   const float* g2;        // LayerNorm2 gamma / beta, zero-padded to 192
   const float* be2;
@@ -187,6 +190,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) hab_tail_kernel(const __grid_cons
       int b, y0, x0;
       tile_coords(tile, b, y0, x0);
       const int wrow = b * a.wp_batch_rows;
+      float dv[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};      // this lane's diagonal entries (rows lane, lane + 32 of each slab): requested before the ring waits
+      if (a.has_cab && a.diag) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) dv[j][h] = __ldg(a.diag + (long long)b * a.diag_ld + j * CH + lane + 32 * h);
+      }
       for (int kb = 0; kb < 3; ++kb) {
         uint8_t* d0 = stage_begin();
         if (elect_one()) {
@@ -202,12 +212,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) hab_tail_kernel(const __grid_cons
         stage_end();
       }
       if (a.has_cab)
+#pragma unroll
         for (int j = 0; j < 3; ++j) {
           uint8_t* d0 = stage_begin();
+          if (a.diag) {
+            // the 64 x 64 diagonal slab diag(alpha * s_b[64 j ..]) written in place (128B-swizzled K-major rows): no per-sample weight
+            // tensor in HBM, no builder launch.  Lane l owns rows l and l + 32.
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = lane + 32 * h;
+              uint8_t* rowp = d0 + KBLK + r * 128;
+              const uint32_t v = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a.diag_alpha * dv[j][h]));
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {      // logical 16-byte chunk q holds columns 8 q .. 8 q + 7
+                uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                if (q == (r >> 3)) {
+                  const uint32_t word = (r & 1) ? (v << 16) : v;
+                  const int wi = (r & 7) >> 1;
+                  z.x = wi == 0 ? word : 0u; z.y = wi == 1 ? word : 0u; z.z = wi == 2 ? word : 0u; z.w = wi == 3 ? word : 0u;
+                }
+                *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) << 4)) = z;
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+          }
           if (elect_one()) {
-            mbar_arrive_expect_tx(&w_full[st], KBLK + CH * KB * 2);
+            mbar_arrive_expect_tx(&w_full[st], a.diag ? KBLK : KBLK + CH * KB * 2);
             tma_load_4d(d0, &tm.A1, &w_full[st], j * KB, x0, y0, b);
-            tma_load_2d(d0 + KBLK, &tm.WpD, &w_full[st], CP + j * KB, wrow + j * CH);      // the 64 x 64 diagonal slab
+            if (!a.diag) tma_load_2d(d0 + KBLK, &tm.WpD, &w_full[st], CP + j * KB, wrow + j * CH);      // the 64 x 64 diagonal slab
           }
           stage_end();
         }
@@ -669,6 +702,7 @@ extern "C" int ff_hab_tail(const FFHabTail* pp, void* stream) {
   FF_CHECK_ARG(al16(p.a0) && al16(p.wp) && al16(p.bp) && al16(p.res) && al16(p.ln2_gamma) && al16(p.ln2_beta) && al16(p.w1) && al16(p.w2) && al16(p.b1) &&
                    al16(p.b2) && al16(p.x), "ff_hab_tail: operands must be 16-byte aligned");
   if (p.a1) FF_CHECK_ARG(al16(p.a1) && p.a1_ld % 8 == 0 && p.a1_ld >= CP, "ff_hab_tail: bad a1 / a1_ld");
+  if (p.a1 && p.a1_diag) FF_CHECK_ARG(p.a1_diag_ld >= CP && p.wp_batch_rows == 0, "ff_hab_tail: a1_diag needs a1_diag_ld >= %d and a shared wp [192][192]", CP);
   if (p.out_bf16) FF_CHECK_ARG(al16(p.out_bf16) && p.out_ld % 8 == 0 && p.out_ld >= CP, "ff_hab_tail: bad out_bf16 / out_ld");
   if (p.ln_out) FF_CHECK_ARG(al16(p.ln_out) && p.ln_out_ld % 8 == 0 && p.ln_out_ld >= CP && p.ln_gamma && p.ln_beta && al16(p.ln_gamma) && al16(p.ln_beta),
                              "ff_hab_tail: bad LayerNorm output operands");
@@ -691,7 +725,7 @@ extern "C" int ff_hab_tail(const FFHabTail* pp, void* stream) {
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   };
-  const int K0 = p.a1 ? 2 * CP : CP;
+  const int K0 = (p.a1 && !p.a1_diag) ? 2 * CP : CP;
   const int wp_rows = p.wp_batch_rows ? p.B * CP : CP;
   const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, F32T = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   bool ok = img_map(&tm.A0, p.a0, p.a0_ld, 2, BF, CU_TENSOR_MAP_SWIZZLE_128B, KB, TW_, TH_, CP) && w_map(&tm.Wp, p.wp, wp_rows, K0, CP) &&
@@ -699,7 +733,7 @@ extern "C" int ff_hab_tail(const FFHabTail* pp, void* stream) {
             img_map(&tm.R, p.res, p.res_ld, 4, F32T, CU_TENSOR_MAP_SWIZZLE_64B, SUB, TW_, 2, CP) &&
             img_map(&tm.O32, p.x, p.x_ld, 4, F32T, CU_TENSOR_MAP_SWIZZLE_64B, SUB, TW_, 2, CP);
   tm.A1 = tm.A0; tm.WpD = tm.Wp; tm.O16 = tm.A0; tm.LN = tm.A0;
-  if (ok && p.a1) ok = img_map(&tm.A1, p.a1, p.a1_ld, 2, BF, CU_TENSOR_MAP_SWIZZLE_128B, KB, TW_, TH_, CP) && w_map(&tm.WpD, p.wp, wp_rows, K0, CH);
+  if (ok && p.a1) ok = img_map(&tm.A1, p.a1, p.a1_ld, 2, BF, CU_TENSOR_MAP_SWIZZLE_128B, KB, TW_, TH_, CP) && (p.a1_diag || w_map(&tm.WpD, p.wp, wp_rows, K0, CH));
   if (ok && p.out_bf16) ok = img_map(&tm.O16, p.out_bf16, p.out_ld, 2, BF, CU_TENSOR_MAP_SWIZZLE_32B, SUB, TW_, 2, CP);
   if (ok && p.ln_out) ok = img_map(&tm.LN, p.ln_out, p.ln_out_ld, 2, BF, CU_TENSOR_MAP_SWIZZLE_32B, SUB, TW_, 2, CP);
   FF_CHECK_ARG(ok, "ff_hab_tail: cuTensorMapEncodeTiled failed");
@@ -710,6 +744,7 @@ extern "C" int ff_hab_tail(const FFHabTail* pp, void* stream) {
   a.m_tiles = a.tiles_per_img * p.B;
   a.has_cab = p.a1 ? 1 : 0;
   a.wp_batch_rows = p.wp_batch_rows;
+  a.diag = p.a1 ? p.a1_diag : nullptr; a.diag_ld = p.a1_diag_ld; a.diag_alpha = p.a1_alpha;
   a.bp = p.bp; a.g2 = p.ln2_gamma; a.be2 = p.ln2_beta; a.b1 = p.b1; a.b2 = p.b2;
   a.ln_gamma = p.ln_gamma; a.ln_beta = p.ln_beta; a.ln_eps = p.ln_eps; a.ln_cols = p.ln_cols;
   a.has_bf16 = p.out_bf16 ? 1 : 0;

@@ -229,9 +229,9 @@ class HATRunner:
                 nxt = layer["habs"][j + 1]["norm1"] if j + 1 < nhab else layer["ocab"]["norm1"]
                 if tail:
                     # everything after the attention as one kernel: x1 stays in TMEM, LN2(x1) in shared memory (csrc/hab_tail.cu)
-                    ops.build_concat_diag_weights(d["proj_w"], se, 0.01, wcat.view(B, CP, 2 * CP))
-                    ops.hab_tail(att, B, H, W, wcat, d["proj_b"], src, d["norm2"], d["fc1_w"], d["fc1_b"], d["fc2_w"], d["fc2_b"], X,
-                                 a1=cab2, wp_batch_rows=CP, ln=(nxt[0], nxt[1], t))
+                    # (the 0.01 * cab * se term is a diagonal K block that the kernel generates from `se`: no per-sample weights)
+                    ops.hab_tail(att, B, H, W, d["proj_w"], d["proj_b"], src, d["norm2"], d["fc1_w"], d["fc1_b"], d["fc2_w"], d["fc2_b"], X,
+                                 a1=cab2, a1_diag=se, a1_alpha=0.01, ln=(nxt[0], nxt[1], t))
                     t_ready = True
                     src = X
                     continue

@@ -48,7 +48,7 @@ class FFMlpFused(C.Structure):
 
 class FFHabTail(C.Structure):
     _fields_ = [
-        ("a0", C.c_void_p), ("a0_ld", C.c_int), ("a1", C.c_void_p), ("a1_ld", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("a0", C.c_void_p), ("a0_ld", C.c_int), ("a1", C.c_void_p), ("a1_ld", C.c_int), ("a1_diag", C.c_void_p), ("a1_diag_ld", C.c_int), ("a1_alpha", C.c_float), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("wp", C.c_void_p), ("wp_batch_rows", C.c_int), ("bp", C.c_void_p), ("res", C.c_void_p), ("res_ld", C.c_int),
         ("ln2_gamma", C.c_void_p), ("ln2_beta", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
         ("x", C.c_void_p), ("x_ld", C.c_int), ("out_bf16", C.c_void_p), ("out_ld", C.c_int), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),

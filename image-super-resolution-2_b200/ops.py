@@ -170,13 +170,16 @@ def hab_tail_enabled():
     return os.environ.get("FFB200_HAB_TAIL", "1") != "0"
 
 
-def hab_tail(a0, B, H, W, wp, bp, res, ln2, w1, b1, w2, b2, x, *, a1=None, wp_batch_rows=0, out_bf16=None, ln=None, eps=1e-5, cols=180):
+def hab_tail(a0, B, H, W, wp, bp, res, ln2, w1, b1, w2, b2, x, *, a1=None, a1_diag=None, a1_alpha=1.0, wp_batch_rows=0, out_bf16=None, ln=None, eps=1e-5, cols=180):
     """x = x1 + fc2(GELU(fc1(LN2(x1)))) with x1 = res + [a0 | a1] . wp^T + bp; ln = (gamma, beta, bf16 out) of the next LayerNorm."""
     _req_cuda(a0, a1, wp, bp, res, ln2[0], ln2[1], w1, b1, w2, b2, x, out_bf16)
     p = L.FFHabTail()
     p.a0 = a0.data_ptr(); p.a0_ld = a0.stride(-2)
     if a1 is not None:
         p.a1 = a1.data_ptr(); p.a1_ld = a1.stride(-2)
+        if a1_diag is not None:      # per-sample channel scale of the a1 term: the diagonal K block is generated inside the kernel
+            _req_cuda(a1_diag)
+            p.a1_diag = a1_diag.data_ptr(); p.a1_diag_ld = a1_diag.stride(0); p.a1_alpha = a1_alpha
     p.B, p.H, p.W = B, H, W
     p.wp = wp.data_ptr(); p.wp_batch_rows = wp_batch_rows; p.bp = bp.data_ptr()
     p.res = res.data_ptr(); p.res_ld = res.stride(-2)

@@ -156,6 +156,8 @@ long long ff_png_encode_rgb8(const unsigned char* rgb, int h, int w, long long r
 typedef struct FFHabTail {
   const void* a0; int a0_ld;
   const void* a1; int a1_ld;     /* optional */
+  const float* a1_diag; int a1_diag_ld; float a1_alpha;   /* optional: the a1 term is a1[p][n] * bf16(a1_alpha * a1_diag[b][n]); the diagonal K block
+                                   is generated on chip and wp is the shared [192][192] matrix (no per-sample weights in HBM) */
   int B, H, W;                   /* the token matrix as an image (tiles are 8 x 16 pixels) */
   const void* wp; int wp_batch_rows;
   const float* bp;

@@ -940,6 +940,19 @@ def test_hab_tail(B, H, W, with_cab, with_bf16, with_ln, inplace):
     torch.cuda.synchronize()
     e = (xd.cpu() - ref).abs().max().item()
     assert e < 3e-2, e              # bf16 LayerNorm2 output and hidden activations through 180 / 360-long contractions
+    if with_cab:
+        # the same block with the diagonal K block generated inside the kernel from the per-sample scale (FFHabTail.a1_diag): identical
+        res2 = res.clone().to(d)
+        x2 = res2 if inplace else torch.full((P, CP), 9.0, device=d)
+        lno2 = torch.full((P, CP), 7.0, dtype=BF16, device=d) if with_ln else None
+        ops.hab_tail(att.to(d), B, H, W, wpd, packing.pack_vector(bp, CP, device=d), res2, (g2.to(d), be2.to(d)),
+                     packing.pack_matrix(w1, 2 * CP, CP, device=d), packing.pack_vector(b1, 2 * CP, device=d),
+                     packing.pack_matrix(w2, CP, 2 * CP, device=d), packing.pack_vector(b2, CP, device=d), x2,
+                     a1=cab.to(d), a1_diag=sed, a1_alpha=0.01, ln=(gn.to(d), ben.to(d), lno2) if with_ln else None)
+        torch.cuda.synchronize()
+        assert torch.equal(x2, xd)
+        if with_ln:
+            assert torch.equal(lno2, lno)
     assert (xd.cpu()[:, C:] == 0).all()
     if with_bf16:
         assert (o16.cpu().float() - ref).abs().max().item() < 8e-2

@@ -37,9 +37,12 @@ def two(c):
         ops.conv_gemm(att, B, S, S, 192, wp, n_store=192, bias=bp, res=x, out_f32=x, ln=(gam, bet, 1e-5, 180, t))
     ops.mlp_fused(t, B, S, S, w1, b1, w2, b2, x, ln=(gam, bet, 1e-5, 180, lno))
 def one(c):
+    if c == 2:      # the diagonal K block generated inside the kernel (what hat.py runs)
+        ops.hab_tail(att, B, S, S, wp, bp, x, (gam, bet), w1, b1, w2, b2, x, a1=cab, a1_diag=se, a1_alpha=0.01, ln=(gam, bet, lno))
+        return
     ops.hab_tail(att, B, S, S, wcat.view(B * 192, 384) if c else wp, bp, x, (gam, bet), w1, b1, w2, b2, x, a1=cab if c else None, wp_batch_rows=192 if c else 0,
                  ln=(gam, bet, lno))
-for c in (True, False):
+for c in (2, True, False):
     a = timed(lambda: two(c))
     b = timed(lambda: one(c))
     byts = M * 192 * (2 * (2 if c else 1) + 8 + 2)
