@@ -56,6 +56,15 @@ class FFHabTail(C.Structure):
     ]
 
 
+class FFNafTail(C.Structure):
+    _fields_ = [
+        ("a0", C.c_void_p), ("a0_ld", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("w3", C.c_void_p), ("w3_batch_rows", C.c_int),
+        ("b3", C.c_void_p), ("res", C.c_void_p), ("res_ld", C.c_int), ("ln2_gamma", C.c_void_p), ("ln2_beta", C.c_void_p),
+        ("w4", C.c_void_p), ("b4", C.c_void_p), ("w5", C.c_void_p), ("b5", C.c_void_p), ("x", C.c_void_p), ("x_ld", C.c_int),
+        ("out_bf16", C.c_void_p), ("out_ld", C.c_int), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float),
+    ]
+
+
 class FFError(RuntimeError):
     pass
 
@@ -75,7 +84,7 @@ def load():
     lib.ff_last_error.restype = C.c_char_p
     lib.ff_launch_count.restype = C.c_longlong
     lib.ff_ssim_y_scratch_bytes.restype = C.c_size_t
-    if lib.ff_abi_version() != 5:
+    if lib.ff_abi_version() != 6:
         raise FFError("libffb200.so ABI version mismatch")
     _lib = lib
     return lib

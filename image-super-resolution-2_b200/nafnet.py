@@ -39,7 +39,7 @@ class NAFNetRunner:
 
         def block(p, c):
             perm = _gate_perm(c)
-            return dict(
+            d = dict(
                 c=c,
                 n1=(g(p + "norm1.weight").to(dev), g(p + "norm1.bias").to(dev)),
                 n2=(g(p + "norm2.weight").to(dev), g(p + "norm2.bias").to(dev)),
@@ -52,6 +52,16 @@ class NAFNetRunner:
                 w5=pack_matrix(g(p + "conv5.weight").reshape(c, c), c, c, device=dev), b5=g(p + "conv5.bias").to(dev),
                 beta=g(p + "beta").reshape(-1).to(dev).contiguous(), gamma=g(p + "gamma").reshape(-1).to(dev).contiguous(),
             )
+            if c == 64:
+                # operands of ff_naf_tail (the block's second half as one kernel): beta / gamma folded into conv3 / conv5, conv4 in the
+                # reference's row order (the kernel pairs column j with column 64 + j)
+                beta, gamma = g(p + "beta").reshape(-1), g(p + "gamma").reshape(-1)
+                w3, w5 = g(p + "conv3.weight").reshape(c, c), g(p + "conv5.weight").reshape(c, c)
+                d.update(w3_beta_f32=(beta[:, None] * w3).to(dev).contiguous(), w3_beta=pack_matrix(beta[:, None] * w3, c, c, device=dev),
+                         b3_beta=(beta * g(p + "conv3.bias")).to(dev),
+                         w4n=pack_matrix(g(p + "conv4.weight").reshape(2 * c, c), 2 * c, c, device=dev), b4n=g(p + "conv4.bias").to(dev),
+                         w5_gamma=pack_matrix(gamma[:, None] * w5, c, c, device=dev), b5_gamma=(gamma * g(p + "conv5.bias")).to(dev))
+            return d
 
         self.intro_w = pack_conv_im2col2(g("intro.weight"), WIDTH, device=dev)      # 3 -> 64 3x3 as an im2col GEMM (ops.pack_taps)
         self.intro_b = g("intro.bias").to(dev)
@@ -97,6 +107,18 @@ class NAFNetRunner:
             ops.dwconv(a, B, H, W, 2 * c, 3, 3, d["dw"], d["dwb"], gt, mode=1)
             ops.gap(gt, B, H * W, c, gapv, scratch)
             ops.vec_linear(gapv, B, c, d["sca_w"], d["sca_b"], c, ACT_NONE, sca)
+        if fused and c == 64 and ops.naf_tail_enabled():
+            # conv3 + residual + norm2 + conv4 + SimpleGate + conv5 + residual + the next block's norm1 in one pass over the fp32 stream
+            if c < H * W:
+                w3b = self.ws.get(f"w3b{c}", B * c, c, BF16)
+                ops.scale_weight_cols(d["w3_beta_f32"], sca, w3b.view(B, c, c))
+                rows = c
+            else:
+                ops.scale_channels(gt, B, H * W, c, sca)
+                w3b, rows = d["w3_beta"], 0
+            ops.naf_tail(gt, B, H, W, w3b, d["b3_beta"], S, d["n2"], d["w4n"], d["b4n"], d["w5_gamma"], d["b5_gamma"], S, w3_batch_rows=rows,
+                         out_bf16=t if next_norm is not None else (Sb if want_bf16 else None), ln=next_norm)
+            return next_norm is not None
         ln2 = (d["n2"][0], d["n2"][1], 1e-6, c, t) if fused else None
         if c < H * W:
             # x * sca folded into per-sample conv3 weights (c*c per sample instead of a pass over H*W*c activations)

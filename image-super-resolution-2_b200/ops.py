@@ -210,6 +210,44 @@ def hab_tail(a0, B, H, W, wp, bp, res, ln2, w1, b1, w2, b2, x, *, a1=None, a1_di
     L.check(L.load().ff_hab_tail(C.byref(p), _stream()), "ff_hab_tail")
 
 
+def naf_tail_enabled():
+    """conv3 + residual + norm2 + conv4 + SimpleGate + conv5 + residual (+ next norm1) of a 64-channel NAFBlock as one kernel
+    (ff_naf_tail); FFB200_NAF_TAIL=0 restores the three ff_conv_gemm passes."""
+    import os
+    return os.environ.get("FFB200_NAF_TAIL", "0") != "0"      # (off until the GPU run of this round has verified it)
+
+
+def naf_tail(a0, B, H, W, w3, b3, res, ln2, w4, b4, w5, b5, x, *, w3_batch_rows=0, out_bf16=None, ln=None, eps=1e-6):
+    """x = y + (u1 * u2) . w5^T + b5 with y = res + a0 . w3^T + b3 and u = LN2(y) . w4^T + b4 (64 channels; beta / gamma / sca folded
+    into w3 / w5 by the caller); ln = (gamma, beta) of the next LayerNorm2d, written to out_bf16 instead of a plain bf16 copy."""
+    _req_cuda(a0, w3, b3, res, ln2[0], ln2[1], w4, b4, w5, b5, x, out_bf16)
+    p = L.FFNafTail()
+    p.a0 = a0.data_ptr(); p.a0_ld = a0.stride(-2)
+    p.B, p.H, p.W = B, H, W
+    p.w3 = w3.data_ptr(); p.w3_batch_rows = w3_batch_rows; p.b3 = b3.data_ptr()
+    p.res = res.data_ptr(); p.res_ld = res.stride(-2)
+    p.ln2_gamma = ln2[0].data_ptr(); p.ln2_beta = ln2[1].data_ptr()
+    p.w4 = w4.data_ptr(); p.b4 = b4.data_ptr(); p.w5 = w5.data_ptr(); p.b5 = b5.data_ptr()
+    p.x = x.data_ptr(); p.x_ld = x.stride(-2)
+    if out_bf16 is not None:
+        p.out_bf16 = out_bf16.data_ptr(); p.out_ld = out_bf16.stride(-2)
+    if ln is not None:
+        _req_cuda(ln[0], ln[1])
+        p.ln_gamma = ln[0].data_ptr(); p.ln_beta = ln[1].data_ptr()
+    p.ln_eps = eps
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.load().ff_naf_tail(C.byref(p), _stream()), "ff_naf_tail")
+        e1.record()
+        M = B * H * W
+        flops = 2.0 * M * (64 * 64 + 128 * 64 + 64 * 64)
+        byts = M * 64 * 2 + (64 * 64 * (B if w3_batch_rows else 1) + 128 * 64 + 64 * 64) * 2 + M * 64 * 8 + (M * 64 * 2 if out_bf16 is not None else 0)
+        PROFILE.records.append((e0, e1, flops, flops, float(byts), ("naf_tail", B, H, W)))
+        return
+    L.check(L.load().ff_naf_tail(C.byref(p), _stream()), "ff_naf_tail")
+
+
 def window_attention(qkv, B, H, W, out, *, bias_table, wh, ww, kh=None, kw=None, kpad=(0, 0), shift=(0, 0), heads=6,
                      head_off=0, bias_head_off=0, rel_sign=1, rel_off=None, rel_stride=None, q_off=0, k_off=192,
                      v_off=384, out_off=0, padded=None):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FFB200_ABI_VERSION 5
+#define FFB200_ABI_VERSION 6
 
 int ff_abi_version(void);
 const char* ff_last_error(void);
@@ -172,6 +172,35 @@ typedef struct FFHabTail {
   float ln_eps; int ln_cols;     /* shared by both LayerNorms (180, 1e-5 in HAT) */
 } FFHabTail;
 int ff_hab_tail(const FFHabTail* p, void* stream);
+
+/*
+ * ff_naf_tail -- everything of a 64-channel NAFBlock that follows the SimpleGate depthwise conv, as ONE kernel (csrc/naf_tail.cu).
+ * Replaces nafnet_arch.py:118-131 (x * sca -> conv3 -> y = inp + x * beta -> norm2 -> conv4 -> SimpleGate -> conv5 ->
+ * y + x * gamma) and the norm1 of the following block (:112) at the 64-channel (full-resolution) levels, where the three
+ * 1x1 convs are HBM-bound passes over the fp32 stream: one read of a0 and res, one write of x and out_bf16.
+ *   y   = res + a0 . w3^T + b3                      w3 [64][64] bf16 with beta (and, per sample, sca) folded in by the caller:
+ *                                                   w3[n][k] = beta[n] * conv3[n][k] * sca[b][k], rows b * w3_batch_rows + n; b3 = beta * bias
+ *   t   = LayerNorm(y; ln2_gamma, ln2_beta)         over the 64 channels, biased variance, ln_eps
+ *   u   = t . w4^T + b4                             w4 [128][64] bf16 in the reference's row order
+ *   x   = y + (u[:, :64] * u[:, 64:]) . w5^T + b5   w5 [64][64] bf16 = gamma[n] * conv5[n][k], b5 = gamma * bias
+ *   out_bf16 = LayerNorm(x; ln_gamma, ln_beta) when ln_gamma is given, else a bf16 copy of x (optional)
+ * a0: bf16 [B*H*W][a0_ld]; res / x: fp32 [B*H*W][ld] (may alias); tiles are 8 x 16 pixels, any H x W.
+ */
+typedef struct FFNafTail {
+  const void* a0; int a0_ld;
+  int B, H, W;
+  const void* w3; int w3_batch_rows;   /* 0 (one matrix) or 64 (one matrix per sample) */
+  const float* b3;
+  const float* res; int res_ld;
+  const float* ln2_gamma; const float* ln2_beta;
+  const void* w4; const float* b4;
+  const void* w5; const float* b5;
+  float* x; int x_ld;
+  void* out_bf16; int out_ld;          /* optional */
+  const float* ln_gamma; const float* ln_beta;   /* optional: out_bf16 receives the next LayerNorm instead of a copy */
+  float ln_eps;
+} FFNafTail;
+int ff_naf_tail(const FFNafTail* p, void* stream);
 
 /*
  * ff_window_attention -- fused window attention (QK^T + relative-position bias + shift mask + softmax + PV).

@@ -27,13 +27,13 @@ def test_library_builds_and_exports_every_declared_symbol():
     exported = set(re.findall(r" T (ff_[a-z0-9_]+)", subprocess.run(["nm", "-D", lib.LIB_PATH], capture_output=True, text=True).stdout))
     extra = sorted(exported - declared - {"ff_set_error", "ff_num_sms"})
     assert not [e for e in extra if not e.startswith("_Z")], f"exported but undeclared: {extra}"
-    assert so.ff_abi_version() == 5
+    assert so.ff_abi_version() == 6
 
 
 def test_ctypes_structs_match_header_field_order():
     from isr2_b200 import lib
     hdr = open(os.path.join(ROOT, "include", "ffb200.h")).read()
-    for name, cls in (("FFConvGemm", lib.FFConvGemm), ("FFWinAttn", lib.FFWinAttn), ("FFMlpFused", lib.FFMlpFused), ("FFHabTail", lib.FFHabTail)):
+    for name, cls in (("FFConvGemm", lib.FFConvGemm), ("FFWinAttn", lib.FFWinAttn), ("FFMlpFused", lib.FFMlpFused), ("FFHabTail", lib.FFHabTail), ("FFNafTail", lib.FFNafTail)):
         body = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + ";", hdr, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []

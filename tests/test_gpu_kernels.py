@@ -961,6 +961,49 @@ def test_hab_tail(B, H, W, with_cab, with_bf16, with_ln, inplace):
         assert (lno.cpu().float()[:, C:] == 0).all()
 
 
+@pytest.mark.parametrize("B,H,W,batch_w,mode,inplace", [(2, 16, 32, True, "ln", True), (1, 24, 40, False, "ln", False), (3, 64, 64, True, "bf16", True),
+                                                         (2, 13, 21, True, "none", True), (5, 96, 160, True, "ln", True)])
+def test_naf_tail(B, H, W, batch_w, mode, inplace):
+    """ff_naf_tail (csrc/naf_tail.cu): conv3 (per-sample weights) + residual -> LayerNorm2d -> conv4 -> SimpleGate -> conv5 + residual
+    (-> next LayerNorm2d / bf16 copy) of a 64-channel NAFBlock as one kernel, against plain fp32 PyTorch on the bf16-rounded operands;
+    whole and partial tiles, more tiles than resident CTAs (B=5, 96x160 = 600 tiles > 2 x 148)."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(71 + B)
+    P, C = B * H * W, 64
+    gt = torch.randn(P, C, generator=g).to(BF16)
+    w3 = (torch.randn(B if batch_w else 1, C, C, generator=g) / math.sqrt(C)).to(BF16)
+    b3 = torch.randn(C, generator=g) * 0.3
+    res = torch.randn(P, C, generator=g) * 2 + 0.5
+    w4 = (torch.randn(2 * C, C, generator=g) / math.sqrt(C)).to(BF16)
+    b4 = torch.randn(2 * C, generator=g) * 0.3
+    w5 = (torch.randn(C, C, generator=g) / math.sqrt(C)).to(BF16)
+    b5 = torch.randn(C, generator=g) * 0.3
+    g2, be2 = 1 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    gn, ben = 1 + 0.2 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    w3p = w3.float().repeat_interleave(H * W, 0) if batch_w else w3.float().expand(P, C, C)
+    y = res + torch.einsum("pk,pnk->pn", gt.float(), w3p) + b3
+    t = F.layer_norm(y, (C,), g2, be2, 1e-6).to(BF16).float()
+    u = t @ w4.float().t() + b4
+    gate = (u[:, :C] * u[:, C:]).to(BF16).float()
+    ref = y + gate @ w5.float().t() + b5
+    ln_ref = F.layer_norm(ref, (C,), gn, ben, 1e-6)
+    d = _dev()
+    resd = res.clone().to(d)
+    xd = resd if inplace else torch.full((P, C), 9.0, device=d)
+    o16 = torch.full((P, C), 7.0, dtype=BF16, device=d) if mode != "none" else None
+    ops.naf_tail(gt.to(d), B, H, W, w3.reshape(-1, C).contiguous().to(d), b3.to(d), resd, (g2.to(d), be2.to(d)), w4.to(d), b4.to(d), w5.to(d), b5.to(d), xd,
+                 w3_batch_rows=C if batch_w else 0, out_bf16=o16, ln=(gn.to(d), ben.to(d)) if mode == "ln" else None)
+    torch.cuda.synchronize()
+    e = (xd.cpu() - ref).abs().max().item()
+    assert e < 3e-2, e              # bf16 LayerNorm2d output and gate products (values up to ~10) through 64-long contractions
+    if not inplace:
+        assert torch.equal(resd.cpu(), res)
+    if mode == "ln":
+        assert (o16.cpu().float() - ln_ref).abs().max().item() < 5e-2
+    elif mode == "bf16":
+        assert (o16.cpu().float() - ref).abs().max().item() < 8e-2
+
+
 def test_conv_gemm_k_concatenated_second_operand():
     """FFConvGemm.x2: out = [x | x2] . W^T with per-sample weights [W | diag(alpha * s_b)] (ff_build_concat_diag_weights) reproduces the
     aux epilogue  x.W^T + bias + alpha * s_b[n] * x2[p, n] + res  of HAT's proj layer (hat_arch.py:306) on the tensor pipe."""
