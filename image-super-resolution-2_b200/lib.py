@@ -84,6 +84,7 @@ def load():
     lib.ff_last_error.restype = C.c_char_p
     lib.ff_launch_count.restype = C.c_longlong
     lib.ff_ssim_y_scratch_bytes.restype = C.c_size_t
+    lib.ff_eval_scratch_bytes.restype = C.c_size_t
     if lib.ff_abi_version() != 6:
         raise FFError("libffb200.so ABI version mismatch")
     _lib = lib

@@ -214,7 +214,7 @@ def naf_tail_enabled():
     """conv3 + residual + norm2 + conv4 + SimpleGate + conv5 + residual (+ next norm1) of a 64-channel NAFBlock as one kernel
     (ff_naf_tail); FFB200_NAF_TAIL=0 restores the three ff_conv_gemm passes."""
     import os
-    return os.environ.get("FFB200_NAF_TAIL", "0") != "0"      # (off until the GPU run of this round has verified it)
+    return os.environ.get("FFB200_NAF_TAIL", "1") != "0"
 
 
 def naf_tail(a0, B, H, W, w3, b3, res, ln2, w4, b4, w5, b5, x, *, w3_batch_rows=0, out_bf16=None, ln=None, eps=1e-6):
@@ -424,4 +424,22 @@ def ssim_y(a, b, crop=4):
     scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=a.device)
     L.check(lib.ff_ssim_y(_ptr(a.contiguous()), _ptr(b.contiguous()), B, H, W, crop, _ptr(out), _ptr(scratch), C.c_size_t(nbytes), _stream()),
             "ff_ssim_y")
+    return out
+
+
+def eval_psnr_ssim_u8(a, b, border=4):
+    """(psnr, ssim) of the reference's evaluation harness (utils/utils_image.py:287-312 cal_psnr_ssim: OpenCV's 8-bit luma,
+    scikit-image's 7x7 uniform-window SSIM) for two uint8 HWC RGB images on the GPU -> float64 [2] on the GPU."""
+    _req_cuda(a, b)
+    if a.dtype != torch.uint8 or b.dtype != torch.uint8 or a.dim() != 3 or a.shape[2] != 3 or a.shape != b.shape:
+        raise ValueError(f"eval_psnr_ssim_u8: two uint8 [H, W, 3] images of the same size are needed, got {tuple(a.shape)} {a.dtype} / {tuple(b.shape)} {b.dtype}")
+    H, W, _ = a.shape
+    lib = L.load()
+    nbytes = int(lib.ff_eval_scratch_bytes(H, W, border))
+    if nbytes == 0:
+        raise ValueError(f"eval_psnr_ssim_u8: image {H}x{W} does not hold a 7x7 window after a crop of {border}")
+    out = torch.empty(2, dtype=torch.float64, device=a.device)
+    scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=a.device)
+    L.check(lib.ff_eval_psnr_ssim_u8(_ptr(a.contiguous()), _ptr(b.contiguous()), H, W, border, _ptr(out), _ptr(scratch), C.c_size_t(nbytes), _stream()),
+            "ff_eval_psnr_ssim_u8")
     return out

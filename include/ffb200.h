@@ -440,6 +440,16 @@ int ff_psnr_y(const float* a, const float* b, int B, int H, int W, int crop, flo
 int ff_ssim_y(const float* a, const float* b, int B, int H, int W, int crop, float* out, double* scratch, size_t scratch_bytes, void* stream);
 size_t ff_ssim_y_scratch_bytes(int B, int H, int W, int crop);
 
+/* The PSNR / SSIM pair of the reference's evaluation harness (eval.py:157 -> utils/utils_image.py:287-312 cal_psnr_ssim) on two
+ * uint8 RGB images [H][W][3] in device memory: crop `border` pixels, Y = OpenCV's 8-bit RGB2YCrCb luma
+ * ((4899 R + 9617 G + 1868 B + 2^13) >> 14), PSNR = 10 log10(255^2 / MSE) (inf for identical images), SSIM = scikit-image's
+ * structural_similarity defaults (7x7 uniform window, sample covariance, K1 0.01, K2 0.03, data_range 255, mean over the windows
+ * inside the cropped image); integer window sums, fp64 formula.  out: device double[2] = {psnr, ssim};
+ * scratch >= ff_eval_scratch_bytes(H, W, border) bytes, 8-byte aligned. */
+int ff_eval_psnr_ssim_u8(const unsigned char* a, const unsigned char* b, int H, int W, int border, double* out, void* scratch,
+                         size_t scratch_bytes, void* stream);
+size_t ff_eval_scratch_bytes(int H, int W, int border);
+
 #ifdef __cplusplus
 }
 #endif
