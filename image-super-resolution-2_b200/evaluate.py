@@ -56,7 +56,7 @@ def partition(n_files, rank, num_gpus):
 def _load_rgb_u8(path):
     """imread_uint(path, 3) (utils_image.py:105-117): uint8 RGB, grey images replicated to three channels, alpha dropped."""
     with Image.open(path) as im:
-        return np.asarray(im.convert("RGB"), dtype=np.uint8)
+        return np.array(im.convert("RGB"), dtype=np.uint8)      # (a writable copy: torch.from_numpy needs one)
 
 
 def evaluate_files(pairs, device):

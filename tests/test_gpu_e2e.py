@@ -195,3 +195,41 @@ def test_io_main_pipeline_mixed_folder_and_sharded(tmp_path):
     for n in imgs:
         a, b = np.array(Image.open(os.path.join(outp, n))).astype(int), np.array(Image.open(os.path.join(outp2, n))).astype(int)
         assert np.abs(a - b).max() <= 1, n
+
+
+@pytest.mark.gpu
+def test_eval_psnr_ssim_kernel_and_harness(tmp_path):
+    """ff_eval_psnr_ssim_u8 (the PSNR / SSIM of the reference's eval.py: OpenCV's 8-bit luma, scikit-image's 7x7 uniform-window SSIM)
+    against oracle/eval_metrics.py, and the harness isr2_b200.evaluate (one and two worker processes) on a folder of PNG pairs."""
+    from PIL import Image
+    from isr2_b200 import evaluate as ev, ops
+    from oracle import eval_metrics as em
+    rng = np.random.default_rng(5)
+    dev = torch.device("cuda:0")
+    for (h, w, noise) in ((15, 15, 20), (23, 30, 9), (79, 141, 3), (200, 333, 40)):
+        base = rng.integers(0, 256, (h // 4 + 2, w // 4 + 2, 3)).astype(np.float32)
+        a = np.asarray(Image.fromarray(base.astype(np.uint8)).resize((w, h), Image.BICUBIC))      # image-like content
+        b = np.clip(a.astype(int) + rng.integers(-noise, noise + 1, a.shape), 0, 255).astype(np.uint8)
+        got = ops.eval_psnr_ssim_u8(torch.from_numpy(a.copy()).to(dev), torch.from_numpy(b).to(dev)).cpu().tolist()
+        want = em.cal_psnr_ssim(a, b)
+        assert abs(got[0] - want[0]) < 1e-9 and abs(got[1] - want[1]) < 1e-9, (h, w, got, want)
+        same = ops.eval_psnr_ssim_u8(torch.from_numpy(a.copy()).to(dev), torch.from_numpy(a.copy()).to(dev)).cpu().tolist()
+        assert same[0] == float("inf") and abs(same[1] - 1.0) < 1e-12
+    with pytest.raises(ValueError):
+        ops.eval_psnr_ssim_u8(torch.zeros(12, 40, 3, dtype=torch.uint8, device=dev), torch.zeros(12, 40, 3, dtype=torch.uint8, device=dev))
+    out_dir, tgt_dir = tmp_path / "team29" / "sr", tmp_path / "HR"
+    out_dir.mkdir(parents=True); tgt_dir.mkdir()
+    want = {}
+    for i in range(5):
+        t = rng.integers(0, 256, (64 + 4 * i, 96, 3), dtype=np.uint8)
+        o = np.clip(t.astype(int) + rng.integers(-6, 7, t.shape), 0, 255).astype(np.uint8)
+        Image.fromarray(o).save(out_dir / f"08{i:02d}x4.png")
+        Image.fromarray(t).save(tgt_dir / f"08{i:02d}.png")
+        want[f"08{i:02d}x4.png"] = em.cal_psnr_ssim(o, t)
+    for gpu_ids in ([0], [0, 0]):      # two workers on one GPU exercise the spawned partitions (eval.py:162-217)
+        res, avg = ev.run(str(out_dir), str(tgt_dir), str(tmp_path / f"IQA{len(gpu_ids)}"), gpu_ids)
+        assert sorted(res) == sorted(want)
+        for k, (p, s_) in want.items():
+            assert abs(res[k]["psnr"] - p) < 1e-9 and abs(res[k]["ssim"] - s_) < 1e-9
+        assert abs(avg["psnr"] - np.mean([v[0] for v in want.values()])) < 1e-9
+        assert os.path.exists(tmp_path / f"IQA{len(gpu_ids)}" / "team29--sr.csv")
