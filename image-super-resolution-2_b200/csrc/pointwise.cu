@@ -1614,6 +1614,171 @@ extern "C" int ff_scale_channels(void* x, int ld, int B, long long pixels_per_sa
   return FF_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Specialised forms of the direct convolution for the small fp32 layers the fusion head runs at OUTPUT resolution (the edge
+// refiner's attention / gate heads, edge_enhancement.py:100-106, 168-180): the generic kernel above pads every layer to groups of
+// eight output channels and walks run-time loops, which costs 8x the FMAs for the 1-channel heads.
+//   conv3x3_small_kernel<CIN, NOUT>  fp32 NHWC -> fp32, 3x3, zero padding.  CTA = 32 x 32 pixels, thread = a column strip of four
+//       rows: per (channel, dx) six vertically adjacent inputs are read once from the shared-memory tile ([row][channel][x], lanes
+//       along x: conflict free) and feed the 4 x 3 x NOUT FMAs that use them; weights are broadcast reads.
+//   conv1x1_rows_kernel<CIN, NOUT>   bf16 NHWC (first CIN channels) -> fp32, one pixel per thread, weights broadcast from smem.
+//   conv1x1_wide_bf16_kernel         3 fp32 channels -> 64 bf16 channels: eight lanes per pixel (16-byte stores, a warp writes
+//       512 contiguous bytes), the lane's 24 weights live in registers across a grid-stride loop.
+// ------------------------------------------------------------------------------------------
+template <int CIN, int NOUT>
+__global__ void __launch_bounds__(256) conv3x3_small_kernel(const __grid_constant__ DirectArgs a) {
+  constexpr int TS = 32, PY = 4, PW = TS + 2, PH = TS + 2, XP = PW + 1;      // tile, rows per thread, tile + halo, padded x pitch
+  extern __shared__ __align__(16) float sm3[];
+  float* sIn = sm3;                          // [PH][CIN][XP]
+  float* sW = sm3 + ((PH * CIN * XP + 3) & ~3);      // [9][CIN][NOUT], 16-byte aligned
+  const int tiles_x = (a.W + TS - 1) / TS, tiles_y = (a.H + TS - 1) / TS;
+  int t = blockIdx.x;
+  const int b = t / (tiles_x * tiles_y);
+  t -= b * tiles_x * tiles_y;
+  const int ty = t / tiles_x, tx = t - ty * tiles_x;
+  const int y0 = ty * TS - 1, x0 = tx * TS - 1;
+  const float* xin = reinterpret_cast<const float*>(a.x);
+  constexpr int CV = (CIN + 3) / 4;
+  if (a.x_ld % 4 == 0 && a.x_ld >= 4 * CV && (reinterpret_cast<uintptr_t>(xin) & 15) == 0) {      // 16-byte loads (may read pitch padding past CIN)
+    for (int i = threadIdx.x; i < PH * PW * CV; i += 256) {
+      const int cv = i % CV, pp = i / CV;
+      const int py = pp / PW, px = pp - py * PW;
+      const int y = y0 + py, x = x0 + px;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y >= 0 && y < a.H && x >= 0 && x < a.W) v = __ldg(reinterpret_cast<const float4*>(xin + ((long long)(b * a.H + y) * a.W + x) * a.x_ld) + cv);
+      float* d = sIn + (py * CIN + cv * 4) * XP + px;
+      d[0] = v.x;
+      if (cv * 4 + 1 < CIN) d[XP] = v.y;
+      if (cv * 4 + 2 < CIN) d[2 * XP] = v.z;
+      if (cv * 4 + 3 < CIN) d[3 * XP] = v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < PH * PW * CIN; i += 256) {
+      const int c = i % CIN, pp = i / CIN;
+      const int py = pp / PW, px = pp - py * PW;
+      const int y = y0 + py, x = x0 + px;
+      float v = 0.f;
+      if (y >= 0 && y < a.H && x >= 0 && x < a.W) v = __ldg(xin + ((long long)(b * a.H + y) * a.W + x) * a.x_ld + c);
+      sIn[(py * CIN + c) * XP + px] = v;
+    }
+  }
+  for (int i = threadIdx.x; i < 9 * CIN * NOUT; i += 256) {
+    const int o = i % NOUT, kk = i / NOUT;
+    sW[i] = __ldg(a.w + (long long)o * (9 * CIN) + kk);
+  }
+  __syncthreads();
+  const int px = threadIdx.x & 31, pg = threadIdx.x >> 5;      // a warp = one strip row group: 32 columns x rows 4 pg .. 4 pg + 3
+  float acc[PY][NOUT];
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) {
+    const float bv = a.bias ? __ldg(a.bias + o) : 0.f;
+#pragma unroll
+    for (int r = 0; r < PY; ++r) acc[r][o] = bv;
+  }
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      float v[PY + 2];
+#pragma unroll
+      for (int j = 0; j < PY + 2; ++j) v[j] = sIn[((pg * PY + j) * CIN + c) * XP + px + dx];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const float* wp = sW + ((dy * 3 + dx) * CIN + c) * NOUT;
+        if constexpr (NOUT % 4 == 0) {
+#pragma unroll
+          for (int o = 0; o < NOUT; o += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wp + o);
+#pragma unroll
+            for (int r = 0; r < PY; ++r) {
+              acc[r][o] = fmaf(v[r + dy], w4.x, acc[r][o]); acc[r][o + 1] = fmaf(v[r + dy], w4.y, acc[r][o + 1]);
+              acc[r][o + 2] = fmaf(v[r + dy], w4.z, acc[r][o + 2]); acc[r][o + 3] = fmaf(v[r + dy], w4.w, acc[r][o + 3]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int o = 0; o < NOUT; ++o) {
+            const float wv = wp[o];
+#pragma unroll
+            for (int r = 0; r < PY; ++r) acc[r][o] = fmaf(v[r + dy], wv, acc[r][o]);
+          }
+        }
+      }
+    }
+  }
+  const int ox = tx * TS + px;
+  if (ox >= a.W) return;
+#pragma unroll
+  for (int r = 0; r < PY; ++r) {
+    const int oy = ty * TS + pg * PY + r;
+    if (oy >= a.H) break;
+    float* q = a.out_f32 + ((long long)(b * a.H + oy) * a.W + ox) * a.out_f32_ld;
+    if constexpr (NOUT % 4 == 0) {
+      if (a.vec_f32) {
+#pragma unroll
+        for (int o = 0; o < NOUT; o += 4)
+          *reinterpret_cast<float4*>(q + o) = make_float4(act_apply(acc[r][o], a.act), act_apply(acc[r][o + 1], a.act), act_apply(acc[r][o + 2], a.act), act_apply(acc[r][o + 3], a.act));
+        continue;
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) q[o] = act_apply(acc[r][o], a.act);
+  }
+}
+
+template <int CIN, int NOUT>
+__global__ void __launch_bounds__(256) conv1x1_rows_kernel(const __grid_constant__ DirectArgs a, long long pixels) {
+  __shared__ __align__(16) float sW[CIN * NOUT];      // [c][o]
+  __shared__ float sB[NOUT];
+  for (int i = threadIdx.x; i < CIN * NOUT; i += 256) sW[i] = __ldg(a.w + (long long)(i % NOUT) * CIN + i / NOUT);
+  if (threadIdx.x < NOUT) sB[threadIdx.x] = a.bias ? __ldg(a.bias + threadIdx.x) : 0.f;
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= pixels) return;
+  const uint4* xin = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.x) + p * a.x_ld);
+  float acc[NOUT];
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) acc[o] = sB[o];
+#pragma unroll
+  for (int c8 = 0; c8 < CIN / 8; ++c8) {
+    const uint4 u = __ldg(xin + c8);
+    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xv = __uint_as_float((j & 1) ? (uw[j >> 1] & 0xffff0000u) : (uw[j >> 1] << 16));
+      const float4* wp = reinterpret_cast<const float4*>(sW + (c8 * 8 + j) * NOUT);
+#pragma unroll
+      for (int o = 0; o < NOUT; o += 4) {
+        const float4 w4 = wp[o >> 2];
+        acc[o] = fmaf(xv, w4.x, acc[o]); acc[o + 1] = fmaf(xv, w4.y, acc[o + 1]); acc[o + 2] = fmaf(xv, w4.z, acc[o + 2]); acc[o + 3] = fmaf(xv, w4.w, acc[o + 3]);
+      }
+    }
+  }
+  float* q = a.out_f32 + p * a.out_f32_ld;
+#pragma unroll
+  for (int o = 0; o < NOUT; o += 4)
+    *reinterpret_cast<float4*>(q + o) = make_float4(act_apply(acc[o], a.act), act_apply(acc[o + 1], a.act), act_apply(acc[o + 2], a.act), act_apply(acc[o + 3], a.act));
+}
+
+__global__ void __launch_bounds__(256) conv1x1_wide_bf16_kernel(const __grid_constant__ DirectArgs a, long long pixels) {
+  const int oct = threadIdx.x & 7;      // output channels 8 oct .. 8 oct + 7
+  float w[3][8], bv[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    bv[o] = a.bias ? __ldg(a.bias + oct * 8 + o) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) w[c][o] = __ldg(a.w + (long long)(oct * 8 + o) * 3 + c);
+  }
+  const float* xin = reinterpret_cast<const float*>(a.x);
+  for (long long p = ((long long)blockIdx.x * 256 + threadIdx.x) >> 3; p < pixels; p += ((long long)gridDim.x * 256) >> 3) {
+    const float x0 = __ldg(xin + p * a.x_ld), x1 = __ldg(xin + p * a.x_ld + 1), x2 = __ldg(xin + p * a.x_ld + 2);
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = act_apply(fmaf(x2, w[2][o], fmaf(x1, w[1][o], fmaf(x0, w[0][o], bv[o]))), a.act);
+    *reinterpret_cast<uint4*>(a.out_bf16 + p * a.out_ld + oct * 8) = pack8(acc);
+  }
+}
+
 extern "C" int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int H, int W, int Cin, int k, const float* w,
                               const float* bias, int Cout_pad, int n_store, int act, const float* mul_f32, int mul_ld,
                               void* out_bf16, int out_ld, float* out_f32, int out_f32_ld, void* stream) {
@@ -1624,6 +1789,44 @@ extern "C" int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int
   const int vb = (out_bf16 && out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0) ? 1 : 0;
   const int vf = (out_f32 && out_f32_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) ? 1 : 0;
   DirectArgs a{x, x_is_bf16, x_ld, B, H, W, Cin, k, w, bias, Cout_pad, n_store, act, mul_f32, mul_ld, reinterpret_cast<bf16*>(out_bf16), out_ld, out_f32, out_f32_ld, vb, vf};
+  cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  // specialised kernels for the small fp32 layers that run at output resolution (see above)
+  if (k == 3 && !x_is_bf16 && !mul_f32 && !out_bf16 && out_f32 && ((n_store == 1 && (Cin == 8 || Cin == 16)) || (n_store == 16 && Cin == 6))) {
+    const int grid = B * ff_cdiv(H, 32) * ff_cdiv(W, 32);
+    auto launch = [&](auto kern, int cin, int nout) -> int {
+      const int smem = (((34 * cin * 35 + 3) & ~3) + 9 * cin * nout) * (int)sizeof(float);
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      // (idempotent, cheap)
+        if (e != cudaSuccess) { ff_set_error("ff_conv_direct: smem %d: %s", smem, cudaGetErrorString(e)); return FF_ERR_CUDA; }
+      }
+      kern<<<grid, 256, smem, st_>>>(a);
+      return FF_OK;
+    };
+    int rc = FF_OK;
+    if (Cin == 8) rc = launch(conv3x3_small_kernel<8, 1>, 8, 1);
+    else if (Cin == 16) rc = launch(conv3x3_small_kernel<16, 1>, 16, 1);
+    else rc = launch(conv3x3_small_kernel<6, 16>, 6, 16);
+    if (rc != FF_OK) return rc;
+    ++g_ff_launches;
+    FF_CHECK_LAUNCH("ff_conv_direct");
+    return FF_OK;
+  }
+  if (k == 1 && x_is_bf16 && Cin == 32 && n_store == 8 && !mul_f32 && !out_bf16 && vf && x_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const long long pixels = (long long)B * H * W;
+    conv1x1_rows_kernel<32, 8><<<ff_cdiv(pixels, 256), 256, 0, st_>>>(a, pixels);
+    ++g_ff_launches;
+    FF_CHECK_LAUNCH("ff_conv_direct");
+    return FF_OK;
+  }
+  if (k == 1 && !x_is_bf16 && Cin == 3 && n_store == 64 && !mul_f32 && !out_f32 && vb) {
+    const long long pixels = (long long)B * H * W;
+    const long long want = (pixels * 8 + 255) / 256;
+    const int grid = (int)(want < (long long)ff_num_sms() * 16 ? want : (long long)ff_num_sms() * 16);
+    conv1x1_wide_bf16_kernel<<<grid, 256, 0, st_>>>(a, pixels);
+    ++g_ff_launches;
+    FF_CHECK_LAUNCH("ff_conv_direct");
+    return FF_OK;
+  }
   const int pad = k / 2;
   // small input-channel counts: one block computes every output-channel group (input patch and all weights staged once)
   const bool all_w = Cin <= 16 && (size_t)k * k * Cin * Cout_pad * sizeof(float) <= 96 * 1024;

@@ -843,6 +843,40 @@ def test_conv_direct_any_size(cin, cout, k, H, W, B):
     assert (out[B * H * W:] == 9.0).all()
 
 
+@pytest.mark.parametrize("cin,cout,k,in_ld,out_ld,in_bf16,out_bf16,act", [
+    (8, 1, 3, 8, 1, False, False, "sigmoid"), (16, 1, 3, 16, 1, False, False, "sigmoid"), (6, 16, 3, 8, 16, False, False, "gelu"),
+    (6, 16, 3, 6, 16, False, False, "gelu"), (32, 8, 1, 64, 8, True, False, "gelu"), (3, 64, 1, 4, 64, False, True, "none")])
+@pytest.mark.parametrize("B,H,W", [(2, 37, 50), (1, 64, 96)])
+def test_conv_direct_specialised_small_layers(cin, cout, k, in_ld, out_ld, in_bf16, out_bf16, act, B, H, W):
+    """The specialised forms ff_conv_direct dispatches to for the edge refiner's small layers at output resolution (3x3 8->1, 16->1,
+    6->16 in fp32; 1x1 32 bf16 -> 8; 1x1 3 -> 64 bf16), on whole and partial tiles, with channel pitches wider than the channel count,
+    against F.conv2d."""
+    from isr2_b200 import ops, packing
+    g = torch.Generator().manual_seed(61 + cin)
+    x = torch.randn(B, cin, H, W, generator=g)
+    if in_bf16:
+        x = x.to(BF16).float()
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    bias = torch.randn(cout, generator=g)
+    y = F.conv2d(x, w, bias, padding=k // 2)
+    y = {"sigmoid": torch.sigmoid, "gelu": F.gelu, "none": lambda v: v}[act](y)
+    ref = _nhwc(y)
+    d = _dev()
+    P = B * H * W
+    xin = torch.full((P, in_ld), 3.0)
+    xin[:, :cin] = _nhwc(x)
+    xin = xin.to(d, BF16 if in_bf16 else F32)
+    cp = (cout + 7) // 8 * 8
+    out = torch.full((P + 16, out_ld), 9.0, device=d, dtype=BF16 if out_bf16 else F32)
+    code = {"sigmoid": ops.ACT_SIGMOID, "gelu": ops.ACT_GELU, "none": ops.ACT_NONE}[act]
+    kw = dict(out_bf16=out[:P]) if out_bf16 else dict(out_f32=out[:P])
+    ops.conv_direct(xin, B, H, W, cin, k, packing.pack_conv_direct(w, cp, d), packing.pack_vector(bias, cp, device=d), n_store=cout, act=code, **kw)
+    torch.cuda.synchronize()
+    e = (out[:P, :cout].float().cpu() - ref).abs().max().item()
+    assert e < (3e-2 if out_bf16 else 2e-5), e
+    assert (out[P:] == 9.0).all()
+
+
 @pytest.mark.parametrize("B,H,W,with_bf16,with_ln", [(2, 32, 32, False, True), (1, 16, 48, True, False), (3, 24, 16, True, True), (1, 128, 128, False, True)])
 def test_mlp_fused(B, H, W, with_bf16, with_ln):
     """ff_mlp_fused: x += fc2(GELU(fc1(t))) with the hidden tile on chip (csrc/mlp_fused.cu), optional bf16 copy and fused LayerNorm
