@@ -7,6 +7,8 @@ python tools/full_forward.py 16 128 2 > $O/p_full.log 2>&1 || { echo "full_forwa
 python tools/bench_attn.py 16 128 > $O/${T}_bench_attn.txt 2>&1 || { echo "bench_attn failed"; exit 1; }
 python tools/bench_tail.py 16 128 > $O/${T}_bench_tail.txt 2>&1 || { echo "bench_tail failed"; exit 1; }
 python tools/bench_dw.py 16 128 > $O/${T}_bench_dw.txt 2>&1 || { echo "bench_dw failed"; exit 1; }
+python tools/bench_naf.py 16 512 > $O/${T}_bench_naf.txt 2>&1 || { echo "bench_naf failed"; exit 1; }
+python tools/bench_small_convs.py 16 512 > $O/${T}_bench_small_convs.txt 2>&1 || { echo "bench_small_convs failed"; exit 1; }
 # 1. launch list of one step at the bench shape (experts serialised for attribution); skip the first (warm-up) forward
 N=$(FFB200_EXPERT_STREAMS=0 FFB200_GRAPHS=0 python -c "
 import sys; sys.path.insert(0,'.')
@@ -26,4 +28,6 @@ ncu --set full --clock-control none --import-source on --kernel-name-base demang
 # 4. the fused HAT-block tail and the SimpleGate depthwise kernel
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:hab_tail -s 30 -c 1 -o $O/${T}_hab_tail -f python tools/bench_tail.py 16 128 > $O/p_ncu6.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:dwconv3x3_gate -s 3 -c 1 -o $O/${T}_dwgate -f python tools/bench_dw.py 16 128 > $O/p_ncu7.log 2>&1
+# 5. the fused NAFBlock tail
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:naf_tail -s 6 -c 1 -o $O/${T}_naf_tail -f python tools/bench_naf.py 16 512 > $O/p_ncu8.log 2>&1
 ls -la $O/*.ncu-rep
