@@ -49,6 +49,51 @@ __global__ void __launch_bounds__(256) cb_embed_ln_kernel(const float* __restric
   }
 }
 
+// The same front end with eight lanes per token: a lane owns eight channels (its 24 projection weights, bias, gamma, beta live in
+// registers across a grid-stride loop), the LayerNorm statistics take three shuffles, and a token's two 128-byte rows leave as
+// 16-byte stores (a warp writes 512 contiguous bytes per store instruction).
+__global__ void __launch_bounds__(256) cb_embed_ln8_kernel(const float* __restrict__ bands, long long tokens,
+                                                          const float* __restrict__ pw, const float* __restrict__ pb,
+                                                          const float* __restrict__ g, const float* __restrict__ bt,
+                                                          bf16* __restrict__ stacked, bf16* __restrict__ normed) {
+  const int oct = threadIdx.x & 7;
+  float w[8][3], bias[8], ga[8], be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = oct * 8 + i;
+    w[i][0] = pw[c * 3]; w[i][1] = pw[c * 3 + 1]; w[i][2] = pw[c * 3 + 2];
+    bias[i] = pb[c]; ga[i] = g[c]; be[i] = bt[c];
+  }
+  const long long stride = ((long long)gridDim.x * 256) >> 3;
+  const long long tok_end = (tokens + 3) & ~3LL;      // whole warps stay in the loop (shuffles), stores are masked
+  for (long long tok = ((long long)blockIdx.x * 256 + threadIdx.x) >> 3; tok < tok_end; tok += stride) {
+    const bool live = tok < tokens;
+    const long long t = live ? tok : tokens - 1;
+    const float b0 = __ldg(bands + t * 3), b1 = __ldg(bands + t * 3 + 1), b2 = __ldg(bands + t * 3 + 2);
+    float v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = w[i][0] * b0 + w[i][1] * b1 + w[i][2] * b2 + bias[i]; s += v[i]; }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / 64.f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q += d * d; }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / 64.f) + 1e-5f);
+    if (live) {
+      float n[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) n[i] = (v[i] - mean) * rstd * ga[i] + be[i];
+      auto pk = [](float lo, float hi) { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); };
+      *reinterpret_cast<uint4*>(stacked + tok * 64 + oct * 8) = make_uint4(pk(v[0], v[1]), pk(v[2], v[3]), pk(v[4], v[5]), pk(v[6], v[7]));
+      *reinterpret_cast<uint4*>(normed + tok * 64 + oct * 8) = make_uint4(pk(n[0], n[1]), pk(n[2], n[3]), pk(n[4], n[5]), pk(n[6], n[7]));
+    }
+  }
+}
+
 // 9-token multi-head attention per pixel (nn.MultiheadAttention core, 4 heads x 16; q pre-scaled by 1/4 in the packed in_proj).
 // qkv: bf16 [tokens][192] (q | k | v); one thread per (token, head).
 // DIM = embedding width (64: cross-band attention, 4 heads; 128: the collaborative branch's cross-expert attention, 8 heads).
@@ -279,6 +324,39 @@ __global__ void __launch_bounds__(256) experts_resize_kernel(const float* __rest
   for (int c = 0; c < 9; ++c) o[c] = __float2bfloat16_rn(v[c]);
 }
 
+// The same resize with 16-byte accesses: three float4 loads per source pixel (pitch 12) and two 16-byte stores per output pixel --
+// channels out_off .. out_off + 8 and seven zeros behind them (the zero padding of the conv input rows, which nothing else writes).
+__global__ void __launch_bounds__(256) experts_resize_vec_kernel(const float* __restrict__ stack, int ld, int B, int H, int W, int factor,
+                                                                bf16* __restrict__ out, int out_ld, int out_off) {
+  const int Ho = H / factor, Wo = W / factor;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)B * Ho * Wo) return;
+  const int xo = (int)(idx % Wo), yo = (int)((idx / Wo) % Ho), b = (int)(idx / ((long long)Wo * Ho));
+  float v[12];
+  if (factor == 1) {
+    const float4* p = reinterpret_cast<const float4*>(stack + idx * ld);
+    const float4 a = __ldg(p), c = __ldg(p + 1), d = __ldg(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w; v[8] = d.x;
+  } else {
+    const int y0 = factor == 2 ? 2 * yo : 4 * yo + 1, x0 = factor == 2 ? 2 * xo : 4 * xo + 1;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) v[c] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {      // (same summation order as the scalar kernel)
+        const float4* p = reinterpret_cast<const float4*>(stack + ((long long)(b * H + y0 + dy) * W + x0 + dx) * ld);
+        const float4 a = __ldg(p), c = __ldg(p + 1), d = __ldg(p + 2);
+        v[0] += 0.25f * a.x; v[1] += 0.25f * a.y; v[2] += 0.25f * a.z; v[3] += 0.25f * a.w;
+        v[4] += 0.25f * c.x; v[5] += 0.25f * c.y; v[6] += 0.25f * c.z; v[7] += 0.25f * c.w; v[8] += 0.25f * d.x;
+      }
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + idx * out_ld + out_off);
+  auto pk = [](float lo, float hi) { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); };
+  o[0] = make_uint4(pk(v[0], v[1]), pk(v[2], v[3]), pk(v[4], v[5]), pk(v[6], v[7]));
+  o[1] = make_uint4(pk(v[8], 0.f), 0u, 0u, 0u);
+}
+
 // SpatialGate (hierarchical_fusion.py:25-43): x *= sigmoid(w2 . gelu(W1 x + b1) + b2), per pixel, in place (bf16 rows).
 // One warp per pixel; C in {32, 64}, hidden = C/4.
 template <int C>
@@ -486,7 +564,12 @@ __global__ void __launch_bounds__(256) edge_final_kernel(const float* __restrict
 extern "C" int ff_cb_embed_ln(const float* bands, long long tokens, const float* proj_w, const float* proj_b, const float* ln_w,
                               const float* ln_b, void* stacked, void* normed, void* stream) {
   FF_CHECK_ARG(bands && proj_w && proj_b && ln_w && ln_b && stacked && normed, "ff_cb_embed_ln: null buffer");
-  cb_embed_ln_kernel<<<ff_cdiv(tokens, 8), 256, 0, ST(stream)>>>(bands, tokens, proj_w, proj_b, ln_w, ln_b, reinterpret_cast<bf16*>(stacked), reinterpret_cast<bf16*>(normed));
+  if ((reinterpret_cast<uintptr_t>(stacked) & 15) == 0 && (reinterpret_cast<uintptr_t>(normed) & 15) == 0) {
+    const long long want = ff_cdiv(tokens * 8, 256);
+    const long long cap = (long long)ff_num_sms() * 16;
+    cb_embed_ln8_kernel<<<(int)(want < cap ? want : cap), 256, 0, ST(stream)>>>(bands, tokens, proj_w, proj_b, ln_w, ln_b, reinterpret_cast<bf16*>(stacked), reinterpret_cast<bf16*>(normed));
+  } else
+    cb_embed_ln_kernel<<<ff_cdiv(tokens, 8), 256, 0, ST(stream)>>>(bands, tokens, proj_w, proj_b, ln_w, ln_b, reinterpret_cast<bf16*>(stacked), reinterpret_cast<bf16*>(normed));
   ++g_ff_launches; FF_CHECK_LAUNCH("ff_cb_embed_ln"); return FF_OK;
 }
 extern "C" int ff_cb_attention(const void* qkv, long long tokens, int num_bands, void* out, void* stream) {
@@ -615,7 +698,10 @@ extern "C" int ff_selector_tail(float* gates_difficulty, long long P, void* stre
 }
 extern "C" int ff_experts_resize(const float* stack, int ld, int B, int H, int W, int factor, void* out, int out_ld, int out_off, void* stream) {
   FF_CHECK_ARG(stack && out && (factor == 1 || factor == 2 || factor == 4) && H % factor == 0 && W % factor == 0 && ld >= 9, "ff_experts_resize: bad args");
-  experts_resize_kernel<<<ff_cdiv((long long)B * (H / factor) * (W / factor), 256), 256, 0, ST(stream)>>>(stack, ld, B, H, W, factor, reinterpret_cast<bf16*>(out), out_ld, out_off);
+  const bool vec = ld % 4 == 0 && ld >= 12 && out_off % 8 == 0 && out_ld % 8 == 0 && out_ld >= out_off + 16 && (reinterpret_cast<uintptr_t>(stack) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec) experts_resize_vec_kernel<<<ff_cdiv((long long)B * (H / factor) * (W / factor), 256), 256, 0, ST(stream)>>>(stack, ld, B, H, W, factor, reinterpret_cast<bf16*>(out), out_ld, out_off);
+  else experts_resize_kernel<<<ff_cdiv((long long)B * (H / factor) * (W / factor), 256), 256, 0, ST(stream)>>>(stack, ld, B, H, W, factor, reinterpret_cast<bf16*>(out), out_ld, out_off);
   ++g_ff_launches; FF_CHECK_LAUNCH("ff_experts_resize"); return FF_OK;
 }
 extern "C" int ff_pixel_gate(void* x, int ld, long long P, int C, const float* w1, const float* b1, const float* w2, float b2, void* stream) {

@@ -1586,6 +1586,65 @@ __global__ void __launch_bounds__(256) pack_taps_kernel(const float* __restrict_
   *reinterpret_cast<uint4*>(out + pix * out_ld + g * 8) = make_uint4(wout[0], wout[1], wout[2], wout[3]);
 }
 
+// The 3-channel 3x3 im2col with two terms (CIN = 3, K = 3, TERMS = 2: 54 of 64 columns) through a shared-memory tile: a CTA covers
+// 32 x 8 pixels, splits every input value of the tile (+ 1-pixel halo, zero outside the image) into (hi, lo) ONCE -- the gather form
+// above does it nine times per value, each behind its own 4-byte global load -- and a lane assembles its eight bf16 from eight
+// 16-bit shared-memory reads at offsets it works out once (the lane's column group is fixed).  A warp stores 512 contiguous bytes.
+__global__ void __launch_bounds__(256) pack_taps3_tile_kernel(const float* __restrict__ x, int x_ld, int B, int H, int W, bf16* __restrict__ out, int out_ld) {
+  constexpr int TX = 32, TY = 8, PW = TX + 2, PH = TY + 2;
+  __shared__ uint16_t sT[2][PH][PW][3];
+  const int tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
+  int t = blockIdx.x;
+  const int b = t / (tiles_x * tiles_y);
+  t -= b * tiles_x * tiles_y;
+  const int ty = t / tiles_x, tx = t - ty * tiles_x;
+  const int y0 = ty * TY - 1, x0 = tx * TX - 1;
+  for (int i = threadIdx.x; i < PH * PW; i += 256) {
+    const int py = i / PW, px = i - py * PW;
+    const int y = y0 + py, xx = x0 + px;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (y >= 0 && y < H && xx >= 0 && xx < W) {
+      const float* p = x + ((long long)(b * H + y) * W + xx) * x_ld;
+      v[0] = __ldg(p); v[1] = __ldg(p + 1); v[2] = __ldg(p + 2);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const bf16 hi = __float2bfloat16_rn(v[c]);
+      const bf16 lo = __float2bfloat16_rn(v[c] - __bfloat162float(hi));
+      sT[0][py][px][c] = __bfloat16_as_ushort(hi);
+      sT[1][py][px][c] = __bfloat16_as_ushort(lo);
+    }
+  }
+  __syncthreads();
+  const int g = threadIdx.x & 7, lx = threadIdx.x >> 3;      // column group (8 of the 64 columns), x inside the tile
+  int off[8];                                                // element offsets into sT relative to the pixel's (row, x); -1 = zero column
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int kidx = g * 8 + e;
+    const int term = kidx / 27, r = kidx - term * 27;
+    const int tap = r / 3, c = r - tap * 3;
+    const int dy = tap / 3, dx = tap - dy * 3;
+    off[e] = kidx < 54 ? ((term * PH + dy) * PW + dx) * 3 + c : -1;
+  }
+  const uint16_t* base = &sT[0][0][0][0];
+  const int ox = tx * TX + lx;
+  if (ox >= W) return;
+#pragma unroll
+  for (int j = 0; j < TY; ++j) {
+    const int oy = ty * TY + j;
+    if (oy >= H) break;
+    const uint16_t* pp = base + (j * PW + lx) * 3;
+    uint32_t w[4];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      const uint32_t lo16 = off[2 * e2] >= 0 ? pp[off[2 * e2]] : 0u;
+      const uint32_t hi16 = off[2 * e2 + 1] >= 0 ? pp[off[2 * e2 + 1]] : 0u;
+      w[e2] = lo16 | (hi16 << 16);
+    }
+    *reinterpret_cast<uint4*>(out + ((long long)(b * H + oy) * W + ox) * out_ld + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 extern "C" int ff_pack_taps(const float* x, int x_ld, int B, int H, int W, int Cin, int k, int terms, void* out, int out_ld, void* stream) {
   FF_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0, "ff_pack_taps: bad args");
   const int tot = k * k * Cin * terms;
@@ -1595,7 +1654,7 @@ extern "C" int ff_pack_taps(const float* x, int x_ld, int B, int H, int W, int C
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nb = ff_cdiv(total, 256);
   bf16* o = reinterpret_cast<bf16*>(out);
-  if (Cin == 3 && k == 3 && terms == 2) pack_taps_kernel<3, 3, 2><<<nb, 256, 0, st>>>(x, x_ld, B, H, W, o, out_ld, out_cols);
+  if (Cin == 3 && k == 3 && terms == 2) pack_taps3_tile_kernel<<<B * ff_cdiv(H, 8) * ff_cdiv(W, 32), 256, 0, st>>>(x, x_ld, B, H, W, o, out_ld);
   else if (Cin == 64 && k == 1 && terms == 3) pack_taps_kernel<64, 1, 3><<<nb, 256, 0, st>>>(x, x_ld, B, H, W, o, out_ld, out_cols);
   else if (Cin == 32 && k == 1 && terms == 3) pack_taps_kernel<32, 1, 3><<<nb, 256, 0, st>>>(x, x_ld, B, H, W, o, out_ld, out_cols);
   else { ff_set_error("ff_pack_taps: (Cin=%d, k=%d, terms=%d) is not an instantiated combination", Cin, k, terms); return FF_ERR_ARG; }

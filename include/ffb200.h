@@ -391,7 +391,9 @@ int ff_bilinear_f32_scaled(const float* in, int B, int Hi, int Wi, int ld_in, in
 int ff_bilinear_up2_bf16(const void* in, int B, int Hi, int Wi, int ld_in, int C, void* out, int ld_out, void* stream);
 /* DynamicExpertSelector tail (fusion_network.py:221-234), in place on [P][4] = (gate0, gate1, gate2, difficulty). */
 int ff_selector_tail(float* gates_difficulty, long long P, void* stream);
-/* Bilinear resize (factor 1, 2 or 4 down) of the 9 stacked expert channels into a bf16 conv-input buffer (hierarchical_fusion.py:140-171). */
+/* Bilinear resize (factor 1, 2 or 4 down) of the 9 stacked expert channels into a bf16 conv-input buffer (hierarchical_fusion.py:140-171).
+ * With 16-byte aligned operands (ld % 4 == 0, out_off % 8 == 0, out_ld >= out_off + 16) the channels out_off + 9 .. out_off + 15 are written
+ * as zeros (they are zero padding of the conv input rows). */
 int ff_experts_resize(const float* stack, int ld, int B, int H, int W, int factor, void* out, int out_ld, int out_off, void* stream);
 /* SpatialGate (hierarchical_fusion.py:25-43), in place: x *= sigmoid(w2 . gelu(W1 x + b1) + b2); C in {32, 64}. */
 int ff_pixel_gate(void* x, int ld, long long P, int C, const float* w1, const float* b1, const float* w2, float b2, void* stream);

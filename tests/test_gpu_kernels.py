@@ -656,6 +656,16 @@ def test_pack_taps_and_split_bf16_convs():
     err = (out.cpu() - ref).abs().max().item()
     assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
     # (b) 3 -> 64 3x3 image layer: im2col (k = 3) with terms = 2, conv_gemm is a 1x1 over one 64-wide k-block
+    for (B, H, W) in ((3, 13, 37), (1, 8, 32)):      # partial and exactly-one 8 x 32 tiles of the packing kernel
+        img = torch.randn(B, 3, H, W, generator=g)
+        rows = torch.full((B * H * W, 4), 7.0)
+        rows[:, :3] = _nhwc(img)
+        im = torch.full((B * H * W, 64), 5.0, dtype=BF16, device=d)
+        ops.pack_taps(rows.to(d), B, H, W, 3, 3, 2, im)
+        torch.cuda.synchronize()
+        cols = F.unfold(img, 3, padding=1).view(B, 3, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 27)
+        chi = cols.to(BF16)
+        assert torch.equal(im.cpu(), torch.cat([chi, (cols - chi.float()).to(BF16), torch.zeros(B * H * W, 10, dtype=BF16)], 1))
     B, H, W = 2, 24, 48
     img = torch.rand(B, 3, H, W, generator=g)
     w = torch.randn(64, 3, 3, 3, generator=g) / math.sqrt(27)
