@@ -1819,6 +1819,43 @@ __global__ void __launch_bounds__(256) conv1x1_rows_kernel(const __grid_constant
     *reinterpret_cast<float4*>(q + o) = make_float4(act_apply(acc[o], a.act), act_apply(acc[o + 1], a.act), act_apply(acc[o + 2], a.act), act_apply(acc[o + 3], a.act));
 }
 
+// fp32 1x1 layer with C inputs and C outputs (the multi-scale mixers of the routing path, fusion_network.py:137-160, which stay fp32 in
+// front of the selector's hard threshold): one pixel per thread, the pixel's C inputs and C accumulators in registers, weights as
+// broadcast 16-byte shared-memory reads ([c][o] layout).  The generic kernel re-stages the input patch once per group of eight
+// output channels.
+template <int C>
+__global__ void __launch_bounds__(128) conv1x1_f32_square_kernel(const __grid_constant__ DirectArgs a, long long pixels) {
+  constexpr int WP = C + 4;                           // row pitch of the transposed weights (16-byte aligned rows, staggered banks)
+  extern __shared__ __align__(16) float sq_w[];      // [C][WP] as [c][o]
+  for (int i = threadIdx.x; i < C * C; i += 128) sq_w[(i % C) * WP + i / C] = __ldg(a.w + i);      // coalesced read of w[o][c], staged once per CTA
+  __syncthreads();
+  for (long long p = (long long)blockIdx.x * 128 + threadIdx.x; p < pixels; p += (long long)gridDim.x * 128) {
+  float xin[C], acc[C];
+  const float4* xp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.x) + p * a.x_ld);
+#pragma unroll
+  for (int i = 0; i < C / 4; ++i) {
+    const float4 v = __ldg(xp + i);
+    xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
+  }
+#pragma unroll
+  for (int o = 0; o < C; ++o) acc[o] = a.bias ? __ldg(a.bias + o) : 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float4* wp = reinterpret_cast<const float4*>(sq_w + c * WP);
+#pragma unroll
+    for (int o = 0; o < C; o += 4) {
+      const float4 w4 = wp[o >> 2];
+      acc[o] = fmaf(xin[c], w4.x, acc[o]); acc[o + 1] = fmaf(xin[c], w4.y, acc[o + 1]);
+      acc[o + 2] = fmaf(xin[c], w4.z, acc[o + 2]); acc[o + 3] = fmaf(xin[c], w4.w, acc[o + 3]);
+    }
+  }
+  float4* q = reinterpret_cast<float4*>(a.out_f32 + p * a.out_f32_ld);
+#pragma unroll
+  for (int o = 0; o < C; o += 4)
+    q[o >> 2] = make_float4(act_apply(acc[o], a.act), act_apply(acc[o + 1], a.act), act_apply(acc[o + 2], a.act), act_apply(acc[o + 3], a.act));
+  }
+}
+
 __global__ void __launch_bounds__(256) conv1x1_wide_bf16_kernel(const __grid_constant__ DirectArgs a, long long pixels) {
   const int oct = threadIdx.x & 7;      // output channels 8 oct .. 8 oct + 7
   float w[3][8], bv[8];
@@ -1873,6 +1910,21 @@ extern "C" int ff_conv_direct(const void* x, int x_is_bf16, int x_ld, int B, int
   if (k == 1 && x_is_bf16 && Cin == 32 && n_store == 8 && !mul_f32 && !out_bf16 && vf && x_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     const long long pixels = (long long)B * H * W;
     conv1x1_rows_kernel<32, 8><<<ff_cdiv(pixels, 256), 256, 0, st_>>>(a, pixels);
+    ++g_ff_launches;
+    FF_CHECK_LAUNCH("ff_conv_direct");
+    return FF_OK;
+  }
+  if (k == 1 && !x_is_bf16 && Cin == 64 && n_store == 64 && !mul_f32 && !out_bf16 && vf && x_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const long long pixels = (long long)B * H * W;
+    static FFPerDeviceFlag sq_configured;
+    bool& conf = sq_configured.get();
+    if (!conf) {
+      cudaError_t e = cudaFuncSetAttribute(conv1x1_f32_square_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 68 * 4);
+      if (e != cudaSuccess) { ff_set_error("ff_conv_direct: smem: %s", cudaGetErrorString(e)); return FF_ERR_CUDA; }
+      conf = true;
+    }
+    const long long want = ff_cdiv(pixels, 128), cap = (long long)ff_num_sms() * 4;
+    conv1x1_f32_square_kernel<64><<<(int)(want < cap ? want : cap), 128, 64 * 68 * 4, st_>>>(a, pixels);
     ++g_ff_launches;
     FF_CHECK_LAUNCH("ff_conv_direct");
     return FF_OK;

@@ -855,11 +855,12 @@ def test_conv_direct_any_size(cin, cout, k, H, W, B):
 
 @pytest.mark.parametrize("cin,cout,k,in_ld,out_ld,in_bf16,out_bf16,act", [
     (8, 1, 3, 8, 1, False, False, "sigmoid"), (16, 1, 3, 16, 1, False, False, "sigmoid"), (6, 16, 3, 8, 16, False, False, "gelu"),
-    (6, 16, 3, 6, 16, False, False, "gelu"), (32, 8, 1, 64, 8, True, False, "gelu"), (3, 64, 1, 4, 64, False, True, "none")])
+    (6, 16, 3, 6, 16, False, False, "gelu"), (32, 8, 1, 64, 8, True, False, "gelu"), (3, 64, 1, 4, 64, False, True, "none"),
+    (64, 64, 1, 64, 64, False, False, "none"), (64, 64, 1, 68, 64, False, False, "gelu")])
 @pytest.mark.parametrize("B,H,W", [(2, 37, 50), (1, 64, 96)])
 def test_conv_direct_specialised_small_layers(cin, cout, k, in_ld, out_ld, in_bf16, out_bf16, act, B, H, W):
     """The specialised forms ff_conv_direct dispatches to for the edge refiner's small layers at output resolution (3x3 8->1, 16->1,
-    6->16 in fp32; 1x1 32 bf16 -> 8; 1x1 3 -> 64 bf16), on whole and partial tiles, with channel pitches wider than the channel count,
+    6->16 in fp32; 1x1 32 bf16 -> 8; 1x1 3 -> 64 bf16) and for the fp32 64 -> 64 mixers of the routing path, on whole and partial tiles, with channel pitches wider than the channel count,
     against F.conv2d."""
     from isr2_b200 import ops, packing
     g = torch.Generator().manual_seed(61 + cin)

@@ -16,7 +16,7 @@ def timed(fn, n=10):
     return e0.elapsed_time(e1) * 1e3 / n
 cases = [("a2 8->1 3x3", 8, 1, 3, 8, 1, False, False, ops.ACT_SIGMOID), ("egate2 16->1 3x3", 16, 1, 3, 16, 1, False, False, ops.ACT_SIGMOID),
          ("egate0 6->16 3x3", 6, 16, 3, 8, 16, False, False, ops.ACT_GELU), ("a0 32->8 1x1", 32, 8, 1, 64, 8, True, False, ops.ACT_GELU),
-         ("pj 3->64 1x1", 3, 64, 1, 4, 64, False, True, ops.ACT_NONE)]
+         ("pj 3->64 1x1", 3, 64, 1, 4, 64, False, True, ops.ACT_NONE), ("ms_mix 64->64 1x1 fp32", 64, 64, 1, 64, 64, False, False, ops.ACT_NONE)]
 for name, cin, cout, k, ild, old, ibf, obf, act in cases:
     x = torch.randn(P, ild, device=dev).to(torch.bfloat16 if ibf else torch.float32)
     cp = (cout + 7) // 8 * 8
