@@ -9,15 +9,9 @@ python tools/bench_tail.py 16 128 > $O/${T}_bench_tail.txt 2>&1 || { echo "bench
 python tools/bench_dw.py 16 128 > $O/${T}_bench_dw.txt 2>&1 || { echo "bench_dw failed"; exit 1; }
 python tools/bench_naf.py 16 512 > $O/${T}_bench_naf.txt 2>&1 || { echo "bench_naf failed"; exit 1; }
 python tools/bench_small_convs.py 16 512 > $O/${T}_bench_small_convs.txt 2>&1 || { echo "bench_small_convs failed"; exit 1; }
-# 1. launch list of one step at the bench shape (experts serialised for attribution); skip the first (warm-up) forward
-N=$(FFB200_EXPERT_STREAMS=0 FFB200_GRAPHS=0 python -c "
-import sys; sys.path.insert(0,'.')
-import torch
-from isr2_b200 import lib
-from isr2_b200.model import FreqFusionB200
-m = FreqFusionB200('cuda:0', verbose=False); x = torch.rand(16,3,128,128,device='cuda:0'); m.forward(x); n0 = lib.launch_count(); m.forward(x); torch.cuda.synchronize(); print(lib.launch_count()-n0)")
-echo "launches per step: $N"
-FFB200_EXPERT_STREAMS=0 FFB200_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:unnamed -s $N -c $N --csv --log-file $O/${T}_launches_B16_S128.csv python tools/full_forward.py 16 128 2 > $O/p_ncu1.log 2>&1
+# 1. launch list of one steady-state step at the bench shape (experts serialised for attribution): the last forward of
+#    tools/full_forward.py sits between cudaProfilerStart / Stop, so every kernel of that step is listed (torch's too, if any)
+FFB200_EXPERT_STREAMS=0 FFB200_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled --profile-from-start off --csv --log-file $O/${T}_launches_B16_S128.csv python tools/full_forward.py 16 128 3 > $O/p_ncu1.log 2>&1
 python tools/agg_launches.py $O/${T}_launches_B16_S128.csv > $O/${T}_full_model_B16_S128_launches.txt
 # 2. --set full of 16 consecutive conv_gemm launches inside HAT blocks (DRAM traffic, tensor pipe, issue)
 FFB200_EXPERT_STREAMS=0 FFB200_GRAPHS=0 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:conv_gemm_tc -s 60 -c 16 -o $O/${T}_conv_gemm -f python tools/full_forward.py 16 128 1 > $O/p_ncu2.log 2>&1
