@@ -54,8 +54,35 @@ def _load_image(path):
     return torch.from_numpy(arr).permute(2, 0, 1).unsqueeze(0)
 
 
+_PNG_SIG = b"\x89PNG\r\n\x1a\n"
+
+
+def _decode_png_native(path):
+    """8-bit grey / grey+alpha / RGB / RGBA non-interlaced PNG -> uint8 [h, w, 3] through ff_png_decode_rgb8 (csrc/png_writer.cu:
+    chunk walk + un-filter in C, zlib's inflate), or None for any other file.  ctypes releases the GIL for the whole decode; PIL
+    holds it for ~0.3 ms per small file, which serialised the decode of a folder's first batch."""
+    import ctypes as C
+    import struct
+    with open(path, "rb") as f:
+        data = f.read()
+    if len(data) < 33 or data[:8] != _PNG_SIG or data[12:16] != b"IHDR":
+        return None
+    w, h = struct.unpack(">II", data[16:24])
+    if not (0 < w <= 65535 and 0 < h <= 65535 and w * h <= (1 << 28)):
+        return None
+    out = np.empty((h, w, 3), dtype=np.uint8)
+    rc = L.load().ff_png_decode_rgb8(data, C.c_longlong(len(data)), C.c_void_p(out.ctypes.data), C.c_longlong(out.nbytes), None, None)
+    return out if rc == 0 else None
+
+
 def _decode_u8(path):
-    """PNG -> uint8 HWC array; the /255 of io._load_image happens on the GPU (ff_u8_to_tiles, bit-identical)."""
+    """Image file -> uint8 HWC RGB array (io._load_image's Image.open(path).convert("RGB"); its /255 happens on the GPU in
+    ff_u8_to_tiles, bit-identical).  PNGs of the common kinds take the native reader, everything else (and FFB200_PNG_READER=pil)
+    goes through PIL."""
+    if os.environ.get("FFB200_PNG_READER", "native") != "pil":
+        arr = _decode_png_native(path)
+        if arr is not None:
+            return arr
     return np.ascontiguousarray(np.array(Image.open(path).convert("RGB"), dtype=np.uint8))
 
 

@@ -142,6 +142,16 @@ long long ff_png_bound_rgb8(int h, int w);
 long long ff_png_encode_rgb8(const unsigned char* rgb, int h, int w, long long row_stride, unsigned char* out, long long cap);
 
 /*
+ * ff_png_decode_rgb8 -- host-side PNG reader of the plugin's load path (models/team29_FreqFusion/io.py:64-68 _load_image:
+ * Image.open(path).convert("RGB")).  file: the n bytes of a PNG file; rgb: uint8 [h][w][3] with cap >= h*w*3 bytes (null: only
+ * out_h / out_w are filled from the header).  Handles 8-bit grey / grey+alpha / RGB / RGBA, non-interlaced (alpha dropped, grey
+ * replicated -- what convert("RGB") does); returns 0, FF_PNG_UNSUPPORTED (1) for any other file (the caller falls back to its
+ * general reader), negative on a bad argument.  Pure CPU code, thread safe; inflate is zlib's (libz.so.1 through dlopen).
+ */
+#define FF_PNG_UNSUPPORTED 1
+int ff_png_decode_rgb8(const unsigned char* file, long long n, unsigned char* rgb, long long cap, int* out_h, int* out_w);
+
+/*
  * ff_hab_tail -- everything of a HAT block after the attention as one kernel (hat_arch.py:303-309 HAB.forward tail,
  * :435-438 OCAB.forward tail):
  *     x1 = res + [a0 | a1] . wp^T + bp                  (attn.proj + shortcut; a1 / the second K half of wp carry the

@@ -398,3 +398,42 @@ def test_native_png_writer_round_trips():
     so.ff_png_encode_rgb8.restype = ctypes.c_longlong
     out = np.empty(16, np.uint8)
     assert so.ff_png_encode_rgb8(ctypes.c_void_p(smooth.ctypes.data), 512, 512, ctypes.c_longlong(1536), ctypes.c_void_p(out.ctypes.data), ctypes.c_longlong(16)) < 0
+
+
+def test_native_png_reader_matches_pil(tmp_path):
+    """ff_png_decode_rgb8 (csrc/png_writer.cu) against PIL's Image.open(path).convert("RGB") -- the reference's _load_image,
+    models/team29_FreqFusion/io.py:64-68 -- for every colour type it accepts (all five scanline filters occur: PIL picks them
+    adaptively), several sizes, files with many IDAT chunks and files of our own writer; palette / 16-bit / interlaced / non-PNG
+    files are declined (the caller then uses PIL)."""
+    import numpy as np
+    from PIL import Image
+    from isr2_b200 import io as ffio
+    rng = np.random.default_rng(9)
+    n = 0
+    for mode, chans in (("RGB", 3), ("RGBA", 4), ("L", 1), ("LA", 2)):
+        for (h, w) in ((1, 1), (7, 5), (64, 96), (339, 510)):
+            base = rng.integers(0, 256, (h // 8 + 2, w // 8 + 2, chans)).astype(np.uint8)
+            img = Image.fromarray(base.squeeze() if chans == 1 else base, mode=mode).resize((w, h), Image.BICUBIC)      # smooth content: Sub / Up / Avg / Paeth rows
+            for level in (1, 6, 0):
+                p = str(tmp_path / f"{mode}_{h}x{w}_{level}.png")
+                img.save(p, compress_level=level)
+                got = ffio._decode_png_native(p)
+                assert got is not None, p
+                assert np.array_equal(got, np.array(Image.open(p).convert("RGB"))), p
+                n += 1
+    noise = Image.fromarray(rng.integers(0, 256, (200, 300, 3), dtype=np.uint8))
+    p = str(tmp_path / "noise.png")
+    noise.save(p, compress_level=6)      # > 64 KiB of IDAT: PIL splits it into several chunks
+    assert np.array_equal(ffio._decode_png_native(p), np.array(noise))
+    p2 = str(tmp_path / "ours.png")
+    ffio._write_png(np.array(noise), p2)
+    assert np.array_equal(ffio._decode_png_native(p2), np.array(noise))
+    # declined files
+    pal = str(tmp_path / "pal.png"); noise.convert("P").save(pal)
+    i16 = str(tmp_path / "i16.png"); Image.fromarray(rng.integers(0, 65535, (9, 9)).astype(np.uint16)).save(i16)
+    lace = str(tmp_path / "jpeg.jpg"); noise.save(lace, quality=90)
+    trunc = str(tmp_path / "trunc.png"); open(trunc, "wb").write(open(p, "rb").read()[:5000])
+    for q in (pal, i16, lace, trunc):
+        assert ffio._decode_png_native(q) is None, q
+    assert np.array_equal(ffio._decode_u8(pal), np.array(Image.open(pal).convert("RGB")))      # ... and _decode_u8 falls back to PIL
+    assert n == 48
