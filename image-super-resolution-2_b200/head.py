@@ -215,21 +215,47 @@ class HeadRunner:
         return c
 
     def collaborative(self, feats, stack, B, h, w, intermediates=None):
-        """EnhancedCollaborativeWithLKA.forward (large_kernel_attention.py:327-419) on expert features of the LR size:
-        feats = {'hat': [B,180,h,w], 'dat': [B,180,h,w], 'nafnet': [B,64,h,w]} fp32 NCHW on the device.  Modulates channels 0-8 of the
+        """EnhancedCollaborativeWithLKA.forward (large_kernel_attention.py:327-419):
+        feats = {'hat': [B,180,h,w], 'dat': [B,180,h,w], 'nafnet': [B,64,h,w]} fp32 NCHW on the device; as in the reference a map with
+        other channel counts is truncated / zero padded, larger maps are resized to the smallest (which must be the LR size) and a
+        missing expert contributes zeros.  Modulates channels 0-8 of the
         expert stack in place: out_e <- clamp(out_e * (1 + 0.2 (mod_e - 0.5)), 0, 1) with mod_e [B,3] from the e-th modulation head."""
         c = self._pack_collaborative()
         ws, lib, st, ck = self.ws, L.load(), ops._stream, L.check
         P = B * h * w
         T = 3 * P
         stk = ws.get("co_stk", P, 384, BF16)
+        present = [n for n in ("hat", "dat", "nafnet") if feats.get(n) is not None]
+        if not present:
+            return stack                    # no features at all: the expert outputs pass through (large_kernel_attention.py:358-359)
+        for n in present:
+            f = feats[n]
+            if not (torch.is_tensor(f) and f.is_cuda and f.dim() == 4 and f.shape[0] == B):
+                raise L.FFError(f"expert_features['{n}'] must be a CUDA tensor [B={B}, C, H, W], got {tuple(f.shape) if torch.is_tensor(f) else type(f)}")
+        # aligned maps are brought to the smallest spatial size among them (:362-369); the modulation heads run at 4x that size here
+        mh, mw = min(feats[n].shape[2] for n in present), min(feats[n].shape[3] for n in present)
+        if (mh, mw) != (h, w):
+            raise L.FFError(f"the smallest expert feature map is {mh}x{mw}; it must have the LR size {h}x{w} (the SR outputs are 4x that)")
         for e, name in enumerate(("hat", "dat", "nafnet")):
             wgt, bias, cin, cp = c["align"][e]
-            f = feats[name]
-            if tuple(f.shape) != (B, cin, h, w) or not f.is_cuda:
-                raise L.FFError(f"expert_features['{name}'] must be a CUDA tensor of shape {(B, cin, h, w)} (features at the LR size), got {tuple(f.shape)}")
+            if name not in present:         # an expert without features contributes zeros (:374-377)
+                stk[:, 128 * e:128 * (e + 1)].zero_()
+                continue
+            f = feats[name].float()
+            if f.shape[1] > cin:            # too many channels: truncated; too few: zero padded (:346-355)
+                f = f[:, :cin]
+            elif f.shape[1] < cin:
+                f = F.pad(f, (0, 0, 0, 0, 0, cin - f.shape[1]))
+            f = f.contiguous()
+            if tuple(f.shape[2:]) != (h, w):
+                # the reference resizes the ALIGNED map; a 1x1 conv and a bilinear resize commute (the interpolation weights sum
+                # to one, so the bias passes through), so the features are resized instead: every channel plane as a 1-channel image
+                hf, wf = f.shape[2], f.shape[3]
+                fr = ws.get(f"co_fr{e}", B * cin, h * w, F32)
+                ck(lib.ff_bilinear_f32(_ptr(f), B * cin, hf, wf, 1, 1, _ptr(fr), h, w, 1, 0, None, st()), "ff_bilinear_f32")
+                f = fr
             fb = ws.get(f"co_f{e}", P, cp, BF16)
-            ck(lib.ff_nchw_to_nhwc_bf16(_ptr(f.contiguous().float()), B, cin, h, w, _ptr(fb), cp, st()), "ff_nchw_to_nhwc_bf16")
+            ck(lib.ff_nchw_to_nhwc_bf16(_ptr(f), B, cin, h, w, _ptr(fb), cp, st()), "ff_nchw_to_nhwc_bf16")
             ops.conv_gemm(fb, B, h, w, cp, wgt, n_store=128, bias=bias, out_bf16=stk[:, 128 * e:])
         Wt = 3 * w
         stk_t = stk.view(T, 128)

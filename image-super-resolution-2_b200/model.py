@@ -287,9 +287,10 @@ class FreqFusionB200:
         src/models/enhanced_fusion.py:756-812, eval path; BASELINE.json configs[0]).
         expert_outputs: dict with keys 'hat', 'dat', 'nafnet' (the cached-dataset aliases 'drct' -> hat and 'grl' / 'mambair' -> dat
         of src/data/cached_dataset.py are accepted), each fp32 NCHW [B,3,4h,4w] on the device.
-        expert_features: optional dict of the experts' intermediate features at the LR size ({'hat': [B,180,h,w], 'dat': [B,180,h,w],
+        expert_features: optional dict of the experts' intermediate features ({'hat': [B,180,h,w], 'dat': [B,180,h,w],
         'nafnet': [B,64,h,w]}); when given, the collaborative branch (EnhancedCollaborativeWithLKA) modulates the expert outputs first,
-        exactly as the reference does in cached mode."""
+        exactly as the reference does in cached mode -- including its handling of other channel counts (truncated / zero padded), of
+        larger feature maps (resized to the smallest, which must have the LR size) and of experts without features (zeros)."""
         alias = {"drct": "hat", "grl": "dat", "mambair": "dat"}
         ex = {alias.get(k, k): v for k, v in expert_outputs.items()}
         missing = [k for k in ("hat", "dat", "nafnet") if k not in ex]
@@ -310,10 +311,8 @@ class FreqFusionB200:
             if expert_features is not None:
                 # phase 4 of the reference: collaborative feature learning runs whenever features are passed
                 # (apply_collaborative_learning, enhanced_fusion.py:466-496; MODEL_CONFIG enables it)
+                # (an expert without features contributes zeros to the cross-expert attention, large_kernel_attention.py:374-377)
                 fe = {alias.get(k, k): v for k, v in expert_features.items()}
-                miss = [k for k in ("hat", "dat", "nafnet") if k not in fe]
-                if miss:
-                    raise KeyError(f"forward_with_precomputed: missing expert features {miss}")
                 self._runners["head"].collaborative(fe, stack, B, h, w, intermediates=intermediates)
             return self._runners["head"].forward(lr, stack, out=out, intermediates=intermediates)
 

@@ -16,12 +16,31 @@ NAMES = ("hat", "dat", "nafnet")
 
 def collaborative(sd, feats, outputs, return_mod=False):
     """feats: {'hat': [B,180,h,w], 'dat': [B,180,h,w], 'nafnet': [B,64,h,w]}; outputs: [hat, dat, nafnet] SR tensors.
-    Returns the three modulated SR tensors (large_kernel_attention.py:327-419, equal feature sizes and channel counts)."""
+    Returns the three modulated SR tensors (large_kernel_attention.py:327-419).  As in the reference (:337-378) a feature map with
+    more channels than its align layer expects is truncated, one with fewer is zero padded, aligned maps are brought to the smallest
+    spatial size among them (bilinear, align_corners=False), and an expert without features contributes zeros."""
     p = "collaborative."
     dim, heads = 128, 8
-    aligned = [F.conv2d(feats[n], sd[p + f"align_layers.{n}.weight"], sd[p + f"align_layers.{n}.bias"]) for n in NAMES]
-    B, _, H, W = aligned[0].shape
-    flat = torch.stack(aligned, 1).permute(0, 3, 4, 1, 2).reshape(B * H * W, 3, dim)
+    aligned = {}
+    for n in NAMES:
+        if n not in feats:
+            continue
+        w_, b_ = sd[p + f"align_layers.{n}.weight"], sd[p + f"align_layers.{n}.bias"]
+        f, want = feats[n], w_.shape[1]
+        if f.shape[1] > want:
+            f = f[:, :want]
+        elif f.shape[1] < want:
+            f = F.pad(f, (0, 0, 0, 0, 0, want - f.shape[1]))
+        aligned[n] = F.conv2d(f, w_, b_)
+    if not aligned:
+        return (list(outputs), None) if return_mod else list(outputs)
+    H, W = min(a.shape[2] for a in aligned.values()), min(a.shape[3] for a in aligned.values())
+    for n in aligned:
+        if aligned[n].shape[2:] != (H, W):
+            aligned[n] = F.interpolate(aligned[n], size=(H, W), mode="bilinear", align_corners=False)
+    B = next(iter(aligned.values())).shape[0]
+    like = next(iter(aligned.values()))
+    flat = torch.stack([aligned.get(n, torch.zeros_like(like)) for n in NAMES], 1).permute(0, 3, 4, 1, 2).reshape(B * H * W, 3, dim)
     n1 = F.layer_norm(flat, (dim,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
     qkv = F.linear(n1, sd[p + "cross_attn.in_proj_weight"], sd[p + "cross_attn.in_proj_bias"])
     q, k, v = [t.view(-1, 3, heads, dim // heads).transpose(1, 2) for t in qkv.chunk(3, -1)]
@@ -51,3 +70,11 @@ def synth_features(B, h, w, seed):
     g = torch.Generator().manual_seed(seed)
     return {"hat": torch.randn(B, 180, h, w, generator=g) * 0.5, "dat": torch.randn(B, 180, h, w, generator=g) * 0.5,
             "nafnet": torch.randn(B, 64, h, w, generator=g) * 0.5}
+
+
+def synth_features_mixed(B, h, w, seed):
+    """Features that take every branch of the reference's alignment step: 200 channels for hat (truncated to 180), 150 for dat
+    (zero padded to 180), nafnet at twice the spatial size (its aligned map is resized down to h x w)."""
+    g = torch.Generator().manual_seed(seed)
+    return {"hat": torch.randn(B, 200, h, w, generator=g) * 0.5, "dat": torch.randn(B, 150, h, w, generator=g) * 0.5,
+            "nafnet": torch.randn(B, 64, 2 * h, 2 * w, generator=g) * 0.5}

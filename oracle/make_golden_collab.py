@@ -38,6 +38,19 @@ def main():
                 "enhanced": torch.cat([enh[k] for k in ("hat", "dat", "nafnet")], 1).half()}, os.path.join(GOLD, "head_collab_64.pt"))
     print("head_collab_64.pt", os.path.getsize(os.path.join(GOLD, "head_collab_64.pt")), "mean modulation", mods,
           "effect on the output", (out - plain).abs().max().item())
+    # second golden: the feature-handling paths of EnhancedCollaborativeWithLKA.forward (large_kernel_attention.py:337-378) --
+    # too many channels (truncated), too few (zero padded), a larger spatial size (aligned map resized to the smallest)
+    lr2 = lr_image(1, 32, 32, 117)
+    g2 = torch.Generator().manual_seed(118)
+    up2 = F.interpolate(lr2, scale_factor=4, mode="bicubic", align_corners=False)
+    ex2 = {k: (up2 + s * torch.randn(1, 3, 128, 128, generator=g2)).clamp(0, 1) for k, s in (("hat", 0.01), ("dat", 0.02), ("nafnet", 0.03))}
+    feats2 = collab.synth_features_mixed(1, 32, 32, 119)
+    with torch.no_grad():
+        out2, inter2 = model.forward_with_precomputed(lr2, ex2, feats2, return_intermediates=True)
+    enh2 = inter2["enhanced_outputs"]
+    torch.save({"lr": lr2, "expert_seed": 118, "feature_seed": 119, "out": out2,
+                "enhanced": torch.cat([enh2[k] for k in ("hat", "dat", "nafnet")], 1).half()}, os.path.join(GOLD, "head_collab_mixed_32.pt"))
+    print("head_collab_mixed_32.pt", os.path.getsize(os.path.join(GOLD, "head_collab_mixed_32.pt")))
 
 
 if __name__ == "__main__":

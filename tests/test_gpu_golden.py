@@ -106,8 +106,37 @@ def test_forward_with_precomputed_and_expert_features_vs_reference_golden():
     e_out = (out - g["out"]).abs().max().item()
     print(f"collaborative: enhanced expert outputs {e_enh:.2e}, final output {e_out:.2e}")
     assert e_enh < 2e-3 and e_out < 2e-2
-    with pytest.raises(KeyError):
-        m.forward_with_precomputed(lr.cuda(), {k: v.cuda() for k, v in ex.items()}, {"hat": feats["hat"].cuda()})
+    # an expert without features contributes zeros to the cross-expert attention (large_kernel_attention.py:374-377): against the oracle
+    from oracle import collab
+    only_hat = {"hat": feats["hat"]}
+    with torch.no_grad():
+        ref = torch.cat(collab.collaborative(m.state["fusion"], only_hat, [ex["hat"], ex["dat"], ex["nafnet"]]), 1)
+    m.forward_with_precomputed(lr.cuda(), {k: v.cuda() for k, v in ex.items()}, {"hat": feats["hat"].cuda()})
+    stack = m._stack(1, 64, 64).cpu().view(1, 256, 256, 12)[..., :9].permute(0, 3, 1, 2)
+    assert (stack - ref).abs().max().item() < 2e-3
+    with pytest.raises(Exception):      # the smallest feature map must have the LR size
+        m.forward_with_precomputed(lr.cuda(), {k: v.cuda() for k, v in ex.items()}, {"hat": feats["hat"][..., :32, :32].cuda()})
+
+
+def test_collaborative_feature_alignment_paths_vs_reference_golden():
+    """The alignment step of EnhancedCollaborativeWithLKA.forward (large_kernel_attention.py:337-378) on features that take every branch
+    of it -- 200 channels for hat (truncated), 150 for dat (zero padded), nafnet at twice the spatial size (resized to the smallest) --
+    against the reference itself: tests/golden/head_collab_mixed_32.pt (oracle/make_golden_collab.py)."""
+    from isr2_b200 import model as M
+    from oracle import collab
+    g = torch.load(os.path.join(GOLD, "head_collab_mixed_32.pt"))
+    lr = g["lr"]
+    gen = torch.Generator().manual_seed(g["expert_seed"])
+    up = F.interpolate(lr, scale_factor=4, mode="bicubic", align_corners=False)
+    ex = {k: (up + s * torch.randn(1, 3, 128, 128, generator=gen)).clamp(0, 1) for k, s in (("hat", 0.01), ("dat", 0.02), ("nafnet", 0.03))}
+    feats = collab.synth_features_mixed(1, 32, 32, g["feature_seed"])
+    m = M.FreqFusionB200("cuda:0", init_seed=0, verbose=False)
+    out = m.forward_with_precomputed(lr.cuda(), {k: v.cuda() for k, v in ex.items()}, {k: v.cuda() for k, v in feats.items()}).cpu()
+    stack = m._stack(1, 32, 32).cpu().view(1, 128, 128, 12)[..., :9].permute(0, 3, 1, 2)
+    e_enh = (stack - g["enhanced"].float()).abs().max().item()
+    e_out = (out - g["out"]).abs().max().item()
+    print(f"collaborative, mixed features: enhanced expert outputs {e_enh:.2e}, final output {e_out:.2e}")
+    assert e_enh < 2e-3 and e_out < 2e-2
 
 
 def test_collaborative_modulation_vs_oracle_with_strong_heads():
