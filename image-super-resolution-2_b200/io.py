@@ -256,6 +256,18 @@ class _Job:
     __slots__ = ("index", "path", "h", "w", "up", "tiles", "sr", "remaining", "lo", "hi")
 
 
+_POOLS = {}
+
+
+def _shared_pool(kind, n):
+    """Process-wide thread pools of the I/O pipeline, keyed by role and size (joined by the interpreter at exit)."""
+    key = (kind, n)
+    p = _POOLS.get(key)
+    if p is None:
+        p = _POOLS[key] = ThreadPoolExecutor(max_workers=n, thread_name_prefix=f"ffb200-{kind}")
+    return p
+
+
 class ImagePipeline:
     """Runs a list of image files through the model with cross-image batching and overlapped host I/O."""
 
@@ -266,8 +278,9 @@ class ImagePipeline:
         # folder was staged 80 ms late).  numpy / zlib release the GIL, so the encoders scale with the cores.
         ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)      # ranks sharing this host's cores (torchrun sets it)
         n = io_threads or int(os.environ.get("FFB200_IO_THREADS", str(min(32, max(4, (os.cpu_count() or 8) // max(ranks_here, 1))))))
-        self.pool = ThreadPoolExecutor(max_workers=n)                       # PNG encode + file write
-        self.dec_pool = ThreadPoolExecutor(max_workers=min(4, n))           # PNG decode
+        # the pools are process-wide: a second main() call (test.py runs one per split) does not pay for 20 thread starts and joins
+        self.pool = _shared_pool("encode", n)                               # PNG encode + file write
+        self.dec_pool = _shared_pool("decode", min(4, n))                   # PNG decode
         self.inflight = []                                                  # (event, pinned input buffer) of H2D copies not yet known to be done
         self.pinned = _PINNED
         self.copy_stream = torch.cuda.Stream(device=self.dev)
@@ -424,8 +437,10 @@ class ImagePipeline:
         return self.records
 
     def close(self):
-        self.pool.shutdown(wait=True)
-        self.dec_pool.shutdown(wait=True)
+        """run() has already waited for every save; the (shared) pools stay alive for the next call."""
+        for f in self.saves:
+            f.result()
+        self.saves = []
 
 
 def _image_sizes(paths):
