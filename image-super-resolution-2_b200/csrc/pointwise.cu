@@ -1734,7 +1734,9 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(const __grid_constan
 #pragma unroll
     for (int r = 0; r < PY; ++r) acc[r][o] = bv;
   }
-#pragma unroll
+  // (NOUT = 16: the fully unrolled body is ~80 KB of straight-line code, more than the instruction cache holds with eight warps at
+  //  different addresses; one channel per iteration keeps it at ~13 KB)
+#pragma unroll(NOUT >= 8 ? 1 : CIN)
   for (int c = 0; c < CIN; ++c) {
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
