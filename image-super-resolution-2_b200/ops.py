@@ -37,7 +37,15 @@ class KernelProfile:
 PROFILE = None   # set to a KernelProfile instance to record
 
 
+# torch.cuda.current_stream() costs ~4 us of Python per call (device-index plumbing) and every launch asks for it: 1 358 times per
+# forward.  The raw accessors below return the same cudaStream_t (they are what torch.cuda.current_stream wraps).
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_RAW_DEVICE = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream():
+    if _RAW_STREAM is not None and _RAW_DEVICE is not None:
+        return C.c_void_p(_RAW_STREAM(_RAW_DEVICE()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
