@@ -422,7 +422,7 @@ def main():
         traffic, traffic_note = tj["mean_dram_bytes_per_launch"], tj["source"]
     step_ms = ms_total / K
     roofline = {
-        "kernel": "conv_gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear, all instances) + hab_tail_kernel / mlp_fused_kernel (the fused proj + MLP chains of the HAT blocks)",
+        "kernel": "conv_gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear, all instances) + hab_tail_kernel / mlp_fused_kernel (the fused proj + MLP chains of the HAT blocks) + naf_tail_kernel (the fused conv3 / conv4 / conv5 chain of NAFNet's 64-channel blocks)",
         "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
         "peak_source": pk["src"] + " (bf16 cuBLAS, sustained)", "traffic": traffic, "traffic_note": traffic_note,
         "algorithmic_bytes_per_launch": prof["algo_bytes"] / max(prof["launches"], 1),
