@@ -342,6 +342,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_tiles = a.m_tiles * a.n_tiles;
   const int kblocks = a.ntaps * a.cchunks;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -367,6 +368,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();      // everything above touches no tensor of the forward; from here on the predecessor's writes are visible
   const uint32_t tmem_base = tmem_base_smem;
 
   // The producer and MMA warps stay converged: every lane runs the loops and polls the barriers, one elected lane issues
@@ -1308,7 +1310,8 @@ int launch_tc(const Maps& m, const Args& a, cudaStream_t st) {
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < ff_num_sms() ? tiles : ff_num_sms();
-  conv_gemm_tc_kernel<BN, EPI, HALO><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(m.A, m.B, m.O, m.R, m.O32, m.X, m.A2, a);
+  const cudaError_t le = ff_launch_pdl(conv_gemm_tc_kernel<BN, EPI, HALO>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, m.A, m.B, m.O, m.R, m.O32, m.X, m.A2, a);
+  if (le != cudaSuccess) { ff_set_error("ff_conv_gemm: launch failed: %s", cudaGetErrorString(le)); return FF_ERR_CUDA; }
   FF_CHECK_LAUNCH("ff_conv_gemm");
   return FF_OK;
 }

@@ -7,6 +7,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#ifdef __cplusplus
+#include <utility>
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // error plumbing: every C-ABI entry returns 0 or a negative code, message via ff_last_error()
@@ -49,12 +52,43 @@ struct FFPerDeviceFlag {
   }
 };
 
+// Programmatic dependent launch (PDL): a kernel launched through ff_launch_pdl() may become resident while its predecessor in
+// the stream is still draining -- its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch, staging of
+// STATIC parameters) and then block in pdl_wait() until the predecessor has completed and its writes are visible.  Every kernel
+// launched this way executes pdl_wait() before its first access to memory another kernel of the forward writes or reads, and
+// pdl_launch_dependents() at its top so that its own successor may do the same.  The launch attribute is OFF unless FFB200_PDL=1
+// (without it the two instructions are no-ops and the launch is an ordinary one): measured at the bench shape (r02u), the step is
+// 0.6 % SLOWER with it -- the three expert streams already fill the drain of one kernel with CTAs of the other experts, and early
+// resident CTAs parked in pdl_wait() take those SMs away from them.
+bool ff_pdl_enabled();
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ff_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ff_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
+
 typedef __nv_bfloat16 bf16;
 
 // ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// PDL (see ff_launch_pdl above)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

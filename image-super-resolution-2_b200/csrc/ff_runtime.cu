@@ -2,6 +2,7 @@
 #include "ff_common.cuh"
 #include "../../include/ffb200.h"
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 long long g_ff_launches = 0;
@@ -22,6 +23,11 @@ int ff_num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+bool ff_pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("FFB200_PDL"); return e && e[0] == '1'; }();
+  return on;
 }
 
 extern "C" int ff_abi_version(void) { return FFB200_ABI_VERSION; }

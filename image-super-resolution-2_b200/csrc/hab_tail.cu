@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) hab_tail_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = a.m_tiles;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm.A0); tma_prefetch_desc(&tm.Wp); tma_prefetch_desc(&tm.W1); tma_prefetch_desc(&tm.W2);
     if (a.has_cab) { tma_prefetch_desc(&tm.A1); tma_prefetch_desc(&tm.WpD); }
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) hab_tail_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();      // the prologue above reads static parameters only; the predecessor's tensors are touched from here on
   const uint32_t tmem_base = tmem_slot;
 
   auto tile_coords = [&](int tile, int& b, int& y0, int& x0) {
@@ -759,7 +761,8 @@ extern "C" int ff_hab_tail(const FFHabTail* pp, void* stream) {
     configured = true;
   }
   const int grid = a.m_tiles < ff_num_sms() ? a.m_tiles : ff_num_sms();
-  hab_tail_kernel<<<grid, NTHREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tm, a);
+  const cudaError_t le = ff_launch_pdl(hab_tail_kernel, dim3(grid), dim3(NTHREADS), SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tm, a);
+  if (le != cudaSuccess) { ff_set_error("ff_hab_tail: launch failed: %s", cudaGetErrorString(le)); return FF_ERR_CUDA; }
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_hab_tail");
   return FF_OK;

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) naf_tail_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = a.m_tiles;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm.A0); tma_prefetch_desc(&tm.W3); tma_prefetch_desc(&tm.W4); tma_prefetch_desc(&tm.W5); tma_prefetch_desc(&tm.R);
     mbar_init(&w_full, 1);
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) naf_tail_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();      // the prologue above reads static parameters only; the predecessor's tensors are touched from here on
   const uint32_t tmem_base = tmem_slot;
 
   auto tile_coords = [&](int tile, int& b, int& y0, int& x0) {
@@ -426,7 +428,8 @@ extern "C" int ff_naf_tail(const FFNafTail* pp, void* stream) {
   }
   const int cap = 2 * ff_num_sms();
   const int grid = a.m_tiles < cap ? a.m_tiles : cap;
-  naf_tail_kernel<<<grid, NTHREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tm, a);
+  const cudaError_t le = ff_launch_pdl(naf_tail_kernel, dim3(grid), dim3(NTHREADS), SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tm, a);
+  if (le != cudaSuccess) { ff_set_error("ff_naf_tail: launch failed: %s", cudaGetErrorString(le)); return FF_ERR_CUDA; }
   ++g_ff_launches;
   FF_CHECK_LAUNCH("ff_naf_tail");
   return FF_OK;

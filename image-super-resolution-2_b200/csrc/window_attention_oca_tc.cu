@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) ocab_attention_tc_kernel(const __
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head_l = blockIdx.x % p.heads;       // heads are the fast index: the CTAs sharing a window run together
   const int head = p.head_off + head_l;
+  pdl_launch_dependents();
+  pdl_wait();      // the first thing this kernel does is fetch q / k / v, which the predecessor wrote
   int win = blockIdx.x / p.heads;
   const int nwx = p.W >> 4, nwy = p.H >> 4;
   const int b = win / (nwx * nwy);
@@ -376,7 +378,8 @@ int ff_window_attention_oca_tc_try(const FFWinAttn& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((unsigned)(p.B * (p.H / 16) * (p.W / 16) * p.heads));
-  ocab_attention_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
+  const cudaError_t le = ff_launch_pdl(ocab_attention_tc_kernel, grid, dim3(NTHREADS), SMEM_BYTES, st, p);
+  if (le != cudaSuccess) { ff_set_error("ff_window_attention(oca tc): launch failed: %s", cudaGetErrorString(le)); return FF_ERR_CUDA; }
   FF_CHECK_LAUNCH("ff_window_attention(oca tc)");
   return FF_OK;
 }

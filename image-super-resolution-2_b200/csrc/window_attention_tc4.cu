@@ -232,6 +232,8 @@ __global__ void __launch_bounds__(NTHREADS, 4) window_attention_tc4_kernel(const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head_l = blockIdx.x % p.heads;       // heads are the fast index: the CTAs sharing a window run together
   const int head = p.head_off + head_l;
+  pdl_launch_dependents();
+  pdl_wait();      // the first thing this kernel does is fetch q / k / v, which the predecessor wrote
   // Padded geometry (DAT, dat_arch.py:505-528): windows / shift / mask regions on the Hp x Wp grid, tokens beyond H x W are
   // all-zero q / k / v rows (their V row keeps the all-ones column: as keys they still take softmax mass), never stored.
   const int Hp = p.Hp > 0 ? p.Hp : p.H, Wp = p.Wp > 0 ? p.Wp : p.W;
@@ -475,7 +477,8 @@ int launch_tc4(const FFWinAttn& p, cudaStream_t st) {
   }
   if (!use_tma) memset(&tm, 0, sizeof(tm));
   dim3 grid((unsigned)(p.B * (Hp / G::WH) * (Wp / G::WW) * p.heads));
-  window_attention_tc4_kernel<G><<<grid, NTHREADS, G::SMEM_BYTES, st>>>(p, tm, use_tma);
+  const cudaError_t le = ff_launch_pdl(window_attention_tc4_kernel<G>, grid, dim3(NTHREADS), G::SMEM_BYTES, st, p, tm, use_tma);
+  if (le != cudaSuccess) { ff_set_error("ff_window_attention(tc4): launch failed: %s", cudaGetErrorString(le)); return FF_ERR_CUDA; }
   FF_CHECK_LAUNCH("ff_window_attention(tc4)");
   return FF_OK;
 }
