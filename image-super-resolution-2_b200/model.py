@@ -199,7 +199,9 @@ class FreqFusionB200:
         # function returns -- `lr` / `stack` are therefore never used by a side stream outside this call, which is why no
         # record_stream() is needed on them.
         if not hasattr(self, "_streams"):
-            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+            # FFB200_STREAM_PRIO="<dat>,<nafnet>" (0 = default, -1 = high): block-scheduling priority of the side streams
+            prio = [int(v) for v in os.environ.get("FFB200_STREAM_PRIO", "0,0").split(",")]
+            self._streams = [torch.cuda.Stream(device=self.device, priority=prio[i]) for i in range(2)]
         cur = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
         ev.record(cur)
